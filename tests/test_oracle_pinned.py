@@ -1,0 +1,90 @@
+"""CPU: pin the oracle (oracle/*.py) against golden vectors produced by the reference's own Triton
+kernels (tools/make_golden.py).  Quantizer codes and scales: bit-exact.  Attention: tolerance below."""
+import pytest
+import torch
+
+from conftest import cos_sim, golden_names, load_golden
+from oracle import attention as A
+from oracle import quant as Q
+
+ATTN = golden_names("attn_")
+
+
+@pytest.mark.parametrize("name", ATTN)
+def test_q1_q4_bit_exact(name):
+    g = load_golden(name)
+    qi, qs, ki, ks = Q.per_block_int8_q1(g["q"], g["k"], g["km"], sm_scale=g["sm_scale"], tensor_layout=g["layout"])
+    assert torch.equal(qi, g["q_int8"]) and torch.equal(ki, g["k_int8"])
+    assert torch.equal(qs, g["q_scale"]) and torch.equal(ks, g["k_scale"])
+    _, _, k4, k4s = Q.per_block_int8_q1(g["q"], g["k"], g["km"], sm_scale=g["sm_scale"], tensor_layout=g["layout"], kbits=4)
+    assert torch.equal(k4, g["k_int4"]) and torch.equal(k4s, g["k_int4_scale"])
+    assert int(k4.abs().max()) <= 7
+
+
+@pytest.mark.parametrize("name", [n for n in ATTN if "causal" not in n])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_q3_per_thread_bit_exact(name, bits):
+    g = load_golden(name)
+    qi, qs, ki, ks = Q.per_thread(g["q"], g["k"], g["km"], tensor_layout=g["layout"], bits=bits)
+    p = f"pt{bits}_"
+    assert torch.equal(qi, g[p + "q"]) and torch.equal(ki, g[p + "k"])
+    assert torch.equal(qs, g[p + "qs"]) and torch.equal(ks, g[p + "ks"])
+
+
+@pytest.mark.parametrize("name", ATTN)
+def test_attention_emulator_matches_reference_kernel(name):
+    """Tolerance: the emulator restates the block algorithm in fp32 torch ops; the interpreter's exp2 and
+    fp16 dot differ in the last bit -> allow 4 output ulps (fp16: 2^-10 relative at |o|<=4; bf16: 2^-7)."""
+    g = load_golden(name)
+    o, lse2 = A.attn_block_emulator(g["q_int8"], g["k_int8"], g["v"].to(torch.float16), g["q_scale"], g["k_scale"],
+                                    g["layout"], bool(g["causal"]), output_dtype=g["o"].dtype, return_lse=True)
+    tol = 4e-3 if g["o"].dtype == torch.float16 else 3.2e-2
+    assert (o.float() - g["o"].float()).abs().max() <= tol
+    assert (lse2 - g["lse2"]).abs().max() <= 1e-4
+    assert cos_sim(o, g["o"]) > 0.99999
+    o4, _ = A.attn_block_emulator(g["q_int8"], g["k_int4"], g["v"].to(torch.float16), g["q_scale"], g["k_int4_scale"],
+                                  g["layout"], bool(g["causal"]), output_dtype=g["o"].dtype)
+    assert (o4.float() - g["o_k4"].float()).abs().max() <= tol
+
+
+@pytest.mark.parametrize("name", ATTN)
+def test_api_glue_vs_sdpa(name):
+    """End-to-end oracle (core.py:269-352 restated) stays close to FP32 SDPA -- the reference's own
+    acceptance procedure (example/test_sageattn_operator.py:92-94) with an explicit threshold."""
+    g = load_golden(name)
+    causal = bool(g["causal"])
+    o, lse = A.lowbit_fa_api(g["q"], g["k"], g["v"], g["layout"], causal, return_lse=True, compat_tail=False)
+    ref, lse_ref = A.sdpa_fp32(g["q"], g["k"], g["v"], g["layout"], causal, return_lse=True)
+    assert cos_sim(o, ref) > 0.999
+    assert (lse - lse_ref).abs().max() < 0.05
+
+
+@pytest.mark.parametrize("bit", [2, 4, 8])
+def test_q5_kivi_pack_bit_exact(bit):
+    g = load_golden(f"kivi_b{bit}")
+    code, scale, mn = Q.kivi_quantize_and_pack(g["data"], int(g["group_size"]), bit)
+    assert torch.equal(code, g["code"])
+    assert torch.equal(scale.view(torch.int16), g["scale"].view(torch.int16))
+    assert torch.equal(mn.view(torch.int16), g["mn"].view(torch.int16))
+    x = Q.kivi_unpack_and_dequant(code, scale, mn, 32, bit)
+    err = (x.float() - g["data"].float()).abs().max()
+    assert err <= (g["data"].float().amax() - g["data"].float().amin()) / (2 ** bit - 1)
+
+
+def test_pack_unpack_roundtrip():
+    for bits, lim in ((4, 7), (2, 1)):
+        c = torch.randint(-lim, lim + 1, (2, 3, 17, 64), dtype=torch.int8)
+        p = Q.pack_codes(c, bits)
+        assert p.shape[-1] == 64 * bits // 8
+        assert torch.equal(Q.unpack_codes(p, bits), c)
+
+
+def test_k_mean_order_independent():
+    torch.manual_seed(1)
+    k = (torch.randn(1, 2, 300, 64) * 3 + 5).half()
+    km = Q.k_mean(k)
+    perm = torch.randperm(300)
+    assert torch.equal(km, Q.k_mean(k[:, :, perm]))
+    assert (km.float() - k.float().mean(dim=2, keepdim=True)).abs().max() < 4e-3
+    kn = k.permute(0, 2, 1, 3).contiguous()
+    assert torch.equal(Q.k_mean(kn, "NHD").permute(0, 2, 1, 3), km)
