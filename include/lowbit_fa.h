@@ -1,0 +1,158 @@
+/* lowbit_fa.h -- C ABI of liblowbit_fa_b200.so (hand-written sm_100a CUDA).
+ *
+ * This is the drop-in boundary for the reference's low-bit FlashAttention hot path
+ * (Charles2530/lowbit_quant_fa2_paddle; paths below are relative to that repository).
+ * Every entry point takes plain device pointers, sizes, element strides and a cudaStream_t
+ * (as void*).  No framework types cross this boundary; the Python host code in
+ * lowbit_quant_fa2_paddle_b200/ obtains pointers from Paddle / torch tensors (DLPack hand-off)
+ * and calls these through ctypes.
+ *
+ * Conventions
+ *   - tensors are addressed as logical [B, H, N, D] with element strides (stride_b, stride_h,
+ *     stride_n); the last dimension is contiguous (src/core.py:288-290).  HND and NHD layouts of
+ *     the reference differ only in the strides the host passes (quant_per_block.py:188-201).
+ *   - every function returns 0 on success, non-zero on error; lowbit_last_error() returns a
+ *     thread-local message.  Nothing allocates device memory: outputs and scratch belong to
+ *     the caller (reference: paddle.empty in the Python wrappers).
+ *   - nothing synchronises the stream or the device.
+ */
+#ifndef LOWBIT_FA_H_
+#define LOWBIT_FA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOWBIT_ABI_VERSION 1
+
+/* element types of the floating-point inputs / outputs */
+enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
+
+/* rounding / arithmetic conventions of the per-block quantizers */
+enum {
+  LOWBIT_QMODE_TRITON = 0, /* Q1: src/triton/quant_per_block.py:132-178 -- x/scale, +-0.5, trunc; no eps;
+                                  K smoothing subtracts in the input dtype (:186-187) */
+  LOWBIT_QMODE_CUDA = 1    /* Q2: csrc/fused/fused.cu:64-198 -- amax floor 1e-7, x*(127/amax), RNE+sat;
+                                  K smoothing subtracts in fp32 (:120-126) */
+};
+
+/* Q*K^T operand formats of the attention kernel */
+enum {
+  LOWBIT_QK_I8 = 0,     /* Q int8, K int8 (one code per byte)                               */
+  LOWBIT_QK_Q8K4 = 1,   /* Q int8, K int4 packed two codes per byte (low nibble = even d)   */
+  LOWBIT_QK_Q8KMIX = 2  /* Q int8, K per-64-block bit width from `kbits` (8/4/2), packed    */
+};
+enum { LOWBIT_PV_F16 = 0, LOWBIT_PV_E4M3 = 1 };
+
+/* attention flags */
+enum {
+  LOWBIT_ATTN_CAUSAL = 1,      /* attn_qk_int8_per_block_causal.py:24-79 (requires Nq == Nk)          */
+  LOWBIT_ATTN_COMPAT_TAIL = 2  /* reproduce the reference's unmasked tail keys when Nk % 64 != 0
+                                  (attn_qk_int8_per_block.py:48-49)                  */
+};
+
+int lowbit_version(void);
+const char* lowbit_last_error(void);
+
+/* S1 -- K mean over the sequence (src/core.py:293 `k.mean(dim=seq_dim, keepdim=True)`).
+ * km_out: [B, H, D] contiguous, same dtype as k.  workspace: >= lowbit_k_mean_workspace_bytes().
+ * fp16: exact fixed-point sum (order independent) -> fp32 -> / N -> fp16; bf16: fp64 partial sums. */
+int64_t lowbit_k_mean_workspace_bytes(int B, int H, int N, int D);
+int lowbit_k_mean(const void* k, void* km_out, void* workspace, int B, int H, int N, int D,
+                  int64_t stride_b, int64_t stride_h, int64_t stride_n, int dtype, void* stream);
+
+/* Q1/Q2/Q4 (+INT2) -- symmetric per-block quantizer.
+ * Replaces: quant_per_block_int8_kernel / quant_per_block_int4_unpack_kernel
+ *           (src/triton/quant_per_block.py:132-178, :22-71) and QuantInt8Kernel
+ *           (csrc/fused/fused.cu:64-198; launchers :430-683, pybind csrc/fused/pybind.cpp:21-33).
+ * in: [B,H,N,D] fp16/bf16; km: NULL or [B,H,D] (same dtype) subtracted before quantizing (K smoothing);
+ * codes: int8, same logical shape with its own strides; if `pack` != 0 and bits < 8 the last dim holds
+ * D*bits/8 bytes (strides are then in bytes of the packed tensor); scale: f32 [B,H,ceil(N/blk)] contiguous.
+ * x = f32(in) [- km] * sm_scale_arg;  bits in {8,4,2} -> QMAX {127,7,1}. D in {64,128}; blk in {32,64,128}. */
+int lowbit_quant_per_block(const void* in, const void* km, void* codes, float* scale,
+                           int B, int H, int N, int D,
+                           int64_t in_stride_b, int64_t in_stride_h, int64_t in_stride_n,
+                           int64_t out_stride_b, int64_t out_stride_h, int64_t out_stride_n,
+                           int blk, int bits, int pack, float sm_scale_arg, int mode, int dtype, void* stream);
+
+/* Q3 -- per-thread-group quantizer (src/triton/quant_per_thread.py:22-219, hosts :222-411).
+ * is_key == 0: groups of rows {8i+t} inside each `warp_blk`(32)-row block, 8 scales per block;
+ * is_key == 1: groups of rows {8i+2t, 8i+2t+1} inside each `warp_blk`(64)-row block, 4 scales per block.
+ * scale = amax/QMAX + 1e-7; n_scale = number of scale slots per (b,h) (slots past the data get 1e-7). */
+int lowbit_quant_per_thread(const void* in, const void* km, void* codes, float* scale,
+                            int B, int H, int N, int D,
+                            int64_t in_stride_b, int64_t in_stride_h, int64_t in_stride_n,
+                            int64_t out_stride_b, int64_t out_stride_h, int64_t out_stride_n,
+                            int warp_blk, int n_scale, int is_key, int bits, int dtype, void* stream);
+
+/* Q5 -- KIVI asymmetric group quantize + pack along the last dim
+ * (src/triton/utils/quant/new_pack.py:198-300).  data: [rows, T] fp16 contiguous; group = 32;
+ * bits in {2,4,8}; code: int8 [rows, T*bits/8]; scale, mn: fp16 [rows, T/group]. */
+int lowbit_quant_pack_lastdim(const void* data, void* code, void* scale, void* mn,
+                              int64_t rows, int T, int group, int bits, int dtype, void* stream);
+
+/* Q6 -- V -> FP8 e4m3 per channel, transposed, padded, token-permuted
+ * (src/quant.py:210-291; TransposePadPermuteKernel + MeanScaleKernel csrc/fused/fused.cu:263-428).
+ * v8: [B,H,D,Npad64] e4m3 contiguous; v_scale: f32 [B,H,D]; vm: NULL or f32 [B,H,D] (smooth_v). */
+int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
+                             int B, int H, int N, int D,
+                             int64_t stride_b, int64_t stride_h, int64_t stride_n,
+                             float scale_max, int dtype, void* stream);
+
+/* E4 -- global max|x| of a tensor (compute_scale, src/core.py:1039-1047).  out: one f32 (device). */
+int lowbit_abs_max(const void* x, float* out, int B, int H, int N, int D,
+                   int64_t stride_b, int64_t stride_h, int64_t stride_n, int dtype, void* stream);
+
+/* A1/A2/A3 -- fused low-bit attention forward.
+ * Replaces: _attn_fwd (src/triton/attn_qk_int8_per_block.py:24-167, host forward :169-238),
+ *           _attn_fwd_base (src/triton/attn_qk_int8_per_block_causal.py:216-334),
+ *           forward_merging (src/triton/quantization/attn_qk_int4_per_block.py:248-317) and the
+ *           FP8-PV semantics of csrc/qattn/qk_int_sv_f8_cuda.cu:44-692.
+ * q_codes int8 [B,Hq,Nq,D]; k_codes int8 [B,Hkv,Nk,D] (or packed, see qk_mode); v fp16 [B,Hkv,Nk,D]
+ * (pv_mode F16) or e4m3 [B,Hkv,D,Npad64] as produced by lowbit_v_fp8_per_channel (pv_mode E4M3);
+ * q_scale f32 [B,Hq,ceil(Nq/128)], k_scale f32 [B,Hkv,ceil(Nk/64)] contiguous; v_scale/v_mean f32 [B,Hkv,D]
+ * or NULL; kbits int32 [B,Hkv,ceil(Nk/64)] or NULL; o [B,Hq,Nq,D] of out_dtype; lse NULL or f32
+ * [B,Hq,Nq] (base-2: log2(l)+m, as the reference kernel stores it).  D in {64,128}. */
+int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const void* v,
+                    const float* q_scale, const float* k_scale,
+                    const float* v_scale, const float* v_mean, const int32_t* kbits,
+                    void* o, float* lse,
+                    int B, int Hq, int Hkv, int Nq, int Nk, int D,
+                    int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_n,
+                    int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_n,
+                    int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_n,
+                    int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_n,
+                    int qk_mode, int pv_mode, int out_dtype, int flags, void* stream);
+
+/* Ring / sequence-parallel step: same contraction over one K/V shard, carrying un-normalised state.
+ * m_io, l_io: f32 [B,Hq,Nq]; o_acc_io: f32 [B,Hq,Nq,D] contiguous.  q_offset/k_offset are the global
+ * token positions of row 0 / key 0 (causal masking across shards).  first != 0 initialises the state.
+ * Call lowbit_attn_finalize afterwards to produce o (and lse). */
+int lowbit_attn_fwd_partial(const void* q_codes, const void* k_codes, const void* v,
+                            const float* q_scale, const float* k_scale,
+                            float* m_io, float* l_io, float* o_acc_io,
+                            int B, int Hq, int Hkv, int Nq, int Nk, int D,
+                            int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_n,
+                            int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_n,
+                            int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_n,
+                            int64_t q_offset, int64_t k_offset, int qk_mode, int flags, int first, void* stream);
+int lowbit_attn_finalize(const float* m, const float* l, const float* o_acc, void* o, float* lse,
+                         int B, int Hq, int Nq, int D,
+                         int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_n,
+                         int out_dtype, void* stream);
+
+/* lse[b,h,n] = lse2/1.44269504 + (q . km) * sm_scale  -- the LSE fix-up of src/core.py:296-304,344-350. */
+int lowbit_lse_fixup(float* lse, const void* q, const void* km, int B, int Hq, int Hkv, int Nq, int D,
+                     int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_n,
+                     float sm_scale, int dtype, void* stream);
+
+/* diagnostics (not part of the reference surface): when set to a device buffer of 128*64 int32, the next
+ * lowbit_attn_fwd launches make CTA (0,0,0) dump its raw int32 Q.K^T scores of key block 0. NULL disables. */
+void lowbit_attn_set_debug_buffer(void* dev_buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOWBIT_FA_H_ */

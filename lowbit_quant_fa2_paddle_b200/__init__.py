@@ -1,0 +1,28 @@
+"""lowbit_quant_fa2_paddle_b200 -- B200-native low-bit FlashAttention operator behind the API of
+Charles2530/lowbit_quant_fa2_paddle (`src/__init__.py:1-17`): per-block INT8/INT4 quantizers with K
+mean-smoothing and a fused tcgen05/TMEM/TMA attention kernel, hand-written for sm_100a."""
+from .core import (  # noqa: F401
+    # legacy names (backward compatible)
+    sageattn_qk_int8_pv_fp16_triton,
+    sageattn_qk_int4_pv_fp16_triton,
+    sageattn_multi_precision,
+    # preferred names
+    lowbit_fa_multi_precision,
+    lowbit_fa_qk_int8_pv_fp16_triton,
+    lowbit_fa_qk_int4_pv_fp16_triton,
+    lowbit_fa_q_int8_k_int4_pv_fp16,
+    compute_scale,
+    select_quantization,
+)
+from .quant import (  # noqa: F401
+    k_mean,
+    per_block_int8,
+    per_block_int8_cuda,
+    per_block_int4_unpack,
+    per_block_int4,
+    per_block_q_int8_k_int4,
+    per_block_k_lowbit,
+)
+from .attention import forward, forward_causal  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,138 @@
+"""Public operator API -- drop-in for the reference's `src/core.py` low-bit attention entry points.
+
+  lowbit_fa_qk_int8_pv_fp16_triton   src/core.py:194-352  (alias :1102)
+  lowbit_fa_qk_int4_pv_fp16_triton   src/core.py:945-1036 (alias :1105)
+  lowbit_fa_q_int8_k_int4_pv_fp16    mixed entry: quant_per_block.py:391-458 + utils/paddle_package.py:321-417
+  lowbit_fa_multi_precision          src/core.py:1064-1096 (select_quantization :1050-1061)
+
+Same names, keyword arguments, return values, assertion / ValueError behaviour.  The "_triton" suffix is kept
+because callers import these names; the implementation is hand-written sm_100a CUDA (csrc/) reached through
+the C ABI -- there is no Triton, no backend dispatch and no CPU fallback.  `quantization_backend` selects the
+reference's two *rounding conventions* ("triton": Q1, "cuda": Q2), both executed by the same CUDA kernel.
+"""
+from typing import Any, Optional
+
+import torch
+
+from . import _native as N
+from . import _tensor as T
+from . import attention as A
+from . import quant as Qz
+
+LOG2E = 1.44269504
+
+
+def _pad_head(x, to):
+    d = x.shape[-1]
+    return x if d == to else torch.nn.functional.pad(x, (0, to - d))
+
+
+def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
+               qk, compat_tail=False):
+    qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
+    dtype = qt.dtype
+    assert dtype in [torch.float16, torch.bfloat16], \
+        "Input tensors must be in dtype of torch.float16 or torch.bfloat16"
+    assert qt.device == kt.device == vt.device, "All tensors must be on the same device."
+    assert qt.dtype == kt.dtype == vt.dtype, "All tensors must have the same dtype."
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if quantization_backend not in ("triton", "cuda"):
+        raise ValueError(f"Unsupported quantization backend: {quantization_backend}")
+    dev = T.require_cuda(qt, kt, vt)
+    head_dim_og = qt.shape[-1]
+    if head_dim_og > 128:
+        raise ValueError(f"Unsupported head_dim: {head_dim_og}")
+    d_to = 64 if head_dim_og <= 64 else 128
+    qt, kt, vt = _pad_head(qt, d_to), _pad_head(kt, d_to), _pad_head(vt, d_to)
+    assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    with torch.cuda.device(dev):
+        km = Qz.k_mean(kt, tensor_layout) if smooth_k else None
+        if dtype == torch.bfloat16:
+            vt = vt.to(torch.float16)
+        if sm_scale is None:
+            sm_scale = 1.0 / head_dim_og ** 0.5
+        kbits = 8 if qk == "int8" else 4
+        q_c, q_s, k_c, k_s = Qz._per_block(qt, kt, km, 128, 64, sm_scale, tensor_layout, 8, kbits,
+                                           qk != "int8", quantization_backend)
+        qk_mode = N.QK_I8 if qk == "int8" else N.QK_Q8K4
+        o, lse = A._forward(q_c, k_c, vt, q_s, k_s, tensor_layout, dtype, return_lse, bool(is_causal),
+                            qk_mode=qk_mode, compat_tail=compat_tail)
+        o = o[..., :head_dim_og]
+        if return_lse:
+            b, hq, nq, d, sb, sh, sn = T.bhnd(qt, tensor_layout)
+            hkv = T.bhnd(kt, tensor_layout)[1]
+            kmp = Qz._km_bhd(km, b, hkv, d, tensor_layout) if smooth_k else None
+            N.call("lowbit_lse_fixup", lse.data_ptr(), qt.data_ptr(), kmp.data_ptr() if kmp is not None else None,
+                   b, hq, hkv, nq, d, sb, sh, sn, float(sm_scale), T.dtype_code(dtype), T.stream_ptr(dev))
+            return T.like(o, q), T.like(lse, q)
+    return T.like(o, q)
+
+
+def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantization_backend: str = "triton",
+                                    is_causal: bool = False, sm_scale: Optional[float] = None,
+                                    smooth_k: bool = True, return_lse: bool = False, **kwargs: Any):
+    """Per-block INT8 Q.K^T (Q blocks of 128, K blocks of 64, K mean-smoothed) + FP16 P.V.
+    q: [B,Hq,Nq,D] (HND) or [B,Nq,Hq,D] (NHD), k/v likewise with Hkv heads; fp16 or bf16.
+    Returns o (same shape/dtype as q) or (o, lse [B,Hq,Nq] f32 natural log) when return_lse."""
+    return _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
+                      "int8", compat_tail=bool(kwargs.get("compat_tail", False)))
+
+
+def sageattn_qk_int4_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantization_backend: str = "triton",
+                                    is_causal: bool = False, sm_scale: Optional[float] = None,
+                                    smooth_k: bool = True, return_lse: bool = False, **kwargs: Any):
+    """INT4 entry point (core.py:945-1036).  The reference quantizes Q to 8 bit and K to 4 bit (:999-1004);
+    coherent semantics per SURVEY 2.3-A: Q INT8 per block, K symmetric INT4 per 64-row block (codes in
+    [-7,7], packed two per byte in HBM, unpacked to int8 in shared memory so QK^T stays exact)."""
+    return _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
+                      "int4", compat_tail=bool(kwargs.get("compat_tail", False)))
+
+
+def lowbit_fa_q_int8_k_int4_pv_fp16(q, k, v, tensor_layout: str = "HND", quantization_backend: str = "triton",
+                                    is_causal: bool = False, sm_scale: Optional[float] = None,
+                                    smooth_k: bool = True, return_lse: bool = False, **kwargs: Any):
+    """Mixed q_int8 / k_int4 entry point (quantizer quant_per_block.py:391-458; the reference ships the
+    harness utils/paddle_package.py:321-417 but no kernel)."""
+    return _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
+                      "q8k4", compat_tail=bool(kwargs.get("compat_tail", False)))
+
+
+def compute_scale(tensor, bits=8, symmetric=True, tensor_layout="HND"):
+    """core.py:1039-1047 -- symmetric: max|x| / (2^(bits-1) - 1), as a 0-d device tensor."""
+    if not symmetric:
+        raise NotImplementedError("asymmetric compute_scale is not on the hot path")
+    t = T.as_torch(tensor)
+    d = t.shape[-1]
+    if d not in (64, 128):
+        t = _pad_head(t, 64 if d <= 64 else 128)
+    return Qz.abs_max(t, tensor_layout) / (2 ** (bits - 1) - 1)
+
+
+def select_quantization(q, k, v, tensor_layout="HND"):
+    """core.py:1050-1061: mean of the three global scales -> "FP16" (>0.2) | "INT8" (>0.05) | "INT4".
+    One device->host read, like the reference."""
+    avg = (compute_scale(q, 8, True, tensor_layout) + compute_scale(k, 8, True, tensor_layout)
+           + compute_scale(v, 8, True, tensor_layout)) / 3.0
+    avg = float(avg)
+    if avg > 0.2:
+        return "FP16"
+    if avg > 0.05:
+        return "INT8"
+    return "INT4"
+
+
+def sageattn_multi_precision(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                             sm_scale: Optional[float] = None, return_lse: bool = False, **kwargs: Any):
+    """core.py:1064-1096.  The reference's "FP16" branch calls a pure-Paddle SDPA that is wrong for either
+    layout and is not part of the low-bit path; here the widest low-bit format (INT8) serves
+    that class."""
+    kind = select_quantization(q, k, v, tensor_layout)
+    fn = sageattn_qk_int4_pv_fp16_triton if kind == "INT4" else sageattn_qk_int8_pv_fp16_triton
+    return fn(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal, sm_scale=sm_scale, return_lse=return_lse)
+
+
+# preferred names (core.py:1099-1105)
+lowbit_fa_multi_precision = sageattn_multi_precision
+lowbit_fa_qk_int8_pv_fp16_triton = sageattn_qk_int8_pv_fp16_triton
+lowbit_fa_qk_int4_pv_fp16_triton = sageattn_qk_int4_pv_fp16_triton

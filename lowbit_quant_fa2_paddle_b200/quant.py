@@ -1,0 +1,127 @@
+"""Quantizers of the low-bit attention path -- host side (Python over framework tensors, kernels in
+csrc/quant.cu via the C ABI).  Names, arguments, return values and error behaviour mirror the reference:
+
+  per_block_int8            src/triton/quant_per_block.py:181-248 (backend "triton", Q1)
+                            src/quant.py:21-98                    (backend "cuda",   Q2)
+  per_block_int4_unpack     src/triton/quant_per_block.py:251-318
+  per_block_int4            src/triton/quant_per_block.py:321-388 (intent: packed INT4)
+  per_block_q_int8_k_int4   src/triton/quant_per_block.py:391-458 (intent: Q INT8 + K packed INT4)
+  k_mean                    src/core.py:293
+
+Unlike the reference, `k - km` is never materialised: the subtraction is fused into the quantize kernel.
+"""
+import torch
+
+from . import _native as N
+from . import _tensor as T
+
+LOG2E = 1.44269504
+
+
+def k_mean(k, tensor_layout="HND"):
+    """Mean of k over the sequence dimension, keepdim (core.py:293), in k's dtype.
+    fp16: exact order-independent sum -> fp32 -> /N -> fp16 (SURVEY 2.3-H contract)."""
+    kt = T.as_torch(k)
+    dev = T.require_cuda(kt)
+    b, h, n, d, sb, sh, sn = T.bhnd(kt, tensor_layout)
+    km = torch.empty((b, h, d), dtype=kt.dtype, device=dev)
+    ws = torch.empty(N.lib().lowbit_k_mean_workspace_bytes(b, h, n, d), dtype=torch.uint8, device=dev)
+    N.call("lowbit_k_mean", kt.data_ptr(), km.data_ptr(), ws.data_ptr(), b, h, n, d, sb, sh, sn,
+           T.dtype_code(kt.dtype), T.stream_ptr(dev))
+    km = km.unsqueeze(2) if tensor_layout == "HND" else km.unsqueeze(1)
+    return T.like(km, k)
+
+
+def _km_bhd(km, b, h, d, tensor_layout):
+    """Accept km as [B,H,1,D] / [B,1,H,D] (keepdim mean) or [B,H,D]; return contiguous [B,H,D]."""
+    if km is None:
+        return None
+    kmt = T.as_torch(km)
+    if kmt.dim() == 4:
+        kmt = kmt.squeeze(2 if tensor_layout == "HND" else 1)
+    assert tuple(kmt.shape) == (b, h, d), f"km must have shape [{b},{h},{d}] (got {tuple(kmt.shape)})"
+    return kmt.contiguous()
+
+
+def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout):
+    """Quantize one [B,H,N,D] tensor per block of `blk` rows. Returns (codes, scale)."""
+    xt = T.as_torch(x)
+    dev = T.require_cuda(xt)
+    b, h, n, d, sb, sh, sn = T.bhnd(xt, tensor_layout)
+    if d not in (64, 128):
+        raise ValueError(f"Unsupported head_dim: {d} (the kernels take 64 or 128; core pads smaller ones)")
+    kmt = _km_bhd(km, b, h, d, tensor_layout)
+    if kmt is not None:
+        assert kmt.dtype == xt.dtype, "km must have the same dtype as k"
+    dd = d * bits // 8 if (pack and bits < 8) else d
+    shape = list(xt.shape)
+    shape[-1] = dd
+    codes = torch.empty(shape, dtype=torch.int8, device=dev)
+    _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
+    nblk = (n + blk - 1) // blk
+    scale = torch.empty((b, h, nblk), dtype=torch.float32, device=dev)
+    N.call("lowbit_quant_per_block", xt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
+           codes.data_ptr(), scale.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osn,
+           blk, bits, int(bool(pack)), float(sm_arg), mode, T.dtype_code(xt.dtype), T.stream_ptr(dev))
+    return T.like(codes, x), T.like(scale, x)
+
+
+def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpack, backend):
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if backend == "triton":
+        mode = N.QMODE_TRITON
+    elif backend == "cuda":
+        mode = N.QMODE_CUDA
+    else:
+        raise ValueError(f"Unsupported quantization backend: {backend}")
+    head_dim = T.as_torch(q).shape[-1]
+    if sm_scale is None:
+        sm_scale = head_dim ** -0.5
+    q_c, q_s = _quant_one(q, None, BLKQ, qbits, False, sm_scale * LOG2E, mode, tensor_layout)
+    k_c, k_s = _quant_one(k, km, BLKK, kbits, kpack, 1.0, mode, tensor_layout)
+    return q_c, q_s, k_c, k_s
+
+
+def per_block_int8(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND", backend="triton"):
+    """-> (q_int8, q_scale [B,Hq,ceil(Nq/BLKQ)] f32, k_int8, k_scale [B,Hkv,ceil(Nk/BLKK)] f32).
+    Q is scaled by sm_scale*1.44269504 before quantization; K is smoothed by km when given."""
+    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 8, 8, False, backend)
+
+
+def per_block_int8_cuda(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND"):
+    """src/quant.py:21-98 conventions (RNE, reciprocal multiply, amax floor 1e-7, fp32 mean subtraction)."""
+    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 8, 8, False, "cuda")
+
+
+def per_block_int4_unpack(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND"):
+    """quant_per_block.py:251-318: both Q and K to INT4 codes in [-7,7], one code per int8."""
+    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 4, 4, False, "triton")
+
+
+def per_block_int4(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND"):
+    """Intent of quant_per_block.py:321-388: Q and K INT4, K packed two codes per byte
+    along head_dim (low nibble = even d); Q codes stay unpacked for the int8 tensor-core operand."""
+    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 4, 4, True, "triton")
+
+
+def per_block_q_int8_k_int4(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND", pack=True):
+    """Intent of quant_per_block.py:391-458: Q INT8 per 128-row block, K INT4 per 64-row block,
+    K packed two codes per byte (pack=False keeps one code per int8)."""
+    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 8, 4, pack, "triton")
+
+
+def per_block_k_lowbit(k, km=None, BLKK=64, bits=2, tensor_layout="HND", pack=True):
+    """K only, INT2/INT4/INT8 symmetric per block (dynamic bit allocation building block)."""
+    return _quant_one(k, km, BLKK, bits, pack, 1.0, N.QMODE_TRITON, tensor_layout)
+
+
+def abs_max(x, tensor_layout="HND"):
+    """Global max|x| as a 0-d device tensor (compute_scale numerator, core.py:1039-1047)."""
+    xt = T.as_torch(x)
+    dev = T.require_cuda(xt)
+    b, h, n, d, sb, sh, sn = T.bhnd(xt, tensor_layout)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    N.call("lowbit_abs_max", xt.data_ptr(), out.data_ptr(), b, h, n, d, sb, sh, sn, T.dtype_code(xt.dtype),
+           T.stream_ptr(dev))
+    return out
