@@ -12,6 +12,11 @@ from . import _native as N
 from . import _tensor as T
 
 
+# INT4 K codes travel packed (two per byte) when the kernel unpacks them in shared memory; until that variant
+# lands the INT4 entry points feed one code per int8 to the same kind::i8 contraction (identical arithmetic).
+PACKED_K4_KERNEL = False
+
+
 def _out_dtype(output_dtype, default):
     if output_dtype is None:
         return default

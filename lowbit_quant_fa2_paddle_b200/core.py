@@ -39,10 +39,10 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
     if quantization_backend not in ("triton", "cuda"):
         raise ValueError(f"Unsupported quantization backend: {quantization_backend}")
-    dev = T.require_cuda(qt, kt, vt)
     head_dim_og = qt.shape[-1]
     if head_dim_og > 128:
         raise ValueError(f"Unsupported head_dim: {head_dim_og}")
+    dev = T.require_cuda(qt, kt, vt)
     d_to = 64 if head_dim_og <= 64 else 128
     qt, kt, vt = _pad_head(qt, d_to), _pad_head(kt, d_to), _pad_head(vt, d_to)
     assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
@@ -53,9 +53,10 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
         if sm_scale is None:
             sm_scale = 1.0 / head_dim_og ** 0.5
         kbits = 8 if qk == "int8" else 4
+        packed = (qk != "int8") and A.PACKED_K4_KERNEL
         q_c, q_s, k_c, k_s = Qz._per_block(qt, kt, km, 128, 64, sm_scale, tensor_layout, 8, kbits,
-                                           qk != "int8", quantization_backend)
-        qk_mode = N.QK_I8 if qk == "int8" else N.QK_Q8K4
+                                           packed, quantization_backend)
+        qk_mode = N.QK_Q8K4 if packed else N.QK_I8
         o, lse = A._forward(q_c, k_c, vt, q_s, k_s, tensor_layout, dtype, return_lse, bool(is_causal),
                             qk_mode=qk_mode, compat_tail=compat_tail)
         o = o[..., :head_dim_og]

@@ -11,7 +11,7 @@
 // from HBM exactly once; K smoothing is fused (no materialised `k - km`).  All arithmetic that defines
 // the codes uses explicit round-to-nearest intrinsics (__fmul_rn/__fdiv_rn/...) so nvcc can neither
 // contract to FMA nor substitute approximate division: codes and scales are bit-exact against the
-// IEEE-fp32 oracle.  This translation unit is compiled WITHOUT --use_fast_math.
+// IEEE-fp32 restatement of the reference.  This translation unit is compiled WITHOUT --use_fast_math.
 #include "common.cuh"
 
 #include <stdarg.h>

@@ -169,7 +169,7 @@ def lowbit_fa_api(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, 
             qh, kmh = _hnd(q, tensor_layout), _hnd(km, tensor_layout)
             g = qh.shape[1] // kmh.shape[1]
             kmh = kmh.repeat_interleave(g, dim=1) if g > 1 else kmh
-            lse_corr = torch.matmul(qh.float(), kmh.float().transpose(2, 3)).squeeze(-1)
+            lse_corr = torch.matmul(qh.float(), kmh.float().transpose(2, 3)).squeeze(-1).to(dtype).float()  # matmul in the input dtype (:296-304)
     else:
         km = None
     if dtype == torch.bfloat16:
