@@ -35,18 +35,27 @@ static int32_t* g_attn_debug = nullptr;
 
 constexpr int kBM = 128;  // Q rows per CTA (= TMEM lanes)
 constexpr int kBN = 64;   // keys per step (= the reference's k_scale granularity)
+constexpr int kKS = 4;    // K ring depth
+constexpr int kVS = 3;    // V ring depth
+constexpr int kSoftmaxThreads = 128;
+constexpr int kThreads = kSoftmaxThreads + 64;  // + MMA-issue warp + TMA-producer warp
 
 template <int D>
 struct AttnSmem {
   static constexpr int kQ = kBM * D;       // int8
   static constexpr int kK = kBN * D;       // int8
   static constexpr int kV = kBN * D * 2;   // fp16
-  static constexpr int kStages = 2;
-  static constexpr int kBytes = kQ + kStages * (kK + kV) + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kBytes = kQ + kKS * kK + kVS * kV + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
+// Warp roles:  warps 0-3  softmax (thread t <-> query row t <-> TMEM lane t)
+//              warp 4     tcgen05 issue (one elected lane) + TMEM alloc/dealloc
+//              warp 5     TMA producer (one elected lane)
+// TMEM columns: S/P buffer 0 [0,64)  S/P buffer 1 [64,128)  O [128,128+D)
+// Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the
+// fp16 P.V of the previous one run on the tensor pipe while the softmax warps work on block j.
 template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using SM = AttnSmem<D>;
@@ -54,30 +63,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + SM::kQ;
-  uint8_t* sV = sK + SM::kStages * SM::kK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + SM::kStages * SM::kV);
+  uint8_t* sV = sK + kKS * SM::kK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVS * SM::kV);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_kv = bars + 1;  // [2]
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kfull = bars + 1;                  // [kKS] TMA -> MMA
+  uint64_t* kfree = kfull + kKS;               // [kKS] MMA (commit) -> TMA
+  uint64_t* vfull = kfree + kKS;               // [kVS]
+  uint64_t* vfree = vfull + kVS;               // [kVS]
+  uint64_t* bar_s = vfree + kVS;               // [2] QK done: S buffer b holds scores
+  uint64_t* p_ready = bar_s + 2;               // [2] 128 softmax threads wrote P into buffer b
+  uint64_t* bar_o = p_ready + 2;               // PV_j done (one phase per key block)
+  uint64_t* bar_final = bar_o + 1;             // last PV done (single phase: parity waits must never lag 2 phases)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
   const int hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (p.Hq / p.Hkv);
 
-  constexpr uint32_t kTmemCols = (D == 64) ? 128 : 256;  // S/P: [0,64)  O: [64, 64+D)
-  if (warp == 0) {
+  constexpr uint32_t kTmemCols = 256;
+  if (warp == 4) {
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
-  if (tid == 32) {
+  if (tid == 160) {
     ptx::mbar_init(bar_q, 1);
-    ptx::mbar_init(bar_kv + 0, 1);
-    ptx::mbar_init(bar_kv + 1, 1);
-    ptx::mbar_init(bar_s, 1);
+    for (int i = 0; i < kKS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
+    for (int i = 0; i < kVS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kSoftmaxThreads); }
     ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(bar_final, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
@@ -87,167 +102,185 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;         // int32 scores, 64 columns
-  const uint32_t tP = tmem_base;         // fp16 probabilities alias S (32 columns)
-  const uint32_t tO = tmem_base + kBN;   // fp32 output accumulator, D columns
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t tO = tmem_base + 2 * kBN;  // fp32 output accumulator, D columns
 
   // key-block range of this Q tile
   int nblk = p.nkb;
   if (CAUSAL) nblk = min(nblk, (qt + 1) * (kBM / kBN));
 
-  constexpr uint32_t kKVBytes = SM::kK + SM::kV;
-  auto load_kv = [&](int j, int st) {
-    ptx::mbar_expect_tx(bar_kv + st, kKVBytes);
-    ptx::tma_load_4d(sK + st * SM::kK, &tmK, bar_kv + st, 0, j * kBN, hkv, b);
-    ptx::tma_load_4d(sV + st * SM::kV, &tmV, bar_kv + st, 0, j * kBN, hkv, b);
-    if (D == 128) ptx::tma_load_4d(sV + st * SM::kV + kBN * 128, &tmV, bar_kv + st, 64, j * kBN, hkv, b);
-  };
-  if (tid == 0) {
-    ptx::mbar_expect_tx(bar_q, SM::kQ);
-    ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
-    load_kv(0, 0);
-  }
-
-  // descriptors
-  constexpr uint32_t kSwzQK = (D == 64) ? ptx::kSwz64 : ptx::kSwz128;
-  constexpr uint32_t kSboQK = 8 * D;  // 8 rows of D bytes
-  constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, kBN);
-  constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
-
-  const int row = qt * kBM + tid;  // global query row owned by this thread
-  const float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
-  const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
-  const bool mask_tail = !(p.flags & LOWBIT_ATTN_COMPAT_TAIL) && (p.Nk % kBN != 0);
-
-  float m_ref = -INFINITY, l = 0.f;
-
-  for (int j = 0; j < nblk; ++j) {
-    const int st = j & 1;
-    const uint32_t ph = j & 1;
-    if (tid == 0) {
-      if (j + 1 < nblk) load_kv(j + 1, st ^ 1);  // stage st^1 was released by the PV MMA of step j-1
-      if (j == 0) ptx::mbar_wait(bar_q, 0, 1);
-      ptx::mbar_wait(bar_kv + st, (j >> 1) & 1, 2);
-      ptx::tc_fence_after();
-      const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sK + st * SM::kK);
-#pragma unroll
-      for (int kk = 0; kk < D / 32; ++kk) {
-        const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, kSboQK, kSwzQK);
-        const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, kSboQK, kSwzQK);
-        ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+  if (warp == 5) {
+    // ================================ TMA producer ================================
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(bar_q, SM::kQ);
+      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int ks = j % kKS, vs = j % kVS;
+        ptx::mbar_wait(kfree + ks, ((j / kKS) & 1) ^ 1, 10);
+        ptx::mbar_expect_tx(kfull + ks, SM::kK);
+        ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * kBN, hkv, b);
+        ptx::mbar_wait(vfree + vs, ((j / kVS) & 1) ^ 1, 11);
+        ptx::mbar_expect_tx(vfull + vs, SM::kV);
+        ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, j * kBN, hkv, b);
+        if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + kBN * 128, &tmV, vfull + vs, 64, j * kBN, hkv, b);
       }
-      ptx::umma_commit(bar_s);
     }
-    ptx::mbar_wait(bar_s, ph, 3);
-    ptx::tc_fence_after();
-
-    // ---- softmax for this thread's row -------------------------------------------------------
-    uint32_t s[kBN];
-    ptx::tmem_ld_x32(tS + lane_off, s);
-    ptx::tmem_ld_x32(tS + lane_off + 32, s + 32);
-    ptx::tmem_wait_ld();
-
-    if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+  } else if (warp == 4) {
+    // ================================ tcgen05 issuer ================================
+    if (ptx::elect_one()) {
+      constexpr uint32_t kSwzQK = (D == 64) ? ptx::kSwz64 : ptx::kSwz128;
+      constexpr uint32_t kSboQK = 8 * D;  // 8 rows of D bytes
+      constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, kBN);
+      constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
+      const uint32_t aq = ptx::smem_u32(sQ);
+      auto issue_qk = [&](int j) {
+        const int ks = j % kKS;
+        ptx::mbar_wait(kfull + ks, (j / kKS) & 1, 20);
+        ptx::tc_fence_after();
+        const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
+        const uint32_t tS = tmem_base + (j & 1) * kBN;
 #pragma unroll
-      for (int c = 0; c < kBN; ++c) p.dbg[tid * kBN + c] = (int)s[c];
+        for (int kk = 0; kk < D / 32; ++kk) {
+          const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, kSboQK, kSwzQK);
+          const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, kSboQK, kSwzQK);
+          ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+        }
+        ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
+        ptx::umma_commit(kfree + ks);       // K stage may be refilled
+      };
+      ptx::mbar_wait(bar_q, 0, 21);
+      issue_qk(0);
+      if (nblk > 1) issue_qk(1);
+      for (int j = 0; j < nblk; ++j) {
+        const int vs = j % kVS;
+        ptx::mbar_wait(p_ready + (j & 1), (j >> 1) & 1, 22);
+        ptx::mbar_wait(vfull + vs, (j / kVS) & 1, 23);
+        ptx::tc_fence_after();
+        const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
+        const uint32_t tP = tmem_base + (j & 1) * kBN;
+#pragma unroll
+        for (int kk = 0; kk < kBN / 16; ++kk) {
+          // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); 64-wide d atoms kBN*128 B apart (LBO)
+          const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, kBN * 128, 1024, ptx::kSwz128);
+          ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+        }
+        ptx::umma_commit(vfree + vs);
+        ptx::umma_commit(bar_o);
+        if (j == nblk - 1) ptx::umma_commit(bar_final);
+        if (j + 2 < nblk) issue_qk(j + 2);  // overwrites S/P buffer (j&1): ordered after PV_j on the tensor pipe
+      }
     }
-    const int c0 = j * kBN;
-    int lim = kBN;  // columns [0, lim] are live
-    if (CAUSAL && c0 + kBN - 1 > qt * kBM) lim = min(lim, row - c0);
-    if (mask_tail && j == p.nkb - 1) lim = min(lim, p.Nk - 1 - c0);
-    const bool masked = lim < kBN - 1;
+  } else {
+    // ================================ softmax warps ================================
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int row = qt * kBM + tid;  // global query row owned by this thread
+    const float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
+    const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
+    const bool mask_tail = !(p.flags & LOWBIT_ATTN_COMPAT_TAIL) && (p.Nk % kBN != 0);
+    float m_ref = -INFINITY, l = 0.f;
 
-    int imax = INT_MIN;
-    if (!masked) {
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t tS = tmem_base + (j & 1) * kBN;
+      const float sc = qs * ks_ptr[j];
+      ptx::mbar_wait(bar_s + (j & 1), (j >> 1) & 1, 30);
+      ptx::tc_fence_after();
+      uint32_t s[kBN];
+      ptx::tmem_ld_x32(tS + lane_off, s);
+      ptx::tmem_ld_x32(tS + lane_off + 32, s + 32);
+      ptx::tmem_wait_ld();
+
+      if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-      for (int c = 0; c < kBN; ++c) imax = max(imax, (int)s[c]);
-    } else {
+        for (int c = 0; c < kBN; ++c) p.dbg[tid * kBN + c] = (int)s[c];
+      }
+      const int c0 = j * kBN;
+      int lim = kBN;  // columns [0, lim] are live
+      if (CAUSAL && c0 + kBN - 1 > qt * kBM) lim = min(lim, row - c0);
+      if (mask_tail && j == p.nkb - 1) lim = min(lim, p.Nk - 1 - c0);
+      const bool masked = lim < kBN - 1;
+
+      int imax = INT_MIN;
+      if (!masked) {
 #pragma unroll
-      for (int c = 0; c < kBN; ++c) imax = max(imax, c <= lim ? (int)s[c] : INT_MIN);
-    }
-    const float sc = qs * ks_ptr[j];
-    const float mblk = (imax == INT_MIN) ? -INFINITY : (float)imax * sc;
-    // lazy rescale: move the reference max only when it grows by more than 2^8 (warp-uniform decision,
-    // tcgen05.ld/st are warp collectives)
-    const bool need = mblk > m_ref + 8.f;
-    if (__any_sync(0xffffffffu, need)) {
-      const float m_new = fmaxf(m_ref, mblk);
-      const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
-      l *= alpha;
-      m_ref = m_new;
-      if (j > 0) {
+        for (int c = 0; c < kBN; ++c) imax = max(imax, (int)s[c]);
+      } else {
 #pragma unroll
-        for (int c = 0; c < D; c += 32) {
-          uint32_t o[32];
-          ptx::tmem_ld_x32(tO + lane_off + c, o);
-          ptx::tmem_wait_ld();
+        for (int c = 0; c < kBN; ++c) imax = max(imax, c <= lim ? (int)s[c] : INT_MIN);
+      }
+      const float mblk = (imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+      // lazy rescale: move the reference max only when it grows by more than 2^8 (warp-uniform decision,
+      // tcgen05.ld/st are warp collectives)
+      const bool need = mblk > m_ref + 8.f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_ref, mblk);
+        const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
+        l *= alpha;
+        m_ref = m_new;
+        if (j > 0) {
+          // PV_{j-1} must have landed in O.  S_j being ready implies PV_{j-2} completed (commit order) and PV_j
+          // cannot start before our p_ready arrive, so bar_o is in phase j-1 or j: the parity wait is unambiguous.
+          ptx::mbar_wait(bar_o, (j - 1) & 1, 31);
+          ptx::tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          ptx::tmem_st_x32(tO + lane_off + c, o);
+          for (int c = 0; c < D; c += 32) {
+            uint32_t o[32];
+            ptx::tmem_ld_x32(tO + lane_off + c, o);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st_x32(tO + lane_off + c, o);
+          }
         }
       }
-    }
-    uint32_t pk[kBN / 2];
-    float lsum = 0.f;
-    const float neg_m = -m_ref;
+      uint32_t pk[kBN / 2];
+      float lsum0 = 0.f, lsum1 = 0.f;
+      const float neg_m = -m_ref;
 #pragma unroll
-    for (int c = 0; c < kBN; c += 2) {
-      float p0 = ptx::ex2(fmaf(ptx::i2f_small((int)s[c]), sc, neg_m));
-      float p1 = ptx::ex2(fmaf(ptx::i2f_small((int)s[c + 1]), sc, neg_m));
-      if (masked) {
-        p0 = (c <= lim) ? p0 : 0.f;
-        p1 = (c + 1 <= lim) ? p1 : 0.f;
+      for (int c = 0; c < kBN; c += 2) {
+        float p0 = ptx::ex2(fmaf(ptx::i2f_small((int)s[c]), sc, neg_m));
+        float p1 = ptx::ex2(fmaf(ptx::i2f_small((int)s[c + 1]), sc, neg_m));
+        if (masked) {
+          p0 = (c <= lim) ? p0 : 0.f;
+          p1 = (c + 1 <= lim) ? p1 : 0.f;
+        }
+        lsum0 += p0;
+        lsum1 += p1;
+        pk[c / 2] = ptx::pack_f16x2(p0, p1);
       }
-      lsum += p0 + p1;
-      pk[c / 2] = ptx::pack_f16x2(p0, p1);
+      l += lsum0 + lsum1;
+      ptx::tmem_st_x32(tS + lane_off, pk);  // P (fp16) aliases the first 32 columns of its S buffer
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_ready + (j & 1));
     }
-    l += lsum;
-    ptx::tmem_st_x32(tP + lane_off, pk);
-    ptx::tmem_wait_st();
-    ptx::tc_fence_before();
-    __syncthreads();
 
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint32_t av = ptx::smem_u32(sV + st * SM::kV);
-#pragma unroll
-      for (int kk = 0; kk < kBN / 16; ++kk) {
-        // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); 64-wide d atoms kBN*128 B apart (LBO)
-        const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, kBN * 128, 1024, ptx::kSwz128);
-        ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
-      }
-      ptx::umma_commit(bar_o);
-    }
-    ptx::mbar_wait(bar_o, ph, 4);
+    // ---- epilogue: O / l -> out dtype, lse2 = log2(l) + m ------------------------------------------
+    ptx::mbar_wait(bar_final, 0, 32);
     ptx::tc_fence_after();
-  }
-
-  // ---- epilogue: O / l -> out dtype, lse2 = log2(l) + m --------------------------------------------
-  const float inv_l = 1.0f / l;
-  const bool live_row = row < p.Nq;
-  uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + ((int64_t)b * p.osb + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
+    const float inv_l = 1.0f / l;
+    const bool live_row = row < p.Nq;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + ((int64_t)b * p.osb + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
 #pragma unroll
-  for (int c = 0; c < D; c += 32) {
-    uint32_t o[32];
-    ptx::tmem_ld_x32(tO + lane_off + c, o);  // warp collective: every lane executes it
-    ptx::tmem_wait_ld();
-    uint32_t w[16];
+    for (int c = 0; c < D; c += 32) {
+      uint32_t o[32];
+      ptx::tmem_ld_x32(tO + lane_off + c, o);  // warp collective: every lane executes it
+      ptx::tmem_wait_ld();
+      uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a = __uint_as_float(o[2 * i]) * inv_l, bb = __uint_as_float(o[2 * i + 1]) * inv_l;
-      w[i] = (p.out_dtype == LOWBIT_F16) ? ptx::pack_f16x2(a, bb) : ptx::pack_bf16x2(a, bb);
+      for (int i = 0; i < 16; ++i) {
+        const float a = __uint_as_float(o[2 * i]) * inv_l, bb = __uint_as_float(o[2 * i + 1]) * inv_l;
+        w[i] = (p.out_dtype == LOWBIT_F16) ? ptx::pack_f16x2(a, bb) : ptx::pack_bf16x2(a, bb);
+      }
+      if (live_row) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
     }
-    if (live_row) {
-      uint4* dst = reinterpret_cast<uint4*>(orow + c * 2);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-    }
+    if (live_row && p.lse) p.lse[((int64_t)b * p.Hq + hq) * p.Nq + row] = ptx::lg2(l) + m_ref;
   }
-  if (live_row && p.lse) p.lse[((int64_t)b * p.Hq + hq) * p.Nq + row] = ptx::lg2(l) + m_ref;
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -300,7 +333,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, 128, AttnSmem<D>::kBytes, st>>>(tq, tk, tv, p);
+  kern<<<grid, kThreads, AttnSmem<D>::kBytes, st>>>(tq, tk, tv, p);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
