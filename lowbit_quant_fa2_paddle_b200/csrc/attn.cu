@@ -16,6 +16,7 @@
 
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace lowbit {
 
@@ -33,47 +34,100 @@ struct AttnParams {
 
 static int32_t* g_attn_debug = nullptr;
 
-constexpr int kBM = 128;  // Q rows per CTA (= TMEM lanes)
-constexpr int kBN = 64;   // keys per step (= the reference's k_scale granularity)
-constexpr int kKS = 4;    // K ring depth
-constexpr int kVS = 3;    // V ring depth
+constexpr int kBM = 128;      // Q rows per CTA (= TMEM lanes)
+constexpr int kScaleBlk = 64; // k_scale granularity of the reference quantizer (BLKK)
 constexpr int kSoftmaxThreads = 128;
-constexpr int kThreads = kSoftmaxThreads + 64;  // + MMA-issue warp + TMA-producer warp
+constexpr int kThreads = kSoftmaxThreads + 32;  // + one helper warp (TMA producer + tcgen05 issuer, one elected lane)
+
+// Per-head-dim tiling.  D=64 is exp2(MUFU)-bound: small 32-key steps keep the register footprint under 96 so that
+// four CTAs (16 softmax warps) share an SM and hide each other's latencies.  D=128 has twice the tensor work per
+// exp2 and runs 64-key steps with two CTAs per SM.
+template <int D> struct AttnCfg;
+template <> struct AttnCfg<64> {
+  static constexpr int BN = 32, CTAS = 4, KS = 4, VS = 3, TMEM_COLS = 128;
+};
+template <> struct AttnCfg<128> {
+  static constexpr int BN = 64, CTAS = 2, KS = 4, VS = 3, TMEM_COLS = 256;
+};
 
 template <int D>
 struct AttnSmem {
-  static constexpr int kQ = kBM * D;       // int8
-  static constexpr int kK = kBN * D;       // int8
-  static constexpr int kV = kBN * D * 2;   // fp16
-  static constexpr int kBytes = kQ + kKS * kK + kVS * kV + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  using C = AttnCfg<D>;
+  static constexpr int kQ = kBM * D;        // int8
+  static constexpr int kK = C::BN * D;      // int8
+  static constexpr int kV = C::BN * D * 2;  // fp16
+  static constexpr int kBytes = kQ + C::KS * kK + C::VS * kV + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
+template <int VAR>
+__device__ __forceinline__ float score_to_f32(uint32_t v) {
+  return (VAR & 1) ? ptx::i2f_small((int)v) : __int2float_rn((int)v);
+}
+// One softmax step over a BN-key block for one query row: p = exp2(S*sc - m), packed to fp16 pairs, row sum in fp32.
+// MASKED: columns > lim contribute 0 (causal diagonal band / masked tail keys).
+template <int BN, bool MASKED, int VAR>
+__device__ __forceinline__ float softmax_block(const uint32_t (&s)[BN], float sc, float neg_m, int lim,
+                                               uint32_t (&pk)[BN / 2]) {
+  float lsum0 = 0.f, lsum1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < BN; c += 2) {
+    float p0 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c]), sc, neg_m));
+    float p1 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c + 1]), sc, neg_m));
+    if (MASKED) {
+      p0 = (c <= lim) ? p0 : 0.f;
+      p1 = (c + 1 <= lim) ? p1 : 0.f;
+    }
+    lsum0 += p0;
+    lsum1 += p1;
+    pk[c / 2] = ptx::pack_f16x2(p0, p1);
+  }
+  return lsum0 + lsum1;
+}
+template <int BN, bool MASKED>
+__device__ __forceinline__ int row_max(const uint32_t (&s)[BN], int lim) {
+  int m4[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};  // 4 independent chains (latency, not throughput, bound)
+#pragma unroll
+  for (int c = 0; c < BN; ++c) m4[c & 3] = max(m4[c & 3], (!MASKED || c <= lim) ? (int)s[c] : INT_MIN);
+  return max(max(m4[0], m4[1]), max(m4[2], m4[3]));
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+  if constexpr (N == 32) ptx::tmem_ld_x32(taddr, r);
+  else { ptx::tmem_ld_x32(taddr, r); ptx::tmem_ld_x32(taddr + 32, r + 32); }
+}
+template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N == 16) ptx::tmem_st_x16(taddr, r);
+  else ptx::tmem_st_x32(taddr, r);
+}
+
 // Warp roles:  warps 0-3  softmax (thread t <-> query row t <-> TMEM lane t)
-//              warp 4     tcgen05 issue (one elected lane) + TMEM alloc/dealloc
-//              warp 5     TMA producer (one elected lane)
-// TMEM columns: S/P buffer 0 [0,64)  S/P buffer 1 [64,128)  O [128,128+D)
-// Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the
-// fp16 P.V of the previous one run on the tensor pipe while the softmax warps work on block j.
-template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(kThreads, 2)
+//              warp 4     helper: one elected lane is both the TMA producer and the tcgen05 issuer; the warp also
+//                         owns the TMEM allocation
+// TMEM columns: S/P buffer 0 [0,BN)  S/P buffer 1 [BN,2BN)  O [2BN, 2BN+D)
+// Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the fp16
+// P.V of the previous one run on the tensor pipe while the softmax warps work on block j; K/V stages are refilled
+// by the same thread as soon as the MMAs that read them have committed.
+template <int D, bool CAUSAL, int VAR>
+__global__ void __launch_bounds__(kThreads, AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = AttnCfg<D>;
   using SM = AttnSmem<D>;
+  constexpr int BN = C::BN, KS = C::KS, VS = C::VS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + SM::kQ;
-  uint8_t* sV = sK + kKS * SM::kK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVS * SM::kV);
+  uint8_t* sV = sK + KS * SM::kK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + VS * SM::kV);
   uint64_t* bar_q = bars + 0;
-  uint64_t* kfull = bars + 1;                  // [kKS] TMA -> MMA
-  uint64_t* kfree = kfull + kKS;               // [kKS] MMA (commit) -> TMA
-  uint64_t* vfull = kfree + kKS;               // [kVS]
-  uint64_t* vfree = vfull + kVS;               // [kVS]
-  uint64_t* bar_s = vfree + kVS;               // [2] QK done: S buffer b holds scores
-  uint64_t* p_ready = bar_s + 2;               // [2] 128 softmax threads wrote P into buffer b
-  uint64_t* bar_o = p_ready + 2;               // PV_j done (one phase per key block)
-  uint64_t* bar_final = bar_o + 1;             // last PV done (single phase: parity waits must never lag 2 phases)
+  uint64_t* kfull = bars + 1;        // [KS] TMA -> MMA
+  uint64_t* kfree = kfull + KS;      // [KS] MMA (commit) -> TMA
+  uint64_t* vfull = kfree + KS;      // [VS]
+  uint64_t* vfree = vfull + VS;      // [VS]
+  uint64_t* bar_s = vfree + VS;      // [2] QK done: S buffer b holds scores
+  uint64_t* p_ready = bar_s + 2;     // [2] 128 softmax threads wrote P into buffer b
+  uint64_t* bar_o = p_ready + 2;     // PV_j done (one phase per key block)
+  uint64_t* bar_final = bar_o + 1;   // last PV done (single phase: parity waits must never lag 2 phases)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -81,15 +135,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (p.Hq / p.Hkv);
 
-  constexpr uint32_t kTmemCols = 256;
   if (warp == 4) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (tid == 160) {
+  if (tid == 0) {
     ptx::mbar_init(bar_q, 1);
-    for (int i = 0; i < kKS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
-    for (int i = 0; i < kVS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
+    for (int i = 0; i < KS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
+    for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kSoftmaxThreads); }
     ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_final, 1);
@@ -102,42 +155,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tO = tmem_base + 2 * kBN;  // fp32 output accumulator, D columns
+  const uint32_t tO = tmem_base + 2 * BN;  // fp32 output accumulator, D columns
 
-  // key-block range of this Q tile
-  int nblk = p.nkb;
-  if (CAUSAL) nblk = min(nblk, (qt + 1) * (kBM / kBN));
+  // key-block range of this Q tile.  compat_tail walks the reference's whole 64-key blocks (phantom zero keys).
+  const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
+  const int nk_eff = compat ? p.nkb * kScaleBlk : p.Nk;
+  int nblk = (nk_eff + BN - 1) / BN;
+  if (CAUSAL) nblk = min(nblk, (qt + 1) * (kBM / BN));
 
-  if (warp == 5) {
-    // ================================ TMA producer ================================
-    if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(bar_q, SM::kQ);
-      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int ks = j % kKS, vs = j % kVS;
-        ptx::mbar_wait(kfree + ks, ((j / kKS) & 1) ^ 1, 10);
-        ptx::mbar_expect_tx(kfull + ks, SM::kK);
-        ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * kBN, hkv, b);
-        ptx::mbar_wait(vfree + vs, ((j / kVS) & 1) ^ 1, 11);
-        ptx::mbar_expect_tx(vfull + vs, SM::kV);
-        ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, j * kBN, hkv, b);
-        if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + kBN * 128, &tmV, vfull + vs, 64, j * kBN, hkv, b);
-      }
-    }
-  } else if (warp == 4) {
-    // ================================ tcgen05 issuer ================================
+  if (warp == 4) {
+    // ================================ helper: TMA producer + tcgen05 issuer ================================
     if (ptx::elect_one()) {
       constexpr uint32_t kSwzQK = (D == 64) ? ptx::kSwz64 : ptx::kSwz128;
       constexpr uint32_t kSboQK = 8 * D;  // 8 rows of D bytes
-      constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, kBN);
+      constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
       constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
       const uint32_t aq = ptx::smem_u32(sQ);
+      auto load_k = [&](int j) {
+        const int ks = j % KS;
+        ptx::mbar_wait(kfree + ks, ((j / KS) & 1) ^ 1, 10);
+        ptx::mbar_expect_tx(kfull + ks, SM::kK);
+        ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * BN, hkv, b);
+      };
+      auto load_v = [&](int j) {
+        const int vs = j % VS;
+        ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
+        ptx::mbar_expect_tx(vfull + vs, SM::kV);
+        ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, j * BN, hkv, b);
+        if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + BN * 128, &tmV, vfull + vs, 64, j * BN, hkv, b);
+      };
       auto issue_qk = [&](int j) {
-        const int ks = j % kKS;
-        ptx::mbar_wait(kfull + ks, (j / kKS) & 1, 20);
+        const int ks = j % KS;
+        ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
         ptx::tc_fence_after();
         const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
-        const uint32_t tS = tmem_base + (j & 1) * kBN;
+        const uint32_t tS = tmem_base + (j & 1) * BN;
 #pragma unroll
         for (int kk = 0; kk < D / 32; ++kk) {
           const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, kSboQK, kSwzQK);
@@ -147,26 +199,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
         ptx::umma_commit(kfree + ks);       // K stage may be refilled
       };
+      ptx::mbar_expect_tx(bar_q, SM::kQ);
+      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
+      for (int j = 0; j < min(KS, nblk); ++j) load_k(j);
+      for (int j = 0; j < min(2, nblk); ++j) load_v(j);
       ptx::mbar_wait(bar_q, 0, 21);
       issue_qk(0);
       if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
-        const int vs = j % kVS;
+        const int vs = j % VS;
         ptx::mbar_wait(p_ready + (j & 1), (j >> 1) & 1, 22);
-        ptx::mbar_wait(vfull + vs, (j / kVS) & 1, 23);
+        ptx::mbar_wait(vfull + vs, (j / VS) & 1, 23);
         ptx::tc_fence_after();
         const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
-        const uint32_t tP = tmem_base + (j & 1) * kBN;
+        const uint32_t tP = tmem_base + (j & 1) * BN;
 #pragma unroll
-        for (int kk = 0; kk < kBN / 16; ++kk) {
-          // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); 64-wide d atoms kBN*128 B apart (LBO)
-          const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, kBN * 128, 1024, ptx::kSwz128);
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); 64-wide d atoms BN*128 B apart (LBO)
+          const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
           ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
         }
         ptx::umma_commit(vfree + vs);
         ptx::umma_commit(bar_o);
         if (j == nblk - 1) ptx::umma_commit(bar_final);
         if (j + 2 < nblk) issue_qk(j + 2);  // overwrites S/P buffer (j&1): ordered after PV_j on the tensor pipe
+        // refill: K stage of QK_j (long complete) and V stage of PV_{j-1} (complete in steady state)
+        if (j + KS < nblk) load_k(j + KS);
+        if (j + 2 < nblk) load_v(j + 2);
       }
     }
   } else {
@@ -175,37 +234,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = qt * kBM + tid;  // global query row owned by this thread
     const float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
     const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
-    const bool mask_tail = !(p.flags & LOWBIT_ATTN_COMPAT_TAIL) && (p.Nk % kBN != 0);
+    const bool mask_tail = !compat && (p.Nk % BN != 0);
+    const int last_kblk = (p.Nk + BN - 1) / BN - 1;
     float m_ref = -INFINITY, l = 0.f;
+    float ks_next = ks_ptr[0];
 
     for (int j = 0; j < nblk; ++j) {
-      const uint32_t tS = tmem_base + (j & 1) * kBN;
-      const float sc = qs * ks_ptr[j];
+      const uint32_t tS = tmem_base + (j & 1) * BN;
+      const float sc = qs * ks_next;
+      ks_next = ks_ptr[min((j + 1) * BN / kScaleBlk, p.nkb - 1)];  // prefetch: L2 latency off the critical path
       ptx::mbar_wait(bar_s + (j & 1), (j >> 1) & 1, 30);
       ptx::tc_fence_after();
-      uint32_t s[kBN];
-      ptx::tmem_ld_x32(tS + lane_off, s);
-      ptx::tmem_ld_x32(tS + lane_off + 32, s + 32);
+      uint32_t s[BN];
+      tmem_ld_n<BN>(tS + lane_off, s);
       ptx::tmem_wait_ld();
 
-      if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      const int c0 = j * BN;
+      if (p.dbg != nullptr && c0 < 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-        for (int c = 0; c < kBN; ++c) p.dbg[tid * kBN + c] = (int)s[c];
+        for (int c = 0; c < BN; ++c) p.dbg[tid * 64 + c0 + c] = (int)s[c];
       }
-      const int c0 = j * kBN;
-      int lim = kBN;  // columns [0, lim] are live
-      if (CAUSAL && c0 + kBN - 1 > qt * kBM) lim = min(lim, row - c0);
-      if (mask_tail && j == p.nkb - 1) lim = min(lim, p.Nk - 1 - c0);
-      const bool masked = lim < kBN - 1;
-
-      int imax = INT_MIN;
-      if (!masked) {
-#pragma unroll
-        for (int c = 0; c < kBN; ++c) imax = max(imax, (int)s[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < kBN; ++c) imax = max(imax, c <= lim ? (int)s[c] : INT_MIN);
-      }
+      int lim = BN;  // columns [0, lim] are live
+      if (CAUSAL && c0 + BN - 1 > qt * kBM) lim = min(lim, row - c0);
+      if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
+      // warp-uniform choice of the masked code path (only diagonal / tail blocks ever take it)
+      const bool masked = __any_sync(0xffffffffu, lim < BN - 1);
+      const int imax = masked ? row_max<BN, true>(s, lim) : row_max<BN, false>(s, lim);
       const float mblk = (imax == INT_MIN) ? -INFINITY : (float)imax * sc;
       // lazy rescale: move the reference max only when it grows by more than 2^8 (warp-uniform decision,
       // tcgen05.ld/st are warp collectives)
@@ -231,23 +285,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      uint32_t pk[kBN / 2];
-      float lsum0 = 0.f, lsum1 = 0.f;
+      uint32_t pk[BN / 2];
       const float neg_m = -m_ref;
-#pragma unroll
-      for (int c = 0; c < kBN; c += 2) {
-        float p0 = ptx::ex2(fmaf(ptx::i2f_small((int)s[c]), sc, neg_m));
-        float p1 = ptx::ex2(fmaf(ptx::i2f_small((int)s[c + 1]), sc, neg_m));
-        if (masked) {
-          p0 = (c <= lim) ? p0 : 0.f;
-          p1 = (c + 1 <= lim) ? p1 : 0.f;
-        }
-        lsum0 += p0;
-        lsum1 += p1;
-        pk[c / 2] = ptx::pack_f16x2(p0, p1);
-      }
-      l += lsum0 + lsum1;
-      ptx::tmem_st_x32(tS + lane_off, pk);  // P (fp16) aliases the first 32 columns of its S buffer
+      l += masked ? softmax_block<BN, true, VAR>(s, sc, neg_m, lim, pk) : softmax_block<BN, false, VAR>(s, sc, neg_m, lim, pk);
+      tmem_st_n<BN / 2>(tS + lane_off, pk);  // P (fp16) aliases the first BN/2 columns of its S buffer
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_ready + (j & 1));
@@ -280,7 +321,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,10 +364,10 @@ static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int
   return 0;
 }
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, int VAR>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                        cudaStream_t st) {
-  auto kern = attn_fwd_kernel<D, CAUSAL>;
+  auto kern = attn_fwd_kernel<D, CAUSAL, VAR>;
   static bool configured = false;
   if (!configured) {
     LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D>::kBytes));
@@ -367,8 +408,8 @@ extern "C" int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const v
   CUtensorMap tq, tk, tv;
   const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   if (make_map(&tq, q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, Hq, Nq, D, qsb, qsh, qsn, D, kBM, swz_qk)) return 1;
-  if (make_map(&tk, k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, Hkv, Nk, D, ksb, ksh, ksn, D, kBN, swz_qk)) return 1;
-  if (make_map(&tv, v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, Hkv, Nk, D, vsb, vsh, vsn, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  if (make_map(&tk, k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, Hkv, Nk, D, ksb, ksh, ksn, D, (D == 64 ? AttnCfg<64>::BN : AttnCfg<128>::BN), swz_qk)) return 1;
+  if (make_map(&tv, v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, Hkv, Nk, D, vsb, vsh, vsn, 64, (D == 64 ? AttnCfg<64>::BN : AttnCfg<128>::BN), CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
 
   AttnParams p;
   p.q_scale = q_scale; p.k_scale = k_scale; p.o = o; p.lse = lse;
@@ -376,6 +417,12 @@ extern "C" int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const v
   p.nqb = (Nq + 127) / 128; p.nkb = (Nk + 63) / 64;
   p.osb = osb; p.osh = osh; p.osn = osn;
   p.flags = flags; p.out_dtype = out_dtype; p.dbg = g_attn_debug;
-  if (D == 64) return causal ? launch_attn<64, true>(tq, tk, tv, p, B, st) : launch_attn<64, false>(tq, tk, tv, p, B, st);
-  return causal ? launch_attn<128, true>(tq, tk, tv, p, B, st) : launch_attn<128, false>(tq, tk, tv, p, B, st);
+  static int variant = -1;  // development switch (LOWBIT_ATTN_VARIANT): A/B of softmax instruction selection
+  if (variant < 0) { const char* e = getenv("LOWBIT_ATTN_VARIANT"); variant = e ? atoi(e) : 0; }
+#define LAUNCH(VAR)                                                                                              \
+  if (D == 64) return causal ? launch_attn<64, true, VAR>(tq, tk, tv, p, B, st) : launch_attn<64, false, VAR>(tq, tk, tv, p, B, st); \
+  return causal ? launch_attn<128, true, VAR>(tq, tk, tv, p, B, st) : launch_attn<128, false, VAR>(tq, tk, tv, p, B, st);
+  if (variant == 1) { LAUNCH(1) }
+  LAUNCH(0)
+#undef LAUNCH
 }

@@ -39,17 +39,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (with a diagnostic) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+// Blocking wait.  Fast path: one try_wait.  Slow path: try_wait with a suspend-time hint, so a waiting warp sleeps in
+// hardware (woken by the completing arrive) instead of burning issue slots.  Bounded: a broken pipeline traps
+// after ~10 s instead of hanging the GPU (define LOWBIT_DEBUG_WAIT for a diagnostic printf).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+  for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 10000u); ++spins) {
+    if (spins > (1u << 20)) {
+#ifdef LOWBIT_DEBUG_WAIT
       printf("lowbit_fa: mbarrier wait timed out (tag %d, block %d,%d,%d thread %d parity %u)\n", tag, blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, parity);
+#endif
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
