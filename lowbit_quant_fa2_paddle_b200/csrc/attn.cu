@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace lowbit {
 
@@ -106,7 +107,7 @@ template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const
 // Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the fp16
 // P.V of the previous one run on the tensor pipe while the softmax warps work on block j; K/V stages are refilled
 // by the same thread as soon as the MMAs that read them have committed.
-template <int D, bool CAUSAL, int VAR>
+template <int D, bool CAUSAL, int VAR, bool DBG>
 __global__ void __launch_bounds__(kThreads, AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -236,35 +237,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
     const bool mask_tail = !compat && (p.Nk % BN != 0);
     const int last_kblk = (p.Nk + BN - 1) / BN - 1;
+    const uint32_t tS0 = tmem_base + lane_off, tS1 = tS0 + BN, tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
-    float ks_next = ks_ptr[0];
 
-    for (int j = 0; j < nblk; ++j) {
-      const uint32_t tS = tmem_base + (j & 1) * BN;
-      const float sc = qs * ks_next;
-      ks_next = ks_ptr[min((j + 1) * BN / kScaleBlk, p.nkb - 1)];  // prefetch: L2 latency off the critical path
-      ptx::mbar_wait(bar_s + (j & 1), (j >> 1) & 1, 30);
+    // one key block: wait for S, row max, (rare) rescale of O, P = exp2(S*sc - m) -> TMEM, signal the issuer
+    auto step = [&](auto masked_tag, const uint32_t tSb, uint64_t* bs, uint64_t* pr, const uint32_t ph, const int j,
+                    const float sc, const int lim) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      ptx::mbar_wait(bs, ph, 30);
       ptx::tc_fence_after();
       uint32_t s[BN];
-      tmem_ld_n<BN>(tS + lane_off, s);
+      tmem_ld_n<BN>(tSb, s);
       ptx::tmem_wait_ld();
-
-      const int c0 = j * BN;
-      if (p.dbg != nullptr && c0 < 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      if constexpr (DBG) {
+        if (p.dbg != nullptr && j * BN < 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-        for (int c = 0; c < BN; ++c) p.dbg[tid * 64 + c0 + c] = (int)s[c];
+          for (int c = 0; c < BN; ++c) p.dbg[tid * 64 + j * BN + c] = (int)s[c];
+        }
       }
-      int lim = BN;  // columns [0, lim] are live
-      if (CAUSAL && c0 + BN - 1 > qt * kBM) lim = min(lim, row - c0);
-      if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
-      // warp-uniform choice of the masked code path (only diagonal / tail blocks ever take it)
-      const bool masked = __any_sync(0xffffffffu, lim < BN - 1);
-      const int imax = masked ? row_max<BN, true>(s, lim) : row_max<BN, false>(s, lim);
-      const float mblk = (imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+      const int imax = row_max<BN, MASKED>(s, lim);
+      const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
       // lazy rescale: move the reference max only when it grows by more than 2^8 (warp-uniform decision,
       // tcgen05.ld/st are warp collectives)
-      const bool need = mblk > m_ref + 8.f;
-      if (__any_sync(0xffffffffu, need)) {
+      if (__any_sync(0xffffffffu, mblk > m_ref + 8.f)) {
         const float m_new = fmaxf(m_ref, mblk);
         const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
         l *= alpha;
@@ -275,23 +270,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::mbar_wait(bar_o, (j - 1) & 1, 31);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < D; c += 32) {
-            uint32_t o[32];
-            ptx::tmem_ld_x32(tO + lane_off + c, o);
+          for (int c = 0; c < D; c += 16) {
+            uint32_t o[16];
+            ptx::tmem_ld_x16(tOl + c, o);
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st_x32(tO + lane_off + c, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st_x16(tOl + c, o);
           }
         }
       }
       uint32_t pk[BN / 2];
-      const float neg_m = -m_ref;
-      l += masked ? softmax_block<BN, true, VAR>(s, sc, neg_m, lim, pk) : softmax_block<BN, false, VAR>(s, sc, neg_m, lim, pk);
-      tmem_st_n<BN / 2>(tS + lane_off, pk);  // P (fp16) aliases the first BN/2 columns of its S buffer
+      l += softmax_block<BN, MASKED, VAR>(s, sc, -m_ref, lim, pk);
+      tmem_st_n<BN / 2>(tSb, pk);  // P (fp16) aliases the first BN/2 columns of its S buffer
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(p_ready + (j & 1));
+      ptx::mbar_arrive(pr);
+    };
+
+    // blocks [0, n_full) need no mask: unrolled by two so buffer / barrier addresses are loop constants
+    int n_full = nblk;
+    if (CAUSAL) n_full = min(n_full, (qt * kBM) / BN);
+    if (mask_tail) n_full = min(n_full, last_kblk);
+    int j = 0;
+    uint32_t ph = 0;
+    constexpr int kPerScale = kScaleBlk / BN;  // key blocks per k_scale entry (2 for BN=32, 1 for BN=64)
+    float ks_cur = ks_ptr[0];
+    for (; j + 1 < n_full; j += 2, ph ^= 1) {
+      const float sc0 = qs * ks_cur;
+      float sc1 = sc0;
+      if (kPerScale == 1) sc1 = qs * ks_ptr[j + 1];
+      const float ks_nxt = ks_ptr[min((j + 2) / kPerScale, p.nkb - 1)];  // prefetch for the next pair
+      step(std::false_type{}, tS0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
+      step(std::false_type{}, tS1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
+      ks_cur = ks_nxt;
+    }
+    // remaining blocks (odd leftover, causal diagonal band, masked tail): generic path
+    for (; j < nblk; ++j) {
+      const float sc = qs * ks_ptr[min(j / kPerScale, p.nkb - 1)];
+      const int c0 = j * BN;
+      int lim = BN;  // columns [0, lim] are live
+      if (CAUSAL && c0 + BN - 1 > qt * kBM) lim = min(lim, row - c0);
+      if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
+      step(std::true_type{}, (j & 1) ? tS1 : tS0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc, lim);
     }
 
     // ---- epilogue: O / l -> out dtype, lse2 = log2(l) + m ------------------------------------------
@@ -303,7 +324,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int c = 0; c < D; c += 32) {
       uint32_t o[32];
-      ptx::tmem_ld_x32(tO + lane_off + c, o);  // warp collective: every lane executes it
+      ptx::tmem_ld_x32(tOl + c, o);  // warp collective: every lane executes it
       ptx::tmem_wait_ld();
       uint32_t w[16];
 #pragma unroll
@@ -364,10 +385,10 @@ static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int
   return 0;
 }
 
-template <int D, bool CAUSAL, int VAR>
+template <int D, bool CAUSAL, int VAR, bool DBG = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                        cudaStream_t st) {
-  auto kern = attn_fwd_kernel<D, CAUSAL, VAR>;
+  auto kern = attn_fwd_kernel<D, CAUSAL, VAR, DBG>;
   static bool configured = false;
   if (!configured) {
     LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D>::kBytes));
@@ -422,6 +443,8 @@ extern "C" int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const v
 #define LAUNCH(VAR)                                                                                              \
   if (D == 64) return causal ? launch_attn<64, true, VAR>(tq, tk, tv, p, B, st) : launch_attn<64, false, VAR>(tq, tk, tv, p, B, st); \
   return causal ? launch_attn<128, true, VAR>(tq, tk, tv, p, B, st) : launch_attn<128, false, VAR>(tq, tk, tv, p, B, st);
+  if (p.dbg != nullptr && !causal)  // diagnostics build of the kernel (raw score dump)
+    return D == 64 ? launch_attn<64, false, 0, true>(tq, tk, tv, p, B, st) : launch_attn<128, false, 0, true>(tq, tk, tv, p, B, st);
   if (variant == 1) { LAUNCH(1) }
   LAUNCH(0)
 #undef LAUNCH
