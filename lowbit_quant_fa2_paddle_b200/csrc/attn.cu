@@ -69,20 +69,45 @@ __device__ __forceinline__ float score_to_f32(uint32_t v) {
 template <int BN, bool MASKED, int VAR>
 __device__ __forceinline__ float softmax_block(const uint32_t (&s)[BN], float sc, float neg_m, int lim,
                                                uint32_t (&pk)[BN / 2]) {
-  float lsum0 = 0.f, lsum1 = 0.f;
+  if constexpr ((VAR & 2) == 0) {
+    // packed fp32x2 arithmetic (FFMA2 / FADD2): one instruction scales, or accumulates, two scores
+    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < BN; c += 2) {
-    float p0 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c]), sc, neg_m));
-    float p1 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c + 1]), sc, neg_m));
-    if (MASKED) {
-      p0 = (c <= lim) ? p0 : 0.f;
-      p1 = (c + 1 <= lim) ? p1 : 0.f;
+    for (int c = 0; c < BN; c += 4) {
+      const float2 x0 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c]), score_to_f32<VAR>(s[c + 1])), sc2, nm2);
+      const float2 x1 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c + 2]), score_to_f32<VAR>(s[c + 3])), sc2, nm2);
+      float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
+      float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
+      if (MASKED) {
+        p0.x = (c <= lim) ? p0.x : 0.f;
+        p0.y = (c + 1 <= lim) ? p0.y : 0.f;
+        p1.x = (c + 2 <= lim) ? p1.x : 0.f;
+        p1.y = (c + 3 <= lim) ? p1.y : 0.f;
+      }
+      acc0 = __fadd2_rn(acc0, p0);
+      acc1 = __fadd2_rn(acc1, p1);
+      pk[c / 2] = ptx::pack_f16x2(p0.x, p0.y);
+      pk[c / 2 + 1] = ptx::pack_f16x2(p1.x, p1.y);
     }
-    lsum0 += p0;
-    lsum1 += p1;
-    pk[c / 2] = ptx::pack_f16x2(p0, p1);
+    const float2 t = __fadd2_rn(acc0, acc1);
+    return t.x + t.y;
+  } else {
+    float lsum0 = 0.f, lsum1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < BN; c += 2) {
+      float p0 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c]), sc, neg_m));
+      float p1 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c + 1]), sc, neg_m));
+      if (MASKED) {
+        p0 = (c <= lim) ? p0 : 0.f;
+        p1 = (c + 1 <= lim) ? p1 : 0.f;
+      }
+      lsum0 += p0;
+      lsum1 += p1;
+      pk[c / 2] = ptx::pack_f16x2(p0, p1);
+    }
+    return lsum0 + lsum1;
   }
-  return lsum0 + lsum1;
 }
 template <int BN, bool MASKED>
 __device__ __forceinline__ int row_max(const uint32_t (&s)[BN], int lim) {
@@ -446,6 +471,7 @@ extern "C" int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const v
   if (p.dbg != nullptr && !causal)  // diagnostics build of the kernel (raw score dump)
     return D == 64 ? launch_attn<64, false, 0, true>(tq, tk, tv, p, B, st) : launch_attn<128, false, 0, true>(tq, tk, tv, p, B, st);
   if (variant == 1) { LAUNCH(1) }
+  if (variant == 2) { LAUNCH(2) }
   LAUNCH(0)
 #undef LAUNCH
 }
