@@ -95,10 +95,16 @@ int lowbit_quant_pack_lastdim(const void* data, void* code, void* scale, void* m
 
 /* Q6 -- V -> FP8 e4m3 per channel, transposed, padded, token-permuted
  * (src/quant.py:210-291; TransposePadPermuteKernel + MeanScaleKernel csrc/fused/fused.cu:263-428).
- * v8: [B,H,D,Npad64] e4m3 contiguous; v_scale: f32 [B,H,D]; vm: NULL or f32 [B,H,D] (smooth_v). */
-int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
+ * v8: e4m3 bytes addressed as [b][h][d][pos], pos contiguous in [0, Npad64), with byte strides
+ * (v8_stride_b, v8_stride_h, v8_stride_d) -- the reference allocates [B,H,D,Npad] for HND and [B,D,H,Npad]
+ * for NHD (src/quant.py:262-274); v_scale: f32 [B,H,D]; vm: NULL (smooth_v=False) or f32 [B,H,D].
+ * Token r of every aligned 16-group lands at position (r/8)*2 + ((r/2)%4)*4 + (r%2) (fused.cu:290-292).
+ * workspace: >= lowbit_v_fp8_workspace_bytes(). */
+int64_t lowbit_v_fp8_workspace_bytes(int B, int H, int N, int D);
+int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm, void* workspace,
                              int B, int H, int N, int D,
                              int64_t stride_b, int64_t stride_h, int64_t stride_n,
+                             int64_t v8_stride_b, int64_t v8_stride_h, int64_t v8_stride_d,
                              float scale_max, int dtype, void* stream);
 
 /* E4 -- global max|x| of a tensor (compute_scale, src/core.py:1039-1047).  out: one f32 (device). */

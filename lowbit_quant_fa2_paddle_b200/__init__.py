@@ -22,6 +22,11 @@ from .quant import (  # noqa: F401
     per_block_int4,
     per_block_q_int8_k_int4,
     per_block_k_lowbit,
+    per_thread_int8,
+    per_thread_int4,
+    per_warp_int8,
+    per_channel_fp8,
+    triton_quantize_and_pack_along_last_dim,
 )
 from .attention import forward, forward_causal  # noqa: F401
 

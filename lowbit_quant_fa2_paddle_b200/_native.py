@@ -28,7 +28,8 @@ SIGNATURES = {
     "lowbit_quant_per_block": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I, _I, _I, _F, _I, _I, _P]),
     "lowbit_quant_per_thread": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I] * 5 + [_P]),
     "lowbit_quant_pack_lastdim": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
-    "lowbit_v_fp8_per_channel": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 3 + [_F, _I, _P]),
+    "lowbit_v_fp8_workspace_bytes": (_L, [_I] * 4),
+    "lowbit_v_fp8_per_channel": (_I, [_P, _P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_F, _I, _P]),
     "lowbit_abs_max": (_I, [_P, _P] + [_I] * 4 + [_L] * 3 + [_I, _P]),
     "lowbit_attn_fwd": (_I, [_P] * 10 + [_I] * 6 + [_L] * 12 + [_I] * 4 + [_P]),
     "lowbit_attn_fwd_partial": (_I, [_P] * 8 + [_I] * 6 + [_L] * 9 + [_L, _L] + [_I] * 3 + [_P]),

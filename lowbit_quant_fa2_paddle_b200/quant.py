@@ -116,6 +116,97 @@ def per_block_k_lowbit(k, km=None, BLKK=64, bits=2, tensor_layout="HND", pack=Tr
     return _quant_one(k, km, BLKK, bits, pack, 1.0, N.QMODE_TRITON, tensor_layout)
 
 
+def _per_thread(q, k, km, BLKQ, BLKK, WARPQ, WARPK, tensor_layout, bits):
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    outs = []
+    for x, kmx, warp_blk, blk, is_key in ((q, None, WARPQ, BLKQ, 0), (k, km, WARPK, BLKK, 1)):
+        xt = T.as_torch(x)
+        dev = T.require_cuda(xt)
+        b, h, n, d, sb, sh, sn = T.bhnd(xt, tensor_layout)
+        if d not in (64, 128):
+            raise ValueError(f"Unsupported head_dim: {d}")
+        kmt = _km_bhd(kmx, b, h, d, tensor_layout)
+        codes = torch.empty(xt.shape, dtype=torch.int8, device=dev)
+        _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
+        n_scale = (n + blk - 1) // blk * (blk // warp_blk) * (4 if is_key else 8)  # quant_per_thread.py:269-278
+        scale = torch.empty((b, h, n_scale), dtype=torch.float32, device=dev)
+        N.call("lowbit_quant_per_thread", xt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
+               codes.data_ptr(), scale.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osn, warp_blk, n_scale, is_key,
+               bits, T.dtype_code(xt.dtype), T.stream_ptr(dev))
+        outs += [T.like(codes, x), T.like(scale, x)]
+    return tuple(outs)
+
+
+def per_thread_int8(q, k, km=None, BLKQ=128, BLKK=64, WARPQ=32, WARPK=64, sm_scale=None, tensor_layout="HND"):
+    """src/triton/quant_per_thread.py:222-315: scales per mma-fragment row group -- Q [B,H,ceil(N/128)*4*8],
+    K [B,Hkv,ceil(N/64)*4]; scale = amax/127 + 1e-7; sm_scale is NOT folded (the attention kernel applies it)."""
+    return _per_thread(q, k, km, BLKQ, BLKK, WARPQ, WARPK, tensor_layout, 8)
+
+
+def per_thread_int4(q, k, km=None, BLKQ=128, BLKK=64, WARPQ=32, WARPK=64, sm_scale=None, tensor_layout="HND"):
+    """src/triton/quant_per_thread.py:317-411: as per_thread_int8 with QMAX 7, one code per int8."""
+    return _per_thread(q, k, km, BLKQ, BLKK, WARPQ, WARPK, tensor_layout, 4)
+
+
+def per_warp_int8(q, k, km=None, tensor_layout="HND", sm_scale=None):
+    """src/quant.py:101-172: Q per 32-row warp block (scale [B,H,ceil(N/128)*4]), K per 64-row block, CUDA
+    rounding conventions (Q2); sm_scale is not folded."""
+    qt = T.as_torch(q)
+    b, h, n, d, *_ = T.bhnd(qt, tensor_layout)
+    q_c, q_s = _quant_one(q, None, 32, 8, False, 1.0, N.QMODE_CUDA, tensor_layout)
+    want = (n + 127) // 128 * 4
+    if q_s.shape[2] < want:  # warp blocks wholly past the data: amax floor 1e-7
+        pad = torch.full((b, h, want - q_s.shape[2]), 1e-7, dtype=torch.float32, device=T.as_torch(q_s).device) / 127.0
+        q_s = T.like(torch.cat([T.as_torch(q_s), pad], dim=2), q)
+    k_c, k_s = _quant_one(k, km, 64, 8, False, 1.0, N.QMODE_CUDA, tensor_layout)
+    return q_c, q_s, k_c, k_s
+
+
+def triton_quantize_and_pack_along_last_dim(data, group_size: int, bit: int):
+    """src/triton/utils/quant/new_pack.py:247-300 (KIVI): asymmetric per-group (32) quantization along the last
+    dim in fp16 arithmetic, packed 8/bit codes per byte.  data [B, D, nh, T] fp16 ->
+    (code int8 [B,D,nh,T*bit/8], scale fp16 [B,D,nh,T/32], mn fp16 [B,D,nh,T/32])."""
+    dt = T.as_torch(data)
+    assert dt.dim() == 4
+    dev = T.require_cuda(dt)
+    B, D, nh, Tn = dt.shape
+    assert Tn % group_size == 0
+    assert dt.dtype == torch.float16, "KIVI pack operates on float16 data"
+    dt = dt.contiguous()
+    ng = Tn // group_size
+    code = torch.empty((B, D, nh, Tn * bit // 8), dtype=torch.int8, device=dev)
+    scale = torch.empty((B, D, nh, ng), dtype=torch.float16, device=dev)
+    mn = torch.empty((B, D, nh, ng), dtype=torch.float16, device=dev)
+    N.call("lowbit_quant_pack_lastdim", dt.data_ptr(), code.data_ptr(), scale.data_ptr(), mn.data_ptr(),
+           B * D * nh, Tn, group_size, bit, N.F16, T.stream_ptr(dev))
+    return T.like(code, data), T.like(scale, data), T.like(mn, data)
+
+
+def per_channel_fp8(v, tensor_layout="HND", scale_max=448.0, smooth_v=True):
+    """src/quant.py:210-291: V -> float8_e4m3fn per channel, transposed to [B,H,D,Npad64] (HND) / [B,D,H,Npad64]
+    (NHD), tokens permuted inside 16-groups; returns (v_fp8, v_scale [B,H,D] f32, vm [B,H,D] f32 | None)."""
+    vt = T.as_torch(v)
+    dev = T.require_cuda(vt)
+    b, h, n, d, sb, sh, sn = T.bhnd(vt, tensor_layout)
+    if d not in (64, 128):
+        raise ValueError(f"Unsupported head_dim: {d}")
+    npad = (n + 63) // 64 * 64
+    if tensor_layout == "HND":
+        v8 = torch.empty((b, h, d, npad), dtype=torch.float8_e4m3fn, device=dev)
+        osb, osh, osd = v8.stride(0), v8.stride(1), v8.stride(2)
+    else:
+        v8 = torch.empty((b, d, h, npad), dtype=torch.float8_e4m3fn, device=dev)
+        osb, osd, osh = v8.stride(0), v8.stride(1), v8.stride(2)
+    v_scale = torch.empty((b, h, d), dtype=torch.float32, device=dev)
+    vm = torch.empty((b, h, d), dtype=torch.float32, device=dev) if smooth_v else None
+    ws = torch.empty(N.lib().lowbit_v_fp8_workspace_bytes(b, h, n, d), dtype=torch.uint8, device=dev)
+    N.call("lowbit_v_fp8_per_channel", vt.data_ptr(), v8.data_ptr(), v_scale.data_ptr(),
+           vm.data_ptr() if vm is not None else None, ws.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osd,
+           float(scale_max), T.dtype_code(vt.dtype), T.stream_ptr(dev))
+    return T.like(v8, v), T.like(v_scale, v), T.like(vm, v)
+
+
 def abs_max(x, tensor_layout="HND"):
     """Global max|x| as a 0-d device tensor (compute_scale numerator, core.py:1039-1047)."""
     xt = T.as_torch(x)

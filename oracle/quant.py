@@ -290,7 +290,7 @@ def kivi_quantize_and_pack(data, group_size, bit):
     y = x - mn.unsqueeze(-1)
     y = y / scale.unsqueeze(-1)
     y = y.clamp(0, qm)
-    yf = y.float()
+    yf = torch.nan_to_num(y.float(), nan=0.0)  # constant group: 0/0 in the reference; defined here as code 0
     yr = torch.where(yf >= 0, torch.floor(yf + 0.5), torch.ceil(yf - 0.5))  # Paddle round = half away
     c = yr.to(torch.int32).reshape(-1, T)
     per = 8 // bit
@@ -355,11 +355,12 @@ def per_channel_fp8(v, tensor_layout="HND", scale_max=448.0, smooth_v=True):
         vm = None
         amax = torch.maximum(mx.abs(), mnv.abs())
         xs = vt.float()
-    amax = torch.maximum(amax, _f32(1e-7))
     v_scale = amax / _f32(scale_max)
-    r = _f32(scale_max) / amax
+    r = torch.where(amax > 0, _f32(scale_max) / amax, torch.zeros_like(amax))  # all-zero channel: codes 0 (reference: 0/0)
     y = (xs * r[..., None]).clamp(-448.0, 448.0)
     v8 = y.to(torch.float8_e4m3fn)
+    if tensor_layout == "NHD":
+        v8 = v8.permute(0, 2, 1, 3).contiguous()  # the reference allocates [B,D,H,Npad] for NHD (quant.py:269-274)
     return v8, v_scale, vm
 
 

@@ -248,3 +248,66 @@ def test_multi_precision_and_select(L, cuda_dev):
     assert kind == ("FP16" if avg > 0.2 else "INT8" if avg > 0.05 else "INT4")
     o = L.lowbit_fa_multi_precision(q, k, v)
     assert o.shape == q.shape and not torch.isnan(o).any()
+
+
+# ------------------------------------------------------------------------------------------------ Q3 / Q5 / Q6
+@pytest.mark.parametrize("name", [n for n in ATTN if "causal" not in n])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_per_thread_quant_matches_reference_golden(L, cuda_dev, name, bits):
+    """Q3: codes + scales bit-exact against the reference's per-thread Triton kernels."""
+    g = load_golden(name)
+    fn = L.per_thread_int8 if bits == 8 else L.per_thread_int4
+    qi, qs, ki, ks = fn(g["q"].to(cuda_dev), g["k"].to(cuda_dev), km=g["km"].to(cuda_dev), tensor_layout=g["layout"])
+    p = f"pt{bits}_"
+    assert torch.equal(qi.cpu(), g[p + "q"]) and torch.equal(qs.cpu(), g[p + "qs"])
+    assert torch.equal(ki.cpu(), g[p + "k"]) and torch.equal(ks.cpu(), g[p + "ks"])
+
+
+def test_per_warp_quant_vs_oracle(L, cuda_dev):
+    from oracle import quant as OQ
+    for layout, (b, h, n, d) in (("HND", (1, 2, 300, 64)), ("NHD", (2, 2, 130, 128))):
+        q = mk(b, h, n, d, layout, torch.float16, 41)
+        k = mk(b, h, n, d, layout, torch.float16, 42, bias=2.0)
+        km = OQ.k_mean(k, layout)
+        got = L.per_warp_int8(q.to(cuda_dev), k.to(cuda_dev), km=km.to(cuda_dev), tensor_layout=layout)
+        ref = OQ.per_warp_int8_q2(q, k, km, tensor_layout=layout)
+        for a, r in zip(got, ref):
+            assert torch.equal(a.cpu(), r)
+
+
+@pytest.mark.parametrize("bit", [2, 4, 8])
+def test_kivi_pack_matches_reference_golden(L, cuda_dev, bit):
+    """Q5: packed codes, scales and zero points bit-exact against the reference's min/max + pack kernels."""
+    from oracle import quant as OQ
+    g = load_golden(f"kivi_b{bit}")
+    code, scale, mn = L.triton_quantize_and_pack_along_last_dim(g["data"].to(cuda_dev), 32, bit)
+    assert torch.equal(code.cpu(), g["code"])
+    assert torch.equal(scale.cpu().view(torch.int16), g["scale"].view(torch.int16))
+    assert torch.equal(mn.cpu().view(torch.int16), g["mn"].view(torch.int16))
+    big = (torch.randn(2, 64, 4, 256) * 3).half()
+    big[0, 0, 0, :32] = 1.5  # constant group
+    c2, s2, m2 = L.triton_quantize_and_pack_along_last_dim(big.to(cuda_dev), 32, bit)
+    rc, rs, rm = OQ.kivi_quantize_and_pack(big, 32, bit)
+    assert torch.equal(c2.cpu(), rc) and torch.equal(s2.cpu().view(torch.int16), rs.view(torch.int16))
+    assert torch.equal(m2.cpu().view(torch.int16), rm.view(torch.int16))
+
+
+@pytest.mark.parametrize("layout", ["HND", "NHD"])
+@pytest.mark.parametrize("smooth_v", [True, False])
+@pytest.mark.parametrize("shape,dtype", [((1, 2, 200, 64), torch.float16), ((2, 3, 77, 128), torch.bfloat16),
+                                         ((1, 2, 1024, 128), torch.float16)])
+def test_v_fp8_per_channel_vs_oracle(L, cuda_dev, layout, smooth_v, shape, dtype):
+    """Q6: e4m3 bytes, scales and means bit-exact against the IEEE restatement of fused.cu (parity unpinned:
+    the reference CUDA cannot be built here)."""
+    from oracle import quant as OQ
+    b, h, n, d = shape
+    v = mk(b, h, n, d, layout, dtype, 51, bias=1.0)
+    v8, vs, vm = L.per_channel_fp8(v.to(cuda_dev), tensor_layout=layout, smooth_v=smooth_v)
+    r8, rs, rm = OQ.per_channel_fp8(v, tensor_layout=layout, smooth_v=smooth_v)
+    assert v8.shape == r8.shape and v8.dtype == torch.float8_e4m3fn
+    assert torch.equal(vs.cpu(), rs)
+    if smooth_v:
+        assert torch.equal(vm.cpu(), rm)
+    else:
+        assert vm is None
+    assert torch.equal(v8.cpu().view(torch.uint8), r8.view(torch.uint8))
