@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LOWBIT_ABI_VERSION 1
+#define LOWBIT_ABI_VERSION 2
 
 /* element types of the floating-point inputs / outputs */
 enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
@@ -117,7 +117,8 @@ int lowbit_abs_max(const void* x, float* out, int B, int H, int N, int D,
  *           forward_merging (src/triton/quantization/attn_qk_int4_per_block.py:248-317) and the
  *           FP8-PV semantics of csrc/qattn/qk_int_sv_f8_cuda.cu:44-692.
  * q_codes int8 [B,Hq,Nq,D]; k_codes int8 [B,Hkv,Nk,D] (or packed, see qk_mode); v fp16 [B,Hkv,Nk,D]
- * (pv_mode F16) or e4m3 [B,Hkv,D,Npad64] as produced by lowbit_v_fp8_per_channel (pv_mode E4M3);
+ * (pv_mode F16) or e4m3 [b][h][d][pos] as produced by lowbit_v_fp8_per_channel (pv_mode E4M3: the three v strides
+ * are then the byte strides of (b, h, d), positions contiguous, Npad64 of them);
  * q_scale f32 [B,Hq,ceil(Nq/128)], k_scale f32 [B,Hkv,ceil(Nk/64)] contiguous; v_scale/v_mean f32 [B,Hkv,D]
  * or NULL; kbits int32 [B,Hkv,ceil(Nk/64)] or NULL; o [B,Hq,Nq,D] of out_dtype; lse NULL or f32
  * [B,Hq,Nq] (base-2: log2(l)+m, as the reference kernel stores it).  D in {64,128}. */
@@ -132,18 +133,22 @@ int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const void* v,
                     int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_n,
                     int qk_mode, int pv_mode, int out_dtype, int flags, void* stream);
 
-/* Ring / sequence-parallel step: same contraction over one K/V shard, carrying un-normalised state.
- * m_io, l_io: f32 [B,Hq,Nq]; o_acc_io: f32 [B,Hq,Nq,D] contiguous.  q_offset/k_offset are the global
- * token positions of row 0 / key 0 (causal masking across shards).  first != 0 initialises the state.
- * Call lowbit_attn_finalize afterwards to produce o (and lse). */
+/* Ring / sequence-parallel step: same contraction over one K/V shard, merged into un-normalised running state.
+ * m_io, l_io: f32 [B,Hq,Nq]; o_acc_io: f32 [B,Hq,Nq,D] contiguous, all in true (dequantized) units:
+ * O = o_acc / l relative to the running maximum m (base-2 log units).  q_offset / k_offset are the global token
+ * positions of query row 0 / key 0 of the shards (causal masking across shards: key c is visible to row r iff
+ * k_offset + c <= q_offset + r; a shard wholly in the future leaves the state untouched).  first != 0 initialises
+ * the state instead of reading it.  Call lowbit_attn_finalize afterwards to produce o (and lse). */
 int lowbit_attn_fwd_partial(const void* q_codes, const void* k_codes, const void* v,
                             const float* q_scale, const float* k_scale,
+                            const float* v_scale, const float* v_mean, const int32_t* kbits,
                             float* m_io, float* l_io, float* o_acc_io,
                             int B, int Hq, int Hkv, int Nq, int Nk, int D,
                             int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_n,
                             int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_n,
                             int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_n,
-                            int64_t q_offset, int64_t k_offset, int qk_mode, int flags, int first, void* stream);
+                            int64_t q_offset, int64_t k_offset, int qk_mode, int pv_mode, int flags, int first,
+                            void* stream);
 int lowbit_attn_finalize(const float* m, const float* l, const float* o_acc, void* o, float* lse,
                          int B, int Hq, int Nq, int D,
                          int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_n,

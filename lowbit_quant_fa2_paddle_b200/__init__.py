@@ -6,11 +6,14 @@ from .core import (  # noqa: F401
     sageattn_qk_int8_pv_fp16_triton,
     sageattn_qk_int4_pv_fp16_triton,
     sageattn_multi_precision,
+    sageattn_qk_int8_pv_fp8_cuda,
     # preferred names
     lowbit_fa_multi_precision,
     lowbit_fa_qk_int8_pv_fp16_triton,
     lowbit_fa_qk_int4_pv_fp16_triton,
     lowbit_fa_q_int8_k_int4_pv_fp16,
+    lowbit_fa_qk_int8_pv_fp8_cuda,
+    lowbit_fa_qk_int4_pv_fp8,
     compute_scale,
     select_quantization,
 )
@@ -28,6 +31,6 @@ from .quant import (  # noqa: F401
     per_channel_fp8,
     triton_quantize_and_pack_along_last_dim,
 )
-from .attention import forward, forward_causal  # noqa: F401
+from .attention import forward, forward_causal, forward_partial, finalize, PartialState  # noqa: F401
 
 __version__ = "0.1.0"

@@ -4,6 +4,8 @@
   lowbit_fa_qk_int4_pv_fp16_triton   src/core.py:945-1036 (alias :1105)
   lowbit_fa_q_int8_k_int4_pv_fp16    mixed entry: quant_per_block.py:391-458 + utils/paddle_package.py:321-417
   lowbit_fa_multi_precision          src/core.py:1064-1096 (select_quantization :1050-1061)
+  lowbit_fa_qk_int8_pv_fp8_cuda      src/core.py:735-941  (alias :1104) -- FP8 P.V semantics on the sm_100a kernel
+  lowbit_fa_qk_int4_pv_fp8           INT4 K + FP8 P.V (BASELINE config 3)
 
 Same names, keyword arguments, return values, assertion / ValueError behaviour.  The "_triton" suffix is kept
 because callers import these names; the implementation is hand-written sm_100a CUDA (csrc/) reached through
@@ -28,7 +30,7 @@ def _pad_head(x, to):
 
 
 def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
-               qk, compat_tail=False):
+               qk, compat_tail=False, pv="fp16", smooth_v=False):
     qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
     dtype = qt.dtype
     assert dtype in [torch.float16, torch.bfloat16], \
@@ -48,7 +50,10 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
     assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
     with torch.cuda.device(dev):
         km = Qz.k_mean(kt, tensor_layout) if smooth_k else None
-        if dtype == torch.bfloat16:
+        v_scale = v_mean = None
+        if pv == "fp8":  # V -> e4m3 per channel, transposed (src/quant.py:210-291; core.py:882-884)
+            vt, v_scale, v_mean = Qz.per_channel_fp8(vt, tensor_layout=tensor_layout, smooth_v=smooth_v)
+        elif dtype == torch.bfloat16:
             vt = vt.to(torch.float16)
         if sm_scale is None:
             sm_scale = 1.0 / head_dim_og ** 0.5
@@ -58,7 +63,8 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
                                            packed, quantization_backend)
         qk_mode = N.QK_Q8K4 if packed else N.QK_I8
         o, lse = A._forward(q_c, k_c, vt, q_s, k_s, tensor_layout, dtype, return_lse, bool(is_causal),
-                            qk_mode=qk_mode, compat_tail=compat_tail)
+                            qk_mode=qk_mode, pv_mode=N.PV_E4M3 if pv == "fp8" else N.PV_F16,
+                            compat_tail=compat_tail, v_scale=v_scale, v_mean=v_mean)
         o = o[..., :head_dim_og]
         if return_lse:
             b, hq, nq, d, sb, sh, sn = T.bhnd(qt, tensor_layout)
@@ -99,6 +105,34 @@ def lowbit_fa_q_int8_k_int4_pv_fp16(q, k, v, tensor_layout: str = "HND", quantiz
                       "q8k4", compat_tail=bool(kwargs.get("compat_tail", False)))
 
 
+def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                                 qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None,
+                                 pv_accum_dtype: str = "fp32+fp32", smooth_k: bool = True, smooth_v: bool = False,
+                                 return_lse: bool = False, **kwargs: Any):
+    """INT8 Q.K^T + FP8 (e4m3) P.V with fp32 accumulation -- the signature of src/core.py:735-941.  V is quantized
+    per channel by per_channel_fp8 (:882-884); P~ = e4m3(exp2(s - m + offset)), the denominator sums the rounded P~
+    (attn_utils.cuh:424-428,550-562), the epilogue applies v_scale (+ v_mean when smooth_v).  The sm_100a kernel
+    dequantizes with per-block scales, so `qk_quant_gran` is accepted for signature compatibility and the
+    quantizer is the per-block one; `pv_accum_dtype` "fp32+fp32" ignores smooth_v like the reference (:878-881)."""
+    if qk_quant_gran not in ("per_warp", "per_thread"):
+        raise ValueError(f"Unsupported qk_quant_gran: {qk_quant_gran}")
+    if pv_accum_dtype not in ("fp32", "fp32+fp32"):
+        raise ValueError(f"Unsupported pv_accum_dtype: {pv_accum_dtype}")
+    if pv_accum_dtype == "fp32+fp32":
+        smooth_v = False
+    return _lowbit_fa(q, k, v, tensor_layout, kwargs.get("quantization_backend", "triton"), is_causal, sm_scale,
+                      smooth_k, return_lse, "int8", pv="fp8", smooth_v=smooth_v)
+
+
+def lowbit_fa_qk_int4_pv_fp8(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                             sm_scale: Optional[float] = None, smooth_k: bool = True, smooth_v: bool = False,
+                             return_lse: bool = False, **kwargs: Any):
+    """INT4 K (packed, per 64-row block) x INT8 Q + FP8 (e4m3) P.V: the combination BASELINE config 3 names.
+    The reference has the two halves (core.py:945-1036 and :735-941) but no kernel that combines them."""
+    return _lowbit_fa(q, k, v, tensor_layout, kwargs.get("quantization_backend", "triton"), is_causal, sm_scale,
+                      smooth_k, return_lse, "int4", pv="fp8", smooth_v=smooth_v)
+
+
 def compute_scale(tensor, bits=8, symmetric=True, tensor_layout="HND"):
     """core.py:1039-1047 -- symmetric: max|x| / (2^(bits-1) - 1), as a 0-d device tensor."""
     if not symmetric:
@@ -137,3 +171,4 @@ def sageattn_multi_precision(q, k, v, tensor_layout: str = "HND", is_causal: boo
 lowbit_fa_multi_precision = sageattn_multi_precision
 lowbit_fa_qk_int8_pv_fp16_triton = sageattn_qk_int8_pv_fp16_triton
 lowbit_fa_qk_int4_pv_fp16_triton = sageattn_qk_int4_pv_fp16_triton
+lowbit_fa_qk_int8_pv_fp8_cuda = sageattn_qk_int8_pv_fp8_cuda

@@ -3,14 +3,23 @@
 // Replaces, behind include/lowbit_fa.h (paths relative to the reference repository):
 //   _attn_fwd / _attn_fwd_inner   src/triton/attn_qk_int8_per_block.py:24-167        (non-causal)
 //   _attn_fwd_base                src/triton/attn_qk_int8_per_block_causal.py:216-334 (causal)
+//   forward_merging               src/triton/quantization/attn_qk_int4_per_block.py:248-317 (INT4 K)
+//   FP8 P.V semantics             csrc/qattn/qk_int_sv_f8_cuda.cu:44-692, attn_utils.cuh:30,424-428,550-562
 //
-// Per CTA: one 128-row Q tile of one (batch, q-head).  Q (int8), K (int8) and V (fp16) tiles are staged in
-// shared memory by TMA (hardware swizzle, OOB rows zero-filled = the reference's masked loads);
-// S = Q.K^T runs on tcgen05 kind::i8 (exact int32 in TMEM); each of the 128 threads owns one row (one TMEM
-// lane): integer row-max, dequant by q_scale*k_scale, exp2 online softmax in registers, P written back to TMEM
-// as fp16 (aliasing S) and consumed as the A operand of the P.V tcgen05 kind::f16 MMA whose fp32
-// accumulator O stays resident in TMEM for the whole key loop (rescaled only when the running max moves by
-// more than 2^8).  Epilogue: O/l -> fp16/bf16, lse2 = log2(l) + m.
+// Per CTA: one 128-row Q tile of one (batch, q-head).  Q (int8), K (int8, or INT4 packed two codes per byte) and
+// V (fp16, or e4m3 transposed) tiles are staged in shared memory by TMA (OOB rows zero-filled = the reference's
+// masked loads); S = Q.K^T runs on tcgen05 kind::i8 (exact int32 in TMEM); each of the 128 softmax threads owns one
+// row (one TMEM lane): integer row-max, dequant by q_scale*k_scale, exp2 online softmax in registers, P written back
+// to TMEM as fp16 / e4m3 (aliasing S) and consumed as the A operand of the P.V tcgen05 MMA (kind::f16 or
+// kind::f8f6f4) whose fp32 accumulator O stays resident in TMEM for the whole key loop (rescaled only when the
+// running max moves by more than a threshold).  Epilogue: O/l (* v_scale + v_mean) -> fp16/bf16, lse2 = log2(l) + m;
+// or, for ring / sequence-parallel steps, a merge into the fp32 running state (m, l, O_acc) in HBM.
+//
+// INT4 K: packed tiles land linearly in a staging ring; the softmax threads expand the nibbles to int8 (as
+// code*16: a shift and a mask per 8 codes, no sign extension) straight into the swizzled operand layout.  The
+// expansion yields head-dim order [d0 d2 d4 d6 d1 d3 d5 d7] inside every group of 8, so the Q tile is permuted the
+// same way once per CTA (a contraction is invariant under a common permutation of its reduction index) and the
+// factor 16 is folded into the dequantization scale (exact: a power of two).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,13 +33,19 @@ namespace lowbit {
 struct AttnParams {
   const float* q_scale;
   const float* k_scale;
+  const float* v_scale;  // PV e4m3: [B,Hkv,D]
+  const float* v_mean;   // PV e4m3: [B,Hkv,D] or null
   void* o;
   float* lse;
+  float* m_io;           // partial (ring) state: [B,Hq,Nq]; oacc_io != null selects the merge epilogue
+  float* l_io;
+  float* oacc_io;        // [B,Hq,Nq,D] fp32
   int Hq, Hkv, Nq, Nk;
-  int nqb, nkb;  // scale blocks per (b,h): ceil(Nq/128), ceil(Nk/64)
+  int nqb, nkb;          // scale blocks per (b,h): ceil(Nq/128), ceil(Nk/64)
   int64_t osb, osh, osn;
-  int flags, out_dtype;
-  int32_t* dbg;  // diagnostics: when non-null, CTA (0,0,0) dumps the int32 scores of key block 0 ([128][64])
+  int delta;             // q_offset - k_offset: global position of query row 0 minus that of key 0 (causal)
+  int flags, out_dtype, first;
+  int32_t* dbg;          // diagnostics: when non-null, CTA (0,0,0) dumps the int32 scores of key block 0 ([128][64])
 };
 
 static int32_t* g_attn_debug = nullptr;
@@ -39,6 +54,9 @@ constexpr int kBM = 128;      // Q rows per CTA (= TMEM lanes)
 constexpr int kScaleBlk = 64; // k_scale granularity of the reference quantizer (BLKK)
 constexpr int kSoftmaxThreads = 128;
 constexpr int kThreads = kSoftmaxThreads + 32;  // + one helper warp (TMA producer + tcgen05 issuer, one elected lane)
+
+enum { KM_I8 = 0, KM_K4 = 1 };
+enum { PV_F16 = 0, PV_E4M3 = 1 };
 
 // Per-head-dim tiling.  D=64 is exp2(MUFU)-bound: small 32-key steps keep the register footprint under 96 so that
 // four CTAs (16 softmax warps) share an SM and hide each other's latencies.  D=128 has twice the tensor work per
@@ -51,34 +69,49 @@ template <> struct AttnCfg<128> {
   static constexpr int BN = 64, CTAS = 2, KS = 4, VS = 3, TMEM_COLS = 256;
 };
 
-template <int D>
+// PV-mode constants: THR = how far a block maximum may exceed the reference maximum before O is rescaled (P stays
+// below 2^THR * 2^OFF: 256 in fp16, 448 in e4m3); OFF = exponent offset of the stored P (attn_utils.cuh:30 uses
+// 8.807 with an exact running maximum; a lazy maximum needs THR of headroom below the e4m3 limit 448 = 2^8.807).
+template <int PV> struct PvCfg;
+template <> struct PvCfg<PV_F16> { static constexpr float THR = 8.f, OFF = 0.f; };
+template <> struct PvCfg<PV_E4M3> { static constexpr float THR = 2.f, OFF = 6.807f; };
+
+template <int D, int KM, int PV>
 struct AttnSmem {
   using C = AttnCfg<D>;
-  static constexpr int kQ = kBM * D;        // int8
-  static constexpr int kK = C::BN * D;      // int8
-  static constexpr int kV = C::BN * D * 2;  // fp16
-  static constexpr int kBytes = kQ + C::KS * kK + C::VS * kV + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kQ = kBM * D;                                  // int8
+  static constexpr int kK = C::BN * D;                                // int8 operand stage
+  static constexpr int kKStages = (KM == KM_I8) ? C::KS : 2;
+  static constexpr int kKp = C::BN * D / 2;                           // packed INT4 staging stage
+  static constexpr int kKpStages = (KM == KM_K4) ? 4 : 0;
+  static constexpr int kV = (PV == PV_F16) ? C::BN * D * 2 : C::BN * D;  // fp16 [key][d] / e4m3 [d][key]
+  static constexpr int kBytes = kQ + kKStages * kK + C::VS * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 template <int VAR>
 __device__ __forceinline__ float score_to_f32(uint32_t v) {
   return (VAR & 1) ? ptx::i2f_small((int)v) : __int2float_rn((int)v);
 }
-// One softmax step over a BN-key block for one query row: p = exp2(S*sc - m), packed to fp16 pairs, row sum in fp32.
+
+// One softmax step over a BN-key block for one query row: p = exp2(S*sc + nm), packed to fp16 pairs, row sum in fp32.
 // MASKED: columns > lim contribute 0 (causal diagonal band / masked tail keys).
+// VAR bit 2: one pair in every four goes through the FMA-pipe polynomial instead of MUFU.EX2.
 template <int BN, bool MASKED, int VAR>
-__device__ __forceinline__ float softmax_block(const uint32_t (&s)[BN], float sc, float neg_m, int lim,
-                                               uint32_t (&pk)[BN / 2]) {
+__device__ __forceinline__ float softmax_block_f16(const uint32_t (&s)[BN], float sc, float nm, int lim,
+                                                   uint32_t (&pk)[BN / 2]) {
   if constexpr ((VAR & 2) == 0) {
     // packed fp32x2 arithmetic (FFMA2 / FADD2): one instruction scales, or accumulates, two scores
-    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
     float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < BN; c += 4) {
       const float2 x0 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c]), score_to_f32<VAR>(s[c + 1])), sc2, nm2);
       const float2 x1 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c + 2]), score_to_f32<VAR>(s[c + 3])), sc2, nm2);
-      float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
-      float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
+      float2 p0, p1;
+      if ((VAR & 4) && (c % 8 == 4)) p0 = ptx::ex2_poly2(x0);
+      else p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
+      if ((VAR & 8) && (c % 8 == 0)) p1 = ptx::ex2_poly2(x1);
+      else p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
       if (MASKED) {
         p0.x = (c <= lim) ? p0.x : 0.f;
         p0.y = (c + 1 <= lim) ? p0.y : 0.f;
@@ -96,8 +129,8 @@ __device__ __forceinline__ float softmax_block(const uint32_t (&s)[BN], float sc
     float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
     for (int c = 0; c < BN; c += 2) {
-      float p0 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c]), sc, neg_m));
-      float p1 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c + 1]), sc, neg_m));
+      float p0 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c]), sc, nm));
+      float p1 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c + 1]), sc, nm));
       if (MASKED) {
         p0 = (c <= lim) ? p0 : 0.f;
         p1 = (c + 1 <= lim) ? p1 : 0.f;
@@ -109,6 +142,45 @@ __device__ __forceinline__ float softmax_block(const uint32_t (&s)[BN], float sc
     return lsum0 + lsum1;
   }
 }
+
+// FP8 variant: p~ = e4m3_rn_satfinite(exp2(S*sc + nm)) (nm carries -m + OFF), four codes per TMEM word.  The row sum
+// is taken over the ROUNDED values (accumulate_d_f8, attn_utils.cuh:550-562), here through exact e4m3 -> f16
+// conversion and short f16x2 partial sums.  Key c of an aligned 16-group sits at the K index the reference's V layout
+// expects (fused.cu:290-292): word w of a group = keys {2w, 2w+1, 8+2w, 9+2w}.
+template <int BN, bool MASKED, int VAR>
+__device__ __forceinline__ float softmax_block_e4m3(const uint32_t (&s)[BN], float sc, float nm, int lim,
+                                                    uint32_t (&pk)[BN / 4]) {
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
+  uint32_t hacc[BN / 16];
+#pragma unroll
+  for (int g = 0; g < BN / 16; ++g) {
+    uint32_t h = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int c0 = 16 * g + 2 * w, c1 = c0 + 8;
+      const float2 x0 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c0]), score_to_f32<VAR>(s[c0 + 1])), sc2, nm2);
+      const float2 x1 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c1]), score_to_f32<VAR>(s[c1 + 1])), sc2, nm2);
+      float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
+      float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
+      if (MASKED) {
+        p0.x = (c0 <= lim) ? p0.x : 0.f;
+        p0.y = (c0 + 1 <= lim) ? p0.y : 0.f;
+        p1.x = (c1 <= lim) ? p1.x : 0.f;
+        p1.y = (c1 + 1 <= lim) ? p1.y : 0.f;
+      }
+      const uint16_t lo = ptx::pack_e4m3x2(p0.x, p0.y), hi = ptx::pack_e4m3x2(p1.x, p1.y);
+      pk[4 * g + w] = (uint32_t)lo | ((uint32_t)hi << 16);
+      const uint32_t hs = ptx::hadd2(ptx::e4m3x2_to_f16x2(lo), ptx::e4m3x2_to_f16x2(hi));
+      h = (w == 0) ? hs : ptx::hadd2(h, hs);
+    }
+    hacc[g] = h;  // 4 values per f16 lane, each <= 448: no overflow, relative error <= 2^-10
+  }
+  float t = 0.f;
+#pragma unroll
+  for (int g = 0; g < BN / 16; ++g) t += ptx::f16x2_sum(hacc[g]);
+  return t;
+}
+
 template <int BN, bool MASKED>
 __device__ __forceinline__ int row_max(const uint32_t (&s)[BN], int lim) {
   int m4[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};  // 4 independent chains (latency, not throughput, bound)
@@ -121,45 +193,108 @@ template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint3
   else { ptx::tmem_ld_x32(taddr, r); ptx::tmem_ld_x32(taddr + 32, r + 32); }
 }
 template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
-  if constexpr (N == 16) ptx::tmem_st_x16(taddr, r);
+  if constexpr (N == 8) ptx::tmem_st_x8(taddr, r);
+  else if constexpr (N == 16) ptx::tmem_st_x16(taddr, r);
   else ptx::tmem_st_x32(taddr, r);
 }
 
-// Warp roles:  warps 0-3  softmax (thread t <-> query row t <-> TMEM lane t)
+// INT4 K: expand one packed staging tile (BN rows x D/2 bytes, linear) into the int8 operand stage (BN rows x D
+// bytes, K-major, 64B / 128B hardware swizzle).  Every 16-byte packed chunk (32 codes) becomes two 16-byte chunks.
+template <int D, int BN>
+__device__ __forceinline__ void unpack_k4_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int tid) {
+  constexpr int kChunks = BN * D / 32;  // packed 16-byte chunks in the tile
+  constexpr int kCPR = D / 32;          // packed chunks per row
+  constexpr uint32_t kSwzMask = (D == 64) ? 3u : 7u;
+  constexpr uint32_t kM = 0xF0F0F0F0u;
+#pragma unroll
+  for (int q = tid; q < kChunks; q += kSoftmaxThreads) {
+    const uint4 w = *reinterpret_cast<const uint4*>(src + q * 16);
+    const uint32_t off0 = (uint32_t)(q / kCPR) * D + (uint32_t)(q % kCPR) * 32, off1 = off0 + 16;
+    uint4 a, b;
+    a.x = (w.x << 4) & kM; a.y = w.x & kM; a.z = (w.y << 4) & kM; a.w = w.y & kM;
+    b.x = (w.z << 4) & kM; b.y = w.z & kM; b.z = (w.w << 4) & kM; b.w = w.w & kM;
+    *reinterpret_cast<uint4*>(dst + (off0 ^ (((off0 >> 7) & kSwzMask) << 4))) = a;
+    *reinterpret_cast<uint4*>(dst + (off1 ^ (((off1 >> 7) & kSwzMask) << 4))) = b;
+  }
+}
+// the matching permutation of the Q tile: [d0..d7] -> [d0 d2 d4 d6 d1 d3 d5 d7] inside every 8-byte group
+// (16-byte chunks move as units under the hardware swizzle, so the tile can be walked linearly)
+template <int D>
+__device__ __forceinline__ void permute_q_tile(uint8_t* sQ, int tid) {
+#pragma unroll
+  for (int q = tid; q < kBM * D / 16; q += kSoftmaxThreads) {
+    uint4 w = *reinterpret_cast<uint4*>(sQ + q * 16), r;
+    r.x = __byte_perm(w.x, w.y, 0x6420); r.y = __byte_perm(w.x, w.y, 0x7531);
+    r.z = __byte_perm(w.z, w.w, 0x6420); r.w = __byte_perm(w.z, w.w, 0x7531);
+    *reinterpret_cast<uint4*>(sQ + q * 16) = r;
+  }
+}
+
+// Warp roles:  warps 0-3  softmax (thread t <-> query row t <-> TMEM lane t); in INT4-K mode they also expand K tiles
 //              warp 4     helper: one elected lane is both the TMA producer and the tcgen05 issuer; the warp also
 //                         owns the TMEM allocation
 // TMEM columns: S/P buffer 0 [0,BN)  S/P buffer 1 [BN,2BN)  O [2BN, 2BN+D)
-// Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the fp16
+// Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the
 // P.V of the previous one run on the tensor pipe while the softmax warps work on block j; K/V stages are refilled
 // by the same thread as soon as the MMAs that read them have committed.
-template <int D, bool CAUSAL, int VAR, bool DBG>
+template <int D, int KM, int PV, int VAR, bool DBG>
 __global__ void __launch_bounds__(kThreads, AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using C = AttnCfg<D>;
-  using SM = AttnSmem<D>;
-  constexpr int BN = C::BN, KS = C::KS, VS = C::VS;
+  using SM = AttnSmem<D, KM, PV>;
+  using PC = PvCfg<PV>;
+  constexpr int BN = C::BN, VS = C::VS;
+  constexpr int KS = SM::kKStages;                   // int8 operand stages (INT4 mode: 2, indexed like the S buffers)
+  constexpr int KPS = (KM == KM_K4) ? SM::kKpStages : C::KS;  // TMA-filled K stages
+  constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;     // TMEM columns of one P tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + SM::kQ;
   uint8_t* sV = sK + KS * SM::kK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + VS * SM::kV);
+  uint8_t* sKp = sV + VS * SM::kV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + SM::kKpStages * SM::kKp);
   uint64_t* bar_q = bars + 0;
-  uint64_t* kfull = bars + 1;        // [KS] TMA -> MMA
-  uint64_t* kfree = kfull + KS;      // [KS] MMA (commit) -> TMA
-  uint64_t* vfull = kfree + KS;      // [VS]
+  uint64_t* kfull = bars + 1;        // [KPS] TMA -> consumer (MMA issuer, or the expanding softmax threads)
+  uint64_t* kfree = kfull + KPS;     // [KPS] consumer -> TMA
+  uint64_t* vfull = kfree + KPS;     // [VS]
   uint64_t* vfree = vfull + VS;      // [VS]
   uint64_t* bar_s = vfree + VS;      // [2] QK done: S buffer b holds scores
-  uint64_t* p_ready = bar_s + 2;     // [2] 128 softmax threads wrote P into buffer b
+  uint64_t* p_ready = bar_s + 2;     // [2] 128 softmax threads wrote P into buffer b (INT4: and expanded K_{j+2})
   uint64_t* bar_o = p_ready + 2;     // PV_j done (one phase per key block)
   uint64_t* bar_final = bar_o + 1;   // last PV done (single phase: parity waits must never lag 2 phases)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
+  uint64_t* bar_k01 = bar_final + 1; // INT4: Q permuted and K_0, K_1 expanded
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_k01 + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
+  const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
+  const int qt = causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
   const int hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (p.Hq / p.Hkv);
+
+  // key-block range of this Q tile.  compat_tail walks the reference's whole 64-key blocks (phantom zero keys).
+  const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
+  const int nk_eff = compat ? p.nkb * kScaleBlk : p.Nk;
+  int nblk = (nk_eff + BN - 1) / BN;
+  // causal: key (global k_off + c) is visible to row (global q_off + r) iff c <= delta + r
+  const int dq = p.delta + qt * kBM;  // delta + first row of the tile
+  if (causal) nblk = max(0, min(nblk, (dq + kBM + BN - 1) / BN));
+  if (nblk == 0) {
+    // ring step whose K/V shard lies wholly in this tile's future: the running state is unchanged
+    if (p.oacc_io != nullptr && p.first && tid < kSoftmaxThreads) {
+      const int row = qt * kBM + tid;
+      if (row < p.Nq) {
+        const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
+        p.m_io[idx] = -INFINITY;
+        p.l_io[idx] = 0.f;
+        float4* od = reinterpret_cast<float4*>(p.oacc_io + idx * D);
+#pragma unroll
+        for (int i = 0; i < D / 4; ++i) od[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
 
   if (warp == 4) {
     ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -167,11 +302,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (tid == 0) {
     ptx::mbar_init(bar_q, 1);
-    for (int i = 0; i < KS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
+    for (int i = 0; i < KPS; ++i) {
+      ptx::mbar_init(kfull + i, 1);
+      ptx::mbar_init(kfree + i, KM == KM_K4 ? kSoftmaxThreads : 1);
+    }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kSoftmaxThreads); }
     ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_final, 1);
+    ptx::mbar_init(bar_k01, kSoftmaxThreads);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
@@ -183,36 +322,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tO = tmem_base + 2 * BN;  // fp32 output accumulator, D columns
 
-  // key-block range of this Q tile.  compat_tail walks the reference's whole 64-key blocks (phantom zero keys).
-  const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
-  const int nk_eff = compat ? p.nkb * kScaleBlk : p.Nk;
-  int nblk = (nk_eff + BN - 1) / BN;
-  if (CAUSAL) nblk = min(nblk, (qt + 1) * (kBM / BN));
-
   if (warp == 4) {
     // ================================ helper: TMA producer + tcgen05 issuer ================================
     if (ptx::elect_one()) {
       constexpr uint32_t kSwzQK = (D == 64) ? ptx::kSwz64 : ptx::kSwz128;
       constexpr uint32_t kSboQK = 8 * D;  // 8 rows of D bytes
       constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
-      constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
+      constexpr uint32_t idesc_pv = (PV == PV_F16) ? ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D)
+                                                   : ptx::make_idesc(ptx::kCF32, ptx::kE4M3, ptx::kE4M3, 0, 0, kBM, D);
       const uint32_t aq = ptx::smem_u32(sQ);
-      auto load_k = [&](int j) {
-        const int ks = j % KS;
-        ptx::mbar_wait(kfree + ks, ((j / KS) & 1) ^ 1, 10);
-        ptx::mbar_expect_tx(kfull + ks, SM::kK);
-        ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * BN, hkv, b);
+      auto load_k = [&](int j) {  // int8 tile (swizzled) or packed INT4 tile (linear) into TMA stage j % KPS
+        const int ks = j % KPS;
+        ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
+        if constexpr (KM == KM_I8) {
+          ptx::mbar_expect_tx(kfull + ks, SM::kK);
+          ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * BN, hkv, b);
+        } else {
+          ptx::mbar_expect_tx(kfull + ks, SM::kKp);
+          ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, j * BN, hkv, b);
+        }
       };
       auto load_v = [&](int j) {
         const int vs = j % VS;
         ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
         ptx::mbar_expect_tx(vfull + vs, SM::kV);
-        ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, j * BN, hkv, b);
-        if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + BN * 128, &tmV, vfull + vs, 64, j * BN, hkv, b);
+        if constexpr (PV == PV_F16) {
+          ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, j * BN, hkv, b);
+          if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + BN * 128, &tmV, vfull + vs, 64, j * BN, hkv, b);
+        } else {
+          ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, j * BN, 0, hkv, b);  // [d][key] tile, keys contiguous
+        }
       };
       auto issue_qk = [&](int j) {
         const int ks = j % KS;
-        ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+        if constexpr (KM == KM_I8) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
         ptx::tc_fence_after();
         const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
         const uint32_t tS = tmem_base + (j & 1) * BN;
@@ -223,13 +366,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
         }
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
-        ptx::umma_commit(kfree + ks);       // K stage may be refilled
+        if constexpr (KM == KM_I8) ptx::umma_commit(kfree + ks);  // K stage may be refilled
       };
       ptx::mbar_expect_tx(bar_q, SM::kQ);
       ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
-      for (int j = 0; j < min(KS, nblk); ++j) load_k(j);
+      for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
       for (int j = 0; j < min(2, nblk); ++j) load_v(j);
-      ptx::mbar_wait(bar_q, 0, 21);
+      if constexpr (KM == KM_I8) {
+        ptx::mbar_wait(bar_q, 0, 21);
+      } else {
+        ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted, K_0 / K_1 expanded (their packed stages are free again)
+        if (KPS < nblk) load_k(KPS);
+        if (KPS + 1 < nblk) load_k(KPS + 1);
+      }
       issue_qk(0);
       if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
@@ -239,31 +388,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
         const uint32_t tP = tmem_base + (j & 1) * BN;
+        if constexpr (PV == PV_F16) {
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); 64-wide d atoms BN*128 B apart (LBO)
-          const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
-          ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); 64-wide d atoms BN*128 B apart (LBO)
+            const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
+            ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < BN / 32; ++kk) {
+            // V^T tile: K-major (keys contiguous), rows of BN bytes (32B / 64B swizzle), 8 channel rows = 8*BN B (SBO)
+            const uint64_t db = ptx::make_smem_desc(av + kk * 32, 16, 8 * BN, BN == 32 ? ptx::kSwz32 : ptx::kSwz64);
+            ptx::umma_f8_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+          }
         }
         ptx::umma_commit(vfree + vs);
         ptx::umma_commit(bar_o);
         if (j == nblk - 1) ptx::umma_commit(bar_final);
         if (j + 2 < nblk) issue_qk(j + 2);  // overwrites S/P buffer (j&1): ordered after PV_j on the tensor pipe
-        // refill: K stage of QK_j (long complete) and V stage of PV_{j-1} (complete in steady state)
-        if (j + KS < nblk) load_k(j + KS);
+        // refill: the K stage consumed longest ago and the V stage of PV_{j-1} (complete in steady state)
+        if constexpr (KM == KM_I8) {
+          if (j + KPS < nblk) load_k(j + KPS);
+        } else {
+          if (j + 2 + KPS < nblk) load_k(j + 2 + KPS);  // softmax step j expanded K_{j+2}: its packed stage is free
+        }
         if (j + 2 < nblk) load_v(j + 2);
       }
     }
   } else {
     // ================================ softmax warps ================================
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const int row = qt * kBM + tid;  // global query row owned by this thread
-    const float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
+    const int row = qt * kBM + tid;  // query row owned by this thread
+    float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
+    if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
     const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
     const bool mask_tail = !compat && (p.Nk % BN != 0);
     const int last_kblk = (p.Nk + BN - 1) / BN - 1;
     const uint32_t tS0 = tmem_base + lane_off, tS1 = tS0 + BN, tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
+
+    if constexpr (KM == KM_K4) {
+      ptx::mbar_wait(bar_q, 0, 33);
+      permute_q_tile<D>(sQ, tid);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j < nblk) {
+          ptx::mbar_wait(kfull + j, 0, 34);
+          unpack_k4_tile<D, BN>(sKp + j * SM::kKp, sK + j * SM::kK, tid);
+          ptx::mbar_arrive(kfree + j);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(bar_k01);
+    }
 
     // one key block: wait for S, row max, (rare) rescale of O, P = exp2(S*sc - m) -> TMEM, signal the issuer
     auto step = [&](auto masked_tag, const uint32_t tSb, uint64_t* bs, uint64_t* pr, const uint32_t ph, const int j,
@@ -282,9 +460,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const int imax = row_max<BN, MASKED>(s, lim);
       const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
-      // lazy rescale: move the reference max only when it grows by more than 2^8 (warp-uniform decision,
+      // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision,
       // tcgen05.ld/st are warp collectives)
-      if (__any_sync(0xffffffffu, mblk > m_ref + 8.f)) {
+      if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
         const float m_new = fmaxf(m_ref, mblk);
         const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
         l *= alpha;
@@ -305,9 +483,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      uint32_t pk[BN / 2];
-      l += softmax_block<BN, MASKED, VAR>(s, sc, -m_ref, lim, pk);
-      tmem_st_n<BN / 2>(tSb, pk);  // P (fp16) aliases the first BN/2 columns of its S buffer
+      uint32_t pk[PCOLS];
+      const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
+      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, VAR>(s, sc, nm, lim, pk);
+      else l += softmax_block_e4m3<BN, MASKED, VAR>(s, sc, nm, lim, pk);
+      tmem_st_n<PCOLS>(tSb, pk);  // P aliases the first columns of its S buffer
+      if constexpr (KM == KM_K4) {
+        // expand K_{j+2} into the operand stage QK_j just released (S_j ready => QK_j complete)
+        if (j + 2 < nblk) {
+          const int kps = (j + 2) % KPS;
+          ptx::mbar_wait(kfull + kps, ((j + 2) / KPS) & 1, 35);
+          unpack_k4_tile<D, BN>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid);
+          ptx::mbar_arrive(kfree + kps);
+          ptx::fence_proxy_async_smem();
+        }
+      }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::mbar_arrive(pr);
@@ -315,7 +505,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // blocks [0, n_full) need no mask: unrolled by two so buffer / barrier addresses are loop constants
     int n_full = nblk;
-    if (CAUSAL) n_full = min(n_full, (qt * kBM) / BN);
+    if (causal) n_full = max(0, min(n_full, (dq + 1) / BN));
     if (mask_tail) n_full = min(n_full, last_kblk);
     int j = 0;
     uint32_t ph = 0;
@@ -335,39 +525,115 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float sc = qs * ks_ptr[min(j / kPerScale, p.nkb - 1)];
       const int c0 = j * BN;
       int lim = BN;  // columns [0, lim] are live
-      if (CAUSAL && c0 + BN - 1 > qt * kBM) lim = min(lim, row - c0);
+      if (causal) lim = min(lim, p.delta + row - c0);
       if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
       step(std::true_type{}, (j & 1) ? tS1 : tS0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc, lim);
     }
 
-    // ---- epilogue: O / l -> out dtype, lse2 = log2(l) + m ------------------------------------------
+    // ---- epilogue ------------------------------------------------------------------------------------
     ptx::mbar_wait(bar_final, 0, 32);
     ptx::tc_fence_after();
-    const float inv_l = 1.0f / l;
     const bool live_row = row < p.Nq;
-    uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + ((int64_t)b * p.osb + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
+    const float* vsc = (PV == PV_E4M3) ? p.v_scale + ((int64_t)b * p.Hkv + hkv) * D : nullptr;
+    const float* vmn = (PV == PV_E4M3 && p.v_mean) ? p.v_mean + ((int64_t)b * p.Hkv + hkv) * D : nullptr;
+    if (p.oacc_io == nullptr) {
+      // O / l (* v_scale + v_mean) -> out dtype, lse2 = log2(l) + m - OFF
+      const float inv_l = 1.0f / l;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + ((int64_t)b * p.osb + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
 #pragma unroll
-    for (int c = 0; c < D; c += 32) {
-      uint32_t o[32];
-      ptx::tmem_ld_x32(tOl + c, o);  // warp collective: every lane executes it
-      ptx::tmem_wait_ld();
-      uint32_t w[16];
+      for (int c = 0; c < D; c += 32) {
+        uint32_t o[32];
+        ptx::tmem_ld_x32(tOl + c, o);  // warp collective: every lane executes it
+        ptx::tmem_wait_ld();
+        uint32_t w[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = __uint_as_float(o[2 * i]) * inv_l, bb = __uint_as_float(o[2 * i + 1]) * inv_l;
-        w[i] = (p.out_dtype == LOWBIT_F16) ? ptx::pack_f16x2(a, bb) : ptx::pack_bf16x2(a, bb);
+        for (int i = 0; i < 16; ++i) {
+          float a = __uint_as_float(o[2 * i]) * inv_l, bb = __uint_as_float(o[2 * i + 1]) * inv_l;
+          if constexpr (PV == PV_E4M3) {
+            a *= vsc[c + 2 * i];
+            bb *= vsc[c + 2 * i + 1];
+            if (vmn) { a += vmn[c + 2 * i]; bb += vmn[c + 2 * i + 1]; }
+          }
+          w[i] = (p.out_dtype == LOWBIT_F16) ? ptx::pack_f16x2(a, bb) : ptx::pack_bf16x2(a, bb);
+        }
+        if (live_row) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+      }
+      if (live_row && p.lse) p.lse[((int64_t)b * p.Hq + hq) * p.Nq + row] = ptx::lg2(l) + m_ref - PC::OFF;
+    } else {
+      // ring step: merge (m_ref, l, O) of this K/V shard into the running fp32 state, in true (dequantized) units
+      const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
+      float m_prev = -INFINITY, l_prev = 0.f;
+      if (!p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }
+      const float m_cur = (l > 0.f) ? m_ref : -INFINITY;  // a row that saw only masked keys contributes nothing
+      const float m_new = fmaxf(m_prev, m_cur);
+      const float wa = (m_prev == -INFINITY) ? 0.f : ptx::ex2(m_prev - m_new);
+      const float wb0 = (m_cur == -INFINITY) ? 0.f : ptx::ex2(m_cur - m_new);
+      const float wb = wb0 * ((PV == PV_E4M3) ? exp2f(-PC::OFF) : 1.f);  // stored P carries 2^OFF
+      const float l_cur = l * wb;
+      float* od = p.oacc_io + idx * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 16) {
+        uint32_t o[16];
+        ptx::tmem_ld_x16(tOl + c, o);
+        ptx::tmem_wait_ld();
+        if (live_row) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!p.first) prev = *reinterpret_cast<const float4*>(od + c + i);
+            float v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float cur = __uint_as_float(o[i + t]) * wb;
+              if constexpr (PV == PV_E4M3) {
+                cur *= vsc[c + i + t];
+                if (vmn) cur += vmn[c + i + t] * l_cur;
+              }
+              v[t] = cur;
+            }
+            prev.x = prev.x * wa + v[0]; prev.y = prev.y * wa + v[1];
+            prev.z = prev.z * wa + v[2]; prev.w = prev.w * wa + v[3];
+            *reinterpret_cast<float4*>(od + c + i) = prev;
+          }
+        }
       }
       if (live_row) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c * 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        p.m_io[idx] = m_new;
+        p.l_io[idx] = l_prev * wa + l_cur;
       }
     }
-    if (live_row && p.lse) p.lse[((int64_t)b * p.Hq + hq) * p.Nq + row] = ptx::lg2(l) + m_ref;
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 4) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// o = O_acc / l, lse2 = log2(l) + m  (end of a ring / sequence-parallel pass)
+__global__ void attn_finalize_kernel(const float* __restrict__ m, const float* __restrict__ l,
+                                     const float* __restrict__ oacc, void* __restrict__ o, float* __restrict__ lse,
+                                     int Hq, int Nq, int D, int64_t osb, int64_t osh, int64_t osn, int out_dtype,
+                                     int64_t total4) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 output elements
+  if (i4 >= total4) return;
+  const int64_t rowi = i4 / (D / 4);
+  const int c = (int)(i4 % (D / 4)) * 4;
+  const int n = (int)(rowi % Nq), h = (int)((rowi / Nq) % Hq), b = (int)(rowi / ((int64_t)Nq * Hq));
+  const float inv_l = 1.0f / l[rowi];
+  const float4 v = *reinterpret_cast<const float4*>(oacc + rowi * D + c);
+  uint2 w;
+  if (out_dtype == LOWBIT_F16) {
+    w.x = ptx::pack_f16x2(v.x * inv_l, v.y * inv_l);
+    w.y = ptx::pack_f16x2(v.z * inv_l, v.w * inv_l);
+  } else {
+    w.x = ptx::pack_bf16x2(v.x * inv_l, v.y * inv_l);
+    w.y = ptx::pack_bf16x2(v.z * inv_l, v.w * inv_l);
+  }
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(o) + (b * osb + h * osh + (int64_t)n * osn + c) * 2) = w;
+  if (lse != nullptr && c == 0) lse[rowi] = ptx::lg2(l[rowi]) + m[rowi];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,20 +655,21 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// logical [B,H,N,D] tensor with element strides -> 4-D tensor map (d, n, h, b), box (box_d, box_n, 1, 1)
-static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, int B, int H, int N, int D,
-                    int64_t sb, int64_t sh, int64_t sn, int box_d, int box_n, CUtensorMapSwizzle swz) {
+// 4-D tensor map: dims (d0 innermost .. d3), byte strides of dims 1..3, box (box0, box1, 1, 1)
+static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, const int64_t (&dim)[4],
+                    const int64_t (&stride_elems)[3], int box0, int box1, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   LOWBIT_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   LOWBIT_CHECK(((uintptr_t)ptr & 15) == 0, "tensor base address must be 16-byte aligned");
-  LOWBIT_CHECK((sn * esize) % 16 == 0 && (sh * esize) % 16 == 0 && (sb * esize) % 16 == 0,
-               "tensor strides must be multiples of 16 bytes");
-  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)(sn * esize), (cuuint64_t)(sh * esize), (cuuint64_t)(sb * esize)};
-  // a size-1 dimension may carry any stride in the caller's tensor; TMA still wants a legal (non-zero, 16B) one
-  for (int i = 0; i < 3; ++i)
+  cuuint64_t dims[4], strides[3];
+  for (int i = 0; i < 4; ++i) dims[i] = (cuuint64_t)dim[i];
+  for (int i = 0; i < 3; ++i) {
+    LOWBIT_CHECK((stride_elems[i] * esize) % 16 == 0, "tensor strides must be multiples of 16 bytes");
+    strides[i] = (cuuint64_t)(stride_elems[i] * esize);
+    // a size-1 dimension may carry any stride in the caller's tensor; TMA still wants a legal (non-zero, 16B) one
     if (strides[i] == 0) strides[i] = 16;
-  cuuint32_t box[4] = {(cuuint32_t)box_d, (cuuint32_t)box_n, 1, 1};
+  }
+  cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -410,19 +677,91 @@ static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int
   return 0;
 }
 
-template <int D, bool CAUSAL, int VAR, bool DBG = false>
+template <int D, int KM, int PV, int VAR, bool DBG = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                        cudaStream_t st) {
-  auto kern = attn_fwd_kernel<D, CAUSAL, VAR, DBG>;
+  auto kern = attn_fwd_kernel<D, KM, PV, VAR, DBG>;
+  using SM = AttnSmem<D, KM, PV>;
   static bool configured = false;
   if (!configured) {
-    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<D>::kBytes));
+    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
     configured = true;
   }
   dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, kThreads, AttnSmem<D>::kBytes, st>>>(tq, tk, tv, p);
+  kern<<<grid, kThreads, SM::kBytes, st>>>(tq, tk, tv, p);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int D>
+static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                         int B, int km, int pv, cudaStream_t st) {
+  static int variant = -1;  // development switch (LOWBIT_ATTN_VARIANT): A/B of softmax instruction selection
+  if (variant < 0) { const char* e = getenv("LOWBIT_ATTN_VARIANT"); variant = e ? atoi(e) : 0; }
+  if (km == KM_I8 && pv == PV_F16) {
+    if (p.dbg != nullptr) return launch_attn<D, KM_I8, PV_F16, 0, true>(tq, tk, tv, p, B, st);
+    switch (variant) {
+      case 1: return launch_attn<D, KM_I8, PV_F16, 1>(tq, tk, tv, p, B, st);
+      case 4: return launch_attn<D, KM_I8, PV_F16, 4>(tq, tk, tv, p, B, st);
+      case 12: return launch_attn<D, KM_I8, PV_F16, 12>(tq, tk, tv, p, B, st);
+      default: return launch_attn<D, KM_I8, PV_F16, 0>(tq, tk, tv, p, B, st);
+    }
+  }
+  if (km == KM_K4 && pv == PV_F16) return launch_attn<D, KM_K4, PV_F16, 0>(tq, tk, tv, p, B, st);
+  if (km == KM_I8 && pv == PV_E4M3) return launch_attn<D, KM_I8, PV_E4M3, 0>(tq, tk, tv, p, B, st);
+  return launch_attn<D, KM_K4, PV_E4M3, 0>(tq, tk, tv, p, B, st);
+}
+
+struct AttnArgs {
+  const void *q_codes, *k_codes, *v;
+  const float *q_scale, *k_scale, *v_scale, *v_mean;
+  const int32_t* kbits;
+  int B, Hq, Hkv, Nq, Nk, D;
+  int64_t qsb, qsh, qsn, ksb, ksh, ksn, vsb, vsh, vsn;
+  int qk_mode, pv_mode, flags;
+};
+
+static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStream_t st) {
+  LOWBIT_CHECK(a.q_codes && a.k_codes && a.v && a.q_scale && a.k_scale, "%s: null pointer", who);
+  LOWBIT_CHECK(a.D == 64 || a.D == 128, "%s: head_dim must be 64 or 128 (got %d)", who, a.D);
+  LOWBIT_CHECK(a.B > 0 && a.Hq > 0 && a.Hkv > 0 && a.Nq > 0 && a.Nk > 0, "%s: empty tensor", who);
+  LOWBIT_CHECK(a.Hq % a.Hkv == 0, "%s: num_qo_heads (%d) must be divisible by num_kv_heads (%d)", who, a.Hq, a.Hkv);
+  LOWBIT_CHECK(a.qk_mode == LOWBIT_QK_I8 || a.qk_mode == LOWBIT_QK_Q8K4, "%s: qk_mode %d not implemented", who, a.qk_mode);
+  LOWBIT_CHECK(a.pv_mode == LOWBIT_PV_F16 || a.pv_mode == LOWBIT_PV_E4M3, "%s: bad pv_mode %d", who, a.pv_mode);
+  LOWBIT_CHECK(a.pv_mode != LOWBIT_PV_E4M3 || a.v_scale != nullptr, "%s: the FP8 P.V path needs v_scale", who);
+  (void)a.kbits;
+  const int D = a.D, BN = (D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN;
+  const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : KM_I8;
+  const int pv = (a.pv_mode == LOWBIT_PV_E4M3) ? PV_E4M3 : PV_F16;
+
+  CUtensorMap tq, tk, tv;
+  const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  {
+    const int64_t dim[4] = {D, a.Nq, a.Hq, a.B}, str[3] = {a.qsn, a.qsh, a.qsb};
+    if (make_map(&tq, a.q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, kBM, swz_qk)) return 1;
+  }
+  if (km == KM_I8) {
+    const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
+    if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, swz_qk)) return 1;
+  } else {  // packed INT4: rows of D/2 bytes, landed linearly (no swizzle) for the in-kernel expansion
+    const int64_t dim[4] = {D / 2, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
+    if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  if (pv == PV_F16) {
+    const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.vsn, a.vsh, a.vsb};
+    if (make_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dim, str, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else {  // e4m3 [b][h][d][pos]: (vsb, vsh, vsn) are the byte strides of (b, h, d); positions contiguous
+    const int64_t npad = (a.Nk + 63) / 64 * 64;
+    const int64_t dim[4] = {npad, D, a.Hkv, a.B}, str[3] = {a.vsn, a.vsh, a.vsb};
+    if (make_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, BN, D,
+                 BN == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
+  p.q_scale = a.q_scale; p.k_scale = a.k_scale; p.v_scale = a.v_scale; p.v_mean = a.v_mean;
+  p.Hq = a.Hq; p.Hkv = a.Hkv; p.Nq = a.Nq; p.Nk = a.Nk;
+  p.nqb = (a.Nq + 127) / 128; p.nkb = (a.Nk + 63) / 64;
+  p.flags = a.flags;
+  if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, a.B, km, pv, st);
+  return dispatch_attn<128>(tq, tk, tv, p, a.B, km, pv, st);
 }
 
 }  // namespace lowbit
@@ -437,41 +776,53 @@ extern "C" int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const v
                                int64_t qsb, int64_t qsh, int64_t qsn, int64_t ksb, int64_t ksh, int64_t ksn,
                                int64_t vsb, int64_t vsh, int64_t vsn, int64_t osb, int64_t osh, int64_t osn,
                                int qk_mode, int pv_mode, int out_dtype, int flags, void* stream) {
-  LOWBIT_CHECK(q_codes && k_codes && v && q_scale && k_scale && o, "lowbit_attn_fwd: null pointer");
-  LOWBIT_CHECK(D == 64 || D == 128, "lowbit_attn_fwd: head_dim must be 64 or 128 (got %d)", D);
-  LOWBIT_CHECK(B > 0 && Hq > 0 && Hkv > 0 && Nq > 0 && Nk > 0, "lowbit_attn_fwd: empty tensor");
-  LOWBIT_CHECK(Hq % Hkv == 0, "lowbit_attn_fwd: num_qo_heads (%d) must be divisible by num_kv_heads (%d)", Hq, Hkv);
+  LOWBIT_CHECK(o != nullptr, "lowbit_attn_fwd: null pointer");
   LOWBIT_CHECK(out_dtype == LOWBIT_F16 || out_dtype == LOWBIT_BF16, "lowbit_attn_fwd: bad out_dtype %d", out_dtype);
-  LOWBIT_CHECK(qk_mode == LOWBIT_QK_I8, "lowbit_attn_fwd: qk_mode %d not implemented yet", qk_mode);
-  LOWBIT_CHECK(pv_mode == LOWBIT_PV_F16, "lowbit_attn_fwd: pv_mode %d not implemented yet", pv_mode);
   const bool causal = flags & LOWBIT_ATTN_CAUSAL;
   LOWBIT_CHECK(!causal || Nq == Nk, "lowbit_attn_fwd: causal attention requires qo_len == kv_len");
   LOWBIT_CHECK((osn % 8) == 0 && (osh % 8) == 0 && (osb % 8) == 0 && ((uintptr_t)o & 15) == 0,
                "lowbit_attn_fwd: output must keep 16-byte row alignment");
-  (void)v_scale; (void)v_mean; (void)kbits;
-  cudaStream_t st = (cudaStream_t)stream;
+  AttnArgs a{q_codes, k_codes, v, q_scale, k_scale, v_scale, v_mean, kbits, B, Hq, Hkv, Nq, Nk, D,
+             qsb, qsh, qsn, ksb, ksh, ksn, vsb, vsh, vsn, qk_mode, pv_mode, flags};
+  AttnParams p{};
+  p.o = o; p.lse = lse; p.osb = osb; p.osh = osh; p.osn = osn;
+  p.out_dtype = out_dtype; p.delta = 0; p.first = 1;
+  p.dbg = (qk_mode == LOWBIT_QK_I8 && pv_mode == LOWBIT_PV_F16 && !causal) ? g_attn_debug : nullptr;
+  return run_attn("lowbit_attn_fwd", a, p, (cudaStream_t)stream);
+}
 
-  CUtensorMap tq, tk, tv;
-  const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  if (make_map(&tq, q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, Hq, Nq, D, qsb, qsh, qsn, D, kBM, swz_qk)) return 1;
-  if (make_map(&tk, k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, B, Hkv, Nk, D, ksb, ksh, ksn, D, (D == 64 ? AttnCfg<64>::BN : AttnCfg<128>::BN), swz_qk)) return 1;
-  if (make_map(&tv, v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, B, Hkv, Nk, D, vsb, vsh, vsn, 64, (D == 64 ? AttnCfg<64>::BN : AttnCfg<128>::BN), CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+extern "C" int lowbit_attn_fwd_partial(const void* q_codes, const void* k_codes, const void* v, const float* q_scale,
+                                       const float* k_scale, const float* v_scale, const float* v_mean,
+                                       const int32_t* kbits, float* m_io, float* l_io, float* o_acc_io,
+                                       int B, int Hq, int Hkv, int Nq, int Nk, int D,
+                                       int64_t qsb, int64_t qsh, int64_t qsn, int64_t ksb, int64_t ksh, int64_t ksn,
+                                       int64_t vsb, int64_t vsh, int64_t vsn, int64_t q_offset, int64_t k_offset,
+                                       int qk_mode, int pv_mode, int flags, int first, void* stream) {
+  LOWBIT_CHECK(m_io && l_io && o_acc_io, "lowbit_attn_fwd_partial: null state pointer");
+  LOWBIT_CHECK(((uintptr_t)o_acc_io & 15) == 0, "lowbit_attn_fwd_partial: o_acc must be 16-byte aligned");
+  LOWBIT_CHECK(!(flags & LOWBIT_ATTN_COMPAT_TAIL), "lowbit_attn_fwd_partial: compat_tail is not defined for ring steps");
+  int64_t delta = q_offset - k_offset;
+  if (delta > (1 << 30)) delta = 1 << 30;
+  if (delta < -(1 << 30)) delta = -(1 << 30);
+  AttnArgs a{q_codes, k_codes, v, q_scale, k_scale, v_scale, v_mean, kbits, B, Hq, Hkv, Nq, Nk, D,
+             qsb, qsh, qsn, ksb, ksh, ksn, vsb, vsh, vsn, qk_mode, pv_mode, flags};
+  AttnParams p{};
+  p.m_io = m_io; p.l_io = l_io; p.oacc_io = o_acc_io;
+  p.delta = (int)delta; p.first = first ? 1 : 0; p.out_dtype = LOWBIT_F16;
+  return run_attn("lowbit_attn_fwd_partial", a, p, (cudaStream_t)stream);
+}
 
-  AttnParams p;
-  p.q_scale = q_scale; p.k_scale = k_scale; p.o = o; p.lse = lse;
-  p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
-  p.nqb = (Nq + 127) / 128; p.nkb = (Nk + 63) / 64;
-  p.osb = osb; p.osh = osh; p.osn = osn;
-  p.flags = flags; p.out_dtype = out_dtype; p.dbg = g_attn_debug;
-  static int variant = -1;  // development switch (LOWBIT_ATTN_VARIANT): A/B of softmax instruction selection
-  if (variant < 0) { const char* e = getenv("LOWBIT_ATTN_VARIANT"); variant = e ? atoi(e) : 0; }
-#define LAUNCH(VAR)                                                                                              \
-  if (D == 64) return causal ? launch_attn<64, true, VAR>(tq, tk, tv, p, B, st) : launch_attn<64, false, VAR>(tq, tk, tv, p, B, st); \
-  return causal ? launch_attn<128, true, VAR>(tq, tk, tv, p, B, st) : launch_attn<128, false, VAR>(tq, tk, tv, p, B, st);
-  if (p.dbg != nullptr && !causal)  // diagnostics build of the kernel (raw score dump)
-    return D == 64 ? launch_attn<64, false, 0, true>(tq, tk, tv, p, B, st) : launch_attn<128, false, 0, true>(tq, tk, tv, p, B, st);
-  if (variant == 1) { LAUNCH(1) }
-  if (variant == 2) { LAUNCH(2) }
-  LAUNCH(0)
-#undef LAUNCH
+extern "C" int lowbit_attn_finalize(const float* m, const float* l, const float* o_acc, void* o, float* lse,
+                                    int B, int Hq, int Nq, int D, int64_t osb, int64_t osh, int64_t osn,
+                                    int out_dtype, void* stream) {
+  LOWBIT_CHECK(m && l && o_acc && o, "lowbit_attn_finalize: null pointer");
+  LOWBIT_CHECK(D % 4 == 0 && B > 0 && Hq > 0 && Nq > 0, "lowbit_attn_finalize: bad shape");
+  LOWBIT_CHECK(out_dtype == LOWBIT_F16 || out_dtype == LOWBIT_BF16, "lowbit_attn_finalize: bad out_dtype %d", out_dtype);
+  LOWBIT_CHECK((osn % 4) == 0 && (osh % 4) == 0 && (osb % 4) == 0 && ((uintptr_t)o & 7) == 0,
+               "lowbit_attn_finalize: output must keep 8-byte alignment");
+  const int64_t total4 = (int64_t)B * Hq * Nq * (D / 4);
+  attn_finalize_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      m, l, o_acc, o, lse, Hq, Nq, D, osb, osh, osn, out_dtype, total4);
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
 }

@@ -234,6 +234,48 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// two fp32 -> packed e4m3x2 (lo in bits [0,8), hi in bits [8,16)), round to nearest even, saturate to +-448
+__device__ __forceinline__ uint16_t pack_e4m3x2(float lo, float hi) {
+  uint16_t d;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// packed e4m3x2 -> packed f16x2 (exact)
+__device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint16_t v) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(d) : "h"(v));
+  return d;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ float f16x2_sum(uint32_t v) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo), "=f"(hi) : "r"(v));
+  return lo + hi;
+}
+// exp2 on the FMA/ALU pipes (no MUFU): Cody-Waite range reduction with the 1.5*2^23 magic constant, degree-3
+// minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5), exponent inserted by an integer multiply-add.
+// Valid for x <= 126; x is clamped below at -126.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 mg = make_float2(kMagic, kMagic);
+  const float2 r = __fadd2_rn(x, mg);                          // low mantissa bits = round(x)
+  const float2 t = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
+  const float2 f = __fadd2_rn(x, make_float2(-t.x, -t.y));     // f in [-0.5, 0.5]
+  float2 p = __ffma2_rn(make_float2(0.05517103523015976f, 0.05517103523015976f), f,
+                        make_float2(0.24260984361171722f, 0.24260984361171722f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999281764030457f, 0.9999281764030457f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(r.x) * 0x00800000 + __float_as_int(p.x));
+  y.y = __int_as_float(__float_as_int(r.y) * 0x00800000 + __float_as_int(p.y));
+  return y;
+}
 // exact int32 -> fp32 for |v| < 2^22 without the conversion pipe (IADD + FADD)
 __device__ __forceinline__ float i2f_small(int v) { return __int_as_float(v + 0x4B400000) - 12582912.0f; }
 

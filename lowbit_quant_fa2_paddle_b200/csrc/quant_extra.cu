@@ -336,13 +336,4 @@ int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
   return 0;
 }
 
-int lowbit_attn_fwd_partial(const void*, const void*, const void*, const float*, const float*, float*, float*, float*,
-                            int, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                            int64_t, int64_t, int64_t, int64_t, int, int, int, void*) {
-  return fail("lowbit_attn_fwd_partial: not implemented yet");
-}
-int lowbit_attn_finalize(const float*, const float*, const float*, void*, float*, int, int, int, int, int64_t, int64_t,
-                         int64_t, int, void*) {
-  return fail("lowbit_attn_finalize: not implemented yet");
-}
-}
+}  // extern "C"

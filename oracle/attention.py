@@ -148,8 +148,23 @@ def _pad_head(x, d_to):
     return x if d == d_to else torch.nn.functional.pad(x, (0, d_to - d))
 
 
+def v8_to_natural(v8, n, tensor_layout="HND"):
+    """Undo the transpose + within-16 token permutation of per_channel_fp8 (fused.cu:290-292): returns the e4m3
+    values as float in the caller's layout, [B,H,N,D] (HND) or [B,N,H,D] (NHD)."""
+    x = v8.float()
+    if tensor_layout == "NHD":  # [B,D,H,Npad] -> [B,H,D,Npad]
+        x = x.permute(0, 2, 1, 3)
+    npad = x.shape[-1]
+    inv = Q.token_perm(npad)          # dest position -> source token
+    nat = torch.empty_like(x)
+    nat[..., inv] = x                 # source token -> value
+    nat = nat[..., :n].permute(0, 1, 3, 2)  # [B,H,N,D]
+    return nat.contiguous() if tensor_layout == "HND" else nat.permute(0, 2, 1, 3).contiguous()
+
+
 def lowbit_fa_api(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, smooth_k=True,
-                  return_lse=False, qk="int8", pv_accum="fp16_block", compat_tail=True, km=None):
+                  return_lse=False, qk="int8", pv_accum="fp16_block", compat_tail=True, km=None,
+                  pv="fp16", smooth_v=False):
     """E1/E2/E3 glue restated from src/core.py:269-352: head-dim pad (:277-287), km (:291-306; contract
     SURVEY 2.3-H via oracle.quant.k_mean), bf16 V -> fp16 (:307-308), sm_scale from the un-padded
     head dim (:309-310), Q1 quantize (:311-314), attention (:321-342), slice (:343), LSE fix-up (:344-350).
@@ -172,14 +187,20 @@ def lowbit_fa_api(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, 
             lse_corr = torch.matmul(qh.float(), kmh.float().transpose(2, 3)).squeeze(-1).to(dtype).float()  # matmul in the input dtype (:296-304)
     else:
         km = None
-    if dtype == torch.bfloat16:
+    v_scale = v_mean = None
+    if pv == "fp8":  # core.py:882-884 -> A3 (attn_utils.cuh:424-428,550-562)
+        n = v.shape[2] if tensor_layout == "HND" else v.shape[1]
+        v8, v_scale, v_mean = Q.per_channel_fp8(v, tensor_layout, smooth_v=smooth_v)
+        v = v8_to_natural(v8, n, tensor_layout)
+    elif dtype == torch.bfloat16:
         v = v.to(torch.float16)
     if sm_scale is None:
         sm_scale = 1.0 / d_og ** 0.5
     kbits = 8 if qk == "int8" else 4
     qi, qs, ki, ks = Q.per_block_int8_q1(q, k, km, sm_scale=sm_scale, tensor_layout=tensor_layout, kbits=kbits)
     o, lse2 = attn_block_emulator(qi, ki, v, qs, ks, tensor_layout, is_causal, dtype, return_lse,
-                                  pv_accum=pv_accum, compat_tail=compat_tail)
+                                  pv_accum=pv_accum, compat_tail=compat_tail,
+                                  pv_mode="e4m3" if pv == "fp8" else "f16", v_scale=v_scale, v_mean=v_mean)
     o = o[..., :d_og]
     if return_lse:
         lse = lse2 / LOG2E

@@ -311,3 +311,193 @@ def test_v_fp8_per_channel_vs_oracle(L, cuda_dev, layout, smooth_v, shape, dtype
     else:
         assert vm is None
     assert torch.equal(v8.cpu().view(torch.uint8), r8.view(torch.uint8))
+
+
+# ------------------------------------------------------------------------------------------------ INT4-K / FP8-PV / ring
+K4_CASES = [
+    # b, hq, hkv, n, d, layout, causal
+    (1, 2, 2, 512, 64, "HND", False),
+    (1, 2, 2, 512, 64, "HND", True),
+    (2, 4, 2, 384, 128, "NHD", False),
+    (1, 2, 1, 320, 128, "HND", True),
+    (1, 2, 2, 200, 64, "NHD", False),   # ragged tail
+    (1, 2, 2, 77, 128, "HND", True),
+    (1, 1, 1, 1, 64, "HND", False),
+    (1, 1, 1, 33, 64, "HND", True),
+    (1, 3, 3, 1000, 64, "NHD", True),
+]
+
+
+@pytest.mark.parametrize("case", K4_CASES)
+def test_packed_int4_k_is_bit_identical_to_unpacked(L, cuda_dev, case):
+    """qk_mode Q8K4 (K packed two codes per byte in HBM, expanded to code*16 in shared memory, Q tile permuted,
+    1/16 folded into the scale) must give bit-identical O and lse to the same codes fed one per int8."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    b, hq, hkv, n, d, layout, causal = case
+    q = mk(b, hq, n, d, layout, torch.float16, 41).to(cuda_dev)
+    k = mk(b, hkv, n, d, layout, torch.float16, 42, bias=2.0).to(cuda_dev)
+    v = mk(b, hkv, n, d, layout, torch.float16, 43).to(cuda_dev)
+    km = L.k_mean(k, layout)
+    qc, qs, k4, ks = L.per_block_q_int8_k_int4(q, k, km=km, tensor_layout=layout, pack=False)
+    _, _, k4p, ksp = L.per_block_q_int8_k_int4(q, k, km=km, tensor_layout=layout, pack=True)
+    assert torch.equal(ks, ksp) and k4p.shape[-1] == d // 2
+    fn = L.forward_causal if causal else L.forward
+    o_u, lse_u = fn(qc, k4, v, qs, ks, tensor_layout=layout, return_lse=True)
+    o_p, lse_p = fn(qc, k4p, v, qs, ks, tensor_layout=layout, return_lse=True, qk_mode=NV.QK_Q8K4)
+    assert torch.equal(o_u, o_p) and torch.equal(lse_u, lse_p)
+
+
+@pytest.mark.parametrize("entry", ["int4", "q8k4"])
+@pytest.mark.parametrize("case", K4_CASES[:6])
+def test_int4_api_vs_oracle_and_sdpa(L, cuda_dev, case, entry):
+    """E2 / E3 entry points (packed INT4 K path) against the oracle's Q INT8 / K INT4 per-block semantics
+    (reference kernel parity unpinned) and FP32 SDPA."""
+    from oracle import attention as OA
+    b, hq, hkv, n, d, layout, causal = case
+    q = mk(b, hq, n, d, layout, torch.float16, 51)
+    k = mk(b, hkv, n, d, layout, torch.float16, 52, bias=3.0)
+    v = mk(b, hkv, n, d, layout, torch.float16, 53)
+    fn = L.lowbit_fa_qk_int4_pv_fp16_triton if entry == "int4" else L.lowbit_fa_q_int8_k_int4_pv_fp16
+    o, lse = fn(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout, is_causal=causal, return_lse=True)
+    oref, lref = OA.lowbit_fa_api(q, k, v, layout, causal, return_lse=True, compat_tail=False, pv_accum="fp32", qk="int4")
+    assert (o.cpu().float() - oref.float()).abs().max() <= 4e-3
+    assert (lse.cpu() - lref).abs().max() <= 1e-2
+    if n >= 64:
+        assert cos_sim(o.cpu(), OA.sdpa_fp32(q, k, v, layout, causal)) >= 0.98  # 4-bit K codes: format error, not kernel error
+
+
+FP8_CASES = [
+    # b, hq, hkv, n, d, layout, causal, dtype, qk
+    (1, 2, 2, 512, 64, "HND", False, torch.float16, "int8"),
+    (1, 2, 2, 512, 128, "HND", True, torch.float16, "int4"),   # BASELINE config 3 combination
+    (2, 4, 2, 384, 128, "NHD", False, torch.float16, "int8"),
+    (1, 4, 1, 320, 64, "NHD", True, torch.bfloat16, "int4"),
+    (1, 2, 2, 200, 64, "HND", False, torch.float16, "int4"),
+    (1, 2, 2, 77, 128, "NHD", True, torch.float16, "int8"),
+    (1, 1, 1, 1, 64, "HND", False, torch.float16, "int8"),
+    (1, 2, 2, 1030, 128, "HND", False, torch.float16, "int4"),
+]
+
+
+@pytest.mark.parametrize("smooth_v", [False, True])
+@pytest.mark.parametrize("case", FP8_CASES)
+def test_fp8_pv_vs_oracle_and_sdpa(L, cuda_dev, case, smooth_v):
+    """A3 semantics (P~ = e4m3(exp2(s-m+off)), denominator over the rounded P~, epilogue * v_scale + v_mean) on
+    tcgen05 kind::f8f6f4.  The kernel keeps a lazy reference maximum (P~ max in [112, 448]) where the spec uses the
+    exact running maximum (P~ max = 448): same algorithm, different e4m3 rounding grid, so the comparison with
+    the oracle is by tolerance: max-abs <= 0.05 (e4m3 has 3 mantissa bits), cos >= 0.999; vs FP32 SDPA cos >= 0.998."""
+    from oracle import attention as OA
+    b, hq, hkv, n, d, layout, causal, dtype, qk = case
+    q = mk(b, hq, n, d, layout, dtype, 61)
+    k = mk(b, hkv, n, d, layout, dtype, 62, bias=3.0)
+    v = mk(b, hkv, n, d, layout, dtype, 63, bias=1.0 if smooth_v else 0.0)
+    if qk == "int8":
+        o, lse = L.lowbit_fa_qk_int8_pv_fp8_cuda(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout,
+                                                 is_causal=causal, pv_accum_dtype="fp32", smooth_v=smooth_v,
+                                                 return_lse=True)
+    else:
+        o, lse = L.lowbit_fa_qk_int4_pv_fp8(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout,
+                                            is_causal=causal, smooth_v=smooth_v, return_lse=True)
+    assert o.shape == q.shape and o.dtype == dtype and not torch.isnan(o).any()
+    oref, lref = OA.lowbit_fa_api(q, k, v, layout, causal, return_lse=True, compat_tail=False, qk=qk, pv="fp8",
+                                  smooth_v=smooth_v)
+    err = (o.cpu().float() - oref.float()).abs().max().item()
+    assert err <= 0.05 * max(1.0, float(v.float().abs().max()) / 4), f"max-abs {err}"
+    assert (lse.cpu() - lref).abs().max() <= 3e-2
+    if n >= 64:
+        assert cos_sim(o.cpu(), oref) >= 0.999
+        assert cos_sim(o.cpu(), OA.sdpa_fp32(q, k, v, layout, causal)) >= (0.998 if qk == "int8" else 0.98)
+
+
+def test_fp8_pv_constant_v_is_exact(L, cuda_dev):
+    """Rows of P~ / sum(P~) sum to one by construction (the denominator is taken over the rounded P~): a V that is
+    constant per channel must come back as that constant up to e4m3 rounding of V itself and f16 partial sums."""
+    b, h, n, d = 1, 2, 1024, 64
+    q = mk(b, h, n, d, "HND", torch.float16, 71).to(cuda_dev)
+    k = mk(b, h, n, d, "HND", torch.float16, 72).to(cuda_dev)
+    c = torch.linspace(-2, 2, d).half()
+    v = c.expand(b, h, n, d).contiguous().to(cuda_dev)
+    o = L.lowbit_fa_qk_int8_pv_fp8_cuda(q, k, v, pv_accum_dtype="fp32")
+    assert (o.cpu().float() - c.float()).abs().max() <= 5e-3  # per-channel scale makes a constant channel exact in e4m3
+
+
+@pytest.mark.parametrize("cfg", [
+    # d, layout, causal, qk, pv, nshard
+    (64, "HND", False, "int8", "fp16", 4),
+    (64, "NHD", True, "int8", "fp16", 4),
+    (128, "HND", True, "int4", "fp16", 2),
+    (128, "NHD", False, "int4", "fp8", 4),
+    (64, "HND", True, "int4", "fp8", 8),
+    (128, "HND", True, "int8", "fp8-shard", 4),
+])
+def test_ring_partial_steps_match_single_pass(L, cuda_dev, cfg):
+    """Sequence-parallel decomposition: Q and K/V split into P shards along N; every Q shard visits every K/V
+    shard in ring order through lowbit_attn_fwd_partial (causal masking by global offsets, shards wholly in the
+    future are no-ops, including as the first step) and lowbit_attn_finalize.  With 64-aligned shards and a global
+    km the per-shard codes/scales equal the single-pass ones, so the result must match the single-pass kernel
+    up to fp32 merge rounding (<= 2e-3).  FP8 P.V: "fp8" slices one globally quantized V^T (same e4m3 codes as
+    the single pass; P~ rounding grids still differ because the lazy maximum evolves differently: <= 0.05);
+    "fp8-shard" quantizes every V shard with its own per-channel scale, as ranks of a real ring do, so V codes
+    differ by up to one e4m3 step (2^-3 relative) from the single pass: |diff| <= 0.13 |o| + 0.02."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    from lowbit_quant_fa2_paddle_b200 import attention as A
+    from lowbit_quant_fa2_paddle_b200 import quant as Qz
+    d, layout, causal, qk, pv, P = cfg
+    b, hq, hkv, n = 1, 4, 2, 1024
+    ns = n // P
+    q = mk(b, hq, n, d, layout, torch.float16, 81).to(cuda_dev)
+    k = mk(b, hkv, n, d, layout, torch.float16, 82, bias=2.0).to(cuda_dev)
+    v = mk(b, hkv, n, d, layout, torch.float16, 83).to(cuda_dev)
+    km = L.k_mean(k, layout)
+    kbits, packed = (8, False) if qk == "int8" else (4, True)
+    qk_mode = NV.QK_Q8K4 if packed else NV.QK_I8
+    vq_shard = pv == "fp8-shard"
+    pv = "fp8" if vq_shard else pv
+    pv_mode = NV.PV_E4M3 if pv == "fp8" else NV.PV_F16
+    sm = d ** -0.5
+    seq = 2 if layout == "HND" else 1
+    sh = lambda t, i: t.narrow(seq, i * ns, ns)  # strided views: the kernels take strides
+
+    def quant(qx, kx):
+        return Qz._per_block(qx, kx, km, 128, 64, sm, layout, 8, kbits, packed, "triton")
+
+    def vprep(vx):
+        if pv == "fp8":
+            return Qz.per_channel_fp8(vx, layout, smooth_v=False)
+        return vx, None, None
+
+    # single pass
+    qc, qs, kc, ks = quant(q, k)
+    v1, vs1, vm1 = vprep(v)
+    o_ref, lse_ref = A._forward(qc, kc, v1, qs, ks, layout, torch.float16, True, causal, qk_mode=qk_mode,
+                                pv_mode=pv_mode, v_scale=vs1, v_mean=vm1)
+    # ring
+    shards = []
+    for i in range(P):
+        qci, qsi, kci, ksi = quant(sh(q, i), sh(k, i))
+        if pv == "fp8" and not vq_shard:  # positions [i*ns, (i+1)*ns) of the global V^T (64-aligned: permutation-safe)
+            vi, vsi, vmi = v1.narrow(3, i * ns, ns), vs1, vm1
+        else:
+            vi, vsi, vmi = vprep(sh(v, i))
+        shards.append((qci, qsi, kci, ksi, vi, vsi, vmi))
+    outs, lses = [], []
+    for r in range(P):
+        st = None
+        for step in range(P):
+            s = (r + 1 + step) % P  # start with the NEXT rank's shard: for causal that is a future (no-op) shard
+            qci, qsi = shards[r][0], shards[r][1]
+            _, _, kci, ksi, vi, vsi, vmi = shards[s]
+            st = A.forward_partial(st, qci, kci, vi, qsi, ksi, layout, causal=causal, q_offset=r * ns, k_offset=s * ns,
+                                   qk_mode=qk_mode, pv_mode=pv_mode, v_scale=vsi, v_mean=vmi)
+        o_r, lse_r = A.finalize(st, shards[r][0], layout, torch.float16, return_lse=True)
+        outs.append(o_r)
+        lses.append(lse_r)
+    o_ring = torch.cat(outs, dim=seq)
+    lse_ring = torch.cat(lses, dim=2)
+    diff = (o_ring.float() - o_ref.float()).abs()
+    if vq_shard:
+        assert bool((diff <= 0.13 * o_ref.float().abs() + 0.02).all())
+    else:
+        assert diff.max() <= (2e-3 if pv == "fp16" else 0.05)
+    assert (lse_ring - lse_ref).abs().max() <= (2e-3 if pv == "fp16" else 3e-2)
+    assert cos_sim(o_ring.cpu(), o_ref.cpu()) >= (0.9999 if pv == "fp16" else 0.999)
