@@ -43,8 +43,9 @@ def _km_bhd(km, b, h, d, tensor_layout):
     return kmt.contiguous()
 
 
-def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout):
-    """Quantize one [B,H,N,D] tensor per block of `blk` rows. Returns (codes, scale)."""
+def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout, out=None):
+    """Quantize one [B,H,N,D] tensor per block of `blk` rows. Returns (codes, scale).
+    out: optional (codes, scale) torch tensors to write into (e.g. views of a ring message buffer)."""
     xt = T.as_torch(x)
     dev = T.require_cuda(xt)
     b, h, n, d, sb, sh, sn = T.bhnd(xt, tensor_layout)
@@ -56,10 +57,15 @@ def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout):
     dd = d * bits // 8 if (pack and bits < 8) else d
     shape = list(xt.shape)
     shape[-1] = dd
-    codes = torch.empty(shape, dtype=torch.int8, device=dev)
-    _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
     nblk = (n + blk - 1) // blk
-    scale = torch.empty((b, h, nblk), dtype=torch.float32, device=dev)
+    if out is None:
+        codes = torch.empty(shape, dtype=torch.int8, device=dev)
+        scale = torch.empty((b, h, nblk), dtype=torch.float32, device=dev)
+    else:
+        codes, scale = out
+        assert list(codes.shape) == shape and codes.dtype == torch.int8 and codes.stride(-1) == 1
+        assert tuple(scale.shape) == (b, h, nblk) and scale.dtype == torch.float32 and scale.is_contiguous()
+    _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
     N.call("lowbit_quant_per_block", xt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
            codes.data_ptr(), scale.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osn,
            blk, bits, int(bool(pack)), float(sm_arg), mode, T.dtype_code(xt.dtype), T.stream_ptr(dev))

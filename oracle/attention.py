@@ -233,3 +233,55 @@ def cpu_quantize_and_attend(q, k, v, tensor_layout="HND", is_causal=False, sm_sc
     w = torch.softmax(scores * (1.0 / LOG2E), dim=-1)
     o = torch.matmul(w, vh).to(q.dtype)
     return o if tensor_layout == "HND" else o.permute(0, 2, 1, 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# ring / sequence-parallel steps (our own contract, include/lowbit_fa.h lowbit_attn_fwd_partial):
+# flash-style merge of one K/V shard into an un-normalised running state, in exact-maximum fp32 math
+# ----------------------------------------------------------------------------------------------
+def attn_partial(state, q_codes, k_codes, v, q_scale, k_scale, tensor_layout="HND", causal=False,
+                 q_offset=0, k_offset=0, v_scale=None):
+    """state: None or dict(m [B,Hq,Nq], l [B,Hq,Nq], acc [B,Hq,Nq,D]).  q_codes/k_codes: int8 unpacked codes;
+    v: fp16 values, or e4m3 values as float in natural [.., N, D] order with v_scale [B,Hkv,D] (the rounded
+    P~ of A3 is modelled by rounding p * 2^8.807 to e4m3).  Key c is visible to row r iff
+    k_offset + c <= q_offset + r."""
+    qc = _hnd(q_codes, tensor_layout).double()
+    kc = _hnd(k_codes, tensor_layout).double()
+    vh = _hnd(v, tensor_layout).float()
+    b, hq, nq, d = qc.shape
+    hkv, nk = kc.shape[1], kc.shape[2]
+    g = hq // hkv
+    if g > 1:
+        kc, vh = kc.repeat_interleave(g, dim=1), vh.repeat_interleave(g, dim=1)
+        k_scale = k_scale.repeat_interleave(g, dim=1)
+        v_scale = v_scale.repeat_interleave(g, dim=1) if v_scale is not None else None
+    qs_row = q_scale.float().repeat_interleave(128, dim=2)[:, :, :nq, None]
+    ks_col = k_scale.float().repeat_interleave(64, dim=2)[:, :, None, :nk]
+    qk = (torch.matmul(qc, kc.transpose(2, 3)).float() * qs_row) * ks_col
+    if causal:
+        rows = torch.arange(nq).view(1, 1, -1, 1) + q_offset
+        cols = torch.arange(nk).view(1, 1, 1, -1) + k_offset
+        qk = torch.where(cols <= rows, qk, torch.tensor(float("-inf")))
+    if state is None:
+        state = dict(m=torch.full((b, hq, nq), float("-inf")), l=torch.zeros(b, hq, nq), acc=torch.zeros(b, hq, nq, d))
+    m_cur = qk.amax(dim=-1)
+    m_new = torch.maximum(state["m"], m_cur)
+    safe = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)
+    p = torch.exp2(qk - safe[..., None])
+    if v_scale is not None:
+        p = (p * 2.0 ** FP8_OFFSET).clamp(max=448.0).to(torch.float8_e4m3fn).float() * 2.0 ** -FP8_OFFSET
+        vh = vh * v_scale.float()[:, :, None, :]
+    else:
+        p = p.half().float()
+    alpha = torch.exp2(state["m"] - safe)
+    alpha = torch.where(torch.isinf(state["m"]), torch.zeros_like(alpha), alpha)
+    l_new = state["l"] * alpha + (torch.exp2(qk - safe[..., None]).sum(-1) if v_scale is None else p.sum(-1))
+    acc = state["acc"] * alpha[..., None] + torch.matmul(p, vh)
+    return dict(m=m_new, l=l_new, acc=acc)
+
+
+def attn_finalize(state, like_q, tensor_layout="HND", output_dtype=torch.float16):
+    o = (state["acc"] / state["l"][..., None]).to(output_dtype)
+    out = torch.empty(like_q.shape, dtype=output_dtype)
+    _hnd(out, tensor_layout).copy_(o)
+    return out, torch.log2(state["l"]) + state["m"]

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Multi-GPU check of parallel.ring_attention and head sharding against the single-GPU kernel.
+Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/ring_check.py
+Every rank builds the same full tensors (seeded), keeps its shard, runs the ring, and rank 0 compares the gathered
+result with the single-GPU call on the full tensors.  Prints one line per config and exits non-zero on mismatch."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import lowbit_quant_fa2_paddle_b200 as L  # noqa: E402
+from lowbit_quant_fa2_paddle_b200 import parallel as P  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    cfgs = [
+        # layout, causal, qk, pv, d, b, hq, hkv, n
+        ("HND", False, "int8", "fp16", 64, 1, 4, 4, 2048),
+        ("NHD", True, "int4", "fp16", 64, 2, 4, 2, 4096),
+        ("HND", True, "int4", "fp8", 128, 1, 4, 4, 4096),
+        ("HND", True, "int4", "fp16", 128, 1, 8, 8, 16384),
+    ]
+    for layout, causal, qk, pv, d, b, hq, hkv, n in cfgs:
+        torch.manual_seed(7)
+        seq = 2 if layout == "HND" else 1
+        shp = lambda h: (b, h, n, d) if layout == "HND" else (b, n, h, d)
+        q = torch.randn(shp(hq), dtype=torch.float16, device=dev)
+        k = torch.randn(shp(hkv), dtype=torch.float16, device=dev) + 1.5
+        v = torch.randn(shp(hkv), dtype=torch.float16, device=dev)
+        zig = causal
+        chunks = P.seq_chunks(n, world, rank, zig)
+        take = lambda x: torch.cat([x.narrow(seq, c.offset, c.length) for c in chunks], dim=seq).contiguous()
+        o, lse = P.ring_attention(take(q), take(k), take(v), tensor_layout=layout, is_causal=causal, qk=qk, pv=pv,
+                                  return_lse=True)
+        # reference: the single-GPU entry point on the full tensors
+        if pv == "fp8":
+            fn = L.lowbit_fa_qk_int4_pv_fp8 if qk == "int4" else L.lowbit_fa_qk_int8_pv_fp8_cuda
+        else:
+            fn = L.lowbit_fa_qk_int4_pv_fp16_triton if qk == "int4" else L.lowbit_fa_qk_int8_pv_fp16_triton
+        o_ref, lse_ref = fn(q, k, v, tensor_layout=layout, is_causal=causal, return_lse=True)
+        o_loc, lse_loc = take(o_ref), torch.cat([lse_ref[:, :, c.offset:c.offset + c.length] for c in chunks], dim=2)
+        err = (o.float() - o_loc.float()).abs().max()
+        lerr = (lse - lse_loc).abs().max()
+        stats = torch.stack([err, lerr])
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        tol = 4e-3 if pv == "fp16" else 0.125 * float(v.abs().max())
+        good = bool(stats[0] <= tol) and bool(stats[1] <= (1e-2 if pv == "fp16" else 5e-2))
+        ok = ok and good
+        if rank == 0:
+            print(f"ring world={world} {layout} causal={causal} qk={qk} pv={pv} d={d} n={n}: max|o-o1|={float(stats[0]):.3e} "
+                  f"max|lse-lse1|={float(stats[1]):.3e} {'OK' if good else 'MISMATCH'}", flush=True)
+    # head sharding: each rank computes its head slice; gathered result == single-GPU result, bit for bit
+    torch.manual_seed(9)
+    b, n, h, d = 2, 1200, 8 * world, 64
+    q, k, v = (torch.randn(b, n, h, d, dtype=torch.float16, device=dev) for _ in range(3))
+    o_full = L.lowbit_fa_q_int8_k_int4_pv_fp16(q, k, v, tensor_layout="NHD")
+    o_mine = P.lowbit_fa_head_sharded(q, k, v, L.lowbit_fa_q_int8_k_int4_pv_fp16, world, rank, tensor_layout="NHD")
+    hq0, hq1, _, _ = P.head_shard(h, h, world, rank)
+    same = torch.tensor([int(torch.equal(o_mine, o_full[:, :, hq0:hq1]))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"head-sharded world={world}: slices bit-identical to the single-GPU result: {bool(same.item())}", flush=True)
+    ok = ok and bool(same.item())
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
