@@ -34,13 +34,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (B, Hq, Hkv, N, D, layout, causal, description)
+    # name: (B, Hq, Hkv, N, D, layout, causal, description)        -- INT8 QK + FP16 PV, every rank the same work (weak)
     "c2": (4, 32, 32, 4096, 64, "HND", False, "BASELINE config 2: INT8 QK + FP16 PV, HND, B4 H32 N4096 D64 non-causal"),
     "c2c": (4, 32, 32, 4096, 64, "HND", True, "config 2 shape, causal"),
     "c3_8k": (4, 32, 32, 8192, 128, "HND", True, "config 3 shape (D128 causal 8K), INT8 QK + FP16 PV"),
     "c4": (2, 48, 48, 17776, 64, "NHD", False, "config 4 shape: CogVideoX-5B B2 H48 N17776 D64 NHD"),
 }
+# the other BASELINE configs: (B, Hq, Hkv, N, D, layout, causal, qk, pv, partition, description)
+#   partition "replicate": every rank the whole workload (weak); "heads": kv-head slices, no collective (strong);
+#   "ring": sequence-parallel NCCL P2P ring of quantized K/V (strong)
+EXTRA = {
+    "c3q_8k": (4, 32, 32, 8192, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B4 H32 D128 causal N=8K"),
+    "c3q_16k": (2, 32, 32, 16384, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B2 H32 D128 causal N=16K"),
+    "c3q_32k": (1, 32, 32, 32768, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B1 H32 D128 causal N=32K"),
+    "c4s": (2, 48, 48, 17776, 64, "NHD", False, "q8k4", "fp16", "heads", "BASELINE config 4: q_int8/k_int4, NHD, CogVideoX-5B B2 H48 N17776 D64, head-sharded"),
+    "c5": (1, 32, 32, 131072, 128, "HND", True, "int4", "fp16", "ring", "BASELINE config 5 (INT4 K): B1 H32 N128K D128 causal, sequence-parallel ring of quantized K/V"),
+    "c5f8": (1, 32, 32, 131072, 128, "HND", True, "int4", "fp8", "ring", "BASELINE config 5 (INT4 K, FP8 V): B1 H32 N128K D128 causal, sequence-parallel ring"),
+}
 BASELINE_MD_TOPS = 199.5  # INT8 non-causal B4 H32 D64 N=4096, attention kernel only, hardware unstated
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the attention launch at C2 from the committed `ncu --set full`
+    summary (profiles/r1_attn_c2_ncu_summary.json, latest kernel version listed there)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_attn_c2_ncu_summary.json")) as f:
+            last = list(json.load(f).values())[-1]
+        mb = lambda s: float(s.split()[0]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3}[s.split()[1]]
+        return mb(last["dram__bytes_read.sum"]) + mb(last["dram__bytes_write.sum"])
+    except Exception:
+        return None
 
 
 def peaks():
@@ -163,15 +186,95 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+def run_extra(args):
+    """BASELINE configs 3-5 (not the driver's default line): same metric, API-level step, CUDA events, max over ranks."""
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    import lowbit_quant_fa2_paddle_b200 as L
+    from lowbit_quant_fa2_paddle_b200 import parallel as P
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = EXTRA[args.workload]
+    W, K = max(args.warmup, 3), args.steps
+    torch.manual_seed(0)
+    seq = 2 if layout == "HND" else 1
+    shp = lambda h, n=N: (B, h, n, D) if layout == "HND" else (B, n, h, D)
+    ops_total = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
+    if pv == "fp8":
+        fn = L.lowbit_fa_qk_int4_pv_fp8 if qk != "int8" else L.lowbit_fa_qk_int8_pv_fp8_cuda
+    else:
+        fn = {"int8": L.lowbit_fa_qk_int8_pv_fp16_triton, "int4": L.lowbit_fa_qk_int4_pv_fp16_triton,
+              "q8k4": L.lowbit_fa_q_int8_k_int4_pv_fp16}[qk]
+    if part == "ring" and world > 1:
+        n_loc = N // world
+        q, k, v = (torch.randn(shp(h, n_loc), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
+        step = lambda: P.ring_attention(q, k, v, tensor_layout=layout, is_causal=causal, qk="int4" if qk != "int8" else "int8", pv=pv)
+        scaling, units = "strong", ops_total
+    elif part == "heads" and world > 1:
+        q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
+        step = lambda: P.lowbit_fa_head_sharded(q, k, v, fn, world, rank, tensor_layout=layout, is_causal=causal)
+        scaling, units = "strong", ops_total
+    else:
+        q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
+        step = lambda: fn(q, k, v, tensor_layout=layout, is_causal=causal)
+        scaling, units = ("strong", ops_total) if part != "replicate" else ("weak", ops_total * world)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    if rank == 0:
+        peak_tf, _, peak_src = peaks()
+        value = units / (ms * 1e-3) / 1e12
+        per_gpu = value / world
+        line = {"metric": "attention TOPS (4*B*H*N^2*D / latency), quantize + attention", "value": value, "unit": "TOPS",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None, "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)", "data": "synthetic randn fp16 seed 0",
+                "config": {"workload": desc, "partition": part, "l2": "inputs larger than the 126 MB L2, no flush"},
+                "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel (whole step timed: quantize + attention"
+                             + (" + ring exchange" if part == "ring" else "") + ")", "achieved": per_gpu, "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": per_gpu / peak_tf, "traffic": None, "peak_source": peak_src},
+                "clocks": sampler.summary(), "gpu_launches": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(EXTRA))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.workload in EXTRA:
+        if args.impl == "reference":
+            raise SystemExit("--impl reference is defined for the INT8/FP16 workloads")
+        return run_extra(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -299,7 +402,8 @@ def main():
                     "d2h_bytes_per_step": int(ho.numel() * 2)},
             "gpu_launches": 5 * K,
             "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": ncu_traffic_bytes() if args.workload == "c2" else None, "peak_source": peak_src,
                          "algorithmic_flop_per_launch": ops, "ms_per_launch": attn_ms},
             "clocks": sampler.summary(),
         }

@@ -38,6 +38,11 @@ enum {
                                   K smoothing subtracts in fp32 (:120-126) */
 };
 
+/* validation switch, OR-ed into `mode`: take the Q1 quotient x/scale from the IEEE division instead of the
+ * three-instruction correctly rounded sequence (reciprocal, exact FMA remainder, corrected FMA) the kernel
+ * normally uses; tests assert both give identical codes. */
+#define LOWBIT_QMODE_FLAG_IEEE_DIV 0x100
+
 /* Q*K^T operand formats of the attention kernel */
 enum {
   LOWBIT_QK_I8 = 0,     /* Q int8, K int8 (one code per byte)                               */

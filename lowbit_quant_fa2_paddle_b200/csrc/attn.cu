@@ -656,8 +656,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 4-D tensor map: dims (d0 innermost .. d3), byte strides of dims 1..3, box (box0, box1, 1, 1)
-static int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, const int64_t (&dim)[4],
-                    const int64_t (&stride_elems)[3], int box0, int box1, CUtensorMapSwizzle swz) {
+int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, const int64_t (&dim)[4],
+             const int64_t (&stride_elems)[3], int box0, int box1, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   LOWBIT_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   LOWBIT_CHECK(((uintptr_t)ptr & 15) == 0, "tensor base address must be 16-byte aligned");

@@ -1,5 +1,6 @@
 // common.cuh -- shared host/device helpers for liblowbit_fa_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -27,6 +28,11 @@ int fail(const char* fmt, ...);
       return ::lowbit::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// host: 4-D TMA tensor map over a strided [d3][d2][d1][d0] view (defined in attn.cu): dims (d0 innermost .. d3),
+// element strides of dims 1..3, box (box0, box1, 1, 1); returns non-zero (and sets last_error) on failure
+int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, const int64_t (&dim)[4],
+             const int64_t (&stride_elems)[3], int box0, int box1, CUtensorMapSwizzle swz);
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -48,6 +54,58 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) f[i] = to_f32<T>(h[i]);
 }
+
+// Exact per-thread accumulation.  fp16: every value is an integer X = x * 2^24 with |X| < 2^40; it is split
+// without any conversion instruction into hi = RN(16 x) and lo = X - hi * 2^20 (|lo| <= 2^19) by two magic-constant
+// FMAs (1.5 * 2^23: the integer lands in the low mantissa bits), and the RAW float bits are summed in two int32
+// lanes (the constant's bits are subtracted once at the end; wrap-around is harmless while the true sums fit 31
+// bits, hence the flush every 256 rows).  bf16: fp64 accumulation in a fixed order.
+template <typename T> struct RowAcc;
+template <> struct RowAcc<__half> {
+  int hi[8], lo[8], n;
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi[i] = lo[i] = 0;
+    n = 0;
+  }
+  __device__ __forceinline__ void add(const uint4& raw) {
+    const __half* hv = reinterpret_cast<const __half*>(&raw);
+    const float kM = 12582912.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = __half2float(hv[i]);
+      const float a = __fmaf_rn(x, 16.0f, kM);
+      const float rem = __fmaf_rn(__fadd_rn(a, -kM), -0.0625f, x);  // exact: |rem| <= 2^-5, multiple of 2^-24
+      const float bq = __fmaf_rn(rem, 16777216.0f, kM);
+      hi[i] += __float_as_int(a);
+      lo[i] += __float_as_int(bq);
+    }
+    ++n;
+  }
+  __device__ __forceinline__ void flush(long long (&acc)[8]) {
+    const int off = n * 0x4B400000;  // n * bits(1.5 * 2^23), modulo 2^32 like the lanes themselves
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += (long long)(hi[i] - off) * 1048576ll + (long long)(lo[i] - off);
+    clear();
+  }
+};
+template <> struct RowAcc<__nv_bfloat16> {
+  double s[8];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.0;
+  }
+  __device__ __forceinline__ void add(const uint4& raw) {
+    const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += (double)__bfloat162float(hv[i]);
+  }
+  __device__ __forceinline__ void flush(double (&acc)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += s[i];
+    clear();
+  }
+};
 
 __device__ __forceinline__ float warp_max(float v) {
   // all operands are >= 0, so unsigned integer order == float order

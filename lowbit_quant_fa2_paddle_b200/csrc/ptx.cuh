@@ -51,7 +51,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
   return ok != 0;
 }
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 10000u); ++spins) {
     if (spins > (1u << 20)) {
 #ifdef LOWBIT_DEBUG_WAIT

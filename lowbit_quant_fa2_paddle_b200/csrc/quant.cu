@@ -13,8 +13,10 @@
 // contract to FMA nor substitute approximate division: codes and scales are bit-exact against the
 // IEEE-fp32 restatement of the reference.  This translation unit is compiled WITHOUT --use_fast_math.
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace lowbit {
 
@@ -36,6 +38,73 @@ int fail(const char* fmt, ...) {
 // per-block symmetric quantizer
 // ------------------------------------------------------------------------------------------------
 constexpr int kQuantThreads = 256;
+
+// ---- per-element arithmetic shared by both kernels ------------------------------------------------------
+// Q1 code of x for a block scale sc (rcp = RN(1/sc)): y = RN(x / sc) by Markstein's sequence (q0 = RN(x*rcp), exact
+// FMA remainder, corrected FMA: the correctly rounded quotient in three instructions where __fdiv_rn takes ~25),
+// y += copysign(0.5, y), truncate.  The caller guarantees 1e-30 < sc < 1e30 (so no NaN and no exponent special cases).
+__device__ __forceinline__ int q1_code_fast(float x, float sc, float rcp) {
+  const float q0 = __fmul_rn(x, rcp);
+  const float rem = __fmaf_rn(-q0, sc, x);
+  float y = __fmaf_rn(rem, rcp, q0);
+  y = __fadd_rn(y, __uint_as_float(0x3f000000u | (__float_as_uint(y) & 0x80000000u)));
+  return __float2int_rz(y);
+}
+__device__ __forceinline__ int q1_code_ieee(float x, float sc) {
+  float y = __fdiv_rn(x, sc);
+  y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
+  return (y == y) ? __float2int_rz(y) : 0;  // 0/0 block -> code 0
+}
+// four int32 codes in [-128,127] -> one word of int8 (cvt.pack: two instructions)
+__device__ __forceinline__ uint32_t pack_s8x4(int c0, int c1, int c2, int c3) {
+  // d[7:0] = sat(b), d[15:8] = sat(a), d[31:16] = c[15:0]
+  uint32_t hi, w;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(c3), "r"(c2));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(c1), "r"(c0), "r"(hi));
+  return w;
+}
+// store 8 codes of one row chunk: int8 (8 B), packed INT4 (4 B) or packed INT2 (2 B)
+__device__ __forceinline__ void store_codes8(int8_t* dst_row, int c8, const int (&c)[8], int bits, int pack) {
+  if (bits == 8 || !pack) {
+    uint2 w;
+    w.x = pack_s8x4(c[0], c[1], c[2], c[3]);
+    w.y = pack_s8x4(c[4], c[5], c[6], c[7]);
+    *reinterpret_cast<uint2*>(dst_row + c8) = w;
+  } else if (bits == 4) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w |= (uint32_t)(c[i] & 0xf) << (4 * i);
+    *reinterpret_cast<uint32_t*>(dst_row + c8 / 2) = w;
+  } else {
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w |= (uint32_t)(c[i] & 0x3) << (2 * i);
+    *reinterpret_cast<uint16_t*>(dst_row + c8 / 4) = (uint16_t)w;
+  }
+}
+template <int NPASS>
+__device__ __forceinline__ void quantize_rows(const float (&x)[NPASS][8], int8_t* dst, int64_t osn, int row0, int rpp,
+                                              int r0, int c8, int blk, int N, float sc, float rcp, bool triton,
+                                              bool slow_div, int bits, int pack) {
+#pragma unroll
+  for (int p = 0; p < NPASS; ++p) {
+    const int rl = p * rpp + r0;
+    const int row = row0 + rl;
+    if (!(rl < blk && row < N)) continue;
+    int c[8];
+    if (triton && !slow_div) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] = q1_code_fast(x[p][i], sc, rcp);
+    } else if (triton) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] = q1_code_ieee(x[p][i], sc);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] = max(-128, min(127, __float2int_rn(__fmul_rn(x[p][i], rcp))));
+    }
+    store_codes8(dst + (int64_t)row * osn, c8, c, bits, pack);
+  }
+}
 
 template <typename T, int D, int BLK>
 __global__ void __launch_bounds__(kQuantThreads)
@@ -79,7 +148,7 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
       float v = x[p][i];
       if (has_km) {
         v = __fsub_rn(v, kmf[i]);
-        if (mode == LOWBIT_QMODE_TRITON) v = to_f32<T>(from_f32<T>(v));  // `k - km` in the input dtype
+        if ((mode & 0xff) == LOWBIT_QMODE_TRITON) v = to_f32<T>(from_f32<T>(v));  // `k - km` in the input dtype
       }
       v = __fmul_rn(v, sm);
       v = live ? v : 0.f;  // rows >= N contribute 0 (masked load), even when km != 0
@@ -98,8 +167,14 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
 
   const float qmax = bits == 8 ? 127.f : (bits == 4 ? 7.f : 1.f);
   float sc, rcp = 0.f;
-  if (mode == LOWBIT_QMODE_TRITON) {
+  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
+  bool slow_div = (mode & LOWBIT_QMODE_FLAG_IEEE_DIV) != 0;
+  if (triton) {
     sc = __fdiv_rn(bmax, qmax);
+    rcp = __frcp_rn(sc);  // correctly rounded 1/scale, once per block
+    // bf16 blocks near the ends of the fp32 exponent range (1/scale denormal or infinite), and all-zero blocks,
+    // take the IEEE division: a block-uniform branch
+    slow_div = slow_div || !(sc > 1e-30f && sc < 1e30f);
   } else {
     bmax = fmaxf(bmax, 1e-7f);
     sc = __fdiv_rn(bmax, qmax);
@@ -108,40 +183,7 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
   if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = sc;
 
   int8_t* dst = out + b * osb + h * osh;
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    const int rl = p * RPP + r0;
-    const int row = jb * BLK + rl;
-    if (!(rl < BLK && row < N)) continue;
-    int c[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (mode == LOWBIT_QMODE_TRITON) {
-        float y = __fdiv_rn(x[p][i], sc);
-        y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
-        c[i] = (y == y) ? __float2int_rz(y) : 0;  // 0/0 block -> code 0
-      } else {
-        int q = __float2int_rn(__fmul_rn(x[p][i], rcp));
-        c[i] = max(-128, min(127, q));
-      }
-    }
-    if (bits == 8 || !pack) {
-      uint2 w;
-      w.x = (c[0] & 0xff) | ((c[1] & 0xff) << 8) | ((c[2] & 0xff) << 16) | ((c[3] & 0xff) << 24);
-      w.y = (c[4] & 0xff) | ((c[5] & 0xff) << 8) | ((c[6] & 0xff) << 16) | ((c[7] & 0xff) << 24);
-      *reinterpret_cast<uint2*>(dst + (int64_t)row * osn + c8) = w;
-    } else if (bits == 4) {
-      uint32_t w = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w |= (uint32_t)(c[i] & 0xf) << (4 * i);
-      *reinterpret_cast<uint32_t*>(dst + (int64_t)row * osn + c8 / 2) = w;
-    } else {
-      uint32_t w = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w |= (uint32_t)(c[i] & 0x3) << (2 * i);
-      *reinterpret_cast<uint16_t*>(dst + (int64_t)row * osn + c8 / 4) = (uint16_t)w;
-    }
-  }
+  quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack);
 }
 
 template <typename T, int D, int BLK>
@@ -152,6 +194,153 @@ static int launch_qpb(const void* in, const void* km, void* codes, float* scale,
   dim3 grid(nblk, H, B);
   quant_per_block_kernel<T, D, BLK><<<grid, kQuantThreads, 0, st>>>(
       (const T*)in, (const T*)km, (int8_t*)codes, scale, N, nblk, isb, ish, isn, osb, osh, osn, sm, bits, pack, mode, H);
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// per-block symmetric quantizer, TMA-pipelined persistent form (the one normally launched)
+// ------------------------------------------------------------------------------------------------
+// The kernel above lives through load -> reduce -> quantize -> store once per CTA, so the whole chip moves through
+// those phases together and HBM idles during the arithmetic.  Here CTAs are persistent (a few per SM), tiles of one
+// quantization block ([BLK rows][D] elements, OOB rows zero-filled) arrive through a ring of TMA stages that stays
+// several tiles ahead, and the threads quantize tile i while the TMA engine fetches tiles i+1 .. i+STAGES-1.
+// Same arithmetic, same results.
+template <int D, int BLK> struct QuantTmaCfg {
+  static constexpr int kTileBytes = BLK * D * 2;
+  static constexpr int kStages = (kTileBytes >= 32768) ? 3 : (kTileBytes >= 16384 ? 4 : 6);
+  static constexpr int kSmem = kStages * kTileBytes + 1024 + 256;
+};
+
+template <typename T, int D, int BLK>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_per_block_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const T* __restrict__ km,
+                           int8_t* __restrict__ out, float* __restrict__ scale, int N, int nblk, int H, int total,
+                           int64_t osb, int64_t osh, int64_t osn, float sm, int bits, int pack, int mode) {
+  using C = QuantTmaCfg<D, BLK>;
+  constexpr int S = C::kStages;
+  constexpr int TPR = D / 8;                 // threads per row
+  constexpr int RPP = kQuantThreads / TPR;   // rows per pass
+  constexpr int NP = (BLK + RPP - 1) / RPP;  // passes
+  extern __shared__ uint8_t qsmem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qsmem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * C::kTileBytes);
+  __shared__ float s_w[2][kQuantThreads / 32];
+  const int tid = threadIdx.x;
+  const int c8 = (tid % TPR) * 8, r0 = tid / TPR;
+  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
+  const float qmax = bits == 8 ? 127.f : (bits == 4 ? 7.f : 1.f);
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) ptx::mbar_init(full + i, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmIn);
+  }
+  __syncthreads();
+  auto issue = [&](int t, int stage) {  // thread 0: fetch tile t (linear over b, h, block) into `stage`
+    const int j = t % nblk, h = (t / nblk) % H, b = t / (nblk * H);
+    ptx::mbar_expect_tx(full + stage, C::kTileBytes);
+    ptx::tma_load_4d(smem + stage * C::kTileBytes, &tmIn, full + stage, 0, j * BLK, h, b);
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i)
+      if (first + i * stride < total) issue(first + i * stride, i);
+  }
+  int it = 0;
+  for (int t = first; t < total; t += stride, ++it) {
+    const int stage = it % S;
+    const int jb = t % nblk, h = (t / nblk) % H, b = t / (nblk * H);
+    float kmf[8];
+    const bool has_km = km != nullptr;
+    if (has_km) {
+      uint4 raw = *reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8);
+      unpack8<T>(raw, kmf);
+    }
+    ptx::mbar_wait(full + stage, (it / S) & 1, 40);
+    const uint8_t* tile = smem + stage * C::kTileBytes;
+    float x[NP][8];
+    float amax = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int rl = p * RPP + r0;
+      const bool live = (rl < BLK) && (jb * BLK + rl < N);
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (rl < BLK) raw = *reinterpret_cast<const uint4*>(tile + ((size_t)rl * D + c8) * 2);
+      unpack8<T>(raw, x[p]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = x[p][i];
+        if (has_km) {
+          v = __fsub_rn(v, kmf[i]);
+          if (triton) v = to_f32<T>(from_f32<T>(v));  // `k - km` in the input dtype
+        }
+        v = __fmul_rn(v, sm);
+        v = live ? v : 0.f;  // rows >= N contribute 0 (masked load), even when km != 0
+        x[p][i] = v;
+        amax = fmaxf(amax, fabsf(v));
+      }
+    }
+    amax = warp_max(amax);
+    if ((tid & 31) == 0) s_w[it & 1][tid >> 5] = amax;
+    __syncthreads();  // every thread has finished reading this stage
+    if (tid == 0 && t + S * stride < total) issue(t + S * stride, stage);
+    float bmax = s_w[it & 1][0];
+#pragma unroll
+    for (int w = 1; w < kQuantThreads / 32; ++w) bmax = fmaxf(bmax, s_w[it & 1][w]);
+
+    float sc, rcp = 0.f;
+    bool slow_div = (mode & LOWBIT_QMODE_FLAG_IEEE_DIV) != 0;
+    if (triton) {
+      sc = __fdiv_rn(bmax, qmax);
+      rcp = __frcp_rn(sc);
+      slow_div = slow_div || !(sc > 1e-30f && sc < 1e30f);
+    } else {
+      bmax = fmaxf(bmax, 1e-7f);
+      sc = __fdiv_rn(bmax, qmax);
+      rcp = __fdiv_rn(qmax, bmax);
+    }
+    if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = sc;
+
+    int8_t* dst = out + b * osb + h * osh;
+    quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <typename T, int D, int BLK>
+static int launch_qpb_tma(const void* in, const void* km, void* codes, float* scale, int B, int H, int N,
+                          int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
+                          float sm, int bits, int pack, int mode, cudaStream_t st) {
+  using C = QuantTmaCfg<D, BLK>;
+  const int nblk = (N + BLK - 1) / BLK;
+  const int64_t total64 = (int64_t)B * H * nblk;
+  LOWBIT_CHECK(total64 < (1ll << 31), "lowbit_quant_per_block: too many blocks");
+  CUtensorMap tm;
+  const int64_t dim[4] = {D, N, H, B}, str[3] = {isn, ish, isb};
+  if (make_map(&tm, in, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dim, str, D, BLK, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  auto kern = quant_per_block_tma_kernel<T, D, BLK>;
+  static bool configured = false;
+  if (!configured) {
+    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    configured = true;
+  }
+  int ctas_per_sm = (227 * 1024) / (C::kSmem + 1024);
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+  const int grid = (int)(total64 < cap ? total64 : cap);
+  kern<<<grid, kQuantThreads, C::kSmem, st>>>(tm, (const T*)km, (int8_t*)codes, scale, N, nblk, H, (int)total64,
+                                              osb, osh, osn, sm, bits, pack, mode);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -192,21 +381,23 @@ k_mean_partial_kernel(const T* __restrict__ k, typename MeanAcc<T>::type* __rest
   A acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = A(0);
-  // rows in 64-row blocks, sequential inside a thread (fixed order; matters only for bf16/fp64)
-  for (int row = ch * chunk + r0; row < row_end; row += 4 * RPP) {
-    uint4 raw[4];
+  RowAcc<T> ra;
+  ra.clear();
+  int since_flush = 0;
+  // rows in a fixed order inside a thread (matters only for bf16/fp64); 8 loads in flight per thread
+  for (int row = ch * chunk + r0; row < row_end; row += 8 * RPP) {
+    uint4 raw[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       raw[u] = make_uint4(0, 0, 0, 0);
       if (row + u * RPP < row_end) raw[u] = ld_stream_v4(src + (int64_t)(row + u * RPP) * sn);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const T* hv = reinterpret_cast<const T*>(&raw[u]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += MeanAcc<T>::cvt(hv[i]);
-    }
+    for (int u = 0; u < 8; ++u) ra.add(raw[u]);
+    since_flush += 8;
+    if (since_flush >= 256) { ra.flush(acc); since_flush = 0; }
   }
+  ra.flush(acc);
   __shared__ A s[RPP][D + 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[r0][c8 + i] = acc[i];
@@ -328,18 +519,24 @@ int lowbit_quant_per_block(const void* in, const void* km, void* codes, float* s
   LOWBIT_CHECK(D == 64 || D == 128, "lowbit_quant_per_block: head_dim must be 64 or 128 (got %d)", D);
   LOWBIT_CHECK(blk == 32 || blk == 64 || blk == 128, "lowbit_quant_per_block: blk must be 32, 64 or 128 (got %d)", blk);
   LOWBIT_CHECK(bits == 8 || bits == 4 || bits == 2, "lowbit_quant_per_block: bits must be 8, 4 or 2 (got %d)", bits);
-  LOWBIT_CHECK(mode == LOWBIT_QMODE_TRITON || mode == LOWBIT_QMODE_CUDA, "lowbit_quant_per_block: bad mode %d", mode);
+  LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_quant_per_block: bad mode %d", mode);
   LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_quant_per_block: empty tensor");
   LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0, "lowbit_quant_per_block: input strides must keep 16-byte alignment");
   const int ob = (pack && bits < 8) ? bits : 8;  // bytes of 8 codes
   LOWBIT_CHECK(osn % ob == 0 && osh % ob == 0 && osb % ob == 0, "lowbit_quant_per_block: output strides misaligned");
   cudaStream_t st = (cudaStream_t)stream;
 #define ARGS in, km, codes, scale, B, H, N, isb, ish, isn, osb, osh, osn, sm, bits, pack, mode, st
-#define BY_BLK(T, DD)                                            \
-  switch (blk) {                                                 \
-    case 32: return launch_qpb<T, DD, 32>(ARGS);                 \
-    case 64: return launch_qpb<T, DD, 64>(ARGS);                 \
-    default: return launch_qpb<T, DD, 128>(ARGS);                \
+  // 128-row blocks go through the TMA-pipelined persistent kernel, 64-row blocks through the one-block-per-CTA
+  // kernel (measured faster at that tile size: 8-16 KB tiles do not amortise the per-tile barrier).
+  // LOWBIT_QUANT_TMA=0 / 2 force neither / both (A/B measurements).
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("LOWBIT_QUANT_TMA"); use_tma = e ? atoi(e) : 1; }
+  const bool tma_ok = use_tma && ((uintptr_t)in & 15) == 0;
+#define BY_BLK(T, DD)                                                                        \
+  switch (blk) {                                                                             \
+    case 32: return launch_qpb<T, DD, 32>(ARGS);                                             \
+    case 64: return (tma_ok && use_tma > 1) ? launch_qpb_tma<T, DD, 64>(ARGS) : launch_qpb<T, DD, 64>(ARGS); \
+    default: return tma_ok ? launch_qpb_tma<T, DD, 128>(ARGS) : launch_qpb<T, DD, 128>(ARGS); \
   }
   if (dtype == LOWBIT_F16) {
     if (D == 64) { BY_BLK(__half, 64) } else { BY_BLK(__half, 128) }

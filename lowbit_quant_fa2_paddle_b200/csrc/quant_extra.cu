@@ -133,18 +133,17 @@ kivi_pack_kernel(const __half* __restrict__ data, uint8_t* __restrict__ code, __
 template <typename T> struct SumAcc;
 template <> struct SumAcc<__half> {
   using type = long long;  // exact fixed point, units of 2^-24
-  static __device__ __forceinline__ type cvt(__half v) { return __float2ll_rn(__half2float(v) * 16777216.f); }
   static __device__ __forceinline__ float to_f32(type s) { return __ll2float_rn(s) * 5.9604644775390625e-08f; }
 };
 template <> struct SumAcc<__nv_bfloat16> {
   using type = double;
-  static __device__ __forceinline__ type cvt(__nv_bfloat16 v) { return (double)__bfloat162float(v); }
   static __device__ __forceinline__ float to_f32(type s) { return __double2float_rn(s); }
 };
 constexpr int kVChunks = 16;
 struct VPartial { float mx, mn; long long sum_bits; };  // sum as raw 8 bytes (int64 or double)
 
-template <typename T, int D>
+// pass 1: per-channel max / min (/ exact sum when the mean is wanted) over one chunk of rows; 8 loads in flight
+template <typename T, int D, bool SUM>
 __global__ void __launch_bounds__(256)
 v_stats_partial_kernel(const T* __restrict__ v, VPartial* __restrict__ part, int N, int chunk, int nchunk,
                        int64_t sb, int64_t sh, int64_t sn, int H) {
@@ -158,26 +157,50 @@ v_stats_partial_kernel(const T* __restrict__ v, VPartial* __restrict__ part, int
   A acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mx[i] = -INFINITY; mn[i] = INFINITY; acc[i] = A(0); }
-  for (int row = ch * chunk + r0; row < row_end; row += RPP) {
-    const uint4 raw = ld_stream_v4(src + (int64_t)row * sn);
-    const T* hv = reinterpret_cast<const T*>(&raw);
+  RowAcc<T> ra;
+  ra.clear();
+  int since_flush = 0;
+  for (int row = ch * chunk + r0; row < row_end; row += 8 * RPP) {
+    uint4 raw[8];
+    bool live[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float f = to_f32<T>(hv[i]);
-      mx[i] = fmaxf(mx[i], f);
-      mn[i] = fminf(mn[i], f);
-      acc[i] += SumAcc<T>::cvt(hv[i]);
+    for (int u = 0; u < 8; ++u) {
+      live[u] = row + u * RPP < row_end;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (live[u]) raw[u] = ld_stream_v4(src + (int64_t)(row + u * RPP) * sn);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (!live[u]) continue;
+      float f[8];
+      unpack8<T>(raw[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mx[i] = fmaxf(mx[i], f[i]); mn[i] = fminf(mn[i], f[i]); }
+      if (SUM) ra.add(raw[u]);
+    }
+    if (SUM) {
+      since_flush += 8;
+      if (since_flush >= 256) { ra.flush(acc); since_flush = 0; }
     }
   }
+  if (SUM) ra.flush(acc);
   __shared__ float s_mx[RPP][D + 1], s_mn[RPP][D + 1];
-  __shared__ A s_sum[RPP][D + 1];
+  __shared__ A s_sum[SUM ? RPP : 1][D + 1];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s_mx[r0][c8 + i] = mx[i]; s_mn[r0][c8 + i] = mn[i]; s_sum[r0][c8 + i] = acc[i]; }
+  for (int i = 0; i < 8; ++i) {
+    s_mx[r0][c8 + i] = mx[i];
+    s_mn[r0][c8 + i] = mn[i];
+    if (SUM) s_sum[r0][c8 + i] = acc[i];
+  }
   __syncthreads();
   if (tid < D) {
     float a = -INFINITY, c = INFINITY;
     A t = A(0);
-    for (int r = 0; r < RPP; ++r) { a = fmaxf(a, s_mx[r][tid]); c = fminf(c, s_mn[r][tid]); t += s_sum[r][tid]; }
+    for (int r = 0; r < RPP; ++r) {
+      a = fmaxf(a, s_mx[r][tid]);
+      c = fminf(c, s_mn[r][tid]);
+      if (SUM) t += s_sum[r][tid];
+    }
     VPartial o;
     o.mx = a; o.mn = c;
     o.sum_bits = *reinterpret_cast<long long*>(&t);
@@ -185,18 +208,36 @@ v_stats_partial_kernel(const T* __restrict__ v, VPartial* __restrict__ part, int
   }
 }
 
+// pass 2: every row-group of TPR threads owns one quad of OUTPUT positions, i.e. the four tokens
+// {2w, 2w+1, 8+2w, 9+2w} of a 16-group (fused.cu:290-292 inverted), loads their rows (4 x 16 B in flight), scales,
+// packs the four e4m3 codes of every channel into one word, and the CTA writes [channel][position] rows through a
+// padded shared-memory transpose.
+template <int D> struct VQuantCfg {
+  static constexpr int TPR = D / 8, G = 256 / TPR, TT = G * 4;  // tokens per CTA: 128 (D=64) / 64 (D=128)
+};
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 v_fp8_quant_kernel(const T* __restrict__ v, const VPartial* __restrict__ part, uint8_t* __restrict__ v8,
-                   float* __restrict__ v_scale, float* __restrict__ vm_out, int N, int nchunk, int64_t sb, int64_t sh,
-                   int64_t sn, int64_t osb, int64_t osh, int64_t osd, float scale_max, int H) {
+                   float* __restrict__ v_scale, float* __restrict__ vm_out, int N, int npad, int nchunk, int64_t sb,
+                   int64_t sh, int64_t sn, int64_t osb, int64_t osh, int64_t osd, float scale_max, int H) {
   using A = typename SumAcc<T>::type;
-  constexpr int TPR = D / 8, RPP = 256 / TPR;  // 64 tokens per CTA
-  const int tid = threadIdx.x, c8 = (tid % TPR) * 8, r0 = tid / TPR;
+  using C = VQuantCfg<D>;
+  constexpr int TPR = C::TPR, TT = C::TT, WPR = TT / 4;  // words per channel row of the tile
+  const int tid = threadIdx.x, c8 = (tid % TPR) * 8, g = tid / TPR;
   const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   __shared__ float s_r[D], s_vm[D];
-  __shared__ uint8_t s_t[D][64 + 16];  // [channel][position in tile], padded rows
+  __shared__ uint32_t s_t[D][WPR + 1];
   const int n16 = (N + 15) / 16 * 16;
+  // issue the four row loads before the statistics reduction so their latency overlaps it
+  const int tok0 = tile * TT + (g / 4) * 16 + 2 * (g % 4);
+  const int toks[4] = {tok0, tok0 + 1, tok0 + 8, tok0 + 9};
+  const T* src = v + b * sb + h * sh + c8;
+  uint4 raw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    raw[j] = make_uint4(0, 0, 0, 0);
+    if (toks[j] < N) raw[j] = ld_stream_v4(src + (int64_t)toks[j] * sn);
+  }
   if (tid < D) {
     float mx = -INFINITY, mn = INFINITY;
     A t = A(0);
@@ -221,28 +262,26 @@ v_fp8_quant_kernel(const T* __restrict__ v, const VPartial* __restrict__ part, u
     }
   }
   __syncthreads();
-  const T* src = v + b * sb + h * sh + c8;
+  float f[4][8];
 #pragma unroll
-  for (int p = 0; p < 64 / RPP; ++p) {
-    const int rl = p * RPP + r0, row = tile * 64 + rl;
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (row < N) raw = ld_stream_v4(src + (int64_t)row * sn);
-    float f[8];
-    unpack8<T>(raw, f);
-    const int r = rl & 15;
-    const int pos = (rl & ~15) + (r / 8) * 2 + ((r / 2) % 4) * 4 + (r % 2);  // fused.cu:290-292
+  for (int j = 0; j < 4; ++j) unpack8<T>(raw[j], f[j]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float y = __fmul_rn(__fsub_rn(f[i], s_vm[c8 + i]), s_r[c8 + i]);
-      s_t[c8 + i][pos] = (uint8_t)__nv_cvt_float_to_fp8(y, __NV_SATFINITE, __NV_E4M3);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const float vm = s_vm[c8 + i], r = s_r[c8 + i];
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = __fmul_rn(__fsub_rn(f[j][i], vm), r);
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(y[1]), "f"(y[0]));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(y[3]), "f"(y[2]));
+    s_t[c8 + i][g] = (uint32_t)lo | ((uint32_t)hi << 16);
   }
   __syncthreads();
-  // each channel row of the tile = 64 contiguous output bytes: 4 threads x 16 B per channel
-  uint8_t* dst = v8 + b * osb + h * osh + (int64_t)tile * 64;
-  for (int idx = tid; idx < D * 4; idx += 256) {
-    const int d = idx >> 2, q = idx & 3;
-    *reinterpret_cast<uint4*>(dst + (int64_t)d * osd + q * 16) = *reinterpret_cast<const uint4*>(&s_t[d][q * 16]);
+  // channel rows of the tile: TT contiguous output bytes each, written one word per thread (coalesced)
+  uint8_t* dst = v8 + b * osb + h * osh + (int64_t)tile * TT;
+  for (int idx = tid; idx < D * WPR; idx += 256) {
+    const int d = idx / WPR, w = idx % WPR;
+    if (tile * TT + 4 * w < npad) *reinterpret_cast<uint32_t*>(dst + (int64_t)d * osd + 4 * w) = s_t[d][w];
   }
 }
 
@@ -319,11 +358,13 @@ int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
   int chunk = (N + kVChunks - 1) / kVChunks;
   chunk = (chunk + 63) / 64 * 64;
   const int nchunk = (N + chunk - 1) / chunk;
-  dim3 g1(nchunk, H, B), g2((N + 63) / 64, H, B);
+  const int npad = (N + 63) / 64 * 64;
+  dim3 g1(nchunk, H, B);
 #define LAUNCH(T, DD)                                                                                               \
-  v_stats_partial_kernel<T, DD><<<g1, 256, 0, st>>>((const T*)v, (VPartial*)workspace, N, chunk, nchunk, sb, sh, sn, H); \
-  v_fp8_quant_kernel<T, DD><<<g2, 256, 0, st>>>((const T*)v, (const VPartial*)workspace, (uint8_t*)v8, v_scale, vm, N,  \
-                                                nchunk, sb, sh, sn, osb, osh, osd, scale_max, H);
+  if (vm != nullptr) v_stats_partial_kernel<T, DD, true><<<g1, 256, 0, st>>>((const T*)v, (VPartial*)workspace, N, chunk, nchunk, sb, sh, sn, H); \
+  else v_stats_partial_kernel<T, DD, false><<<g1, 256, 0, st>>>((const T*)v, (VPartial*)workspace, N, chunk, nchunk, sb, sh, sn, H); \
+  v_fp8_quant_kernel<T, DD><<<dim3((N + VQuantCfg<DD>::TT - 1) / VQuantCfg<DD>::TT, H, B), 256, 0, st>>>(           \
+      (const T*)v, (const VPartial*)workspace, (uint8_t*)v8, v_scale, vm, N, npad, nchunk, sb, sh, sn, osb, osh, osd, scale_max, H);
   if (dtype == LOWBIT_F16) {
     if (D == 64) { LAUNCH(__half, 64) } else { LAUNCH(__half, 128) }
   } else if (dtype == LOWBIT_BF16) {

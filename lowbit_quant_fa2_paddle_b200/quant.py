@@ -84,8 +84,9 @@ def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpac
     head_dim = T.as_torch(q).shape[-1]
     if sm_scale is None:
         sm_scale = head_dim ** -0.5
-    q_c, q_s = _quant_one(q, None, BLKQ, qbits, False, sm_scale * LOG2E, mode, tensor_layout)
+    # K first: it was just read by k_mean and is still (partly) L2-resident
     k_c, k_s = _quant_one(k, km, BLKK, kbits, kpack, 1.0, mode, tensor_layout)
+    q_c, q_s = _quant_one(q, None, BLKQ, qbits, False, sm_scale * LOG2E, mode, tensor_layout)
     return q_c, q_s, k_c, k_s
 
 

@@ -533,3 +533,50 @@ def test_ring_attention_world1_cuda_backend(L, cuda_dev):
             assert (lse - lse1).abs().max() <= (1e-2 if pv == "fp16" else 5e-2)
     finally:
         dist.destroy_process_group()
+
+
+def test_fast_exact_division_equals_ieee_division(L, cuda_dev):
+    """The Q1 quantizer takes RN(x/scale) from reciprocal + exact FMA remainder + corrected FMA (3 instructions)
+    instead of the IEEE division (~25).  Both must give identical codes and scales: checked on every finite fp16
+    value against many block maxima and sm_scale factors (~2e8 (x, scale) pairs), on bf16 data spanning the fp32
+    exponent range, and on INT4 / INT2 targets."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    from lowbit_quant_fa2_paddle_b200 import quant as Qz
+    allh = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    allh = allh[torch.isfinite(allh)]                        # 63488 finite fp16 values
+    g = torch.Generator().manual_seed(5)
+    reps = 32
+    x = allh.repeat(reps)[torch.randperm(allh.numel() * reps, generator=g)]
+    n = x.numel() // 64 // 128 * 128
+    x = x[: n * 64].view(1, 1, n, 64).clone()
+    # give the 128-row blocks different magnitudes so the per-block scales differ
+    mag = torch.exp2(torch.randint(-14, 1, (n // 128,), generator=g).float()).repeat_interleave(128).view(1, 1, n, 1)
+    x = (x.float() * mag).clamp(-65504, 65504).half().to(cuda_dev)
+    for sm in (1.0, 0.18033688, 0.7071, 3.3333, 1e-3):
+        for bits in (8, 4, 2):
+            for blk in (128, 64):
+                fast = Qz._quant_one(x, None, blk, bits, False, sm, NV.QMODE_TRITON, "HND")
+                slow = Qz._quant_one(x, None, blk, bits, False, sm, NV.QMODE_TRITON | NV.QMODE_FLAG_IEEE_DIV, "HND")
+                assert torch.equal(fast[0], slow[0]) and torch.equal(fast[1], slow[1]), (sm, bits, blk)
+    xb = (torch.randn(1, 2, 4096, 128, generator=g) * torch.exp2(torch.randint(-120, 120, (1, 2, 64, 1), generator=g).float()
+          ).repeat_interleave(64, dim=2)).bfloat16().to(cuda_dev)
+    fast = Qz._quant_one(xb, None, 64, 8, False, 1.0, NV.QMODE_TRITON, "HND")
+    slow = Qz._quant_one(xb, None, 64, 8, False, 1.0, NV.QMODE_TRITON | NV.QMODE_FLAG_IEEE_DIV, "HND")
+    assert torch.equal(fast[0], slow[0]) and torch.equal(fast[1], slow[1])
+
+
+def test_k_mean_exact_on_all_fp16_values(L, cuda_dev):
+    """The split hi/lo int32 accumulation of k_mean is exact: a column holding every finite fp16 value (sum 0) next
+    to columns with known sums, N large enough to cross the 256-row flush."""
+    from oracle import quant as OQ
+    allh = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    allh = allh[torch.isfinite(allh)]
+    g = torch.Generator().manual_seed(6)
+    n = allh.numel()
+    cols = [allh[torch.randperm(n, generator=g)] for _ in range(60)]
+    cols += [torch.full((n,), 65504.0).half(), torch.full((n,), -65504.0).half(),
+             torch.full((n,), 6e-8).half(), allh.abs()]
+    k = torch.stack(cols, dim=1).view(1, 1, n, 64).contiguous()
+    km = L.k_mean(k.to(cuda_dev)).cpu()
+    assert torch.equal(km, OQ.k_mean(k))
+    assert torch.equal(km.view(-1)[:60], torch.zeros(60).half())
