@@ -43,6 +43,13 @@ enum {
  * normally uses; tests assert both give identical codes. */
 #define LOWBIT_QMODE_FLAG_IEEE_DIV 0x100
 
+/* Q1 as the reference's Triton kernels behave when JIT-compiled for a GPU (not under the interpreter): fp32 `/`
+ * lowers to PTX div.full.f32 (approximate, <= 2 ulp) for `scale = max|x| / 127` and for `x / scale`
+ * (quant_per_block.py:173-174).  OR-ed into LOWBIT_QMODE_TRITON.  Codes differ from the IEEE ones by at most one
+ * step in a small fraction of positions; verified bit-exact against the JIT-compiled reference kernels on B200
+ * (tools/ref_on_b200.py, profiles/r1_reference_on_b200.jsonl). */
+#define LOWBIT_QMODE_FLAG_DIV_FULL 0x200
+
 /* Q*K^T operand formats of the attention kernel */
 enum {
   LOWBIT_QK_I8 = 0,     /* Q int8, K int8 (one code per byte)                               */

@@ -31,6 +31,7 @@ from .quant import (  # noqa: F401
     per_channel_fp8,
     triton_quantize_and_pack_along_last_dim,
 )
+from .host import lowbit_fa_host, plan_chunks  # noqa: F401
 from .attention import forward, forward_causal, forward_partial, finalize, PartialState  # noqa: F401
 
 __version__ = "0.1.0"

@@ -10,7 +10,10 @@
 Same names, keyword arguments, return values, assertion / ValueError behaviour.  The "_triton" suffix is kept
 because callers import these names; the implementation is hand-written sm_100a CUDA (csrc/) reached through
 the C ABI -- there is no Triton, no backend dispatch and no CPU fallback.  `quantization_backend` selects the
-reference's two *rounding conventions* ("triton": Q1, "cuda": Q2), both executed by the same CUDA kernel.
+reference's two *rounding conventions* ("triton": Q1, "cuda": Q2), both executed by the same CUDA kernel;
+"triton_gpu" is Q1 with the approximate fp32 division (PTX div.full.f32) that Triton emits when it JIT-compiles the
+reference kernels for a GPU -- bit-identical to those kernels on a B200, whereas "triton" is the IEEE arithmetic of
+the same kernels under the Triton interpreter (what the golden vectors pin).
 """
 from typing import Any, Optional
 
@@ -39,7 +42,7 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
     assert qt.dtype == kt.dtype == vt.dtype, "All tensors must have the same dtype."
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
-    if quantization_backend not in ("triton", "cuda"):
+    if quantization_backend not in ("triton", "triton_gpu", "cuda"):
         raise ValueError(f"Unsupported quantization backend: {quantization_backend}")
     head_dim_og = qt.shape[-1]
     if head_dim_og > 128:

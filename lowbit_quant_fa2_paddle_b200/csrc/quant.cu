@@ -55,6 +55,19 @@ __device__ __forceinline__ int q1_code_ieee(float x, float sc) {
   y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
   return (y == y) ? __float2int_rz(y) : 0;  // 0/0 block -> code 0
 }
+// The reference's kernels as Triton JIT-compiles them for a GPU: fp32 `/` lowers to PTX div.full.f32 (an approximate,
+// <= 2 ulp division), for the scale (`max|x| / 127`) and for every quotient (`x / scale`); everything else (mul, add,
+// cvt.rzi) is IEEE and uncontracted.  The same instruction here gives the same bits on the same architecture.
+__device__ __forceinline__ float div_full(float a, float b) {
+  float r;
+  asm("div.full.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ int q1_code_divfull(float x, float sc) {
+  float y = div_full(x, sc);
+  y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
+  return (y == y) ? __float2int_rz(y) : 0;
+}
 // four int32 codes in [-128,127] -> one word of int8 (cvt.pack: two instructions)
 __device__ __forceinline__ uint32_t pack_s8x4(int c0, int c1, int c2, int c3) {
   // d[7:0] = sat(b), d[15:8] = sat(a), d[31:16] = c[15:0]
@@ -85,14 +98,17 @@ __device__ __forceinline__ void store_codes8(int8_t* dst_row, int c8, const int 
 template <int NPASS>
 __device__ __forceinline__ void quantize_rows(const float (&x)[NPASS][8], int8_t* dst, int64_t osn, int row0, int rpp,
                                               int r0, int c8, int blk, int N, float sc, float rcp, bool triton,
-                                              bool slow_div, int bits, int pack) {
+                                              bool slow_div, int bits, int pack, bool gpu_div = false) {
 #pragma unroll
   for (int p = 0; p < NPASS; ++p) {
     const int rl = p * rpp + r0;
     const int row = row0 + rl;
     if (!(rl < blk && row < N)) continue;
     int c[8];
-    if (triton && !slow_div) {
+    if (triton && gpu_div) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[i] = q1_code_divfull(x[p][i], sc);
+    } else if (triton && !slow_div) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) c[i] = q1_code_fast(x[p][i], sc, rcp);
     } else if (triton) {
@@ -169,7 +185,10 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
   float sc, rcp = 0.f;
   const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
   bool slow_div = (mode & LOWBIT_QMODE_FLAG_IEEE_DIV) != 0;
-  if (triton) {
+  const bool gpu_div = triton && (mode & LOWBIT_QMODE_FLAG_DIV_FULL) != 0;
+  if (gpu_div) {
+    sc = div_full(bmax, qmax);
+  } else if (triton) {
     sc = __fdiv_rn(bmax, qmax);
     rcp = __frcp_rn(sc);  // correctly rounded 1/scale, once per block
     // bf16 blocks near the ends of the fp32 exponent range (1/scale denormal or infinite), and all-zero blocks,
@@ -183,7 +202,7 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
   if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = sc;
 
   int8_t* dst = out + b * osb + h * osh;
-  quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack);
+  quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack, gpu_div);
 }
 
 template <typename T, int D, int BLK>
@@ -292,7 +311,10 @@ quant_per_block_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const T* __
 
     float sc, rcp = 0.f;
     bool slow_div = (mode & LOWBIT_QMODE_FLAG_IEEE_DIV) != 0;
-    if (triton) {
+    const bool gpu_div = triton && (mode & LOWBIT_QMODE_FLAG_DIV_FULL) != 0;
+    if (gpu_div) {
+      sc = div_full(bmax, qmax);
+    } else if (triton) {
       sc = __fdiv_rn(bmax, qmax);
       rcp = __frcp_rn(sc);
       slow_div = slow_div || !(sc > 1e-30f && sc < 1e30f);
@@ -304,7 +326,7 @@ quant_per_block_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const T* __
     if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = sc;
 
     int8_t* dst = out + b * osb + h * osh;
-    quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack);
+    quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack, gpu_div);
   }
 }
 

@@ -77,6 +77,8 @@ def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpac
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
     if backend == "triton":
         mode = N.QMODE_TRITON
+    elif backend == "triton_gpu":  # Q1 with the JIT-compiled kernels' approximate division (div.full.f32)
+        mode = N.QMODE_TRITON | N.QMODE_FLAG_DIV_FULL
     elif backend == "cuda":
         mode = N.QMODE_CUDA
     else:
@@ -101,9 +103,9 @@ def per_block_int8_cuda(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_
     return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 8, 8, False, "cuda")
 
 
-def per_block_int4_unpack(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND"):
+def per_block_int4_unpack(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND", backend="triton"):
     """quant_per_block.py:251-318: both Q and K to INT4 codes in [-7,7], one code per int8."""
-    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 4, 4, False, "triton")
+    return _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, 4, 4, False, backend)
 
 
 def per_block_int4(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND"):

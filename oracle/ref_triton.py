@@ -7,7 +7,10 @@ from the reference itself (tools/make_golden.py) and so the numpy/torch
 restatements in oracle/ can be pinned against it.
 
 /root/reference does not exist on the GPU box: nothing under tests/ -m gpu,
-bench.py or __graft_entry__.smoke() imports this module.  Nothing in the product
+bench.py or __graft_entry__.smoke() imports this module.  tools/ref_on_b200.py (a measurement
+aid, not a gate) points LOWBIT_REFERENCE_ROOT at oracle/_ref/reference (staged, git-ignored,
+by oracle/stage_ref.sh) with TRITON_INTERPRET=0 to JIT the same unmodified kernels on the B200;
+outputs are allocated on the inputs' device for that purpose.  Nothing in the product
 package imports anything under oracle/.
 
 Reference host wrappers that are re-stated (not imported) here because they call
@@ -70,9 +73,9 @@ def quant_per_block(x, blk, sm_scale_arg, layout="HND", bits=8):
     qb = _load("src/triton/quant_per_block.py")
     kern = qb.quant_per_block_int8_kernel if bits == 8 else qb.quant_per_block_int4_unpack_kernel
     b, h, n, d = _dims(x, layout)
-    out = torch.empty(x.shape, dtype=torch.int8)
+    out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
     nblk = (n + blk - 1) // blk
-    scale = torch.empty((b, h, nblk), dtype=torch.float32)
+    scale = torch.empty((b, h, nblk), dtype=torch.float32, device=x.device)
     kern[(nblk, h, b)](x, out, scale, n, *_strides3(x, layout), *_strides3(out, layout),
                        scale.stride(0), scale.stride(1), sm_scale=sm_scale_arg, C=d, BLK=blk)
     return out, scale
@@ -102,8 +105,8 @@ def attn_forward(qi, ki, v, qs, ks, tensor_layout="HND", causal=False, output_dt
     b, hq, nq, d = _dims(qi, tensor_layout)
     _, hkv, nk, _ = _dims(ki, tensor_layout)
     output_dtype = output_dtype or v.dtype
-    o = torch.empty(qi.shape, dtype=output_dtype)
-    lse = torch.empty((b, hq, nq), dtype=torch.float32)
+    o = torch.empty(qi.shape, dtype=output_dtype, device=qi.device)
+    lse = torch.empty((b, hq, nq), dtype=torch.float32, device=qi.device)
     kern[((nq + 127) // 128, hq, b)](
         qi, ki, v, qs, ks, o, lse,
         *_strides3(qi, tensor_layout), *_strides3(ki, tensor_layout),

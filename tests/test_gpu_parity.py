@@ -580,3 +580,55 @@ def test_k_mean_exact_on_all_fp16_values(L, cuda_dev):
     km = L.k_mean(k.to(cuda_dev)).cpu()
     assert torch.equal(km, OQ.k_mean(k))
     assert torch.equal(km.view(-1)[:60], torch.zeros(60).half())
+
+
+# ------------------------------------------------------------------------------------------------ host streaming
+@pytest.mark.parametrize("layout,b,hq,hkv,n,d,causal,chunks", [
+    ("HND", 2, 4, 4, 700, 64, False, None),
+    ("HND", 1, 8, 2, 512, 128, True, 4),     # GQA: q heads follow their kv head
+    ("NHD", 3, 4, 4, 300, 64, False, 8),     # NHD: whole batch entries only
+    ("HND", 2, 6, 6, 256, 64, True, 1),      # one chunk == the plain call
+])
+def test_host_streaming_matches_device_call(L, cuda_dev, layout, b, hq, hkv, n, d, causal, chunks):
+    """lowbit_fa_host (pinned host tensors, chunked over (batch, head-group) on three streams) is bit-identical
+    to one operator call on device tensors."""
+    q = mk(b, hq, n, d, layout, torch.float16, 11).pin_memory()
+    k = mk(b, hkv, n, d, layout, torch.float16, 12, bias=2.0).pin_memory()
+    v = mk(b, hkv, n, d, layout, torch.float16, 13).pin_memory()
+    ref = L.lowbit_fa_qk_int8_pv_fp16_triton(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout,
+                                             is_causal=causal)
+    out = L.lowbit_fa_host(q, k, v, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev)
+    torch.cuda.synchronize()
+    assert out.device.type == "cpu" and out.shape == q.shape
+    assert torch.equal(out, ref.cpu())
+    # another operator through the same entry point
+    out4 = L.lowbit_fa_host(q, k, v, op=L.lowbit_fa_q_int8_k_int4_pv_fp16, tensor_layout=layout, is_causal=causal,
+                            device=cuda_dev)
+    ref4 = L.lowbit_fa_q_int8_k_int4_pv_fp16(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout,
+                                             is_causal=causal)
+    torch.cuda.synchronize()
+    assert torch.equal(out4, ref4.cpu())
+
+
+# ------------------------------------------------------------------------------------------------ triton_gpu rounding
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("bits", [8, 4])
+def test_triton_gpu_division_mode_is_within_one_step_of_ieee(L, cuda_dev, dtype, bits):
+    """backend="triton_gpu" replaces the two IEEE divisions of Q1 by PTX div.full.f32 (<= 2 ulp), which is what Triton
+    emits for the reference kernels on a GPU.  No CPU restatement of div.full exists (it starts from the hardware
+    reciprocal table), so the bit-exact check against the JIT-compiled reference lives in tools/ref_on_b200.py; here:
+    scales within 2 ulp of the IEEE ones, codes within one step, and only where the quotient sits on a rounding
+    boundary (a tiny fraction)."""
+    q = mk(2, 3, 1000, 64, "HND", dtype, 21).to(cuda_dev)
+    k = mk(2, 3, 1000, 64, "HND", dtype, 22, bias=1.5).to(cuda_dev)
+    km = L.k_mean(k)
+    fn = L.per_block_int8 if bits == 8 else L.per_block_int4_unpack
+    a = fn(q, k, km=km, backend="triton")
+    g = fn(q, k, km=km, backend="triton_gpu")
+    for i in (1, 3):
+        ulp = (a[i].view(torch.int32) - g[i].view(torch.int32)).abs().max().item()
+        assert ulp <= 2, f"scale differs by {ulp} ulp"
+    for i in (0, 2):
+        diff = (a[i].int() - g[i].int()).abs()
+        assert diff.max().item() <= 1
+        assert diff.float().mean().item() < 1e-3
