@@ -52,8 +52,19 @@ static int32_t* g_attn_debug = nullptr;
 
 constexpr int kBM = 128;      // Q rows per CTA (= TMEM lanes)
 constexpr int kScaleBlk = 64; // k_scale granularity of the reference quantizer (BLKK)
-constexpr int kSoftmaxThreads = 128;
-constexpr int kThreads = kSoftmaxThreads + 32;  // + one helper warp (TMA producer + tcgen05 issuer, one elected lane)
+// Softmax warpgroups per CTA.  SP = 1: thread t owns query row t (one TMEM lane, all BN score columns of a step).
+// SP = 2: threads t and t+128 own the two column halves of row t, which doubles the warps that hide each other's
+// TMEM / barrier / MUFU latencies where TMEM (not registers) caps the CTAs per SM (D = 128: 256 columns per CTA).
+// The two warps of a pair share one reference maximum per row: they agree on the (rare) rescale with a 64-thread
+// named barrier per step, keep partial row sums, and split the columns of O in the rescale and the epilogue.
+// Measured on B200 (profiles/r1_attn_d128_ncu_summary.json): the duplicated per-step overhead (+20 % instructions)
+// outweighs the extra warps -- D=128 1288 vs 1341 TOPS, D=64 635 vs 818 -- so SP = 1 is the default and VAR bit 4
+// selects SP = 2 (development A/B; parity-tested the same way).
+template <int D, int VAR> struct AttnSP {
+  static constexpr int value = (VAR & 16) ? 2 : 1;
+  static constexpr int kSoftmaxThreads = 128 * value;
+  static constexpr int kThreads = kSoftmaxThreads + 32;  // + one helper warp (TMA producer + tcgen05 issuer, one elected lane)
+};
 
 enum { KM_I8 = 0, KM_K4 = 1 };
 enum { PV_F16 = 0, PV_E4M3 = 1 };
@@ -97,8 +108,8 @@ __device__ __forceinline__ float score_to_f32(uint32_t v) {
 // MASKED: columns > lim contribute 0 (causal diagonal band / masked tail keys).
 // VAR bit 2: one pair in every four goes through the FMA-pipe polynomial instead of MUFU.EX2.
 template <int BN, bool MASKED, int VAR>
-__device__ __forceinline__ float softmax_block_f16(const uint32_t (&s)[BN], float sc, float nm, int lim,
-                                                   uint32_t (&pk)[BN / 2]) {
+__device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ s, float sc, float nm, int lim,
+                                                   uint32_t* __restrict__ pk) {
   if constexpr ((VAR & 2) == 0) {
     // packed fp32x2 arithmetic (FFMA2 / FADD2): one instruction scales, or accumulates, two scores
     const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
@@ -148,8 +159,8 @@ __device__ __forceinline__ float softmax_block_f16(const uint32_t (&s)[BN], floa
 // conversion and short f16x2 partial sums.  Key c of an aligned 16-group sits at the K index the reference's V layout
 // expects (fused.cu:290-292): word w of a group = keys {2w, 2w+1, 8+2w, 9+2w}.
 template <int BN, bool MASKED, int VAR>
-__device__ __forceinline__ float softmax_block_e4m3(const uint32_t (&s)[BN], float sc, float nm, int lim,
-                                                    uint32_t (&pk)[BN / 4]) {
+__device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__ s, float sc, float nm, int lim,
+                                                    uint32_t* __restrict__ pk) {
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
   uint32_t hacc[BN / 16];
 #pragma unroll
@@ -182,32 +193,34 @@ __device__ __forceinline__ float softmax_block_e4m3(const uint32_t (&s)[BN], flo
 }
 
 template <int BN, bool MASKED>
-__device__ __forceinline__ int row_max(const uint32_t (&s)[BN], int lim) {
+__device__ __forceinline__ int row_max(const uint32_t* __restrict__ s, int lim) {
   int m4[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};  // 4 independent chains (latency, not throughput, bound)
 #pragma unroll
   for (int c = 0; c < BN; ++c) m4[c & 3] = max(m4[c & 3], (!MASKED || c <= lim) ? (int)s[c] : INT_MIN);
   return max(max(m4[0], m4[1]), max(m4[2], m4[3]));
 }
 template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
-  if constexpr (N == 32) ptx::tmem_ld_x32(taddr, r);
+  if constexpr (N == 16) ptx::tmem_ld_x16(taddr, r);
+  else if constexpr (N == 32) ptx::tmem_ld_x32(taddr, r);
   else { ptx::tmem_ld_x32(taddr, r); ptx::tmem_ld_x32(taddr + 32, r + 32); }
 }
 template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
-  if constexpr (N == 8) ptx::tmem_st_x8(taddr, r);
+  if constexpr (N == 4) ptx::tmem_st_x4(taddr, r);
+  else if constexpr (N == 8) ptx::tmem_st_x8(taddr, r);
   else if constexpr (N == 16) ptx::tmem_st_x16(taddr, r);
   else ptx::tmem_st_x32(taddr, r);
 }
 
 // INT4 K: expand one packed staging tile (BN rows x D/2 bytes, linear) into the int8 operand stage (BN rows x D
 // bytes, K-major, 64B / 128B hardware swizzle).  Every 16-byte packed chunk (32 codes) becomes two 16-byte chunks.
-template <int D, int BN>
+template <int D, int BN, int NT>
 __device__ __forceinline__ void unpack_k4_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int tid) {
   constexpr int kChunks = BN * D / 32;  // packed 16-byte chunks in the tile
   constexpr int kCPR = D / 32;          // packed chunks per row
   constexpr uint32_t kSwzMask = (D == 64) ? 3u : 7u;
   constexpr uint32_t kM = 0xF0F0F0F0u;
 #pragma unroll
-  for (int q = tid; q < kChunks; q += kSoftmaxThreads) {
+  for (int q = tid; q < kChunks; q += NT) {
     const uint4 w = *reinterpret_cast<const uint4*>(src + q * 16);
     const uint32_t off0 = (uint32_t)(q / kCPR) * D + (uint32_t)(q % kCPR) * 32, off1 = off0 + 16;
     uint4 a, b;
@@ -219,10 +232,10 @@ __device__ __forceinline__ void unpack_k4_tile(const uint8_t* __restrict__ src, 
 }
 // the matching permutation of the Q tile: [d0..d7] -> [d0 d2 d4 d6 d1 d3 d5 d7] inside every 8-byte group
 // (16-byte chunks move as units under the hardware swizzle, so the tile can be walked linearly)
-template <int D>
+template <int D, int NT>
 __device__ __forceinline__ void permute_q_tile(uint8_t* sQ, int tid) {
 #pragma unroll
-  for (int q = tid; q < kBM * D / 16; q += kSoftmaxThreads) {
+  for (int q = tid; q < kBM * D / 16; q += NT) {
     uint4 w = *reinterpret_cast<uint4*>(sQ + q * 16), r;
     r.x = __byte_perm(w.x, w.y, 0x6420); r.y = __byte_perm(w.x, w.y, 0x7531);
     r.z = __byte_perm(w.z, w.w, 0x6420); r.w = __byte_perm(w.z, w.w, 0x7531);
@@ -238,7 +251,7 @@ __device__ __forceinline__ void permute_q_tile(uint8_t* sQ, int tid) {
 // P.V of the previous one run on the tensor pipe while the softmax warps work on block j; K/V stages are refilled
 // by the same thread as soon as the MMAs that read them have committed.
 template <int D, int KM, int PV, int VAR, bool DBG>
-__global__ void __launch_bounds__(kThreads, AttnCfg<D>::CTAS)
+__global__ void __launch_bounds__((AttnSP<D, VAR>::kThreads), AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using C = AttnCfg<D>;
@@ -248,6 +261,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int KS = SM::kKStages;                   // int8 operand stages (INT4 mode: 2, indexed like the S buffers)
   constexpr int KPS = (KM == KM_K4) ? SM::kKpStages : C::KS;  // TMA-filled K stages
   constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;     // TMEM columns of one P tile
+  constexpr int SP = AttnSP<D, VAR>::value;                   // softmax warpgroups (threads per query row)
+  constexpr int kSoftmaxThreads = AttnSP<D, VAR>::kSoftmaxThreads;
+  constexpr int HW = 4 * SP;                                  // index of the helper warp
+  constexpr int BNH = BN / SP;                                // score columns per softmax thread and step
+  constexpr int PCH = PCOLS / SP;                             // P columns per softmax thread and step
+  constexpr int DH = D / SP;                                  // O columns per softmax thread (rescale, epilogue)
+  __shared__ int s_flag[4][2];                                // SP = 2: "rescale wanted at step j" token per warp pair
+  __shared__ float s_mx[2][kBM], s_l[2][kBM];                 // SP = 2: row-max / row-sum exchange between the halves
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -282,7 +303,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (causal) nblk = max(0, min(nblk, (dq + kBM + BN - 1) / BN));
   if (nblk == 0) {
     // ring step whose K/V shard lies wholly in this tile's future: the running state is unchanged
-    if (p.oacc_io != nullptr && p.first && tid < kSoftmaxThreads) {
+    if (p.oacc_io != nullptr && p.first && tid < kBM) {
       const int row = qt * kBM + tid;
       if (row < p.Nq) {
         const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
@@ -296,7 +317,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     return;
   }
 
-  if (warp == 4) {
+  if (warp == HW) {
     ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
     ptx::tmem_relinquish();
   }
@@ -322,7 +343,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tO = tmem_base + 2 * BN;  // fp32 output accumulator, D columns
 
-  if (warp == 4) {
+  if (warp == HW) {
     // ================================ helper: TMA producer + tcgen05 issuer ================================
     if (ptx::elect_one()) {
       constexpr uint32_t kSwzQK = (D == 64) ? ptx::kSwz64 : ptx::kSwz128;
@@ -418,24 +439,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ================================ softmax warps ================================
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const int row = qt * kBM + tid;  // query row owned by this thread
+    const int half = (SP == 2) ? (tid >> 7) : 0;  // which column half of the score tile this thread owns
+    const int r = tid & (kBM - 1);                // query row inside the tile = TMEM lane
+    const int wq = warp & 3;                      // TMEM lane quadrant (and warp-pair index for SP = 2)
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const int row = qt * kBM + r;  // query row owned by this thread
     float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
     if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
     const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
     const bool mask_tail = !compat && (p.Nk % BN != 0);
     const int last_kblk = (p.Nk + BN - 1) / BN - 1;
-    const uint32_t tS0 = tmem_base + lane_off, tS1 = tS0 + BN, tOl = tO + lane_off;
+    const uint32_t tS0 = tmem_base + lane_off + half * BNH, tS1 = tS0 + BN;  // my score columns in S buffer 0 / 1
+    const uint32_t tP0 = tmem_base + lane_off + half * PCH, tP1 = tP0 + BN;  // my P columns (P aliases S)
+    const uint32_t tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
 
     if constexpr (KM == KM_K4) {
       ptx::mbar_wait(bar_q, 0, 33);
-      permute_q_tile<D>(sQ, tid);
+      permute_q_tile<D, kSoftmaxThreads>(sQ, tid);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (j < nblk) {
           ptx::mbar_wait(kfull + j, 0, 34);
-          unpack_k4_tile<D, BN>(sKp + j * SM::kKp, sK + j * SM::kK, tid);
+          unpack_k4_tile<D, BN, kSoftmaxThreads>(sKp + j * SM::kKp, sK + j * SM::kK, tid);
           ptx::mbar_arrive(kfree + j);
         }
       }
@@ -444,26 +470,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 
     // one key block: wait for S, row max, (rare) rescale of O, P = exp2(S*sc - m) -> TMEM, signal the issuer
-    auto step = [&](auto masked_tag, const uint32_t tSb, uint64_t* bs, uint64_t* pr, const uint32_t ph, const int j,
-                    const float sc, const int lim) {
+    auto step = [&](auto masked_tag, const uint32_t tSb, const uint32_t tPb, uint64_t* bs, uint64_t* pr,
+                    const uint32_t ph, const int j, const float sc, const int lim_tile) {
       constexpr bool MASKED = decltype(masked_tag)::value;
+      const int lim = lim_tile - half * BNH;  // live columns of my half: [0, lim]
       ptx::mbar_wait(bs, ph, 30);
       ptx::tc_fence_after();
-      uint32_t s[BN];
-      tmem_ld_n<BN>(tSb, s);
+      uint32_t s[BNH];
+      tmem_ld_n<BNH>(tSb, s);
       ptx::tmem_wait_ld();
       if constexpr (DBG) {
         if (p.dbg != nullptr && j * BN < 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-          for (int c = 0; c < BN; ++c) p.dbg[tid * 64 + j * BN + c] = (int)s[c];
+          for (int c = 0; c < BNH; ++c) p.dbg[r * 64 + j * BN + half * BNH + c] = (int)s[c];
         }
       }
-      const int imax = row_max<BN, MASKED>(s, lim);
+      const int imax = row_max<BNH, MASKED>(s, lim);
       const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
       // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision,
-      // tcgen05.ld/st are warp collectives)
-      if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
-        const float m_new = fmaxf(m_ref, mblk);
+      // tcgen05.ld/st are warp collectives; pair-uniform for SP = 2)
+      bool want = __any_sync(0xffffffffu, mblk > m_ref + PC::THR);
+      if constexpr (SP == 2) {
+        // The pair barrier also orders the P store below after the partner's score load above: P of the upper half
+        // lands on TMEM columns that hold the lower half's scores.
+        volatile int* flag = &s_flag[wq][j & 1];
+        if (want && (tid & 31) == 0) *flag = j + 1;  // token = step index: never needs clearing
+        ptx::bar_sync(1 + wq, 64);
+        want = (*flag == j + 1);
+      }
+      if (want) {
+        float mb = mblk;
+        if constexpr (SP == 2) {
+          s_mx[half][r] = mblk;
+          ptx::bar_sync(1 + wq, 64);
+          mb = fmaxf(mblk, s_mx[half ^ 1][r]);
+        }
+        const float m_new = fmaxf(m_ref, mb);
         const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
         l *= alpha;
         m_ref = m_new;
@@ -473,7 +515,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::mbar_wait(bar_o, (j - 1) & 1, 31);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < D; c += 16) {
+          for (int cc = 0; cc < DH; cc += 16) {
+            const int c = half * DH + cc;
             uint32_t o[16];
             ptx::tmem_ld_x16(tOl + c, o);
             ptx::tmem_wait_ld();
@@ -483,17 +526,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      uint32_t pk[PCOLS];
+      uint32_t pk[PCH];
       const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, VAR>(s, sc, nm, lim, pk);
-      else l += softmax_block_e4m3<BN, MASKED, VAR>(s, sc, nm, lim, pk);
-      tmem_st_n<PCOLS>(tSb, pk);  // P aliases the first columns of its S buffer
+      if constexpr (PV == PV_F16) l += softmax_block_f16<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
+      else l += softmax_block_e4m3<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
+      tmem_st_n<PCH>(tPb, pk);  // P aliases the first columns of its S buffer
       if constexpr (KM == KM_K4) {
         // expand K_{j+2} into the operand stage QK_j just released (S_j ready => QK_j complete)
         if (j + 2 < nblk) {
           const int kps = (j + 2) % KPS;
           ptx::mbar_wait(kfull + kps, ((j + 2) / KPS) & 1, 35);
-          unpack_k4_tile<D, BN>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid);
+          unpack_k4_tile<D, BN, kSoftmaxThreads>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid);
           ptx::mbar_arrive(kfree + kps);
           ptx::fence_proxy_async_smem();
         }
@@ -503,21 +546,112 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_arrive(pr);
     };
 
-    // blocks [0, n_full) need no mask: unrolled by two so buffer / barrier addresses are loop constants
-    int n_full = nblk;
+    // Development variant (VAR bit 5, D = 128 only; measured SLOWER on B200: 1125 vs 1338 TOPS at B4 H32 N4096, the
+    // second 64-register score array spills at the 168-register cap of two CTAs/SM -- kept for the next tuning round):
+    // the score row of block j+1 is prefetched from TMEM into a second register array while the exponentials of
+    // block j run: the S-ready barrier latency, the tcgen05.ld latency and
+    // (through the scheduler) the integer row max of the next block hide under the MUFU phase instead of adding to it.
+    // The probe of the S barrier is non-blocking and repeated between the four quarters of the block, so a warp never
+    // waits for S_{j+1} with its own exponentials still to do.
+    constexpr bool PF = (D == 128) && (SP == 1) && !DBG && ((VAR & 32) != 0);
+    constexpr int kPerScale = kScaleBlk / BN;  // key blocks per k_scale entry (2 for BN=32, 1 for BN=64)
+    int n_full = nblk;  // blocks [0, n_full) need no mask
     if (causal) n_full = max(0, min(n_full, (dq + 1) / BN));
     if (mask_tail) n_full = min(n_full, last_kblk);
+    if constexpr (PF) {
+      auto issue_ld = [&](uint32_t* dst, const int jn, const bool blocking) -> bool {
+        uint64_t* bs = bar_s + (jn & 1);
+        const uint32_t phn = (jn >> 1) & 1;
+        if (blocking) ptx::mbar_wait(bs, phn, 36);
+        else if (!__all_sync(0xffffffffu, ptx::mbar_test(bs, phn))) return false;
+        ptx::tc_fence_after();
+        tmem_ld_n<BNH>((jn & 1) ? tS1 : tS0, dst);
+        return true;
+      };
+      auto pstep = [&](auto masked_tag, uint32_t* s, uint32_t* sn, const int j, const float sc, const int lim) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        constexpr int QN = BNH / 4, QP = PCH / 4;
+        ptx::tmem_wait_ld();  // s (issued by the previous step, or by the prologue) has landed
+#pragma unroll
+        for (int c = 0; c < BNH; c += 16)
+          asm volatile("" : "+r"(s[c]), "+r"(s[c + 1]), "+r"(s[c + 2]), "+r"(s[c + 3]), "+r"(s[c + 4]), "+r"(s[c + 5]),
+                            "+r"(s[c + 6]), "+r"(s[c + 7]), "+r"(s[c + 8]), "+r"(s[c + 9]), "+r"(s[c + 10]),
+                            "+r"(s[c + 11]), "+r"(s[c + 12]), "+r"(s[c + 13]), "+r"(s[c + 14]), "+r"(s[c + 15]));
+        const int imax = row_max<BNH, MASKED>(s, lim);
+        const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+        if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
+          const float m_new = fmaxf(m_ref, mblk);
+          const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);
+          l *= alpha;
+          m_ref = m_new;
+          if (j > 0) {
+            ptx::mbar_wait(bar_o, (j - 1) & 1, 31);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D; c += 16) {
+              uint32_t o[16];
+              ptx::tmem_ld_x16(tOl + c, o);
+              ptx::tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              ptx::tmem_st_x16(tOl + c, o);
+            }
+          }
+        }
+        uint32_t pk[PCH];
+        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;
+        const bool more = j + 1 < nblk;
+        bool have = !more;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          if (!have) have = issue_ld(sn, j + 1, false);
+          if constexpr (PV == PV_F16) l += softmax_block_f16<QN, MASKED, VAR>(s + qd * QN, sc, nm, lim - qd * QN, pk + qd * QP);
+          else l += softmax_block_e4m3<QN, MASKED, VAR>(s + qd * QN, sc, nm, lim - qd * QN, pk + qd * QP);
+        }
+        tmem_st_n<PCH>((j & 1) ? tP1 : tP0, pk);
+        if constexpr (KM == KM_K4) {
+          if (j + 2 < nblk) {
+            const int kps = (j + 2) % KPS;
+            ptx::mbar_wait(kfull + kps, ((j + 2) / KPS) & 1, 35);
+            unpack_k4_tile<D, BN, kSoftmaxThreads>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid);
+            ptx::mbar_arrive(kfree + kps);
+            ptx::fence_proxy_async_smem();
+          }
+        }
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_ready + (j & 1));
+        if (!have) issue_ld(sn, j + 1, true);
+      };
+      uint32_t sA[BNH], sB[BNH];
+      issue_ld(sA, 0, true);
+      int j = 0;
+      for (; j + 1 < n_full; j += 2) {
+        const float sc0 = qs * ks_ptr[j / kPerScale], sc1 = qs * ks_ptr[(j + 1) / kPerScale];
+        pstep(std::false_type{}, sA, sB, j, sc0, 0);
+        pstep(std::false_type{}, sB, sA, j + 1, sc1, 0);
+      }
+      for (; j < nblk; ++j) {
+        const float sc = qs * ks_ptr[min(j / kPerScale, p.nkb - 1)];
+        const int c0 = j * BN;
+        int lim = BN;  // columns [0, lim] are live
+        if (causal) lim = min(lim, p.delta + row - c0);
+        if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
+        if (j & 1) pstep(std::true_type{}, sB, sA, j, sc, lim);
+        else pstep(std::true_type{}, sA, sB, j, sc, lim);
+      }
+    } else {
+    // unrolled by two so buffer / barrier addresses are loop constants
     int j = 0;
     uint32_t ph = 0;
-    constexpr int kPerScale = kScaleBlk / BN;  // key blocks per k_scale entry (2 for BN=32, 1 for BN=64)
     float ks_cur = ks_ptr[0];
     for (; j + 1 < n_full; j += 2, ph ^= 1) {
       const float sc0 = qs * ks_cur;
       float sc1 = sc0;
       if (kPerScale == 1) sc1 = qs * ks_ptr[j + 1];
       const float ks_nxt = ks_ptr[min((j + 2) / kPerScale, p.nkb - 1)];  // prefetch for the next pair
-      step(std::false_type{}, tS0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
-      step(std::false_type{}, tS1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
+      step(std::false_type{}, tS0, tP0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
+      step(std::false_type{}, tS1, tP1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
       ks_cur = ks_nxt;
     }
     // remaining blocks (odd leftover, causal diagonal band, masked tail): generic path
@@ -527,7 +661,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int lim = BN;  // columns [0, lim] are live
       if (causal) lim = min(lim, p.delta + row - c0);
       if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
-      step(std::true_type{}, (j & 1) ? tS1 : tS0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc, lim);
+      step(std::true_type{}, (j & 1) ? tS1 : tS0, (j & 1) ? tP1 : tP0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc,
+           lim);
+    }
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------
@@ -536,12 +672,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool live_row = row < p.Nq;
     const float* vsc = (PV == PV_E4M3) ? p.v_scale + ((int64_t)b * p.Hkv + hkv) * D : nullptr;
     const float* vmn = (PV == PV_E4M3 && p.v_mean) ? p.v_mean + ((int64_t)b * p.Hkv + hkv) * D : nullptr;
+    const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
+    float m_prev = -INFINITY, l_prev = 0.f;  // ring step: running state, read before the pair barrier below
+    if (p.oacc_io != nullptr && !p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }
+    if constexpr (SP == 2) {  // row sum = the two halves' partial sums
+      s_l[half][r] = l;
+      ptx::bar_sync(1 + wq, 64);
+      l += s_l[half ^ 1][r];
+    }
+    const int cbeg = half * DH;  // my share of the D output columns
     if (p.oacc_io == nullptr) {
       // O / l (* v_scale + v_mean) -> out dtype, lse2 = log2(l) + m - OFF
       const float inv_l = 1.0f / l;
       uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + ((int64_t)b * p.osb + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
 #pragma unroll
-      for (int c = 0; c < D; c += 32) {
+      for (int cc = 0; cc < DH; cc += 32) {
+        const int c = cbeg + cc;
         uint32_t o[32];
         ptx::tmem_ld_x32(tOl + c, o);  // warp collective: every lane executes it
         ptx::tmem_wait_ld();
@@ -562,12 +708,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
       }
-      if (live_row && p.lse) p.lse[((int64_t)b * p.Hq + hq) * p.Nq + row] = ptx::lg2(l) + m_ref - PC::OFF;
+      if (live_row && p.lse && half == 0) p.lse[idx] = ptx::lg2(l) + m_ref - PC::OFF;
     } else {
       // ring step: merge (m_ref, l, O) of this K/V shard into the running fp32 state, in true (dequantized) units
-      const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
-      float m_prev = -INFINITY, l_prev = 0.f;
-      if (!p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }
       const float m_cur = (l > 0.f) ? m_ref : -INFINITY;  // a row that saw only masked keys contributes nothing
       const float m_new = fmaxf(m_prev, m_cur);
       const float wa = (m_prev == -INFINITY) ? 0.f : ptx::ex2(m_prev - m_new);
@@ -576,7 +719,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float l_cur = l * wb;
       float* od = p.oacc_io + idx * D;
 #pragma unroll
-      for (int c = 0; c < D; c += 16) {
+      for (int cc = 0; cc < DH; cc += 16) {
+        const int c = cbeg + cc;
         uint32_t o[16];
         ptx::tmem_ld_x16(tOl + c, o);
         ptx::tmem_wait_ld();
@@ -601,7 +745,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      if (live_row) {
+      if (live_row && half == 0) {  // the partner read m_io / l_io before the pair barrier above
         p.m_io[idx] = m_new;
         p.l_io[idx] = l_prev * wa + l_cur;
       }
@@ -609,7 +753,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == HW) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // o = O_acc / l, lse2 = log2(l) + m  (end of a ring / sequence-parallel pass)
@@ -688,7 +832,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, kThreads, SM::kBytes, st>>>(tq, tk, tv, p);
+  kern<<<grid, AttnSP<D, VAR>::kThreads, SM::kBytes, st>>>(tq, tk, tv, p);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -704,8 +848,15 @@ static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
       case 1: return launch_attn<D, KM_I8, PV_F16, 1>(tq, tk, tv, p, B, st);
       case 4: return launch_attn<D, KM_I8, PV_F16, 4>(tq, tk, tv, p, B, st);
       case 12: return launch_attn<D, KM_I8, PV_F16, 12>(tq, tk, tv, p, B, st);
+      case 16: return launch_attn<D, KM_I8, PV_F16, 16>(tq, tk, tv, p, B, st);
+      case 32: return launch_attn<D, KM_I8, PV_F16, 32>(tq, tk, tv, p, B, st);
       default: return launch_attn<D, KM_I8, PV_F16, 0>(tq, tk, tv, p, B, st);
     }
+  }
+  if (variant == 16) {  // column-split softmax (SP = 2), every mode: parity-tested through LOWBIT_ATTN_VARIANT=16
+    if (km == KM_K4 && pv == PV_F16) return launch_attn<D, KM_K4, PV_F16, 16>(tq, tk, tv, p, B, st);
+    if (km == KM_I8 && pv == PV_E4M3) return launch_attn<D, KM_I8, PV_E4M3, 16>(tq, tk, tv, p, B, st);
+    return launch_attn<D, KM_K4, PV_E4M3, 16>(tq, tk, tv, p, B, st);
   }
   if (km == KM_K4 && pv == PV_F16) return launch_attn<D, KM_K4, PV_F16, 0>(tq, tk, tv, p, B, st);
   if (km == KM_I8 && pv == PV_E4M3) return launch_attn<D, KM_I8, PV_E4M3, 0>(tq, tk, tv, p, B, st);

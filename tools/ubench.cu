@@ -88,6 +88,70 @@ __global__ void __launch_bounds__(128) mix(float* out, long long* cyc, int iters
 }
 
 
+
+// Row-sum / int->float alternatives for the same block (development A/B):
+//  SUM: 0 none, 1 FADD2 x2 accumulators (current), 2 FADD2 x4 accumulators, 3 scalar FADD x4, 4 HADD2 on the packed words (fp16 accumulate),
+//       5 HADD2 pairs then HADD2.F32-style widening every 4 words
+//  CVT: 0 I2FP (current), 1 integer magic add folded into the FFMA constant (IADD + FFMA2, no conversion pipe)
+template <int SUM, int CVT>
+__global__ void __launch_bounds__(128) mix2(float* out, long long* cyc, int iters, float sc, int* in) {
+  int s[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s[i] = in[i] + threadIdx.x;
+  float l = 0.f;
+  uint32_t acc = 0;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+    uint32_t h0 = 0, h1 = 0;
+    int mx = -2147483647;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) mx = max(mx, s[c]);
+    float nm = -(float)mx * sc * 1e-9f;
+    if (CVT == 1) nm = nm - 12582912.0f * sc;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      float v0, v1, v2, v3;
+      if (CVT == 0) { v0 = __int2float_rn(s[c]); v1 = __int2float_rn(s[c + 1]); v2 = __int2float_rn(s[c + 2]); v3 = __int2float_rn(s[c + 3]); }
+      else { v0 = __int_as_float(s[c] + 0x4B400000); v1 = __int_as_float(s[c + 1] + 0x4B400000);
+             v2 = __int_as_float(s[c + 2] + 0x4B400000); v3 = __int_as_float(s[c + 3] + 0x4B400000); }
+      float2 x0 = __ffma2_rn(make_float2(v0, v1), make_float2(sc, sc), make_float2(nm, nm));
+      float2 x1 = __ffma2_rn(make_float2(v2, v3), make_float2(sc, sc), make_float2(nm, nm));
+      float2 p0, p1;
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0.x) : "f"(x0.x));
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0.y) : "f"(x0.y));
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1.x) : "f"(x1.x));
+      asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1.y) : "f"(x1.y));
+      if (SUM == 1) { a0 = __fadd2_rn(a0, p0); a1 = __fadd2_rn(a1, p1); }
+      if (SUM == 2) { if (c % 8 == 0) { a0 = __fadd2_rn(a0, p0); a1 = __fadd2_rn(a1, p1); } else { a2 = __fadd2_rn(a2, p0); a3 = __fadd2_rn(a3, p1); } }
+      if (SUM == 3) { f0 += p0.x; f1 += p0.y; f2 += p1.x; f3 += p1.y; }
+      uint32_t w0, w1;
+      asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w0) : "f"(p0.y), "f"(p0.x));
+      asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w1) : "f"(p1.y), "f"(p1.x));
+      if (SUM == 4 || SUM == 5) {
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h0) : "r"(w0));
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h1) : "r"(w1));
+        if (SUM == 5 && (c % 16 == 12)) {  // widen every 8 words
+          uint32_t hs; asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(hs) : "r"(h0), "r"(h1));
+          float lo, hi;
+          asm volatile("{.reg .b16 a, b; mov.b32 {a, b}, %2; cvt.f32.f16 %0, a; cvt.f32.f16 %1, b;}" : "=f"(lo), "=f"(hi) : "r"(hs));
+          f0 += lo; f1 += hi; h0 = 0; h1 = 0;
+        }
+      }
+      acc ^= w0 ^ w1;
+    }
+    if (SUM == 4) { uint32_t hs; asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(hs) : "r"(h0), "r"(h1));
+      float lo, hi; asm volatile("{.reg .b16 a, b; mov.b32 {a, b}, %2; cvt.f32.f16 %0, a; cvt.f32.f16 %1, b;}" : "=f"(lo), "=f"(hi) : "r"(hs)); f0 += lo + hi; }
+    l += a0.x + a0.y + a1.x + a1.y + a2.x + a2.y + a3.x + a3.y + f0 + f1 + f2 + f3;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] += (int)(acc & 1);
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = l + __uint_as_float(acc);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 // phase-structured variant: (A) convert+scale all 32 in place, (B) 32 MUFU back to back, (C) pack + row sum.
 // MODE bit0: integer row max first; bit1: fp32 row sum; bit2: no max but a (never taken) check of the block sum.
 template <int MODE>
@@ -195,7 +259,7 @@ int main() {
                          "add.f16x2", "ex2.f16", "lop3", "max.f32", "add.f32"};
   for (int bps : {8, 16}) {
 #define R(K, OPI) run(names[K], [](int g, float* o, long long* c, int it) { k<K><<<g, 128>>>(o, c, it, 0.5f); }, bps, OPI, 20000);
-    R(0, 32) R(3, 32) R(4, 32) R(5, 32) R(6, 16) R(7, 32) R(11, 32) R(15, 32)
+    R(0, 32) R(3, 32) R(4, 32) R(5, 32) R(6, 16) R(7, 32) R(8, 32) R(11, 32) R(13, 32) R(15, 32)
   }
   {
     const char* cn[] = {"ex2 + I2FP", "ex2 + F2FP", "ex2 + FFMA", "ex2 + IMNMX", "ex2 + FADD", "ex2 + I2FP + FFMA", "ex2 + IMAD"};
@@ -210,6 +274,16 @@ int main() {
     run("phased: +fadd2 +int max", [=](int g, float* o, long long* c, int it) { mixp<3><<<g, 128>>>(o, c, it, 1e-4f, in); }, bps, 32, 2000);
     run("phased: +fadd2", [=](int g, float* o, long long* c, int it) { mixp<2><<<g, 128>>>(o, c, it, 1e-4f, in); }, bps, 32, 2000);
     run("phased: +fadd2 +sumcheck", [=](int g, float* o, long long* c, int it) { mixp<6><<<g, 128>>>(o, c, it, 1e-4f, in); }, bps, 32, 2000);
+#define M2(S, C, NAME) run(NAME, [=](int g, float* o, long long* c, int it) { mix2<S, C><<<g, 128>>>(o, c, it, 1e-4f, in); }, bps, 32, 2000);
+    M2(0, 0, "mix2 max, no sum")
+    M2(1, 0, "mix2 FADD2 x2acc (current)")
+    M2(2, 0, "mix2 FADD2 x4acc")
+    M2(3, 0, "mix2 scalar FADD x4acc")
+    M2(4, 0, "mix2 HADD2 fp16 accumulate")
+    M2(5, 0, "mix2 HADD2 widen every 8 words")
+    M2(0, 1, "mix2 no sum, magic-add cvt")
+    M2(1, 1, "mix2 FADD2 x2acc, magic-add cvt")
+    M2(4, 1, "mix2 HADD2, magic-add cvt")
     run("phased: no sum", [=](int g, float* o, long long* c, int it) { mixp<0><<<g, 128>>>(o, c, it, 1e-4f, in); }, bps, 32, 2000);
   }
   return 0;
