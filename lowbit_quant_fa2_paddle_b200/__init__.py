@@ -19,6 +19,7 @@ from .core import (  # noqa: F401
 )
 from .quant import (  # noqa: F401
     k_mean,
+    prep_qk,
     per_block_int8,
     per_block_int8_cuda,
     per_block_int4_unpack,

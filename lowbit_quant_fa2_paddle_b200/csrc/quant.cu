@@ -17,6 +17,7 @@
 
 #include <stdarg.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace lowbit {
 
@@ -95,13 +96,15 @@ __device__ __forceinline__ void store_codes8(int8_t* dst_row, int c8, const int 
     *reinterpret_cast<uint16_t*>(dst_row + c8 / 4) = (uint16_t)w;
   }
 }
-template <int NPASS>
+// passes [PB, PB + PC) of x hold the rows of the block that starts at row0 (PC = -1: all passes)
+template <int NPASS, int PB = 0, int PC = -1>
 __device__ __forceinline__ void quantize_rows(const float (&x)[NPASS][8], int8_t* dst, int64_t osn, int row0, int rpp,
                                               int r0, int c8, int blk, int N, float sc, float rcp, bool triton,
                                               bool slow_div, int bits, int pack, bool gpu_div = false) {
+  constexpr int PE = (PC < 0) ? NPASS : PB + PC;
 #pragma unroll
-  for (int p = 0; p < NPASS; ++p) {
-    const int rl = p * rpp + r0;
+  for (int p = PB; p < PE; ++p) {
+    const int rl = (p - PB) * rpp + r0;
     const int row = row0 + rl;
     if (!(rl < blk && row < N)) continue;
     int c[8];
@@ -122,25 +125,60 @@ __device__ __forceinline__ void quantize_rows(const float (&x)[NPASS][8], int8_t
   }
 }
 
-template <typename T, int D, int BLK>
-__global__ void __launch_bounds__(kQuantThreads)
-quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_t* __restrict__ out,
-                       float* __restrict__ scale, int N, int nblk,
-                       int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
-                       float sm, int bits, int pack, int mode, int H) {
+// One quantization block (jb, h, b) by the whole CTA (kQuantThreads threads).  Shared by the per-tensor kernel below
+// and the fused Q+K preparation kernel; ends with every thread past its last read of the shared scratch only after a
+// __syncthreads of the NEXT call (callers that loop put a __syncthreads between blocks).
+// scale / reciprocal of one block from its abs-max (block-uniform)
+struct BlockScale { float sc, rcp; bool slow_div, gpu_div; };
+__device__ __forceinline__ BlockScale block_scale(float bmax, int bits, int mode) {
+  const float qmax = bits == 8 ? 127.f : (bits == 4 ? 7.f : 1.f);
+  BlockScale r;
+  r.rcp = 0.f;
+  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
+  r.slow_div = (mode & LOWBIT_QMODE_FLAG_IEEE_DIV) != 0;
+  r.gpu_div = triton && (mode & LOWBIT_QMODE_FLAG_DIV_FULL) != 0;
+  if (r.gpu_div) {
+    r.sc = div_full(bmax, qmax);
+  } else if (triton) {
+    r.sc = __fdiv_rn(bmax, qmax);
+    r.rcp = __frcp_rn(r.sc);  // correctly rounded 1/scale, once per block
+    // bf16 blocks near the ends of the fp32 exponent range (1/scale denormal or infinite), and all-zero blocks,
+    // take the IEEE division: a block-uniform branch
+    r.slow_div = r.slow_div || !(r.sc > 1e-30f && r.sc < 1e30f);
+  } else {
+    bmax = fmaxf(bmax, 1e-7f);
+    r.sc = __fdiv_rn(bmax, qmax);
+    r.rcp = __fdiv_rn(qmax, bmax);
+  }
+  return r;
+}
+
+// NSUB consecutive quantization blocks of BLK rows, starting at block jb0 of (h, b), by the whole CTA (kQuantThreads
+// threads): all rows are loaded first (NSUB * BLK * D * 2 bytes in flight per CTA), then each block gets its own
+// abs-max, scale and codes.  Shared by the per-tensor kernel below and the fused Q+K preparation kernel; callers
+// that loop put a __syncthreads between calls (s_w: NSUB * kQuantThreads/32 floats of shared scratch).
+template <typename T, int D, int BLK, int NSUB = 1>
+__device__ __forceinline__ void quant_block_body(const T* __restrict__ in, const T* __restrict__ km,
+                                                 int8_t* __restrict__ out, float* __restrict__ scale, int N, int nblk,
+                                                 int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh,
+                                                 int64_t osn, float sm, int bits, int pack, int mode, int H,
+                                                 int jb0, int h, int b, float* s_w) {
   constexpr int TPR = D / 8;                 // threads per row
   constexpr int RPP = kQuantThreads / TPR;   // rows per pass
-  constexpr int NP = (BLK + RPP - 1) / RPP;  // passes
+  constexpr int NPS = (BLK + RPP - 1) / RPP; // passes per block
+  constexpr int NP = NSUB * NPS;
+  constexpr int NW = kQuantThreads / 32;
+  static_assert(NSUB == 1 || BLK % RPP == 0, "sub-blocks must align with passes");
   const int tid = threadIdx.x;
   const int c8 = (tid % TPR) * 8;
   const int r0 = tid / TPR;
-  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const T* src = in + b * isb + h * ish + c8;
+  const int row_base = jb0 * BLK;
 
   float kmf[8];
   const bool has_km = km != nullptr;
-  if (has_km) {
-    uint4 raw = *reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8);
+  if (has_km) {  // L2 load: in the fused kernel km was written by another CTA of the same launch
+    uint4 raw = __ldcg(reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8));
     unpack8<T>(raw, kmf);
   }
 
@@ -148,17 +186,19 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
   uint4 raw[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
-    const int rl = p * RPP + r0;
-    const int row = jb * BLK + rl;
+    const int rl = (p % NPS) * RPP + r0;  // row inside its block
+    const int row = row_base + (p / NPS) * BLK + rl;
     raw[p] = make_uint4(0, 0, 0, 0);
     if (rl < BLK && row < N) raw[p] = ld_stream_v4(src + (int64_t)row * isn);
   }
-  float amax = 0.f;
+  float amax[NSUB];
+#pragma unroll
+  for (int u = 0; u < NSUB; ++u) amax[u] = 0.f;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     unpack8<T>(raw[p], x[p]);
-    const int rl = p * RPP + r0;
-    const bool live = (rl < BLK) && (jb * BLK + rl < N);
+    const int rl = (p % NPS) * RPP + r0;
+    const bool live = (rl < BLK) && (row_base + (p / NPS) * BLK + rl < N);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float v = x[p][i];
@@ -169,40 +209,46 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
       v = __fmul_rn(v, sm);
       v = live ? v : 0.f;  // rows >= N contribute 0 (masked load), even when km != 0
       x[p][i] = v;
-      amax = fmaxf(amax, fabsf(v));
+      amax[p / NPS] = fmaxf(amax[p / NPS], fabsf(v));
     }
   }
   // block abs-max: warp redux + smem
-  __shared__ float s_w[kQuantThreads / 32];
-  amax = warp_max(amax);
-  if ((tid & 31) == 0) s_w[tid >> 5] = amax;
-  __syncthreads();
-  float bmax = s_w[0];
 #pragma unroll
-  for (int w = 1; w < kQuantThreads / 32; ++w) bmax = fmaxf(bmax, s_w[w]);
-
-  const float qmax = bits == 8 ? 127.f : (bits == 4 ? 7.f : 1.f);
-  float sc, rcp = 0.f;
-  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
-  bool slow_div = (mode & LOWBIT_QMODE_FLAG_IEEE_DIV) != 0;
-  const bool gpu_div = triton && (mode & LOWBIT_QMODE_FLAG_DIV_FULL) != 0;
-  if (gpu_div) {
-    sc = div_full(bmax, qmax);
-  } else if (triton) {
-    sc = __fdiv_rn(bmax, qmax);
-    rcp = __frcp_rn(sc);  // correctly rounded 1/scale, once per block
-    // bf16 blocks near the ends of the fp32 exponent range (1/scale denormal or infinite), and all-zero blocks,
-    // take the IEEE division: a block-uniform branch
-    slow_div = slow_div || !(sc > 1e-30f && sc < 1e30f);
-  } else {
-    bmax = fmaxf(bmax, 1e-7f);
-    sc = __fdiv_rn(bmax, qmax);
-    rcp = __fdiv_rn(qmax, bmax);
+  for (int u = 0; u < NSUB; ++u) {
+    const float m = warp_max(amax[u]);
+    if ((tid & 31) == 0) s_w[u * NW + (tid >> 5)] = m;
   }
-  if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = sc;
-
+  __syncthreads();
+  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
   int8_t* dst = out + b * osb + h * osh;
-  quantize_rows<NP>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, sc, rcp, triton, slow_div, bits, pack, gpu_div);
+  auto finish = [&](auto u_tag) {
+    constexpr int U = decltype(u_tag)::value;
+    float bmax = s_w[U * NW];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) bmax = fmaxf(bmax, s_w[U * NW + w]);
+    const BlockScale bs = block_scale(bmax, bits, mode);
+    const int jb = jb0 + U;
+    if (jb < nblk) {
+      if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = bs.sc;
+      quantize_rows<NP, U * NPS, NPS>(x, dst, osn, jb * BLK, RPP, r0, c8, BLK, N, bs.sc, bs.rcp, triton, bs.slow_div,
+                                      bits, pack, bs.gpu_div);
+    }
+  };
+  finish(std::integral_constant<int, 0>{});
+  if constexpr (NSUB > 1) finish(std::integral_constant<int, 1>{});
+  if constexpr (NSUB > 2) finish(std::integral_constant<int, 2>{});
+  if constexpr (NSUB > 3) finish(std::integral_constant<int, 3>{});
+}
+
+template <typename T, int D, int BLK>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_t* __restrict__ out,
+                       float* __restrict__ scale, int N, int nblk,
+                       int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
+                       float sm, int bits, int pack, int mode, int H) {
+  __shared__ float s_w[kQuantThreads / 32];
+  quant_block_body<T, D, BLK>(in, km, out, scale, N, nblk, isb, ish, isn, osb, osh, osn, sm, bits, pack, mode, H,
+                              blockIdx.x, blockIdx.y, blockIdx.z, s_w);
 }
 
 template <typename T, int D, int BLK>
@@ -390,14 +436,15 @@ template <> struct MeanAcc<__nv_bfloat16> {
   static __device__ __forceinline__ float to_sum_f32(type s) { return __double2float_rn(s); }
 };
 
+// partial column sums of one row chunk (ch, h, b) by the whole CTA (256 threads); `s` is [256/(D/8)][D+1] scratch
 template <typename T, int D>
-__global__ void __launch_bounds__(256)
-k_mean_partial_kernel(const T* __restrict__ k, typename MeanAcc<T>::type* __restrict__ part, int N, int chunk,
-                      int nchunk, int64_t sb, int64_t sh, int64_t sn, int H) {
+__device__ __forceinline__ void ksum_chunk_body(const T* __restrict__ k, typename MeanAcc<T>::type* __restrict__ part,
+                                                int N, int chunk, int nchunk, int64_t sb, int64_t sh, int64_t sn,
+                                                int H, int ch, int h, int b,
+                                                typename MeanAcc<T>::type (*s)[D + 1]) {
   using A = typename MeanAcc<T>::type;
   constexpr int TPR = D / 8, RPP = 256 / TPR;
   const int tid = threadIdx.x, c8 = (tid % TPR) * 8, r0 = tid / TPR;
-  const int ch = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const T* src = k + b * sb + h * sh + c8;
   const int row_end = min(N, (ch + 1) * chunk);
   A acc[8];
@@ -420,7 +467,6 @@ k_mean_partial_kernel(const T* __restrict__ k, typename MeanAcc<T>::type* __rest
     if (since_flush >= 256) { ra.flush(acc); since_flush = 0; }
   }
   ra.flush(acc);
-  __shared__ A s[RPP][D + 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[r0][c8 + i] = acc[i];
   __syncthreads();
@@ -429,6 +475,15 @@ k_mean_partial_kernel(const T* __restrict__ k, typename MeanAcc<T>::type* __rest
     for (int r = 0; r < RPP; ++r) t += s[r][tid];
     part[(((int64_t)b * H + h) * nchunk + ch) * D + tid] = t;
   }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+k_mean_partial_kernel(const T* __restrict__ k, typename MeanAcc<T>::type* __restrict__ part, int N, int chunk,
+                      int nchunk, int64_t sb, int64_t sh, int64_t sn, int H) {
+  using A = typename MeanAcc<T>::type;
+  __shared__ A s[256 / (D / 8)][D + 1];
+  ksum_chunk_body<T, D>(k, part, N, chunk, nchunk, sb, sh, sn, H, blockIdx.x, blockIdx.y, blockIdx.z, s);
 }
 
 template <typename T, int D>
@@ -443,6 +498,137 @@ __global__ void k_mean_final_kernel(const typename MeanAcc<T>::type* __restrict_
   for (int c = 0; c < nchunk; ++c) t += part[(bh * nchunk + c) * D + d];
   const float s32 = MeanAcc<T>::to_sum_f32(t);
   km[idx] = from_f32<T>(__fdiv_rn(s32, (float)N));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused Q + K preparation: K column sums -> K mean -> K codes, and Q codes, in ONE persistent launch
+// (src/core.py:291-306 + quant_per_block.py:181-248: `km = k.mean`, `k - km`, two quantizer launches).
+//
+// The four launches of the unfused path are 15-30 us kernels that each ramp the whole chip up and down; here every
+// resident CTA walks one static list of work items, ordered in stages so that a (batch, kv-head) slice of K is summed
+// (A items), then -- one stage later, when its mean has been published -- quantized (K items) while it is still in
+// L2, with the independent Q blocks (Q items) spread evenly over the stages to keep HBM busy in between:
+//     stage s:  A(slices of group s)   K(slices of group s-1)   Q(share s)
+// Dependencies are forward only (K(g) waits for A(g), issued a whole stage earlier) and the grid never exceeds the
+// resident capacity, so the spin-wait cannot deadlock.  The mean is reduced in a fixed chunk order by the CTA that
+// finishes a slice last: bit-identical to lowbit_k_mean.  Arithmetic of the codes: the same device functions as the
+// stand-alone kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPrepMaxSlices = 8192;  // (batch x kv-head) slices one workspace serves: counters / flags sit at fixed offsets
+struct PrepParams {
+  const void *q, *k;
+  void* km;
+  int8_t *qc, *kc;
+  float *qs, *ks;
+  void* part;
+  int *counter, *ready;
+  int epoch;
+  int B, Hq, Hkv, Nq, Nk;
+  int64_t qsb, qsh, qsn, ksb, ksh, ksn, qosb, qosh, qosn, kosb, kosh, kosn;
+  float smq;
+  int qbits, kbits, kpack, mode, smooth;
+  int chunk, nchunk, nqb, nkb;  // K-sum rows per chunk / chunks per slice; Q blocks per (b,hq); K blocks per (b,hkv)
+  int nkb2;                     // K work items per slice (two blocks each)
+  int G, S, qps;                // slices per stage, stages that carry A work, Q items per stage
+  int total;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kQuantThreads)
+prep_qk_kernel(const PrepParams p) {
+  using A = typename MeanAcc<T>::type;
+  __shared__ float s_w[2 * kQuantThreads / 32];
+  __shared__ A s_sum[256 / (D / 8)][D + 1];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int nslice = p.B * p.Hkv;
+  const int nQ = p.B * p.Hq * p.nqb;
+  const T* kmp = p.smooth ? (const T*)p.km : nullptr;
+  for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
+    int i = item, s = 0, na, nk, nq;
+    for (;; ++s) {  // stage of this item (a handful of iterations: stages are thousands of items long)
+      const int a_sl = (p.smooth && s < p.S) ? min(p.G, nslice - s * p.G) : 0;
+      const int k_sl = (s >= 1) ? min(p.G, nslice - (s - 1) * p.G) : 0;
+      na = a_sl * p.nchunk;
+      nk = k_sl * p.nkb2;
+      nq = max(0, min(p.qps, nQ - s * p.qps));
+      if (i < na + nk + nq) break;
+      i -= na + nk + nq;
+    }
+    if (i < na) {
+      // ---- A: partial column sums of one K row chunk; the last chunk of a slice to finish publishes the mean
+      const int slice = s * p.G + i / p.nchunk, ch = i % p.nchunk;
+      ksum_chunk_body<T, D>((const T*)p.k, (A*)p.part, p.Nk, p.chunk, p.nchunk, p.ksb, p.ksh, p.ksn, p.Hkv, ch,
+                            slice % p.Hkv, slice / p.Hkv, s_sum);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_last = (atomicAdd(p.counter + slice, 1) == p.nchunk - 1);
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (tid < D) {
+          A t = A(0);
+          const A* part = (const A*)p.part + (int64_t)slice * p.nchunk * D + tid;
+          for (int c = 0; c < p.nchunk; ++c) t += __ldcg(part + (int64_t)c * D);
+          ((T*)p.km)[(int64_t)slice * D + tid] = from_f32<T>(__fdiv_rn(MeanAcc<T>::to_sum_f32(t), (float)p.Nk));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          p.counter[slice] = 0;  // ready for the next call on this workspace
+          st_release(p.ready + slice, p.epoch);
+        }
+      }
+    } else if (i < na + nk) {
+      // ---- K: two 64-row blocks (16-32 KB in flight) of a slice whose mean was published a stage ago
+      i -= na;
+      const int slice = (s - 1) * p.G + i / p.nkb2, jb = (i % p.nkb2) * 2;
+      if (p.smooth) {
+        if (tid == 0) {
+          // bounded (~2 s): a broken protocol (workspace not zero-filled, epoch reused) traps instead of hanging the GPU
+          int spins = 0;
+          while (ld_acquire(p.ready + slice) != p.epoch) {
+            __nanosleep(128);
+            if (++spins > (1 << 24)) __trap();
+          }
+        }
+        __syncthreads();
+      }
+      quant_block_body<T, D, 64, 2>((const T*)p.k, kmp, p.kc, p.ks, p.Nk, p.nkb, p.ksb, p.ksh, p.ksn, p.kosb, p.kosh,
+                                 p.kosn, 1.0f, p.kbits, p.kpack, p.mode, p.Hkv, jb, slice % p.Hkv, slice / p.Hkv, s_w);
+    } else {
+      // ---- Q: one 128-row block, scaled by sm_scale * log2(e)
+      const int qi = s * p.qps + (i - na - nk);
+      const int jb = qi % p.nqb, h = (qi / p.nqb) % p.Hq, b = qi / (p.nqb * p.Hq);
+      quant_block_body<T, D, 128>((const T*)p.q, nullptr, p.qc, p.qs, p.Nq, p.nqb, p.qsb, p.qsh, p.qsn, p.qosb, p.qosh,
+                                  p.qosn, p.smq, p.qbits, 0, p.mode, p.Hq, jb, h, b, s_w);
+    }
+    __syncthreads();  // shared scratch is reused by the next item
+  }
+}
+
+template <typename T, int D>
+static int launch_prep(PrepParams& p, cudaStream_t st) {
+  auto kern = prep_qk_kernel<T, D>;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    LOWBIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kQuantThreads, 0));
+    LOWBIT_CHECK(ctas_per_sm > 0, "lowbit_prep_qk: kernel does not fit an SM");
+  }
+  const int64_t cap = (int64_t)num_sms() * ctas_per_sm;  // all CTAs resident: the spin-wait on a mean cannot deadlock
+  const int grid = (int)(p.total < cap ? p.total : cap);
+  kern<<<grid, kQuantThreads, 0, st>>>(p);
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -499,6 +685,68 @@ extern "C" {
 
 int lowbit_version(void) { return LOWBIT_ABI_VERSION; }
 const char* lowbit_last_error(void) { return last_error().c_str(); }
+
+int64_t lowbit_prep_qk_workspace_bytes(int B, int Hkv, int Nk, int D) {
+  const int chunk = mean_chunk_rows(Nk);
+  const int nchunk = (Nk + chunk - 1) / chunk;
+  const int64_t part = (int64_t)B * Hkv * nchunk * D * 8;
+  return part + (int64_t)kPrepMaxSlices * 2 * 4;
+}
+
+int lowbit_prep_qk(const void* q, const void* k, void* km_out, void* q_codes, float* q_scale, void* k_codes,
+                   float* k_scale, void* workspace, int epoch, int B, int Hq, int Hkv, int Nq, int Nk, int D,
+                   int64_t qsb, int64_t qsh, int64_t qsn, int64_t ksb, int64_t ksh, int64_t ksn,
+                   int64_t qosb, int64_t qosh, int64_t qosn, int64_t kosb, int64_t kosh, int64_t kosn,
+                   float sm_scale_arg, int qbits, int kbits, int kpack, int mode, int smooth_k, int dtype,
+                   void* stream) {
+  LOWBIT_CHECK(D == 64 || D == 128, "lowbit_prep_qk: head_dim must be 64 or 128 (got %d)", D);
+  LOWBIT_CHECK(q && k && q_codes && q_scale && k_codes && k_scale && workspace, "lowbit_prep_qk: null pointer");
+  LOWBIT_CHECK(!smooth_k || km_out, "lowbit_prep_qk: smooth_k needs km_out");
+  LOWBIT_CHECK(B > 0 && Hq > 0 && Hkv > 0 && Nq > 0 && Nk > 0, "lowbit_prep_qk: empty tensor");
+  LOWBIT_CHECK(Hq % Hkv == 0, "lowbit_prep_qk: num_qo_heads (%d) must be divisible by num_kv_heads (%d)", Hq, Hkv);
+  LOWBIT_CHECK(qbits == 8 || qbits == 4, "lowbit_prep_qk: qbits must be 8 or 4");
+  LOWBIT_CHECK(kbits == 8 || kbits == 4 || kbits == 2, "lowbit_prep_qk: kbits must be 8, 4 or 2");
+  LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_prep_qk: bad mode %d", mode);
+  LOWBIT_CHECK(epoch > 0, "lowbit_prep_qk: epoch must be positive and grow with every call on a workspace");
+  LOWBIT_CHECK(qsn % 8 == 0 && qsh % 8 == 0 && qsb % 8 == 0 && ksn % 8 == 0 && ksh % 8 == 0 && ksb % 8 == 0,
+               "lowbit_prep_qk: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(((uintptr_t)workspace & 7) == 0, "lowbit_prep_qk: workspace must be 8-byte aligned");
+  const int kdiv = kpack ? 8 / kbits : 1;
+  LOWBIT_CHECK((kosn * kdiv) % 8 == 0 && qosn % 8 == 0, "lowbit_prep_qk: code rows must keep 8-byte alignment");
+  PrepParams p{};
+  p.q = q; p.k = k; p.km = km_out; p.qc = (int8_t*)q_codes; p.kc = (int8_t*)k_codes; p.qs = q_scale; p.ks = k_scale;
+  p.chunk = mean_chunk_rows(Nk);
+  p.nchunk = (Nk + p.chunk - 1) / p.chunk;
+  LOWBIT_CHECK((int64_t)B * Hkv <= kPrepMaxSlices, "lowbit_prep_qk: more than %d (batch x kv-head) slices", kPrepMaxSlices);
+  // fixed layout, independent of the shape, so one workspace serves calls of any shape: the counters are always left
+  // at zero and the flags only ever hold past epochs
+  p.counter = reinterpret_cast<int*>(workspace);
+  p.ready = p.counter + kPrepMaxSlices;
+  p.part = reinterpret_cast<uint8_t*>(workspace) + (int64_t)kPrepMaxSlices * 2 * 4;
+  p.epoch = epoch;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+  p.qsb = qsb; p.qsh = qsh; p.qsn = qsn; p.ksb = ksb; p.ksh = ksh; p.ksn = ksn;
+  p.qosb = qosb; p.qosh = qosh; p.qosn = qosn; p.kosb = kosb; p.kosh = kosh; p.kosn = kosn;
+  p.smq = sm_scale_arg; p.qbits = qbits; p.kbits = kbits; p.kpack = kpack; p.mode = mode; p.smooth = smooth_k ? 1 : 0;
+  p.nqb = (Nq + 127) / 128; p.nkb = (Nk + 63) / 64; p.nkb2 = (p.nkb + 1) / 2;
+  const int64_t nslice = (int64_t)B * Hkv, nQ = (int64_t)B * Hq * p.nqb;
+  const int64_t total = nslice * (p.smooth ? p.nchunk : 0) + nslice * p.nkb2 + nQ;
+  LOWBIT_CHECK(total < (1ll << 31), "lowbit_prep_qk: too many blocks");
+  // slices per stage: a group of K slices (summed, then quantized one stage later) should stay L2-resident (<= 8 MiB)
+  // and a stage should hold a few items per resident CTA
+  int64_t G = (8ll << 20) / ((int64_t)Nk * D * 2);
+  if (G < 1) G = 1;
+  if (G > 16) G = 16;
+  if (G > nslice) G = nslice;
+  p.G = (int)G;
+  p.S = (int)((nslice + G - 1) / G);
+  p.qps = (int)((nQ + p.S) / (p.S + 1));
+  p.total = (int)total;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LOWBIT_F16) return D == 64 ? launch_prep<__half, 64>(p, st) : launch_prep<__half, 128>(p, st);
+  if (dtype == LOWBIT_BF16) return D == 64 ? launch_prep<__nv_bfloat16, 64>(p, st) : launch_prep<__nv_bfloat16, 128>(p, st);
+  return lowbit::fail("lowbit_prep_qk: bad dtype %d", dtype);
+}
 
 int64_t lowbit_k_mean_workspace_bytes(int B, int H, int N, int D) {
   const int chunk = mean_chunk_rows(N);

@@ -75,14 +75,9 @@ def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout, out=None):
 def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpack, backend):
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
-    if backend == "triton":
-        mode = N.QMODE_TRITON
-    elif backend == "triton_gpu":  # Q1 with the JIT-compiled kernels' approximate division (div.full.f32)
-        mode = N.QMODE_TRITON | N.QMODE_FLAG_DIV_FULL
-    elif backend == "cuda":
-        mode = N.QMODE_CUDA
-    else:
+    if backend not in _MODES:  # "triton_gpu": Q1 with the JIT-compiled kernels' approximate division (div.full.f32)
         raise ValueError(f"Unsupported quantization backend: {backend}")
+    mode = _MODES[backend]
     head_dim = T.as_torch(q).shape[-1]
     if sm_scale is None:
         sm_scale = head_dim ** -0.5
@@ -90,6 +85,63 @@ def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpac
     k_c, k_s = _quant_one(k, km, BLKK, kbits, kpack, 1.0, mode, tensor_layout)
     q_c, q_s = _quant_one(q, None, BLKQ, qbits, False, sm_scale * LOG2E, mode, tensor_layout)
     return q_c, q_s, k_c, k_s
+
+
+_MODES = {"triton": N.QMODE_TRITON, "triton_gpu": N.QMODE_TRITON | N.QMODE_FLAG_DIV_FULL, "cuda": N.QMODE_CUDA}
+_prep_ws = {}  # (device index, stream handle) -> [workspace tensor (zero-filled once), epoch]
+
+
+def _prep_workspace(dev, nbytes):
+    """Workspace of the fused preparation kernel: partial K sums + per-slice counters / ready flags.  Owned per
+    (device, stream): calls that share one are stream-ordered.  Zero-filled when (re)allocated; the kernel leaves the
+    counters at zero and the flags hold the epoch of the last call, which only ever grows."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ent = _prep_ws.get(key)
+    if ent is None or ent[0].numel() < nbytes:
+        ent = [torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev), 0]
+        _prep_ws[key] = ent
+    ent[1] += 1
+    if ent[1] >= (1 << 30):  # epoch wrap: start over on a clean workspace
+        ent[0].zero_()
+        ent[1] = 1
+    return ent[0], ent[1]
+
+
+def prep_qk(q, k, smooth_k=True, sm_scale=None, tensor_layout="HND", backend="triton", qbits=8, kbits=8, kpack=False):
+    """K mean + K smoothing + per-block Q / K quantization in ONE launch (lowbit_prep_qk): what
+    `km = k.mean(...)` + `per_block_int8(q, k, km=km, sm_scale=...)` compute (core.py:291-319), bit-identical.
+    -> (q_codes, q_scale, k_codes, k_scale, km [B,H,1,D] / [B,1,H,D] or None)."""
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if backend not in _MODES:
+        raise ValueError(f"Unsupported quantization backend: {backend}")
+    qt, kt = T.as_torch(q), T.as_torch(k)
+    dev = T.require_cuda(qt, kt)
+    assert qt.dtype == kt.dtype, "All tensors must have the same dtype."
+    b, hq, nq, d, qsb, qsh, qsn = T.bhnd(qt, tensor_layout)
+    bk, hkv, nk, dk, ksb, ksh, ksn = T.bhnd(kt, tensor_layout)
+    assert b == bk and d == dk, "q and k must agree in batch and head_dim"
+    if d not in (64, 128):
+        raise ValueError(f"Unsupported head_dim: {d} (the kernels take 64 or 128; core pads smaller ones)")
+    if sm_scale is None:
+        sm_scale = d ** -0.5
+    kd = d * kbits // 8 if (kpack and kbits < 8) else d
+    q_c = torch.empty(qt.shape, dtype=torch.int8, device=dev)
+    k_c = torch.empty(list(kt.shape[:-1]) + [kd], dtype=torch.int8, device=dev)
+    q_s = torch.empty((b, hq, (nq + 127) // 128), dtype=torch.float32, device=dev)
+    k_s = torch.empty((b, hkv, (nk + 63) // 64), dtype=torch.float32, device=dev)
+    km = torch.empty((b, hkv, d), dtype=kt.dtype, device=dev) if smooth_k else None
+    _, _, _, _, qosb, qosh, qosn = T.bhnd(q_c, tensor_layout)
+    _, _, _, _, kosb, kosh, kosn = T.bhnd(k_c, tensor_layout)
+    ws, epoch = _prep_workspace(dev, N.lib().lowbit_prep_qk_workspace_bytes(b, hkv, nk, d))
+    N.call("lowbit_prep_qk", qt.data_ptr(), kt.data_ptr(), km.data_ptr() if smooth_k else None,
+           q_c.data_ptr(), q_s.data_ptr(), k_c.data_ptr(), k_s.data_ptr(), ws.data_ptr(), epoch,
+           b, hq, hkv, nq, nk, d, qsb, qsh, qsn, ksb, ksh, ksn, qosb, qosh, qosn, kosb, kosh, kosn,
+           float(sm_scale * LOG2E), qbits, kbits, int(bool(kpack)), _MODES[backend], int(bool(smooth_k)),
+           T.dtype_code(qt.dtype), T.stream_ptr(dev))
+    if km is not None:
+        km = km.unsqueeze(2) if tensor_layout == "HND" else km.unsqueeze(1)
+    return T.like(q_c, q), T.like(q_s, q), T.like(k_c, k), T.like(k_s, k), T.like(km, k)
 
 
 def per_block_int8(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND", backend="triton"):

@@ -632,3 +632,49 @@ def test_triton_gpu_division_mode_is_within_one_step_of_ieee(L, cuda_dev, dtype,
         diff = (a[i].int() - g[i].int()).abs()
         assert diff.max().item() <= 1
         assert diff.float().mean().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ fused preparation
+@pytest.mark.parametrize("layout", ["HND", "NHD"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("b,hq,hkv,nq,nk,d", [
+    (1, 2, 2, 512, 512, 64),      # config 1
+    (2, 6, 2, 200, 333, 128),     # GQA, ragged tails, odd number of K blocks
+    (1, 1, 1, 1, 1, 64),          # single row
+    (3, 4, 4, 1500, 1500, 64),    # several K-sum chunks per slice, several stages
+])
+def test_prep_qk_matches_separate_kernels(L, cuda_dev, layout, dtype, b, hq, hkv, nq, nk, d):
+    """lowbit_prep_qk (K mean + smoothing + both quantizers in one persistent launch) is bit-identical to
+    k_mean + per_block quantizers (which the golden / oracle tests pin), for every rounding convention, packed
+    INT4 K, with and without smoothing, and across repeated calls on the same workspace (epoch protocol)."""
+    q = mk(b, hq, nq, d, layout, dtype, 31).to(cuda_dev)
+    k = mk(b, hkv, nk, d, layout, dtype, 32, bias=2.0).to(cuda_dev)
+    km = L.k_mean(k, layout)
+    for rep in range(2):
+        for backend in ("triton", "cuda", "triton_gpu"):
+            ref = L.per_block_int8(q, k, km=km, tensor_layout=layout, backend=backend)
+            got = L.prep_qk(q, k, True, None, layout, backend)
+            assert torch.equal(got[4], km)
+            for g, r in zip(got[:4], ref):
+                assert torch.equal(g, r), f"{backend} rep {rep}"
+    ref = L.per_block_q_int8_k_int4(q, k, km=km, tensor_layout=layout)
+    got = L.prep_qk(q, k, True, None, layout, "triton", 8, 4, True)
+    for g, r in zip(got[:4], ref):
+        assert torch.equal(g, r)
+    ref = L.per_block_int8(q, k, km=None, sm_scale=0.3, tensor_layout=layout)
+    got = L.prep_qk(q, k, False, 0.3, layout, "triton")
+    assert got[4] is None
+    for g, r in zip(got[:4], ref):
+        assert torch.equal(g, r)
+
+
+def test_prep_qk_full_size_config2(L, cuda_dev):
+    """BASELINE config 2 at full size (B4 H32 N4096 D64): fused preparation == separate kernels, bit for bit."""
+    torch.manual_seed(0)
+    q, k = (torch.randn(4, 32, 4096, 64, dtype=torch.float16, device=cuda_dev) for _ in range(2))
+    km = L.k_mean(k)
+    ref = L.per_block_int8(q, k, km=km)
+    got = L.prep_qk(q, k)
+    assert torch.equal(got[4], km)
+    for g, r in zip(got[:4], ref):
+        assert torch.equal(g, r)

@@ -25,6 +25,12 @@ for name in (sys.argv[1:] or ["c2", "c3"]):
     km = L.k_mean(xs[0], layout)
     elem = b * h * n * d
 
+    def x2(x):  # a different tensor than x (the Q of the pair)
+        for i, t in enumerate(xs):
+            if t is x:
+                return xs[(i + 2) % 4]
+        return xs[0]
+
     def timeit(fn, reps=20):
         for i in range(4):
             fn(xs[i % 4])
@@ -45,6 +51,10 @@ for name in (sys.argv[1:] or ["c2", "c3"]):
         ("V -> fp8 per channel", lambda x: L.per_channel_fp8(x, layout, smooth_v=False), 3.0),
         ("V -> fp8 per channel, smooth", lambda x: L.per_channel_fp8(x, layout, smooth_v=True), 3.0),
     ]
+    # fused preparation: Q and K of the same shape (rotating pairs): 2 x (2 B read + 1 B written) per element of one
+    # tensor = 6 B/elem algorithmic (K crosses HBM once; its second read is an L2 hit)
+    cases.append(("prep_qk fused (mean+K+Q)", lambda x: L.prep_qk(x2(x), x, True, None, layout), 6.0))
+    cases.append(("unfused: k_mean + K + Q", lambda x: L.per_block_int8(x2(x), x, km=L.k_mean(x, layout), tensor_layout=layout), 6.0))
     for label, fn, bpe in cases:
         t = timeit(fn)
         gbs = elem * bpe / t / 1e9
