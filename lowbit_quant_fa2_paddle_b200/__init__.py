@@ -3,11 +3,15 @@ Charles2530/lowbit_quant_fa2_paddle (`src/__init__.py:1-17`): per-block INT8/INT
 mean-smoothing and a fused tcgen05/TMEM/TMA attention kernel, hand-written for sm_100a."""
 from .core import (  # noqa: F401
     # legacy names (backward compatible)
+    sageattn,
+    sageattn_qk_int8_pv_fp16_cuda,
     sageattn_qk_int8_pv_fp16_triton,
     sageattn_qk_int4_pv_fp16_triton,
     sageattn_multi_precision,
     sageattn_qk_int8_pv_fp8_cuda,
     # preferred names
+    lowbit_fa_attn,
+    lowbit_fa_qk_int8_pv_fp16_cuda,
     lowbit_fa_multi_precision,
     lowbit_fa_qk_int8_pv_fp16_triton,
     lowbit_fa_qk_int4_pv_fp16_triton,
@@ -31,6 +35,13 @@ from .quant import (  # noqa: F401
     per_warp_int8,
     per_channel_fp8,
     triton_quantize_and_pack_along_last_dim,
+)
+from .varlen import (  # noqa: F401
+    sageattn_varlen,
+    lowbit_fa_varlen,
+    per_block_int8_varlen,
+    forward_varlen,
+    k_mean_varlen,
 )
 from .host import lowbit_fa_host, plan_chunks  # noqa: F401
 from .attention import forward, forward_causal, forward_partial, finalize, PartialState  # noqa: F401

@@ -61,13 +61,17 @@ def _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale,
 
 
 def _forward(q, k, v, q_scale, k_scale, tensor_layout, output_dtype, return_lse, causal,
-             qk_mode=N.QK_I8, pv_mode=N.PV_F16, compat_tail=False, v_scale=None, v_mean=None, kbits=None):
+             qk_mode=N.QK_I8, pv_mode=N.PV_F16, compat_tail=False, v_scale=None, v_mean=None, kbits=None, out=None):
     dev, qt, ptrs, dims, keep = _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean)
     b, hq, hkv, nq, nk, d = dims[:6]
     if causal:
         assert nq == nk, "qo_len and kv_len must be equal for causal attention"
     odt = _out_dtype(output_dtype, torch.float16)
-    o = torch.empty(qt.shape, dtype=odt, device=dev)
+    if out is None:
+        o = torch.empty(qt.shape, dtype=odt, device=dev)
+    else:  # caller-owned output (e.g. one sequence's rows of a packed varlen tensor)
+        o = out
+        assert o.shape == qt.shape and o.dtype == odt and o.device == dev and o.stride(-1) == 1
     _, _, _, _, osb, osh, osn = T.bhnd(o, tensor_layout)
     lse = torch.empty((b, hq, nq), dtype=torch.float32, device=dev) if return_lse else None
     flags = (N.ATTN_CAUSAL if causal else 0) | (N.ATTN_COMPAT_TAIL if compat_tail else 0)

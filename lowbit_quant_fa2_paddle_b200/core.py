@@ -4,6 +4,8 @@
   lowbit_fa_qk_int4_pv_fp16_triton   src/core.py:945-1036 (alias :1105)
   lowbit_fa_q_int8_k_int4_pv_fp16    mixed entry: quant_per_block.py:391-458 + utils/paddle_package.py:321-417
   lowbit_fa_multi_precision          src/core.py:1064-1096 (select_quantization :1050-1061)
+  lowbit_fa_attn (sageattn)          src/core.py:82-190   (alias :1099) -- plug-and-play dispatcher
+  lowbit_fa_qk_int8_pv_fp16_cuda     src/core.py:495-731  (alias :1103) -- CUDA-API signature on the sm_100a kernel
   lowbit_fa_qk_int8_pv_fp8_cuda      src/core.py:735-941  (alias :1104) -- FP8 P.V semantics on the sm_100a kernel
   lowbit_fa_qk_int4_pv_fp8           INT4 K + FP8 P.V (BASELINE config 3)
 
@@ -110,6 +112,41 @@ def lowbit_fa_q_int8_k_int4_pv_fp16(q, k, v, tensor_layout: str = "HND", quantiz
                       "q8k4", compat_tail=bool(kwargs.get("compat_tail", False)))
 
 
+def sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                                  qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None,
+                                  pv_accum_dtype: str = "fp32", smooth_k: bool = True, smooth_v: bool = False,
+                                  return_lse: bool = False, **kwargs: Any):
+    """The signature of src/core.py:495-731 (INT8 Q.K^T + FP16 P.V, "CUDA" entry point) on the sm_100a kernel.
+    The kernel dequantizes with per-block scales and always accumulates P.V in fp32, so `qk_quant_gran`
+    ("per_warp" | "per_thread") and `pv_accum_dtype` ("fp16" | "fp16+fp32" | "fp32") are validated like the reference
+    (:598-604) and every value is served by the fp32-accumulating kernel; `smooth_v` only exists to protect fp16
+    accumulators (:684-691) and is ignored, as the reference does for "fp32" (:676-679).  Quantizer rounding follows
+    the reference's CUDA quantizer (Q2: RNE, reciprocal multiply, src/quant.py:21-98) unless
+    quantization_backend= is passed."""
+    if qk_quant_gran not in ("per_warp", "per_thread"):
+        raise ValueError(f"Unsupported qk_quant_gran: {qk_quant_gran}")
+    if pv_accum_dtype not in ("fp16", "fp16+fp32", "fp32"):
+        raise ValueError(f"Unsupported pv_accum_dtype: {pv_accum_dtype}")
+    return _lowbit_fa(q, k, v, tensor_layout, kwargs.get("quantization_backend", "cuda"), is_causal, sm_scale,
+                      smooth_k, return_lse, "int8")
+
+
+def sageattn(q, k, v, tensor_layout: str = "HND", is_causal: bool = False, sm_scale: Optional[float] = None,
+             return_lse: bool = False, **kwargs: Any):
+    """The plug-and-play entry point (src/core.py:82-190, alias lowbit_fa_attn :1099), e.g. as a replacement for
+    scaled_dot_product_attention (example/sageattn_cogvideo.py:9-14): extra SDPA keywords (attn_mask, dropout_p, ...)
+    are accepted and ignored like the reference's **kwargs.  The reference picks a kernel per compute capability
+    (sm80 / sm86 / sm89 / sm90) and raises for anything else; this build has one target, sm_100a, served by the
+    INT8-QK / FP16-PV (fp32 accumulate) kernel -- the choice the reference makes for sm80 and sm90."""
+    qt = T.as_torch(q)
+    if qt.device.type == "cuda":
+        cap = torch.cuda.get_device_capability(qt.device)
+        if cap[0] != 10:
+            raise ValueError(f"Unsupported CUDA architecture: sm{cap[0]}{cap[1]}")
+    return sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal, sm_scale=sm_scale,
+                                         return_lse=return_lse, pv_accum_dtype="fp32")
+
+
 def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
                                  qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None,
                                  pv_accum_dtype: str = "fp32+fp32", smooth_k: bool = True, smooth_v: bool = False,
@@ -173,6 +210,8 @@ def sageattn_multi_precision(q, k, v, tensor_layout: str = "HND", is_causal: boo
 
 
 # preferred names (core.py:1099-1105)
+lowbit_fa_attn = sageattn
+lowbit_fa_qk_int8_pv_fp16_cuda = sageattn_qk_int8_pv_fp16_cuda
 lowbit_fa_multi_precision = sageattn_multi_precision
 lowbit_fa_qk_int8_pv_fp16_triton = sageattn_qk_int8_pv_fp16_triton
 lowbit_fa_qk_int4_pv_fp16_triton = sageattn_qk_int4_pv_fp16_triton

@@ -171,3 +171,50 @@ def kivi_quantize_and_pack(data, group_size, bit):
     npk._pack_along_last_dim[(triton.cdiv(y.shape[0], BS), y.shape[1] // per)](
         bit, y, code, y.shape[0], y.shape[1], per, BLOCK_SIZE_N=BS, num_warps=8)
     return code.view(B, D, nh, -1), scale.reshape(B, D, nh, ng), mn.reshape(B, D, nh, ng)
+
+
+# ---------------------------------------------------------------------------------------------- varlen (packed) path
+def varlen_per_block_int8(q, k, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, BLKQ=128, BLKK=64,
+                          sm_scale=None):
+    """Host re-statement of quant_per_block_varlen.py:75-142 around the real varlen quantizer kernel (:22-72).
+    q [Tq,Hq,D], k [Tk,Hkv,D] (k already smoothed by the caller, core.py:447-449)."""
+    import torch
+    m = _load("src/triton/quant_per_block_varlen.py")
+    kern = m.quant_per_block_int8_kernel
+    hq, hkv, d = q.shape[1], k.shape[1], q.shape[-1]
+    b = cu_seqlens_q.shape[0] - 1
+    if sm_scale is None:
+        sm_scale = d ** -0.5
+    outs = []
+    for x, cu, blk, mx, h, sm in ((q, cu_seqlens_q, BLKQ, max_seqlen_q, hq, sm_scale * 1.44269504),
+                                  (k, cu_seqlens_k, BLKK, max_seqlen_k, hkv, 1.0)):
+        lens = cu[1:] - cu[:-1]
+        cs = torch.nn.functional.pad(torch.cumsum((lens + blk - 1) // blk, 0), (1, 0)).to(cu.dtype)
+        codes = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+        scale = torch.empty((int(cs[-1]), h), dtype=torch.float32, device=x.device)
+        kern[((mx + blk - 1) // blk, h, b)](x, codes, scale, cu, cs, x.stride(1), x.stride(0), codes.stride(1),
+                                            codes.stride(0), sm_scale=sm, H=h, C=d, BLK=blk)
+        outs += [codes, scale, cs]
+    return outs[0], outs[1], outs[3], outs[4], outs[2], outs[5]
+
+
+def varlen_attn_forward(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, q_scale, k_scale, cu_q_scale, cu_k_scale,
+                        causal=False, output_dtype=None):
+    """Host re-statement of the varlen `forward` wrappers (attn_qk_int8_block_varlen.py:197-248, causal twin
+    attn_qk_int8_per_block_causal_varlen.py:207-) around the real kernels."""
+    import torch
+    if causal:
+        m = _load("src/triton/attn_qk_int8_per_block_causal_varlen.py")
+        stage = 3
+    else:
+        m = _load("src/triton/attn_qk_int8_block_varlen.py")
+        stage = 1
+    o = torch.empty(q.shape, dtype=output_dtype or v.dtype, device=q.device)
+    b = cu_seqlens_q.shape[0] - 1
+    _, hq, d = q.shape
+    _, hkv, _ = k.shape
+    m._attn_fwd[((max_seqlen_q + 127) // 128, hq, b)](
+        q, k, v, cu_seqlens_q, cu_seqlens_k, q_scale, k_scale, cu_q_scale, cu_k_scale, o,
+        q.stride(1), q.stride(0), k.stride(1), k.stride(0), v.stride(1), v.stride(0), o.stride(1), o.stride(0),
+        hq, hq // hkv, BLOCK_M=128, BLOCK_N=64, HEAD_DIM=d, STAGE=stage)
+    return o

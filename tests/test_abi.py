@@ -93,3 +93,69 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+\.*oracle", txt, flags=re.M), f"{f} imports the oracle"
                 assert "oracle/" not in txt and "oracle." not in txt, f"{f} references the oracle package"
+
+
+# the reference's public surface (src/__init__.py:1-17) and the leading parameters of each entry point
+# (src/core.py:82-91, 194-205, 356-368, 495-508, 735-748, 945-956, 1064-1073)
+REFERENCE_API = {
+    "sageattn": ["q", "k", "v", "tensor_layout", "is_causal", "sm_scale", "return_lse"],
+    "sageattn_varlen": ["q", "k", "v", "cu_seqlens_q", "cu_seqlens_k", "max_seqlen_q", "max_seqlen_k", "is_causal",
+                        "sm_scale", "smooth_k"],
+    "sageattn_qk_int8_pv_fp16_triton": ["q", "k", "v", "tensor_layout", "quantization_backend", "is_causal", "sm_scale",
+                                        "smooth_k", "return_lse"],
+    "sageattn_qk_int8_pv_fp16_cuda": ["q", "k", "v", "tensor_layout", "is_causal", "qk_quant_gran", "sm_scale",
+                                      "pv_accum_dtype", "smooth_k", "smooth_v", "return_lse"],
+    "sageattn_qk_int8_pv_fp8_cuda": ["q", "k", "v", "tensor_layout", "is_causal", "qk_quant_gran", "sm_scale",
+                                     "pv_accum_dtype", "smooth_k", "smooth_v", "return_lse"],
+    "sageattn_qk_int4_pv_fp16_triton": ["q", "k", "v", "tensor_layout", "quantization_backend", "is_causal", "sm_scale",
+                                        "smooth_k", "return_lse"],
+    "sageattn_multi_precision": ["q", "k", "v", "tensor_layout", "is_causal", "sm_scale", "return_lse"],
+}
+ALIASES = {"lowbit_fa_attn": "sageattn", "lowbit_fa_varlen": "sageattn_varlen",
+           "lowbit_fa_multi_precision": "sageattn_multi_precision",
+           "lowbit_fa_qk_int8_pv_fp16_triton": "sageattn_qk_int8_pv_fp16_triton",
+           "lowbit_fa_qk_int8_pv_fp16_cuda": "sageattn_qk_int8_pv_fp16_cuda",
+           "lowbit_fa_qk_int8_pv_fp8_cuda": "sageattn_qk_int8_pv_fp8_cuda",
+           "lowbit_fa_qk_int4_pv_fp16_triton": "sageattn_qk_int4_pv_fp16_triton"}
+
+
+def test_reference_public_surface():
+    """Every name the reference package exports exists here with the same leading parameters (in order), accepts
+    **kwargs like the reference, and the lowbit_fa_* names are the same objects as the sageattn_* ones."""
+    import inspect
+
+    import lowbit_quant_fa2_paddle_b200 as L
+    for name, params in REFERENCE_API.items():
+        fn = getattr(L, name)
+        sig = inspect.signature(fn)
+        got = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert got == params, f"{name}: {got}"
+        assert any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values()), f"{name} must accept **kwargs"
+    for new, old in ALIASES.items():
+        assert getattr(L, new) is getattr(L, old)
+
+
+def test_more_error_conventions():
+    import lowbit_quant_fa2_paddle_b200 as L
+    from lowbit_quant_fa2_paddle_b200._native import LowbitNativeError
+    h = torch.randn(1, 2, 64, 64).half()
+    with pytest.raises(ValueError):
+        L.sageattn_qk_int8_pv_fp16_cuda(h, h, h, qk_quant_gran="per_block")
+    with pytest.raises(ValueError):
+        L.sageattn_qk_int8_pv_fp16_cuda(h, h, h, pv_accum_dtype="fp64")
+    with pytest.raises(ValueError):
+        L.sageattn_qk_int8_pv_fp8_cuda(h, h, h, pv_accum_dtype="fp16")
+    with pytest.raises(LowbitNativeError):
+        L.sageattn(h, h, h, attn_mask=None, dropout_p=0.0)  # SDPA keywords tolerated; CPU tensors refused
+    p = torch.randn(10, 2, 64).half()
+    cu = torch.tensor([0, 4, 10], dtype=torch.int32)
+    with pytest.raises(LowbitNativeError):
+        L.lowbit_fa_varlen(p, p, p, cu, cu, 6, 6)
+    with pytest.raises(AssertionError):
+        L.lowbit_fa_varlen(p.float(), p.float(), p.float(), cu, cu, 6, 6)
+    with pytest.raises(LowbitNativeError):
+        L.lowbit_fa_host(h, h, h, device="cpu")
+    assert L.plan_chunks(4, 32, 32, "HND", None) == [(b, h0, h0 + 16) for b in range(4) for h0 in (0, 16)]
+    assert L.plan_chunks(2, 8, 2, "NHD", 8) == [(0, 0, 2), (1, 0, 2)]
+    with pytest.raises(ValueError):
+        L.plan_chunks(1, 3, 2, "HND", 4)

@@ -678,3 +678,82 @@ def test_prep_qk_full_size_config2(L, cuda_dev):
     assert torch.equal(got[4], km)
     for g, r in zip(got[:4], ref):
         assert torch.equal(g, r)
+
+
+# ------------------------------------------------------------------------------------------------ varlen (packed) path
+VARLEN = golden_names("varlen_")
+
+
+@pytest.mark.parametrize("name", VARLEN)
+def test_varlen_matches_reference_kernel_golden(L, cuda_dev, name):
+    """Packed (cu_seqlens) quantizer: codes, scales (reference block-major layout) and scale offsets bit-exact against
+    the reference's varlen kernel; attention over the same codes within the padded operator's tolerance."""
+    g = load_golden(name)
+    dev = cuda_dev
+    q, k, v = (g[n].to(dev) for n in ("q", "k", "v"))
+    cu_q, cu_k = g["cu_q"].to(dev), g["cu_k"].to(dev)
+    mq = int((g["cu_q"][1:] - g["cu_q"][:-1]).max())
+    mk_ = int((g["cu_k"][1:] - g["cu_k"][:-1]).max())
+    km = L.k_mean_varlen(k)
+    assert torch.equal(km.cpu(), g["km"])
+    got = L.per_block_int8_varlen(q, k, cu_q, cu_k, mq, mk_, sm_scale=g["sm_scale"], km=km)
+    for t, n in zip(got, ("q_int8", "q_scale", "k_int8", "k_scale", "cu_q_scale", "cu_k_scale")):
+        assert torch.equal(t.cpu().to(g[n].dtype), g[n]), n
+    causal = bool(g["causal"])
+    o = L.forward_varlen(got[0], got[2], v.to(torch.float16), cu_q, cu_k, mq, got[1], got[3], got[4], got[5],
+                         output_dtype=g["o"].dtype, causal=causal, compat_tail=not causal)
+    tol = 4e-3 if g["o"].dtype == torch.float16 else 3.2e-2
+    err = (o.cpu().float() - g["o"].float()).abs().max().item()
+    assert err <= tol, f"max-abs {err}"
+    assert cos_sim(o.cpu(), g["o"]) >= 0.999
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype,d", [(torch.float16, 64), (torch.bfloat16, 128), (torch.float16, 80)])
+def test_varlen_api_vs_oracle_and_sdpa(L, cuda_dev, causal, dtype, d):
+    """lowbit_fa_varlen end to end (batch-global K mean, per-sequence blocks, empty and one-token sequences, int64
+    cu_seqlens, padded head_dim) against the CPU oracle of core.py:356-491 and per-sequence FP32 SDPA."""
+    from oracle import attention as OA
+    from oracle import varlen as OV
+    lq = [300, 0, 1, 129, 64]
+    lk = lq if causal else [77, 0, 5, 256, 1]
+    hq, hkv = 4, 2
+    g = torch.Generator().manual_seed(41)
+    q = torch.randn(sum(lq), hq, d, generator=g).to(dtype)
+    k = (torch.randn(sum(lk), hkv, d, generator=g) + 1.5 * torch.randn(1, hkv, d, generator=g)).to(dtype)
+    v = torch.randn(sum(lk), hkv, d, generator=g).to(dtype)
+    cu_q = [0] + torch.tensor(lq).cumsum(0).tolist()
+    cu_k = [0] + torch.tensor(lk).cumsum(0).tolist()
+    o = L.lowbit_fa_varlen(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev),
+                           torch.tensor(cu_q, dtype=torch.int64, device=cuda_dev),
+                           torch.tensor(cu_k, dtype=torch.int32, device=cuda_dev), max(lq), max(lk), is_causal=causal)
+    assert o.shape == q.shape and o.dtype == dtype
+    ref = OV.lowbit_fa_varlen_api(q, k, v, cu_q, cu_k, causal, compat_tail=False, pv_accum="fp32")
+    tol = 4e-3 if dtype == torch.float16 else 3.2e-2
+    assert (o.cpu().float() - ref.float()).abs().max().item() <= tol
+    for i in range(len(lq)):
+        a, b, c, e = cu_q[i], cu_q[i + 1], cu_k[i], cu_k[i + 1]
+        if b == a or e == c:
+            continue
+        sd = OA.sdpa_fp32(q[a:b].unsqueeze(0), k[c:e].unsqueeze(0), v[c:e].unsqueeze(0), "NHD", causal)
+        assert cos_sim(o[a:b].cpu(), sd[0]) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------------ dispatcher / CUDA-API names
+def test_sageattn_dispatcher_and_cuda_api_names(L, cuda_dev):
+    """sageattn / lowbit_fa_attn (core.py:82-190) and the *_fp16_cuda signature (core.py:495-731) run the sm_100a kernel:
+    identical to the _triton entry point under the CUDA quantizer's rounding, SDPA keywords ignored, lse returned."""
+    q = mk(2, 4, 300, 64, "HND", torch.float16, 51).to(cuda_dev)
+    k = mk(2, 2, 300, 64, "HND", torch.float16, 52, bias=2.0).to(cuda_dev)
+    v = mk(2, 2, 300, 64, "HND", torch.float16, 53).to(cuda_dev)
+    ref, lse_ref = L.lowbit_fa_qk_int8_pv_fp16_triton(q, k, v, quantization_backend="cuda", is_causal=True,
+                                                      return_lse=True)
+    o, lse = L.sageattn(q, k, v, is_causal=True, return_lse=True, attn_mask=None, dropout_p=0.0)
+    assert torch.equal(o, ref) and torch.equal(lse, lse_ref)
+    for acc in ("fp16", "fp16+fp32", "fp32"):
+        o2 = L.lowbit_fa_qk_int8_pv_fp16_cuda(q, k, v, is_causal=True, pv_accum_dtype=acc, qk_quant_gran="per_warp",
+                                              smooth_v=True)
+        assert torch.equal(o2, ref)
+    from oracle import attention as OA
+    sd = OA.sdpa_fp32(q.cpu(), k.cpu(), v.cpu(), "HND", True)
+    assert cos_sim(o.cpu(), sd) >= 0.999

@@ -88,3 +88,40 @@ def test_k_mean_order_independent():
     assert (km.float() - k.float().mean(dim=2, keepdim=True)).abs().max() < 4e-3
     kn = k.permute(0, 2, 1, 3).contiguous()
     assert torch.equal(Q.k_mean(kn, "NHD").permute(0, 2, 1, 3), km)
+
+
+# ------------------------------------------------------------------------------------------------ varlen (packed) path
+VARLEN = golden_names("varlen_")
+
+
+@pytest.mark.parametrize("name", VARLEN)
+def test_varlen_oracle_matches_reference_kernels(name):
+    """oracle/varlen.py against the reference's own varlen quantizer + attention kernels (interpreter):
+    codes / scales / scale offsets bit-exact, attention within 4 output ulps."""
+    from oracle import varlen as OV
+    g = load_golden(name)
+    cu_q, cu_k = g["cu_q"].tolist(), g["cu_k"].tolist()
+    km = OV.k_mean_varlen(g["k"])
+    assert torch.equal(km, g["km"])
+    qi, qs, ki, ks, cqs, cks = OV.per_block_int8_varlen(g["q"], g["k"] - km, cu_q, cu_k, sm_scale=g["sm_scale"])
+    assert torch.equal(qi, g["q_int8"]) and torch.equal(ki, g["k_int8"])
+    assert torch.equal(qs, g["q_scale"]) and torch.equal(ks, g["k_scale"])
+    assert cqs == g["cu_q_scale"].tolist() and cks == g["cu_k_scale"].tolist()
+    o = OV.attn_varlen(qi, ki, g["v"].to(torch.float16), cu_q, cu_k, qs, ks, cqs, cks, bool(g["causal"]), g["o"].dtype)
+    tol = 4e-3 if g["o"].dtype == torch.float16 else 3.2e-2
+    assert (o.float() - g["o"].float()).abs().max() <= tol
+    assert cos_sim(o, g["o"]) > 0.99999
+
+
+@pytest.mark.parametrize("name", VARLEN)
+def test_varlen_api_glue_vs_sdpa(name):
+    """core.py:356-491 restated end to end stays close to per-sequence FP32 SDPA."""
+    from oracle import varlen as OV
+    g = load_golden(name)
+    cu_q, cu_k = g["cu_q"].tolist(), g["cu_k"].tolist()
+    causal = bool(g["causal"])
+    o = OV.lowbit_fa_varlen_api(g["q"], g["k"], g["v"], cu_q, cu_k, causal, compat_tail=False, pv_accum="fp32")
+    for i in range(len(cu_q) - 1):
+        a, b, c, e = cu_q[i], cu_q[i + 1], cu_k[i], cu_k[i + 1]
+        ref = A.sdpa_fp32(g["q"][a:b].unsqueeze(0), g["k"][c:e].unsqueeze(0), g["v"][c:e].unsqueeze(0), "NHD", causal)
+        assert cos_sim(o[a:b], ref[0]) > 0.999
