@@ -65,9 +65,8 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
         packed = (qk != "int8") and A.PACKED_K4_KERNEL
         # K mean, then both quantizers with the K smoothing fused (core.py:291-319).  The single-launch form
         # (Qz.prep_qk) is bit-identical but measured slower on B200 (117 vs 89 us at config 2), so it is not used here.
-        km = Qz.k_mean(kt, tensor_layout) if smooth_k else None
-        q_c, q_s, k_c, k_s = Qz._per_block(qt, kt, km, 128, 64, sm_scale, tensor_layout, 8, kbits,
-                                           packed, quantization_backend)
+        q_c, q_s, k_c, k_s, km = Qz.smooth_and_quantize(qt, kt, smooth_k, sm_scale, tensor_layout, 8, kbits, packed,
+                                                        quantization_backend)
         qk_mode = N.QK_Q8K4 if packed else N.QK_I8
         o, lse = A._forward(q_c, k_c, vt, q_s, k_s, tensor_layout, dtype, return_lse, bool(is_causal),
                             qk_mode=qk_mode, pv_mode=N.PV_E4M3 if pv == "fp8" else N.PV_F16,

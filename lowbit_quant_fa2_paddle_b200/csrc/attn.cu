@@ -114,6 +114,7 @@ __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ 
     // packed fp32x2 arithmetic (FFMA2 / FADD2): one instruction scales, or accumulates, two scores
     const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
     float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+    float2 acc2 = make_float2(0.f, 0.f), acc3 = make_float2(0.f, 0.f);  // VAR bit 6: four independent sum chains
 #pragma unroll
     for (int c = 0; c < BN; c += 4) {
       const float2 x0 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c]), score_to_f32<VAR>(s[c + 1])), sc2, nm2);
@@ -129,12 +130,18 @@ __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ 
         p1.x = (c + 2 <= lim) ? p1.x : 0.f;
         p1.y = (c + 3 <= lim) ? p1.y : 0.f;
       }
-      acc0 = __fadd2_rn(acc0, p0);
-      acc1 = __fadd2_rn(acc1, p1);
+      if ((VAR & 64) && (c % 8 == 4)) {
+        acc2 = __fadd2_rn(acc2, p0);
+        acc3 = __fadd2_rn(acc3, p1);
+      } else {
+        acc0 = __fadd2_rn(acc0, p0);
+        acc1 = __fadd2_rn(acc1, p1);
+      }
       pk[c / 2] = ptx::pack_f16x2(p0.x, p0.y);
       pk[c / 2 + 1] = ptx::pack_f16x2(p1.x, p1.y);
     }
-    const float2 t = __fadd2_rn(acc0, acc1);
+    float2 t = __fadd2_rn(acc0, acc1);
+    if (VAR & 64) t = __fadd2_rn(t, __fadd2_rn(acc2, acc3));
     return t.x + t.y;
   } else {
     float lsum0 = 0.f, lsum1 = 0.f;
@@ -850,6 +857,7 @@ static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
       case 12: return launch_attn<D, KM_I8, PV_F16, 12>(tq, tk, tv, p, B, st);
       case 16: return launch_attn<D, KM_I8, PV_F16, 16>(tq, tk, tv, p, B, st);
       case 32: return launch_attn<D, KM_I8, PV_F16, 32>(tq, tk, tv, p, B, st);
+      case 64: return launch_attn<D, KM_I8, PV_F16, 64>(tq, tk, tv, p, B, st);
       default: return launch_attn<D, KM_I8, PV_F16, 0>(tq, tk, tv, p, B, st);
     }
   }

@@ -87,6 +87,50 @@ def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpac
     return q_c, q_s, k_c, k_s
 
 
+_side = {}  # device index -> side stream for the Q quantizer
+
+
+def smooth_and_quantize(q, k, smooth_k, sm_scale, tensor_layout, qbits, kbits, kpack, backend, overlap=None):
+    """`km = k.mean(seq)`, K codes from `k - km`, Q codes (core.py:291-319).  The Q quantizer does not depend on the K
+    chain (mean -> K codes), and each of these 15-30 us HBM-bound launches leaves the chip half idle while it ramps up
+    and drains, so Q runs on a side stream next to the K chain and the caller's stream waits for it before the
+    attention launch (LOWBIT_QUANT_OVERLAP=0 serialises them).  -> (q_codes, q_scale, k_codes, k_scale, km)."""
+    import os
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if backend not in _MODES:
+        raise ValueError(f"Unsupported quantization backend: {backend}")
+    mode = _MODES[backend]
+    qt, kt = T.as_torch(q), T.as_torch(k)
+    dev = T.require_cuda(qt, kt)
+    if sm_scale is None:
+        sm_scale = qt.shape[-1] ** -0.5
+    if overlap is None:
+        overlap = os.environ.get("LOWBIT_QUANT_OVERLAP", "1") != "0"
+    if not overlap:
+        km = k_mean(kt, tensor_layout) if smooth_k else None
+        k_c, k_s = _quant_one(kt, km, 64, kbits, kpack, 1.0, mode, tensor_layout)
+        q_c, q_s = _quant_one(qt, None, 128, qbits, False, sm_scale * LOG2E, mode, tensor_layout)
+        return q_c, q_s, k_c, k_s, km
+    b, h, n, d, _, _, _ = T.bhnd(qt, tensor_layout)
+    q_c = torch.empty(qt.shape, dtype=torch.int8, device=dev)
+    q_s = torch.empty((b, h, (n + 127) // 128), dtype=torch.float32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    side = _side.get(dev.index)
+    if side is None:
+        side = _side[dev.index] = torch.cuda.Stream(dev)
+    fork, join = torch.cuda.Event(), torch.cuda.Event()
+    fork.record(cur)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        _quant_one(qt, None, 128, qbits, False, sm_scale * LOG2E, mode, tensor_layout, out=(q_c, q_s))
+        join.record(side)
+    km = k_mean(kt, tensor_layout) if smooth_k else None
+    k_c, k_s = _quant_one(kt, km, 64, kbits, kpack, 1.0, mode, tensor_layout)
+    cur.wait_event(join)
+    return q_c, q_s, k_c, k_s, km
+
+
 _MODES = {"triton": N.QMODE_TRITON, "triton_gpu": N.QMODE_TRITON | N.QMODE_FLAG_DIV_FULL, "cuda": N.QMODE_CUDA}
 _prep_ws = {}  # (device index, stream handle) -> [workspace tensor (zero-filled once), epoch]
 
