@@ -30,6 +30,28 @@ def _side_streams(dev: torch.device):
     return _streams[key]
 
 
+_NSLOT = 3
+_stage_cache = {}
+
+
+def _staging(dev: torch.device, dtype, shapes):
+    """Persistent device staging buffers (q, k, v chunk + a "slot free" event) x _NSLOT, cached per chunk geometry, so
+    the pipelined loop never goes to the allocator (a cudaMalloc in the loop shows up as a multi-millisecond stall)."""
+    key = (dev.index, dtype, shapes)
+    slots = _stage_cache.get(key)
+    if slots is None:
+        if len(_stage_cache) >= 4:  # a handful of geometries at most: drop the oldest
+            _stage_cache.pop(next(iter(_stage_cache)))
+        slots = []
+        for _ in range(_NSLOT):
+            bufs = [torch.empty(sh, dtype=dtype, device=dev) for sh in shapes]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            slots.append((bufs[0], bufs[1], bufs[2], ev))
+        _stage_cache[key] = slots
+    return slots
+
+
 def plan_chunks(B: int, Hq: int, Hkv: int, tensor_layout: str, chunks: Optional[int]) -> List[Tuple[int, int, int]]:
     """Cut the (batch, kv-head) units into chunks whose host memory is ONE contiguous range per tensor (a strided
     host slice would need a CPU-side gather before the DMA).  Returns [(b, kv_head_begin, kv_head_end), ...].
@@ -88,31 +110,33 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
         s_in, s_out = _side_streams(dev)
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
-        staged = None
+        b0, h0, h1 = plan[0]
+        shapes = tuple(tuple(view(t, b0, a, e).shape) for t, a, e in ((qt, h0 * grp, h1 * grp), (kt, h0, h1), (vt, h0, h1)))
+        slots = _staging(dev, qt.dtype, shapes)
 
         def stage(i):
+            """H2D of chunk i into staging slot i % NSLOT, after the kernels that last read that slot."""
             b, h0, h1 = plan[i]
+            dq, dk, dv, free = slots[i % _NSLOT]
             with torch.cuda.stream(s_in):
-                dk = view(kt, b, h0, h1).to(dev, non_blocking=True)  # K first: its mean + codes head the chunk
-                dq = view(qt, b, h0 * grp, h1 * grp).to(dev, non_blocking=True)
-                dv = view(vt, b, h0, h1).to(dev, non_blocking=True)
+                s_in.wait_event(free)
+                dk.copy_(view(kt, b, h0, h1), non_blocking=True)  # K first: its mean + codes head the chunk
+                dq.copy_(view(qt, b, h0 * grp, h1 * grp), non_blocking=True)
+                dv.copy_(view(vt, b, h0, h1), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s_in)
-            return dq, dk, dv, ev
+            return dq, dk, dv, ev, free
 
         staged = stage(0)
         for i, (b, h0, h1) in enumerate(plan):
-            dq, dk, dv, ev = staged
+            dq, dk, dv, ev, free = staged
             if i + 1 < len(plan):
                 staged = stage(i + 1)  # enqueue the next H2D before this chunk's kernels
             cur.wait_event(ev)
             o = op(dq, dk, dv, tensor_layout=tensor_layout, **op_kwargs)
-            for t in (dq, dk, dv):
-                t.record_stream(cur)
-            done = torch.cuda.Event()
-            done.record(cur)
+            free.record(cur)  # the slot may be overwritten once these kernels are done
             with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
+                s_out.wait_event(free)
                 view(out, b, h0 * grp, h1 * grp).copy_(o, non_blocking=True)
             o.record_stream(s_out)
         cur.wait_stream(s_out)
