@@ -54,7 +54,8 @@ enum {
 enum {
   LOWBIT_QK_I8 = 0,     /* Q int8, K int8 (one code per byte)                               */
   LOWBIT_QK_Q8K4 = 1,   /* Q int8, K int4 packed two codes per byte (low nibble = even d)   */
-  LOWBIT_QK_Q8KMIX = 2  /* Q int8, K per-64-block bit width from `kbits` (8/4/2), packed    */
+  LOWBIT_QK_Q8KMIX = 2  /* Q int8, K per-64-block bit width from `kbits` (8/4/2) in the mixed
+                           container written by lowbit_quant_k_mixed                          */
 };
 enum { LOWBIT_PV_F16 = 0, LOWBIT_PV_E4M3 = 1 };
 
@@ -67,6 +68,19 @@ enum {
 
 int lowbit_version(void);
 const char* lowbit_last_error(void);
+
+/* Dynamic K bit allocation (the reference has thresholds, core.py:1055-1061, and harnesses but no kernel;
+ * semantics stated here, parity unpinned): every 64-row block of (k - km) is quantized symmetrically to INT8, INT4 or
+ * INT2 (codes in [-127,127] / [-7,7] / [-1,1], Q1 or Q2 rounding per `mode`).  The width is kbits_in[b,h,j] when given,
+ * else chosen from the block statistic st = max|k - km| / 127:  st > thr8 -> 8,  st > thr4 -> 4,  else 2.
+ * codes: a container of D bytes per row (strides like any int8 [.., D] tensor, 16-byte aligned); a block of width w
+ * uses the first D*w/8 bytes of each of its rows, in the byte order the attention kernel expands in shared memory
+ * (csrc/quant.cu, "mixed-width K").  scale, kbits_out: [B,H,ceil(N/64)] contiguous.  Consumed by lowbit_attn_fwd /
+ * lowbit_attn_fwd_partial with qk_mode LOWBIT_QK_Q8KMIX, whose K loads move D*w/8 bytes per row. */
+int lowbit_quant_k_mixed(const void* k, const void* km, const int32_t* kbits_in, void* codes, float* scale,
+                         int32_t* kbits_out, int B, int H, int N, int D, int64_t isb, int64_t ish, int64_t isn,
+                         int64_t osb, int64_t osh, int64_t osn, float thr8, float thr4, int mode, int dtype,
+                         void* stream);
 
 /* S1 + Q1/Q2/Q4 fused -- everything the attention kernel needs from q and k in ONE launch: K mean over the sequence
  * (src/core.py:293), K smoothing `k - km` and per-64-row-block K codes, per-128-row-block Q codes scaled by

@@ -16,6 +16,7 @@ from .core import (  # noqa: F401
     lowbit_fa_qk_int8_pv_fp16_triton,
     lowbit_fa_qk_int4_pv_fp16_triton,
     lowbit_fa_q_int8_k_int4_pv_fp16,
+    lowbit_fa_q_int8_k_dynamic,
     lowbit_fa_qk_int8_pv_fp8_cuda,
     lowbit_fa_qk_int4_pv_fp8,
     compute_scale,
@@ -30,6 +31,7 @@ from .quant import (  # noqa: F401
     per_block_int4,
     per_block_q_int8_k_int4,
     per_block_k_lowbit,
+    per_block_k_mixed,
     per_thread_int8,
     per_thread_int4,
     per_warp_int8,

@@ -36,7 +36,7 @@ def _v_strides(vt, tensor_layout, pv_mode):
     return vt.stride(0), vt.stride(2), vt.stride(1)
 
 
-def _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean):
+def _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean, kbits=None):
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"tensor_layout {tensor_layout} not supported")
     qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
@@ -54,15 +54,21 @@ def _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale,
         vs = T.as_torch(v_scale).contiguous()
         vm = T.as_torch(v_mean).contiguous() if v_mean is not None else None
         assert vs.dtype == torch.float32 and tuple(vs.shape) == (b, hkv, d)
+    kb = None
+    if qk_mode == N.QK_Q8KMIX:
+        assert kbits is not None, "mixed-width K needs the kbits map returned by per_block_k_mixed"
+        kb = T.as_torch(kbits)
+        assert kb.dtype == torch.int32 and kb.is_contiguous() and tuple(kb.shape) == (b, hkv, (nk + 63) // 64)
     ptrs = (qt.data_ptr(), kt.data_ptr(), vt.data_ptr(), qs.data_ptr(), ks.data_ptr(),
-            vs.data_ptr() if vs is not None else None, vm.data_ptr() if vm is not None else None, None)
+            vs.data_ptr() if vs is not None else None, vm.data_ptr() if vm is not None else None,
+            kb.data_ptr() if kb is not None else None)
     dims = (b, hq, hkv, nq, nk, d, qsb, qsh, qsn, ksb, ksh, ksn, vsb, vsh, vsn)
-    return dev, qt, ptrs, dims, (vs, vm)
+    return dev, qt, ptrs, dims, (vs, vm, kb)
 
 
 def _forward(q, k, v, q_scale, k_scale, tensor_layout, output_dtype, return_lse, causal,
              qk_mode=N.QK_I8, pv_mode=N.PV_F16, compat_tail=False, v_scale=None, v_mean=None, kbits=None, out=None):
-    dev, qt, ptrs, dims, keep = _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean)
+    dev, qt, ptrs, dims, keep = _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean, kbits)
     b, hq, hkv, nq, nk, d = dims[:6]
     if causal:
         assert nq == nk, "qo_len and kv_len must be equal for causal attention"
@@ -94,10 +100,10 @@ class PartialState:
 
 
 def forward_partial(state, q, k, v, q_scale, k_scale, tensor_layout="HND", causal=False, q_offset=0, k_offset=0,
-                    qk_mode=N.QK_I8, pv_mode=N.PV_F16, v_scale=None, v_mean=None):
+                    qk_mode=N.QK_I8, pv_mode=N.PV_F16, v_scale=None, v_mean=None, kbits=None):
     """One ring step: attend the resident Q shard to one K/V shard and merge into `state` (created on first use
     when None).  q_offset / k_offset: global token positions of the shards' first rows (causal masking)."""
-    dev, qt, ptrs, dims, keep = _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean)
+    dev, qt, ptrs, dims, keep = _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean, kbits)
     b, hq, hkv, nq, nk, d = dims[:6]
     if state is None:
         state = PartialState(b, hq, nq, d, dev)

@@ -35,7 +35,7 @@ def _pad_head(x, to):
 
 
 def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
-               qk, compat_tail=False, pv="fp16", smooth_v=False):
+               qk, compat_tail=False, pv="fp16", smooth_v=False, kmix=None):
     qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
     dtype = qt.dtype
     assert dtype in [torch.float16, torch.bfloat16], \
@@ -65,12 +65,20 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
         packed = (qk != "int8") and A.PACKED_K4_KERNEL
         # K mean, then both quantizers with the K smoothing fused (core.py:291-319).  The single-launch form
         # (Qz.prep_qk) is bit-identical but measured slower on B200 (117 vs 89 us at config 2), so it is not used here.
-        q_c, q_s, k_c, k_s, km = Qz.smooth_and_quantize(qt, kt, smooth_k, sm_scale, tensor_layout, 8, kbits, packed,
-                                                        quantization_backend)
-        qk_mode = N.QK_Q8K4 if packed else N.QK_I8
+        kb = None
+        if qk == "mixed":  # dynamic INT8 / INT4 / INT2 per 64-row K block
+            km = Qz.k_mean(kt, tensor_layout) if smooth_k else None
+            k_c, k_s, kb = Qz.per_block_k_mixed(kt, km, kmix[0], kmix[1], kmix[2], tensor_layout, quantization_backend)
+            q_c, q_s = Qz._quant_one(qt, None, 128, 8, False, sm_scale * LOG2E, Qz._MODES[quantization_backend],
+                                     tensor_layout)
+            qk_mode = N.QK_Q8KMIX
+        else:
+            q_c, q_s, k_c, k_s, km = Qz.smooth_and_quantize(qt, kt, smooth_k, sm_scale, tensor_layout, 8, kbits, packed,
+                                                            quantization_backend)
+            qk_mode = N.QK_Q8K4 if packed else N.QK_I8
         o, lse = A._forward(q_c, k_c, vt, q_s, k_s, tensor_layout, dtype, return_lse, bool(is_causal),
                             qk_mode=qk_mode, pv_mode=N.PV_E4M3 if pv == "fp8" else N.PV_F16,
-                            compat_tail=compat_tail, v_scale=v_scale, v_mean=v_mean)
+                            compat_tail=compat_tail, v_scale=v_scale, v_mean=v_mean, kbits=kb)
         o = o[..., :head_dim_og]
         if return_lse:
             b, hq, nq, d, sb, sh, sn = T.bhnd(qt, tensor_layout)
@@ -172,6 +180,20 @@ def lowbit_fa_qk_int4_pv_fp8(q, k, v, tensor_layout: str = "HND", is_causal: boo
     The reference has the two halves (core.py:945-1036 and :735-941) but no kernel that combines them."""
     return _lowbit_fa(q, k, v, tensor_layout, kwargs.get("quantization_backend", "triton"), is_causal, sm_scale,
                       smooth_k, return_lse, "int4", pv="fp8", smooth_v=smooth_v)
+
+
+def lowbit_fa_q_int8_k_dynamic(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                               sm_scale: Optional[float] = None, smooth_k: bool = True, return_lse: bool = False,
+                               kbits=None, hi: float = 0.2, lo: float = 0.05, pv: str = "fp16", **kwargs: Any):
+    """Dynamic K bit allocation (BASELINE config 5): Q INT8 per 128-row block, every 64-row K block INT8,
+    INT4 or INT2 by the thresholds of select_quantization (core.py:1055-1061) applied to the block scale
+    max|k - km| / 127 (> lo: 8 bits, > lo/4: 4, else 2), or by an explicit `kbits` map [B,Hkv,ceil(N/64)].
+    The attention kernel loads D*bits/8 bytes per K row and expands them to int8 in shared memory, so the integer
+    products stay exact.  pv: "fp16" | "fp8"."""
+    if pv not in ("fp16", "fp8"):
+        raise ValueError(f"Unsupported pv: {pv}")
+    return _lowbit_fa(q, k, v, tensor_layout, kwargs.get("quantization_backend", "triton"), is_causal, sm_scale,
+                      smooth_k, return_lse, "mixed", pv=pv, kmix=(kbits, hi, lo))
 
 
 def compute_scale(tensor, bits=8, symmetric=True, tensor_layout="HND"):

@@ -20,6 +20,12 @@
 // expansion yields head-dim order [d0 d2 d4 d6 d1 d3 d5 d7] inside every group of 8, so the Q tile is permuted the
 // same way once per CTA (a contraction is invariant under a common permutation of its reduction index) and the
 // factor 16 is folded into the dequantization scale (exact: a power of two).
+//
+// Mixed-width K (dynamic INT8 / INT4 / INT2 per 64-key block, `kbits`): K lives in a container of D bytes per row of
+// which a block uses the first D*bits/8; the producer picks one of three tensor maps (box D, D/2, D/4 bytes) per
+// block, so HBM / L2 traffic follows the bit width, and the softmax threads expand 8-bit (copy), 4-bit (as above) or
+// 2-bit (four shift+mask per 16 codes, code*64) rows into the same permuted int8 operand layout; the quantizer
+// writes 8- and 2-bit rows in the byte order that makes those expansions land in that layout (quant.cu).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -35,6 +41,7 @@ struct AttnParams {
   const float* k_scale;
   const float* v_scale;  // PV e4m3: [B,Hkv,D]
   const float* v_mean;   // PV e4m3: [B,Hkv,D] or null
+  const int32_t* kbits;  // mixed-width K: [B,Hkv,nkb] in {8,4,2}
   void* o;
   float* lse;
   float* m_io;           // partial (ring) state: [B,Hq,Nq]; oacc_io != null selects the merge epilogue
@@ -66,7 +73,7 @@ template <int D, int VAR> struct AttnSP {
   static constexpr int kThreads = kSoftmaxThreads + 32;  // + one helper warp (TMA producer + tcgen05 issuer, one elected lane)
 };
 
-enum { KM_I8 = 0, KM_K4 = 1 };
+enum { KM_I8 = 0, KM_K4 = 1, KM_MIX = 2 };  // KM_K4 / KM_MIX: K tiles are expanded in shared memory
 enum { PV_F16 = 0, PV_E4M3 = 1 };
 
 // Per-head-dim tiling.  D=64 is exp2(MUFU)-bound: small 32-key steps keep the register footprint under 96 so that
@@ -93,8 +100,8 @@ struct AttnSmem {
   static constexpr int kQ = kBM * D;                                  // int8
   static constexpr int kK = C::BN * D;                                // int8 operand stage
   static constexpr int kKStages = (KM == KM_I8) ? C::KS : 2;
-  static constexpr int kKp = C::BN * D / 2;                           // packed INT4 staging stage
-  static constexpr int kKpStages = (KM == KM_K4) ? 4 : 0;
+  static constexpr int kKp = (KM == KM_MIX) ? C::BN * D : C::BN * D / 2;  // packed staging stage (worst case)
+  static constexpr int kKpStages = (KM == KM_K4) ? 4 : (KM == KM_MIX ? 3 : 0);
   static constexpr int kV = (PV == PV_F16) ? C::BN * D * 2 : C::BN * D;  // fp16 [key][d] / e4m3 [d][key]
   static constexpr int kBytes = kQ + kKStages * kK + C::VS * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
 };
@@ -237,6 +244,49 @@ __device__ __forceinline__ void unpack_k4_tile(const uint8_t* __restrict__ src, 
     *reinterpret_cast<uint4*>(dst + (off1 ^ (((off1 >> 7) & kSwzMask) << 4))) = b;
   }
 }
+// mixed-width K, 8-bit block: rows are already in the permuted byte order; move 16-byte chunks into the swizzled layout
+template <int D, int BN, int NT>
+__device__ __forceinline__ void copy_k8_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int tid) {
+  constexpr uint32_t kSwzMask = (D == 64) ? 3u : 7u;
+#pragma unroll
+  for (int q = tid; q < BN * D / 16; q += NT) {
+    const uint32_t off = (uint32_t)q * 16;
+    *reinterpret_cast<uint4*>(dst + (off ^ (((off >> 7) & kSwzMask) << 4))) = *reinterpret_cast<const uint4*>(src + off);
+  }
+}
+// mixed-width K, 2-bit block: one packed 16-byte chunk (64 codes, field k of byte i = bits [2k, 2k+2)) becomes four
+// 16-byte chunks of code*64 (field k of every byte -> output chunk k)
+template <int D, int BN, int NT>
+__device__ __forceinline__ void unpack_k2_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int tid) {
+  constexpr int kChunks = BN * D / 64;
+  constexpr int kCPR = D / 64;
+  constexpr uint32_t kSwzMask = (D == 64) ? 3u : 7u;
+  constexpr uint32_t kM = 0xC0C0C0C0u;
+#pragma unroll
+  for (int q = tid; q < kChunks; q += NT) {
+    const uint4 w = *reinterpret_cast<const uint4*>(src + q * 16);
+    const uint32_t off0 = (uint32_t)(q / kCPR) * D + (uint32_t)(q % kCPR) * 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 o;
+      o.x = (w.x << (6 - 2 * k)) & kM; o.y = (w.y << (6 - 2 * k)) & kM;
+      o.z = (w.z << (6 - 2 * k)) & kM; o.w = (w.w << (6 - 2 * k)) & kM;
+      const uint32_t off = off0 + 16 * k;
+      *reinterpret_cast<uint4*>(dst + (off ^ (((off >> 7) & kSwzMask) << 4))) = o;
+    }
+  }
+}
+// expand one staged K tile of the given bit width into the int8 operand stage
+template <int D, int BN, int NT, int KM>
+__device__ __forceinline__ void expand_k_tile(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int tid, int bits) {
+  if constexpr (KM == KM_MIX) {
+    if (bits == 8) copy_k8_tile<D, BN, NT>(src, dst, tid);
+    else if (bits == 4) unpack_k4_tile<D, BN, NT>(src, dst, tid);
+    else unpack_k2_tile<D, BN, NT>(src, dst, tid);
+  } else {
+    unpack_k4_tile<D, BN, NT>(src, dst, tid);
+  }
+}
 // the matching permutation of the Q tile: [d0..d7] -> [d0 d2 d4 d6 d1 d3 d5 d7] inside every 8-byte group
 // (16-byte chunks move as units under the hardware swizzle, so the tile can be walked linearly)
 template <int D, int NT>
@@ -260,13 +310,15 @@ __device__ __forceinline__ void permute_q_tile(uint8_t* sQ, int tid) {
 template <int D, int KM, int PV, int VAR, bool DBG>
 __global__ void __launch_bounds__((AttnSP<D, VAR>::kThreads), AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK8,
+                const __grid_constant__ CUtensorMap tmK2, const AttnParams p) {
   using C = AttnCfg<D>;
   using SM = AttnSmem<D, KM, PV>;
   using PC = PvCfg<PV>;
   constexpr int BN = C::BN, VS = C::VS;
   constexpr int KS = SM::kKStages;                   // int8 operand stages (INT4 mode: 2, indexed like the S buffers)
-  constexpr int KPS = (KM == KM_K4) ? SM::kKpStages : C::KS;  // TMA-filled K stages
+  constexpr bool KX = (KM != KM_I8);                          // K tiles are expanded by the softmax threads
+  constexpr int KPS = KX ? SM::kKpStages : C::KS;             // TMA-filled K stages
   constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;     // TMEM columns of one P tile
   constexpr int SP = AttnSP<D, VAR>::value;                   // softmax warpgroups (threads per query row)
   constexpr int kSoftmaxThreads = AttnSP<D, VAR>::kSoftmaxThreads;
@@ -332,7 +384,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(bar_q, 1);
     for (int i = 0; i < KPS; ++i) {
       ptx::mbar_init(kfull + i, 1);
-      ptx::mbar_init(kfree + i, KM == KM_K4 ? kSoftmaxThreads : 1);
+      ptx::mbar_init(kfree + i, KX ? kSoftmaxThreads : 1);
     }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kSoftmaxThreads); }
@@ -343,6 +395,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
+    if constexpr (KM == KM_MIX) { ptx::prefetch_tmap(&tmK8); ptx::prefetch_tmap(&tmK2); }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -365,9 +418,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if constexpr (KM == KM_I8) {
           ptx::mbar_expect_tx(kfull + ks, SM::kK);
           ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * BN, hkv, b);
-        } else {
+        } else if constexpr (KM == KM_K4) {
           ptx::mbar_expect_tx(kfull + ks, SM::kKp);
           ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, j * BN, hkv, b);
+        } else {  // mixed width: the block's bit width picks the box (first D*bits/8 bytes of every container row)
+          const int bits = p.kbits[((int64_t)b * p.Hkv + hkv) * p.nkb + min(j * BN / kScaleBlk, p.nkb - 1)];
+          const CUtensorMap* tm = (bits == 8) ? &tmK8 : (bits == 4 ? &tmK : &tmK2);
+          ptx::mbar_expect_tx(kfull + ks, BN * D * bits / 8);
+          ptx::tma_load_4d(sKp + ks * SM::kKp, tm, kfull + ks, 0, j * BN, hkv, b);
         }
       };
       auto load_v = [&](int j) {
@@ -383,7 +441,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       auto issue_qk = [&](int j) {
         const int ks = j % KS;
-        if constexpr (KM == KM_I8) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+        if constexpr (!KX) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
         ptx::tc_fence_after();
         const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
         const uint32_t tS = tmem_base + (j & 1) * BN;
@@ -394,13 +452,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
         }
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
-        if constexpr (KM == KM_I8) ptx::umma_commit(kfree + ks);  // K stage may be refilled
+        if constexpr (!KX) ptx::umma_commit(kfree + ks);  // K stage may be refilled
       };
       ptx::mbar_expect_tx(bar_q, SM::kQ);
       ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
       for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
       for (int j = 0; j < min(2, nblk); ++j) load_v(j);
-      if constexpr (KM == KM_I8) {
+      if constexpr (!KX) {
         ptx::mbar_wait(bar_q, 0, 21);
       } else {
         ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted, K_0 / K_1 expanded (their packed stages are free again)
@@ -436,7 +494,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (j == nblk - 1) ptx::umma_commit(bar_final);
         if (j + 2 < nblk) issue_qk(j + 2);  // overwrites S/P buffer (j&1): ordered after PV_j on the tensor pipe
         // refill: the K stage consumed longest ago and the V stage of PV_{j-1} (complete in steady state)
-        if constexpr (KM == KM_I8) {
+        if constexpr (!KX) {
           if (j + KPS < nblk) load_k(j + KPS);
         } else {
           if (j + 2 + KPS < nblk) load_k(j + 2 + KPS);  // softmax step j expanded K_{j+2}: its packed stage is free
@@ -454,6 +512,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
     if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
     const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
+    const int32_t* kb_ptr = (KM == KM_MIX) ? p.kbits + ((int64_t)b * p.Hkv + hkv) * p.nkb : nullptr;
+    auto kb = [&](int jj) -> int {  // bit width of key block jj
+      if constexpr (KM == KM_MIX) return kb_ptr[min(jj * BN / kScaleBlk, p.nkb - 1)];
+      else return 4;
+    };
+    auto kfac = [&](int jj) -> float {  // the expanded operand holds code, code*16 or code*64
+      if constexpr (KM == KM_MIX) { const int bb = kb(jj); return bb == 8 ? 1.f : (bb == 4 ? 0.0625f : 0.015625f); }
+      else return 1.f;
+    };
     const bool mask_tail = !compat && (p.Nk % BN != 0);
     const int last_kblk = (p.Nk + BN - 1) / BN - 1;
     const uint32_t tS0 = tmem_base + lane_off + half * BNH, tS1 = tS0 + BN;  // my score columns in S buffer 0 / 1
@@ -461,14 +528,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
 
-    if constexpr (KM == KM_K4) {
+    if constexpr (KX) {
       ptx::mbar_wait(bar_q, 0, 33);
       permute_q_tile<D, kSoftmaxThreads>(sQ, tid);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (j < nblk) {
           ptx::mbar_wait(kfull + j, 0, 34);
-          unpack_k4_tile<D, BN, kSoftmaxThreads>(sKp + j * SM::kKp, sK + j * SM::kK, tid);
+          expand_k_tile<D, BN, kSoftmaxThreads, KM>(sKp + j * SM::kKp, sK + j * SM::kK, tid, kb(j));
           ptx::mbar_arrive(kfree + j);
         }
       }
@@ -478,8 +545,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // one key block: wait for S, row max, (rare) rescale of O, P = exp2(S*sc - m) -> TMEM, signal the issuer
     auto step = [&](auto masked_tag, const uint32_t tSb, const uint32_t tPb, uint64_t* bs, uint64_t* pr,
-                    const uint32_t ph, const int j, const float sc, const int lim_tile) {
+                    const uint32_t ph, const int j, const float sc_in, const int lim_tile) {
       constexpr bool MASKED = decltype(masked_tag)::value;
+      const float sc = sc_in * kfac(j);
       const int lim = lim_tile - half * BNH;  // live columns of my half: [0, lim]
       ptx::mbar_wait(bs, ph, 30);
       ptx::tc_fence_after();
@@ -538,12 +606,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (PV == PV_F16) l += softmax_block_f16<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
       else l += softmax_block_e4m3<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
       tmem_st_n<PCH>(tPb, pk);  // P aliases the first columns of its S buffer
-      if constexpr (KM == KM_K4) {
+      if constexpr (KX) {
         // expand K_{j+2} into the operand stage QK_j just released (S_j ready => QK_j complete)
         if (j + 2 < nblk) {
           const int kps = (j + 2) % KPS;
           ptx::mbar_wait(kfull + kps, ((j + 2) / KPS) & 1, 35);
-          unpack_k4_tile<D, BN, kSoftmaxThreads>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid);
+          expand_k_tile<D, BN, kSoftmaxThreads, KM>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid, kb(j + 2));
           ptx::mbar_arrive(kfree + kps);
           ptx::fence_proxy_async_smem();
         }
@@ -553,101 +621,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_arrive(pr);
     };
 
-    // Development variant (VAR bit 5, D = 128 only; measured SLOWER on B200: 1125 vs 1338 TOPS at B4 H32 N4096, the
-    // second 64-register score array spills at the 168-register cap of two CTAs/SM -- kept for the next tuning round):
-    // the score row of block j+1 is prefetched from TMEM into a second register array while the exponentials of
-    // block j run: the S-ready barrier latency, the tcgen05.ld latency and
-    // (through the scheduler) the integer row max of the next block hide under the MUFU phase instead of adding to it.
-    // The probe of the S barrier is non-blocking and repeated between the four quarters of the block, so a warp never
-    // waits for S_{j+1} with its own exponentials still to do.
-    constexpr bool PF = (D == 128) && (SP == 1) && !DBG && ((VAR & 32) != 0);
     constexpr int kPerScale = kScaleBlk / BN;  // key blocks per k_scale entry (2 for BN=32, 1 for BN=64)
     int n_full = nblk;  // blocks [0, n_full) need no mask
     if (causal) n_full = max(0, min(n_full, (dq + 1) / BN));
     if (mask_tail) n_full = min(n_full, last_kblk);
-    if constexpr (PF) {
-      auto issue_ld = [&](uint32_t* dst, const int jn, const bool blocking) -> bool {
-        uint64_t* bs = bar_s + (jn & 1);
-        const uint32_t phn = (jn >> 1) & 1;
-        if (blocking) ptx::mbar_wait(bs, phn, 36);
-        else if (!__all_sync(0xffffffffu, ptx::mbar_test(bs, phn))) return false;
-        ptx::tc_fence_after();
-        tmem_ld_n<BNH>((jn & 1) ? tS1 : tS0, dst);
-        return true;
-      };
-      auto pstep = [&](auto masked_tag, uint32_t* s, uint32_t* sn, const int j, const float sc, const int lim) {
-        constexpr bool MASKED = decltype(masked_tag)::value;
-        constexpr int QN = BNH / 4, QP = PCH / 4;
-        ptx::tmem_wait_ld();  // s (issued by the previous step, or by the prologue) has landed
-#pragma unroll
-        for (int c = 0; c < BNH; c += 16)
-          asm volatile("" : "+r"(s[c]), "+r"(s[c + 1]), "+r"(s[c + 2]), "+r"(s[c + 3]), "+r"(s[c + 4]), "+r"(s[c + 5]),
-                            "+r"(s[c + 6]), "+r"(s[c + 7]), "+r"(s[c + 8]), "+r"(s[c + 9]), "+r"(s[c + 10]),
-                            "+r"(s[c + 11]), "+r"(s[c + 12]), "+r"(s[c + 13]), "+r"(s[c + 14]), "+r"(s[c + 15]));
-        const int imax = row_max<BNH, MASKED>(s, lim);
-        const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
-        if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
-          const float m_new = fmaxf(m_ref, mblk);
-          const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);
-          l *= alpha;
-          m_ref = m_new;
-          if (j > 0) {
-            ptx::mbar_wait(bar_o, (j - 1) & 1, 31);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < D; c += 16) {
-              uint32_t o[16];
-              ptx::tmem_ld_x16(tOl + c, o);
-              ptx::tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              ptx::tmem_st_x16(tOl + c, o);
-            }
-          }
-        }
-        uint32_t pk[PCH];
-        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;
-        const bool more = j + 1 < nblk;
-        bool have = !more;
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          if (!have) have = issue_ld(sn, j + 1, false);
-          if constexpr (PV == PV_F16) l += softmax_block_f16<QN, MASKED, VAR>(s + qd * QN, sc, nm, lim - qd * QN, pk + qd * QP);
-          else l += softmax_block_e4m3<QN, MASKED, VAR>(s + qd * QN, sc, nm, lim - qd * QN, pk + qd * QP);
-        }
-        tmem_st_n<PCH>((j & 1) ? tP1 : tP0, pk);
-        if constexpr (KM == KM_K4) {
-          if (j + 2 < nblk) {
-            const int kps = (j + 2) % KPS;
-            ptx::mbar_wait(kfull + kps, ((j + 2) / KPS) & 1, 35);
-            unpack_k4_tile<D, BN, kSoftmaxThreads>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid);
-            ptx::mbar_arrive(kfree + kps);
-            ptx::fence_proxy_async_smem();
-          }
-        }
-        ptx::tmem_wait_st();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(p_ready + (j & 1));
-        if (!have) issue_ld(sn, j + 1, true);
-      };
-      uint32_t sA[BNH], sB[BNH];
-      issue_ld(sA, 0, true);
-      int j = 0;
-      for (; j + 1 < n_full; j += 2) {
-        const float sc0 = qs * ks_ptr[j / kPerScale], sc1 = qs * ks_ptr[(j + 1) / kPerScale];
-        pstep(std::false_type{}, sA, sB, j, sc0, 0);
-        pstep(std::false_type{}, sB, sA, j + 1, sc1, 0);
-      }
-      for (; j < nblk; ++j) {
-        const float sc = qs * ks_ptr[min(j / kPerScale, p.nkb - 1)];
-        const int c0 = j * BN;
-        int lim = BN;  // columns [0, lim] are live
-        if (causal) lim = min(lim, p.delta + row - c0);
-        if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
-        if (j & 1) pstep(std::true_type{}, sB, sA, j, sc, lim);
-        else pstep(std::true_type{}, sA, sB, j, sc, lim);
-      }
-    } else {
+    {
     // unrolled by two so buffer / barrier addresses are loop constants
     int j = 0;
     uint32_t ph = 0;
@@ -830,7 +808,7 @@ int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize,
 
 template <int D, int KM, int PV, int VAR, bool DBG = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
-                       cudaStream_t st) {
+                       cudaStream_t st, const CUtensorMap* tk8 = nullptr, const CUtensorMap* tk2 = nullptr) {
   auto kern = attn_fwd_kernel<D, KM, PV, VAR, DBG>;
   using SM = AttnSmem<D, KM, PV>;
   static bool configured = false;
@@ -839,14 +817,18 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, AttnSP<D, VAR>::kThreads, SM::kBytes, st>>>(tq, tk, tv, p);
+  kern<<<grid, AttnSP<D, VAR>::kThreads, SM::kBytes, st>>>(tq, tk, tv, tk8 ? *tk8 : tk, tk2 ? *tk2 : tk, p);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int D>
 static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
-                         int B, int km, int pv, cudaStream_t st) {
+                         int B, int km, int pv, cudaStream_t st, const CUtensorMap* tk8, const CUtensorMap* tk2) {
+  if (km == KM_MIX) {
+    if (pv == PV_F16) return launch_attn<D, KM_MIX, PV_F16, 0>(tq, tk, tv, p, B, st, tk8, tk2);
+    return launch_attn<D, KM_MIX, PV_E4M3, 0>(tq, tk, tv, p, B, st, tk8, tk2);
+  }
   static int variant = -1;  // development switch (LOWBIT_ATTN_VARIANT): A/B of softmax instruction selection
   if (variant < 0) { const char* e = getenv("LOWBIT_ATTN_VARIANT"); variant = e ? atoi(e) : 0; }
   if (km == KM_I8 && pv == PV_F16) {
@@ -856,7 +838,6 @@ static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
       case 4: return launch_attn<D, KM_I8, PV_F16, 4>(tq, tk, tv, p, B, st);
       case 12: return launch_attn<D, KM_I8, PV_F16, 12>(tq, tk, tv, p, B, st);
       case 16: return launch_attn<D, KM_I8, PV_F16, 16>(tq, tk, tv, p, B, st);
-      case 32: return launch_attn<D, KM_I8, PV_F16, 32>(tq, tk, tv, p, B, st);
       case 64: return launch_attn<D, KM_I8, PV_F16, 64>(tq, tk, tv, p, B, st);
       default: return launch_attn<D, KM_I8, PV_F16, 0>(tq, tk, tv, p, B, st);
     }
@@ -885,15 +866,16 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   LOWBIT_CHECK(a.D == 64 || a.D == 128, "%s: head_dim must be 64 or 128 (got %d)", who, a.D);
   LOWBIT_CHECK(a.B > 0 && a.Hq > 0 && a.Hkv > 0 && a.Nq > 0 && a.Nk > 0, "%s: empty tensor", who);
   LOWBIT_CHECK(a.Hq % a.Hkv == 0, "%s: num_qo_heads (%d) must be divisible by num_kv_heads (%d)", who, a.Hq, a.Hkv);
-  LOWBIT_CHECK(a.qk_mode == LOWBIT_QK_I8 || a.qk_mode == LOWBIT_QK_Q8K4, "%s: qk_mode %d not implemented", who, a.qk_mode);
+  LOWBIT_CHECK(a.qk_mode == LOWBIT_QK_I8 || a.qk_mode == LOWBIT_QK_Q8K4 || a.qk_mode == LOWBIT_QK_Q8KMIX,
+               "%s: bad qk_mode %d", who, a.qk_mode);
+  LOWBIT_CHECK(a.qk_mode != LOWBIT_QK_Q8KMIX || a.kbits != nullptr, "%s: mixed-width K needs kbits", who);
   LOWBIT_CHECK(a.pv_mode == LOWBIT_PV_F16 || a.pv_mode == LOWBIT_PV_E4M3, "%s: bad pv_mode %d", who, a.pv_mode);
   LOWBIT_CHECK(a.pv_mode != LOWBIT_PV_E4M3 || a.v_scale != nullptr, "%s: the FP8 P.V path needs v_scale", who);
-  (void)a.kbits;
   const int D = a.D, BN = (D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN;
-  const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : KM_I8;
+  const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : (a.qk_mode == LOWBIT_QK_Q8KMIX ? KM_MIX : KM_I8);
   const int pv = (a.pv_mode == LOWBIT_PV_E4M3) ? PV_E4M3 : PV_F16;
 
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, tk8, tk2;
   const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   {
     const int64_t dim[4] = {D, a.Nq, a.Hq, a.B}, str[3] = {a.qsn, a.qsh, a.qsb};
@@ -902,9 +884,14 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   if (km == KM_I8) {
     const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
     if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, swz_qk)) return 1;
-  } else {  // packed INT4: rows of D/2 bytes, landed linearly (no swizzle) for the in-kernel expansion
+  } else if (km == KM_K4) {  // packed INT4: rows of D/2 bytes, landed linearly (no swizzle) for the in-kernel expansion
     const int64_t dim[4] = {D / 2, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
     if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  } else {  // mixed width: container rows of D bytes; one map per bit width, the box takes the row prefix in use
+    const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
+    if (make_map(&tk8, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (make_map(&tk2, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 4, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   }
   if (pv == PV_F16) {
     const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.vsn, a.vsh, a.vsb};
@@ -915,12 +902,14 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
     if (make_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, BN, D,
                  BN == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   }
-  p.q_scale = a.q_scale; p.k_scale = a.k_scale; p.v_scale = a.v_scale; p.v_mean = a.v_mean;
+  p.q_scale = a.q_scale; p.k_scale = a.k_scale; p.v_scale = a.v_scale; p.v_mean = a.v_mean; p.kbits = a.kbits;
   p.Hq = a.Hq; p.Hkv = a.Hkv; p.Nq = a.Nq; p.Nk = a.Nk;
   p.nqb = (a.Nq + 127) / 128; p.nkb = (a.Nk + 63) / 64;
   p.flags = a.flags;
-  if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, a.B, km, pv, st);
-  return dispatch_attn<128>(tq, tk, tv, p, a.B, km, pv, st);
+  const CUtensorMap* p8 = (km == KM_MIX) ? &tk8 : nullptr;
+  const CUtensorMap* p2 = (km == KM_MIX) ? &tk2 : nullptr;
+  if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, a.B, km, pv, st, p8, p2);
+  return dispatch_attn<128>(tq, tk, tv, p, a.B, km, pv, st, p8, p2);
 }
 
 }  // namespace lowbit

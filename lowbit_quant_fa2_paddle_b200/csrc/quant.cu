@@ -96,6 +96,24 @@ __device__ __forceinline__ void store_codes8(int8_t* dst_row, int c8, const int 
     *reinterpret_cast<uint16_t*>(dst_row + c8 / 4) = (uint16_t)w;
   }
 }
+// the 8 codes of one thread's row chunk under the block's rounding convention
+__device__ __forceinline__ void codes8(const float (&x)[8], int (&c)[8], float sc, float rcp, bool triton, bool slow_div,
+                                       bool gpu_div) {
+  if (triton && gpu_div) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = q1_code_divfull(x[i], sc);
+  } else if (triton && !slow_div) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = q1_code_fast(x[i], sc, rcp);
+  } else if (triton) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = q1_code_ieee(x[i], sc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = max(-128, min(127, __float2int_rn(__fmul_rn(x[i], rcp))));
+  }
+}
+
 // passes [PB, PB + PC) of x hold the rows of the block that starts at row0 (PC = -1: all passes)
 template <int NPASS, int PB = 0, int PC = -1>
 __device__ __forceinline__ void quantize_rows(const float (&x)[NPASS][8], int8_t* dst, int64_t osn, int row0, int rpp,
@@ -108,19 +126,7 @@ __device__ __forceinline__ void quantize_rows(const float (&x)[NPASS][8], int8_t
     const int row = row0 + rl;
     if (!(rl < blk && row < N)) continue;
     int c[8];
-    if (triton && gpu_div) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) c[i] = q1_code_divfull(x[p][i], sc);
-    } else if (triton && !slow_div) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) c[i] = q1_code_fast(x[p][i], sc, rcp);
-    } else if (triton) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) c[i] = q1_code_ieee(x[p][i], sc);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) c[i] = max(-128, min(127, __float2int_rn(__fmul_rn(x[p][i], rcp))));
-    }
+    codes8(x[p], c, sc, rcp, triton, slow_div, gpu_div);
     store_codes8(dst + (int64_t)row * osn, c8, c, bits, pack);
   }
 }
@@ -263,6 +269,111 @@ static int launch_qpb(const void* in, const void* km, void* codes, float* scale,
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// mixed-width K: dynamic INT8 / INT4 / INT2 per 64-row block (thresholds of core.py:1055-1061)
+// ------------------------------------------------------------------------------------------------
+// Container: D bytes per row; a block of width `bits` uses the first D*bits/8 bytes of each of its rows, in the byte
+// order the attention kernel's in-smem expansion expects (attn.cu: operand order [d0 d2 d4 d6 d1 d3 d5 d7] inside
+// every 8-group):
+//   8 bit: byte 8g+p            = code(d = 8g + perm[p]),  perm = [0 2 4 6 1 3 5 7]
+//   4 bit: byte 4g+i            = code(8g+2i) | code(8g+2i+1) << 4          (same as the packed INT4 format)
+//   2 bit: byte 16c + 8(g%2)+p, bits [2(g/2), 2(g/2)+2) = code(d = 64c + 8g + perm[p]),  g = 8-group inside the
+//          64-code chunk c (the kernel's shift k of a chunk yields output bytes 16k .. 16k+15)
+// Block statistic = max|k - km| / 127 (compute_scale): > thr8 -> 8 bits, > thr4 -> 4, else 2; or kbits_in when given.
+template <typename T, int D>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_k_mixed_kernel(const T* __restrict__ in, const T* __restrict__ km, const int32_t* __restrict__ kbits_in,
+                     int8_t* __restrict__ out, float* __restrict__ scale, int32_t* __restrict__ kbits_out, int N,
+                     int nblk, int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
+                     float thr8, float thr4, int mode, int H) {
+  constexpr int BLK = 64;
+  constexpr int TPR = D / 8, RPP = kQuantThreads / TPR, NP = BLK / RPP, NW = kQuantThreads / 32;
+  __shared__ float s_w[NW];
+  const int tid = threadIdx.x, c8 = (tid % TPR) * 8, r0 = tid / TPR;
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const T* src = in + b * isb + h * ish + c8;
+  float kmf[8];
+  const bool has_km = km != nullptr;
+  if (has_km) unpack8<T>(__ldcg(reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8)), kmf);
+  float x[NP][8];
+  uint4 raw[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int row = jb * BLK + p * RPP + r0;
+    raw[p] = make_uint4(0, 0, 0, 0);
+    if (row < N) raw[p] = ld_stream_v4(src + (int64_t)row * isn);
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    unpack8<T>(raw[p], x[p]);
+    const bool live = jb * BLK + p * RPP + r0 < N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = x[p][i];
+      if (has_km) {
+        v = __fsub_rn(v, kmf[i]);
+        if ((mode & 0xff) == LOWBIT_QMODE_TRITON) v = to_f32<T>(from_f32<T>(v));
+      }
+      v = live ? v : 0.f;
+      x[p][i] = v;
+      amax = fmaxf(amax, fabsf(v));
+    }
+  }
+  amax = warp_max(amax);
+  if ((tid & 31) == 0) s_w[tid >> 5] = amax;
+  __syncthreads();
+  float bmax = s_w[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) bmax = fmaxf(bmax, s_w[w]);
+  const int64_t bidx = ((int64_t)b * H + h) * nblk + jb;
+  int bits;
+  if (kbits_in != nullptr) {
+    bits = kbits_in[bidx];
+  } else {
+    const float st = __fdiv_rn(bmax, 127.f);
+    bits = st > thr8 ? 8 : (st > thr4 ? 4 : 2);
+  }
+  const BlockScale bs = block_scale(bmax, bits, mode);
+  if (tid == 0) {
+    scale[bidx] = bs.sc;
+    kbits_out[bidx] = bits;
+  }
+  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
+  int8_t* dst = out + b * osb + h * osh;
+  const int g = (c8 >> 3) & 7, chunk = c8 >> 6;  // 8-group inside its 64-code chunk, chunk inside the row
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int row = jb * BLK + p * RPP + r0;
+    const bool live = row < N;
+    int c[8];
+    codes8(x[p], c, bs.sc, bs.rcp, triton, bs.slow_div, bs.gpu_div);
+    int8_t* drow = dst + (int64_t)row * osn;
+    if (bits == 8) {
+      if (live) {
+        uint2 w;
+        w.x = pack_s8x4(c[0], c[2], c[4], c[6]);
+        w.y = pack_s8x4(c[1], c[3], c[5], c[7]);
+        *reinterpret_cast<uint2*>(drow + c8) = w;
+      }
+    } else if (bits == 4) {
+      if (live) store_codes8(drow, c8, c, 4, 1);
+    } else {
+      // my 8 codes are one 2-bit field (k = g/2) of 8 bytes; the other three fields of those bytes belong to the
+      // lanes g^2, g^4, g^6 of the same row: OR them together with two shuffles (block-uniform branch, all lanes in)
+      const int sh = 2 * (g >> 1);
+      uint32_t lo = 0, hi = 0;
+      lo |= (uint32_t)(c[0] & 3) << (sh + 0);  lo |= (uint32_t)(c[2] & 3) << (sh + 8);
+      lo |= (uint32_t)(c[4] & 3) << (sh + 16); lo |= (uint32_t)(c[6] & 3) << (sh + 24);
+      hi |= (uint32_t)(c[1] & 3) << (sh + 0);  hi |= (uint32_t)(c[3] & 3) << (sh + 8);
+      hi |= (uint32_t)(c[5] & 3) << (sh + 16); hi |= (uint32_t)(c[7] & 3) << (sh + 24);
+      lo |= __shfl_xor_sync(0xffffffffu, lo, 2); hi |= __shfl_xor_sync(0xffffffffu, hi, 2);
+      lo |= __shfl_xor_sync(0xffffffffu, lo, 4); hi |= __shfl_xor_sync(0xffffffffu, hi, 4);
+      if (live && (g >> 1) == 0) *reinterpret_cast<uint2*>(drow + chunk * 16 + 8 * (g & 1)) = make_uint2(lo, hi);
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // per-block symmetric quantizer, TMA-pipelined persistent form (the one normally launched)
@@ -685,6 +796,31 @@ extern "C" {
 
 int lowbit_version(void) { return LOWBIT_ABI_VERSION; }
 const char* lowbit_last_error(void) { return last_error().c_str(); }
+
+int lowbit_quant_k_mixed(const void* k, const void* km, const int32_t* kbits_in, void* codes, float* scale,
+                         int32_t* kbits_out, int B, int H, int N, int D, int64_t isb, int64_t ish, int64_t isn,
+                         int64_t osb, int64_t osh, int64_t osn, float thr8, float thr4, int mode, int dtype,
+                         void* stream) {
+  LOWBIT_CHECK(D == 64 || D == 128, "lowbit_quant_k_mixed: head_dim must be 64 or 128 (got %d)", D);
+  LOWBIT_CHECK(k && codes && scale && kbits_out, "lowbit_quant_k_mixed: null pointer");
+  LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_quant_k_mixed: empty tensor");
+  LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_quant_k_mixed: bad mode %d", mode);
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0, "lowbit_quant_k_mixed: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(osn % 16 == 0 && osh % 16 == 0 && osb % 16 == 0 && ((uintptr_t)codes & 15) == 0,
+               "lowbit_quant_k_mixed: container rows must keep 16-byte alignment");
+  const int nblk = (N + 63) / 64;
+  dim3 grid(nblk, H, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_MIX(T, DD)                                                                                         \
+  quant_k_mixed_kernel<T, DD><<<grid, kQuantThreads, 0, st>>>((const T*)k, (const T*)km, kbits_in, (int8_t*)codes, \
+      scale, kbits_out, N, nblk, isb, ish, isn, osb, osh, osn, thr8, thr4, mode, H)
+  if (dtype == LOWBIT_F16) { if (D == 64) LAUNCH_MIX(__half, 64); else LAUNCH_MIX(__half, 128); }
+  else if (dtype == LOWBIT_BF16) { if (D == 64) LAUNCH_MIX(__nv_bfloat16, 64); else LAUNCH_MIX(__nv_bfloat16, 128); }
+  else return lowbit::fail("lowbit_quant_k_mixed: bad dtype %d", dtype);
+#undef LAUNCH_MIX
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int64_t lowbit_prep_qk_workspace_bytes(int B, int Hkv, int Nk, int D) {
   const int chunk = mean_chunk_rows(Nk);

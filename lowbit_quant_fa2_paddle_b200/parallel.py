@@ -123,10 +123,12 @@ def kv_fields(b, hkv, d, chunks: List[Chunk], tensor_layout, qk, pv) -> List[Fie
     fs = []
     for i, c in enumerate(chunks):
         n = c.length
-        dk = d // 2 if qk == "int4" else d
+        dk = d // 2 if qk == "int4" else d  # "mixed": the D-byte container (a block uses its first D*bits/8 bytes)
         shp = (lambda dd: (b, hkv, n, dd)) if tensor_layout == "HND" else (lambda dd: (b, n, hkv, dd))
         fs.append(Field(f"k{i}", torch.int8, shp(dk)))
         fs.append(Field(f"ks{i}", torch.float32, (b, hkv, (n + 63) // 64)))
+        if qk == "mixed":
+            fs.append(Field(f"kb{i}", torch.int32, (b, hkv, (n + 63) // 64)))
         if pv == "fp8":
             npad = (n + 63) // 64 * 64
             fs.append(Field(f"v{i}", torch.float8_e4m3fn, (b, hkv, d, npad) if tensor_layout == "HND" else (b, d, hkv, npad)))
@@ -145,7 +147,8 @@ class CudaBackend:
         from . import quant as Qz
         self.A, self.Qz = A, Qz
         self.layout, self.qk, self.pv, self.sm_scale = tensor_layout, qk, pv, sm_scale
-        self.qk_mode = N.QK_Q8K4 if qk == "int4" else N.QK_I8
+        self.qk_mode = N.QK_Q8K4 if qk == "int4" else (N.QK_Q8KMIX if qk == "mixed" else N.QK_I8)
+        self.k_thresholds = (0.2, 0.05)
         self.pv_mode = N.PV_E4M3 if pv == "fp8" else N.PV_F16
 
     def k_sum(self, k, seq_dim):
@@ -157,9 +160,14 @@ class CudaBackend:
         return self.Qz._quant_one(q_chunk, None, 128, 8, False, self.sm_scale * LOG2E, N.QMODE_TRITON, self.layout)
 
     def quantize_kv(self, k_chunk, v_chunk, km, msg: RingMessage, i: int):
-        bits, pack = (4, True) if self.qk == "int4" else (8, False)
-        self.Qz._quant_one(k_chunk, km, 64, bits, pack, 1.0, N.QMODE_TRITON, self.layout,
-                           out=(msg.view(f"k{i}"), msg.view(f"ks{i}")))
+        if self.qk == "mixed":
+            msg.view(f"k{i}").zero_()  # unused row tails of the container
+            self.Qz.per_block_k_mixed(k_chunk, km, None, self.k_thresholds[0], self.k_thresholds[1], self.layout,
+                                      out=(msg.view(f"k{i}"), msg.view(f"ks{i}"), msg.view(f"kb{i}")))
+        else:
+            bits, pack = (4, True) if self.qk == "int4" else (8, False)
+            self.Qz._quant_one(k_chunk, km, 64, bits, pack, 1.0, N.QMODE_TRITON, self.layout,
+                               out=(msg.view(f"k{i}"), msg.view(f"ks{i}")))
         if self.pv == "fp8":
             v8, vs, _ = self.Qz.per_channel_fp8(v_chunk, self.layout, smooth_v=False)
             msg.view(f"v{i}").copy_(v8)
@@ -172,7 +180,8 @@ class CudaBackend:
         return self.A.forward_partial(state, qc, msg.view(f"k{i}"), msg.view(f"v{i}"), qs, msg.view(f"ks{i}"),
                                       self.layout, causal=causal, q_offset=q_off, k_offset=k_off,
                                       qk_mode=self.qk_mode, pv_mode=self.pv_mode,
-                                      v_scale=msg.view(f"vs{i}") if self.pv == "fp8" else None)
+                                      v_scale=msg.view(f"vs{i}") if self.pv == "fp8" else None,
+                                      kbits=msg.view(f"kb{i}") if self.qk == "mixed" else None)
 
     def finalize(self, state, q_pack, out_dtype, return_lse):
         return self.A.finalize(state, q_pack[0], self.layout, out_dtype, return_lse)
@@ -199,7 +208,7 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
     import torch.distributed as dist
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
-    if qk not in ("int8", "int4") or pv not in ("fp16", "fp8"):
+    if qk not in ("int8", "int4", "mixed") or pv not in ("fp16", "fp8"):
         raise ValueError(f"Unsupported ring formats qk={qk} pv={pv}")
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     zigzag = bool(is_causal) if zigzag is None else zigzag

@@ -221,6 +221,43 @@ def per_block_k_lowbit(k, km=None, BLKK=64, bits=2, tensor_layout="HND", pack=Tr
     return _quant_one(k, km, BLKK, bits, pack, 1.0, N.QMODE_TRITON, tensor_layout)
 
 
+def per_block_k_mixed(k, km=None, kbits=None, hi=0.2, lo=0.05, tensor_layout="HND", backend="triton", out=None):
+    """Dynamic K bit allocation: every 64-row block of k - km goes to INT8, INT4 or INT2.
+    kbits: optional int32 [B,H,ceil(N/64)] map to impose; else the block statistic st = max|k - km| / 127
+    (compute_scale, core.py:1039-1047) picks 8 bits when st > lo (both upper classes of select_quantization,
+    core.py:1055-1061: there is no per-block FP16 fallback), 4 when st > lo / 4, else 2.
+    -> (codes: int8 container [.., D] -- a block of width w uses the first D*w/8 bytes of its rows --,
+        k_scale f32 [B,H,nblk], kbits int32 [B,H,nblk]); attention consumes it with qk_mode QK_Q8KMIX."""
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if backend not in _MODES:
+        raise ValueError(f"Unsupported quantization backend: {backend}")
+    kt = T.as_torch(k)
+    dev = T.require_cuda(kt)
+    b, h, n, d, sb, sh, sn = T.bhnd(kt, tensor_layout)
+    if d not in (64, 128):
+        raise ValueError(f"Unsupported head_dim: {d} (the kernels take 64 or 128; core pads smaller ones)")
+    kmt = _km_bhd(km, b, h, d, tensor_layout)
+    nblk = (n + 63) // 64
+    if out is None:
+        codes = torch.zeros(kt.shape, dtype=torch.int8, device=dev)  # unused row tails stay zero
+        scale = torch.empty((b, h, nblk), dtype=torch.float32, device=dev)
+        bits = torch.empty((b, h, nblk), dtype=torch.int32, device=dev)
+    else:
+        codes, scale, bits = out
+    kin = None
+    if kbits is not None:
+        kin = T.as_torch(kbits).to(device=dev, dtype=torch.int32).contiguous()
+        assert tuple(kin.shape) == (b, h, nblk), f"kbits must have shape [{b},{h},{nblk}]"
+    _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
+    thr8 = float(torch.tensor(lo, dtype=torch.float32))
+    thr4 = float(torch.tensor(lo / 4, dtype=torch.float32))
+    N.call("lowbit_quant_k_mixed", kt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
+           kin.data_ptr() if kin is not None else None, codes.data_ptr(), scale.data_ptr(), bits.data_ptr(),
+           b, h, n, d, sb, sh, sn, osb, osh, osn, thr8, thr4, _MODES[backend], T.dtype_code(kt.dtype), T.stream_ptr(dev))
+    return T.like(codes, k), T.like(scale, k), T.like(bits, k)
+
+
 def _per_thread(q, k, km, BLKQ, BLKK, WARPQ, WARPK, tensor_layout, bits):
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")

@@ -164,7 +164,7 @@ def v8_to_natural(v8, n, tensor_layout="HND"):
 
 def lowbit_fa_api(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, smooth_k=True,
                   return_lse=False, qk="int8", pv_accum="fp16_block", compat_tail=True, km=None,
-                  pv="fp16", smooth_v=False):
+                  pv="fp16", smooth_v=False, kmix=None):
     """E1/E2/E3 glue restated from src/core.py:269-352: head-dim pad (:277-287), km (:291-306; contract
     SURVEY 2.3-H via oracle.quant.k_mean), bf16 V -> fp16 (:307-308), sm_scale from the un-padded
     head dim (:309-310), Q1 quantize (:311-314), attention (:321-342), slice (:343), LSE fix-up (:344-350).
@@ -196,8 +196,13 @@ def lowbit_fa_api(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, 
         v = v.to(torch.float16)
     if sm_scale is None:
         sm_scale = 1.0 / d_og ** 0.5
-    kbits = 8 if qk == "int8" else 4
-    qi, qs, ki, ks = Q.per_block_int8_q1(q, k, km, sm_scale=sm_scale, tensor_layout=tensor_layout, kbits=kbits)
+    if qk == "mixed":  # dynamic INT8 / INT4 / INT2 per K block (oracle.quant.quant_k_mixed; `kmix` = (kbits, hi, lo))
+        qi, qs = Q.quant_per_block_q1(q, 128, sm_scale * LOG2E, tensor_layout, 8)
+        kb, hi, lo = kmix if kmix is not None else (None, 0.2, 0.05)
+        ki, ks, _ = Q.quant_k_mixed(k, km, kb, 64, tensor_layout, hi, lo)
+    else:
+        kbits = 8 if qk == "int8" else 4
+        qi, qs, ki, ks = Q.per_block_int8_q1(q, k, km, sm_scale=sm_scale, tensor_layout=tensor_layout, kbits=kbits)
     o, lse2 = attn_block_emulator(qi, ki, v, qs, ks, tensor_layout, is_causal, dtype, return_lse,
                                   pv_accum=pv_accum, compat_tail=compat_tail,
                                   pv_mode="e4m3" if pv == "fp8" else "f16", v_scale=v_scale, v_mean=v_mean)

@@ -271,6 +271,88 @@ def k_bits_map(k_sub, blk=64, layout="HND", hi=0.2, lo=0.05):
     return bits
 
 
+def quant_k_mixed(k, km=None, kbits=None, blk=64, layout="HND", hi=0.2, lo=0.05):
+    """Dynamic K bit allocation (our stated semantics; parity unpinned): k <- k - km in the input dtype
+    (quant_per_block.py:186-187); per 64-row block bits = kbits[b,h,j] when given else k_bits_map(k - km); codes by the
+    Q1 arithmetic with QMAX[bits] (quant_per_block.py:173-176 / :60-63).
+    Returns (codes int8 in k's layout, one code per element, scale f32 [B,H,nblk], kbits int32 [B,H,nblk])."""
+    if km is not None:
+        k = k - km
+    bits = k_bits_map(k, blk, layout, hi, lo) if kbits is None else kbits.to(torch.int32)
+    codes = torch.zeros(k.shape, dtype=torch.int8)
+    ch = _to_hnd(codes, layout)
+    scale = None
+    for w in (8, 4, 2):
+        c_w, s_w = quant_per_block_q1(k, blk, 1.0, layout, w)
+        if scale is None:
+            scale = torch.zeros_like(s_w)
+        sel = bits == w                                       # [B,H,nblk]
+        scale = torch.where(sel, s_w, scale)
+        rows = sel.repeat_interleave(blk, dim=2)[:, :, :ch.shape[2]]
+        ch.copy_(torch.where(rows[..., None], _to_hnd(c_w, layout), ch))
+    return codes, scale.contiguous(), bits.contiguous()
+
+
+_P4 = [0, 2, 4, 6, 1, 3, 5, 7]
+
+
+def pack_mixed(codes, kbits, blk=64, layout="HND"):
+    """The mixed-width container the CUDA quantizer writes (include/lowbit_fa.h, lowbit_quant_k_mixed): D bytes per
+    row; a block of width w uses the first D*w/8 bytes of its rows; byte order (p = position in an 8-group g):
+      8 bit: byte 8g+p = code(8g + P4[p]);   4 bit: byte 4g+i = code(8g+2i) | code(8g+2i+1) << 4;
+      2 bit: byte 16c + 8(g%2) + p, bits [2(g//2), +2) = code(64c + 8g + P4[p])   (c = 64-code chunk, g = group in it).
+    Unused row tails are zero.  Returns int8 in `codes`' layout."""
+    ch = _to_hnd(codes, layout).to(torch.int32)
+    b, h, n, d = ch.shape
+    out = torch.zeros(b, h, n, d, dtype=torch.int32)
+    bits_rows = kbits.repeat_interleave(blk, dim=2)[:, :, :n]
+    perm = torch.tensor([8 * g + p for g in range(d // 8) for p in _P4])
+    c8 = ch[..., perm]                                                       # 8-bit rows
+    c4 = (ch[..., 0::2] & 15) | ((ch[..., 1::2] & 15) << 4)                   # [.., d/2]
+    c2 = torch.zeros(b, h, n, d // 4, dtype=torch.int32)
+    for c in range(d // 64):
+        for g in range(8):
+            for p in range(8):
+                byte = 16 * c + 8 * (g % 2) + p
+                c2[..., byte] |= (ch[..., 64 * c + 8 * g + _P4[p]] & 3) << (2 * (g // 2))
+    out = torch.where((bits_rows == 8)[..., None], c8, out)
+    pad4 = torch.nn.functional.pad(c4, (0, d - d // 2))
+    pad2 = torch.nn.functional.pad(c2, (0, d - d // 4))
+    out = torch.where((bits_rows == 4)[..., None], pad4, out)
+    out = torch.where((bits_rows == 2)[..., None], pad2, out)
+    res = torch.empty(codes.shape, dtype=torch.int8)
+    _to_hnd(res, layout).copy_(out.to(torch.uint8).view(torch.int8))
+    return res
+
+
+def unpack_mixed(container, kbits, blk=64, layout="HND"):
+    """Inverse of pack_mixed: one int8 code per element (what the attention kernel's in-smem expansion yields, before
+    its common head-dim permutation and power-of-two factor)."""
+    ch = _to_hnd(container, layout).view(torch.uint8).to(torch.int32)
+    b, h, n, d = ch.shape
+    bits_rows = kbits.repeat_interleave(blk, dim=2)[:, :, :n]
+
+    def sext(f, w):
+        return torch.where(f >= (1 << (w - 1)), f - (1 << w), f)
+
+    o8 = torch.zeros(b, h, n, d, dtype=torch.int32)
+    o4 = torch.zeros_like(o8)
+    o2 = torch.zeros_like(o8)
+    for g in range(d // 8):
+        for p in range(8):
+            o8[..., 8 * g + _P4[p]] = sext(ch[..., 8 * g + p], 8)
+    o4[..., 0::2] = sext(ch[..., : d // 2] & 15, 4)
+    o4[..., 1::2] = sext((ch[..., : d // 2] >> 4) & 15, 4)
+    for c in range(d // 64):
+        for g in range(8):
+            for p in range(8):
+                o2[..., 64 * c + 8 * g + _P4[p]] = sext((ch[..., 16 * c + 8 * (g % 2) + p] >> (2 * (g // 2))) & 3, 2)
+    out = torch.where((bits_rows == 8)[..., None], o8, torch.where((bits_rows == 4)[..., None], o4, o2))
+    res = torch.empty(container.shape, dtype=torch.int8)
+    _to_hnd(res, layout).copy_(out.to(torch.int8))
+    return res
+
+
 # ----------------------------------------------------------------------------------------------
 # Q5: KIVI asymmetric group quant + pack   src/triton/utils/quant/new_pack.py:198-300
 # ----------------------------------------------------------------------------------------------

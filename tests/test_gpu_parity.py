@@ -757,3 +757,90 @@ def test_sageattn_dispatcher_and_cuda_api_names(L, cuda_dev):
     from oracle import attention as OA
     sd = OA.sdpa_fp32(q.cpu(), k.cpu(), v.cpu(), "HND", True)
     assert cos_sim(o.cpu(), sd) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------------ dynamic K bit allocation
+def _mixed_k(b, h, n, d, layout, dtype, seed):
+    """K whose 64-row blocks fall into all three width classes after smoothing."""
+    k = mk(b, h, n, d, "HND", torch.float32, seed, bias=2.0)
+    km = k.mean(dim=2, keepdim=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    nblk = (n + 63) // 64
+    w = torch.tensor([0.1, 1.0, 3.0])[torch.randint(0, 3, (b, h, nblk), generator=g)]
+    w = w.repeat_interleave(64, dim=2)[:, :, :n].unsqueeze(-1)
+    k = (km + (k - km) * w).to(dtype)
+    return k if layout == "HND" else k.permute(0, 2, 1, 3).contiguous()
+
+
+@pytest.mark.parametrize("layout", ["HND", "NHD"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,d", [(512, 64), (333, 128), (64, 64), (1, 128)])
+def test_mixed_k_quantizer_bit_exact(L, cuda_dev, layout, dtype, n, d):
+    """lowbit_quant_k_mixed: per-block widths, scales and the container bytes (row prefixes in the kernel's expansion
+    order) are bit-exact against oracle.quant.quant_k_mixed + pack_mixed, with thresholds and with an imposed map."""
+    from oracle import quant as OQ
+    k = _mixed_k(2, 3, n, d, layout, dtype, 61)
+    km_ref = OQ.k_mean(k, layout)
+    km = L.k_mean(k.to(cuda_dev), layout)
+    assert torch.equal(km.cpu(), km_ref)
+    codes, scale, kb = L.per_block_k_mixed(k.to(cuda_dev), km, tensor_layout=layout)
+    rc, rs, rb = OQ.quant_k_mixed(k, km_ref, None, 64, layout)
+    assert torch.equal(kb.cpu(), rb) and torch.equal(scale.cpu(), rs)
+    assert torch.equal(codes.cpu(), OQ.pack_mixed(rc, rb, 64, layout))
+    assert torch.equal(OQ.unpack_mixed(codes.cpu(), rb, 64, layout), rc)
+    if n >= 64:
+        assert set(rb.unique().tolist()) == {2, 4, 8}
+    imposed = torch.tensor([2, 4, 8], dtype=torch.int32)[torch.randint(0, 3, rb.shape)]
+    codes, scale, kb = L.per_block_k_mixed(k.to(cuda_dev), km, kbits=imposed, tensor_layout=layout)
+    rc, rs, rb = OQ.quant_k_mixed(k, km_ref, imposed, 64, layout)
+    assert torch.equal(kb.cpu(), imposed) and torch.equal(scale.cpu(), rs)
+    assert torch.equal(codes.cpu(), OQ.pack_mixed(rc, rb, 64, layout))
+
+
+@pytest.mark.parametrize("layout,hq,hkv,n,d,causal,pv", [
+    ("HND", 2, 2, 512, 64, False, "fp16"),
+    ("HND", 4, 2, 384, 128, True, "fp16"),
+    ("NHD", 2, 2, 200, 64, False, "fp16"),    # ragged tail
+    ("NHD", 2, 1, 333, 128, True, "fp8"),
+    ("HND", 2, 2, 1024, 64, True, "fp8"),
+])
+def test_mixed_k_attention_identical_to_int8_path(L, cuda_dev, layout, hq, hkv, n, d, causal, pv):
+    """The mixed-width kernel path (TMA box per bit width, 8/4/2-bit expansion in shared memory, power-of-two factor
+    folded into the scale) yields exactly the same integer scores as the INT8 path fed the unpacked codes, so the
+    outputs are bit-identical."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    from oracle import quant as OQ
+    q = mk(1, hq, n, d, layout, torch.float16, 71).to(cuda_dev)
+    k = _mixed_k(1, hkv, n, d, layout, torch.float16, 72).to(cuda_dev)
+    v = mk(1, hkv, n, d, layout, torch.float16, 73).to(cuda_dev)
+    km = L.k_mean(k, layout)
+    qc, qs, _, _ = L.per_block_int8(q, k, km=km, tensor_layout=layout)
+    kc, ks, kb = L.per_block_k_mixed(k, km, tensor_layout=layout)
+    k_unp = OQ.unpack_mixed(kc.cpu(), kb.cpu(), 64, layout).to(cuda_dev)
+    kw = {}
+    if pv == "fp8":
+        v, vs, _ = L.per_channel_fp8(v, layout, smooth_v=False)
+        kw = dict(pv_mode=NV.PV_E4M3, v_scale=vs)
+    fn = L.forward_causal if causal else L.forward
+    o_mix, lse_mix = fn(qc, kc, v, qs, ks, tensor_layout=layout, return_lse=True, qk_mode=NV.QK_Q8KMIX, kbits=kb, **kw)
+    o_i8, lse_i8 = fn(qc, k_unp, v, qs, ks, tensor_layout=layout, return_lse=True, **kw)
+    assert torch.equal(o_mix, o_i8) and torch.equal(lse_mix, lse_i8)
+
+
+@pytest.mark.parametrize("d,causal,pv", [(64, False, "fp16"), (128, True, "fp16"), (128, True, "fp8")])
+def test_dynamic_k_api_vs_oracle_and_sdpa(L, cuda_dev, d, causal, pv):
+    from oracle import attention as OA
+    q = mk(1, 4, 600, d, "HND", torch.float16, 81)
+    k = _mixed_k(1, 2, 600, d, "HND", torch.float16, 82)
+    v = mk(1, 2, 600, d, "HND", torch.float16, 83)
+    o, lse = L.lowbit_fa_q_int8_k_dynamic(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), is_causal=causal,
+                                          return_lse=True, pv=pv)
+    ref, lse_ref = OA.lowbit_fa_api(q, k, v, "HND", causal, return_lse=True, compat_tail=False, pv_accum="fp32",
+                                    qk="mixed", pv=pv)
+    tol = 4e-3 if pv == "fp16" else 0.125 * float(v.abs().max())
+    assert (o.cpu().float() - ref.float()).abs().max().item() <= tol
+    assert (lse.cpu() - lse_ref).abs().max() <= (2e-3 if pv == "fp16" else 3e-2)
+    # INT2 / INT4 blocks are a coarse approximation by design: accuracy against exact attention is reported, with a
+    # loose floor, not asserted at the INT8 level
+    sd = OA.sdpa_fp32(q, k, v, "HND", causal)
+    assert cos_sim(o.cpu(), sd) >= 0.98

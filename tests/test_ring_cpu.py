@@ -34,9 +34,14 @@ class OracleBackend:
     def quantize_kv(self, k_chunk, v_chunk, km, msg, i):
         seq = 2 if self.layout == "HND" else 1
         ks = k_chunk if km is None else (k_chunk - km.unsqueeze(seq)).to(k_chunk.dtype)  # `k - km` in the input dtype
-        bits = 4 if self.qk == "int4" else 8
-        codes, scale = self.OQ.quant_per_block_q1(ks, 64, 1.0, self.layout, bits=bits)
-        msg.view(f"k{i}").copy_(self.OQ.pack_codes(codes, 4) if bits == 4 else codes)
+        if self.qk == "mixed":
+            codes, scale, kb = self.OQ.quant_k_mixed(ks, None, None, 64, self.layout)
+            msg.view(f"k{i}").copy_(self.OQ.pack_mixed(codes, kb, 64, self.layout))
+            msg.view(f"kb{i}").copy_(kb)
+        else:
+            bits = 4 if self.qk == "int4" else 8
+            codes, scale = self.OQ.quant_per_block_q1(ks, 64, 1.0, self.layout, bits=bits)
+            msg.view(f"k{i}").copy_(self.OQ.pack_codes(codes, 4) if bits == 4 else codes)
         msg.view(f"ks{i}").copy_(scale)
         if self.pv == "fp8":
             v8, vs, _ = self.OQ.per_channel_fp8(v_chunk, self.layout, smooth_v=False)
@@ -49,6 +54,8 @@ class OracleBackend:
         kc = msg.view(f"k{i}")
         if self.qk == "int4":
             kc = self.OQ.unpack_codes(kc, 4)
+        elif self.qk == "mixed":
+            kc = self.OQ.unpack_mixed(kc, msg.view(f"kb{i}"), 64, self.layout)
         v = msg.view(f"v{i}")
         vs = None
         if self.pv == "fp8":
@@ -70,17 +77,31 @@ def _free_port():
     return port
 
 
+def _make_qkv(cfg):
+    layout, causal, qk, pv, zigzag, d, hq, hkv, n = cfg
+    torch.manual_seed(1234)
+    seq = 2 if layout == "HND" else 1
+    shp = lambda h: (1, h, n, d) if layout == "HND" else (1, n, h, d)
+    q = torch.randn(shp(hq)).half()
+    k = (torch.randn(shp(hkv)) + 2.0 * torch.randn(shp(hkv)[:seq] + (1,) + shp(hkv)[seq + 1:])).half()
+    v = torch.randn(shp(hkv)).half()
+    if qk == "mixed":  # block magnitudes spread over the three width classes (around the common mean)
+        km = k.float().mean(dim=seq, keepdim=True)
+        w = torch.ones(n)
+        w[n // 4: n // 2] = 0.15
+        w[n // 2: 3 * n // 4] = 3.0
+        w = w.view(1, 1, n, 1) if layout == "HND" else w.view(1, n, 1, 1)
+        k = (km + (k.float() - km) * w).half()
+    return q, k, v
+
+
 def _worker(rank, world, port, cfg, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         layout, causal, qk, pv, zigzag, d, hq, hkv, n = cfg
-        torch.manual_seed(1234)  # every rank builds the same full tensors, then keeps its shard
         seq = 2 if layout == "HND" else 1
-        shp = lambda h: (1, h, n, d) if layout == "HND" else (1, n, h, d)
-        q = torch.randn(shp(hq)).half()
-        k = (torch.randn(shp(hkv)) + 2.0 * torch.randn(shp(hkv)[:seq] + (1,) + shp(hkv)[seq + 1:])).half()
-        v = torch.randn(shp(hkv)).half()
+        q, k, v = _make_qkv(cfg)  # every rank builds the same full tensors, then keeps its shard
         chunks = P.seq_chunks(n, world, rank, zigzag)
         take = lambda x: torch.cat([x.narrow(seq, c.offset, c.length) for c in chunks], dim=seq).contiguous()
         be = OracleBackend(layout, qk, pv, d ** -0.5)
@@ -97,6 +118,7 @@ RING_CFGS = [
     ("NHD", True, "int4", "fp16", True, 64, 4, 2, 512),
     ("HND", True, "int4", "fp8", True, 128, 2, 1, 512),
     ("NHD", True, "int8", "fp16", False, 64, 2, 2, 256),
+    ("HND", True, "mixed", "fp16", True, 128, 2, 2, 512),   # dynamic INT8/INT4/INT2 K blocks in the D-byte container
 ]
 
 
@@ -113,12 +135,8 @@ def test_ring_attention_gloo_matches_single_process_oracle(cfg, world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), cfg, ret), nprocs=world, join=True)
     # reassemble the ring output in global token order
-    torch.manual_seed(1234)
     seq = 2 if layout == "HND" else 1
-    shp = lambda h: (1, h, n, d) if layout == "HND" else (1, n, h, d)
-    q = torch.randn(shp(hq)).half()
-    k = (torch.randn(shp(hkv)) + 2.0 * torch.randn(shp(hkv)[:seq] + (1,) + shp(hkv)[seq + 1:])).half()
-    v = torch.randn(shp(hkv)).half()
+    q, k, v = _make_qkv(cfg)
     o_ring = torch.empty_like(q)
     lse_ring = torch.empty(1, hq, n)
     for r in range(world):
@@ -129,7 +147,7 @@ def test_ring_attention_gloo_matches_single_process_oracle(cfg, world):
             lse_ring[:, :, off:off + ln] = lse[:, :, pos:pos + ln]
             pos += ln
     o_ref, lse_ref = OA.lowbit_fa_api(q, k, v, layout, causal, return_lse=True, compat_tail=False, pv_accum="fp32",
-                                      qk="int8" if qk == "int8" else "int4", pv=pv)
+                                      qk=qk, pv=pv)
     diff = (o_ring.float() - o_ref.float()).abs()
     if pv == "fp16":
         assert diff.max() <= 4e-3
