@@ -50,6 +50,7 @@ EXTRA = {
     "c3q_32k": (1, 32, 32, 32768, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B1 H32 D128 causal N=32K"),
     "c4s": (2, 48, 48, 17776, 64, "NHD", False, "q8k4", "fp16", "heads", "BASELINE config 4: q_int8/k_int4, NHD, CogVideoX-5B B2 H48 N17776 D64, head-sharded"),
     "c5": (1, 32, 32, 131072, 128, "HND", True, "int4", "fp16", "ring", "BASELINE config 5 (INT4 K): B1 H32 N128K D128 causal, sequence-parallel ring of quantized K/V"),
+    "c5dyn": (1, 32, 32, 131072, 128, "HND", True, "mixed", "fp16", "ring", "BASELINE config 5: dynamic INT4/INT2 K bit allocation (per 64-key block), B1 H32 N128K D128 causal, sequence-parallel ring of quantized K/V"),
     "c5f8": (1, 32, 32, 131072, 128, "HND", True, "int4", "fp8", "ring", "BASELINE config 5 (INT4 K, FP8 V): B1 H32 N128K D128 causal, sequence-parallel ring"),
 }
 BASELINE_MD_TOPS = 199.5  # INT8 non-causal B4 H32 D64 N=4096, attention kernel only, hardware unstated
@@ -221,15 +222,28 @@ def run_extra(args):
     seq = 2 if layout == "HND" else 1
     shp = lambda h, n=N: (B, h, n, D) if layout == "HND" else (B, n, h, D)
     ops_total = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
-    if pv == "fp8":
+    if qk == "mixed":
+        fn = L.lowbit_fa_q_int8_k_dynamic
+    elif pv == "fp8":
         fn = L.lowbit_fa_qk_int4_pv_fp8 if qk != "int8" else L.lowbit_fa_qk_int8_pv_fp8_cuda
     else:
         fn = {"int8": L.lowbit_fa_qk_int8_pv_fp16_triton, "int4": L.lowbit_fa_qk_int4_pv_fp16_triton,
               "q8k4": L.lowbit_fa_q_int8_k_int4_pv_fp16}[qk]
+
+    def dyn(k):
+        """dynamic-K workloads: every other 64-key block at 0.2x magnitude, so that the block statistic
+        max|k|/127 puts it in the INT2 class (<= 0.0125) and the rest in the INT4 class (randn: ~0.035)"""
+        if qk != "mixed":
+            return k
+        n = k.shape[seq]
+        w = torch.where((torch.arange(n, device=dev) // 64) % 2 == 1, 0.2, 1.0).to(k.dtype)
+        return k * (w.view(1, 1, n, 1) if layout == "HND" else w.view(1, n, 1, 1))
     if part == "ring" and world > 1:
         n_loc = N // world
         q, k, v = (torch.randn(shp(h, n_loc), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
-        step = lambda: P.ring_attention(q, k, v, tensor_layout=layout, is_causal=causal, qk="int4" if qk != "int8" else "int8", pv=pv)
+        k = dyn(k)
+        step = lambda: P.ring_attention(q, k, v, tensor_layout=layout, is_causal=causal,
+                                        qk=qk if qk in ("int8", "mixed") else "int4", pv=pv)
         scaling, units = "strong", ops_total
     elif part == "heads" and world > 1:
         q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
@@ -237,6 +251,7 @@ def run_extra(args):
         scaling, units = "strong", ops_total
     else:
         q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
+        k = dyn(k)
         step = lambda: fn(q, k, v, tensor_layout=layout, is_causal=causal)
         scaling, units = ("strong", ops_total) if part != "replicate" else ("weak", ops_total * world)
     stream = torch.cuda.current_stream(dev)
@@ -270,7 +285,8 @@ def run_extra(args):
         per_gpu = value / world
         line = {"metric": "attention TOPS (4*B*H*N^2*D / latency), quantize + attention", "value": value, "unit": "TOPS",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
-                "vs_baseline": None, "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)", "data": "synthetic randn fp16 seed 0",
+                "vs_baseline": None, "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)",
+                "data": "synthetic randn fp16 seed 0" + ("; every other 64-key block of K at 0.2x (INT2 class)" if qk == "mixed" else ""),
                 "config": {"workload": desc, "partition": part, "l2": "inputs larger than the 126 MB L2, no flush"},
                 "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel (whole step timed: quantize + attention"
                              + (" + ring exchange" if part == "ring" else "") + ")", "achieved": per_gpu, "peak": peak_tf,

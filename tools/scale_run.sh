@@ -11,7 +11,7 @@ if [ "$N" -gt 1 ]; then
 else
   RUN="python bench.py --gpus 1"
 fi
-for w in c4s c5 c5f8; do
+for w in c4s c5 c5dyn c5f8; do
   S=5; [ "$w" = c4s ] && S=30   # a 1.5 ms step: 5 steps would time host jitter, not the GPUs
   timeout 400 $RUN --workload $w --steps $S --warmup 3 2>&1 | grep '^{"metric"' | tee -a $OUT
 done
