@@ -208,80 +208,98 @@ v_stats_partial_kernel(const T* __restrict__ v, VPartial* __restrict__ part, int
   }
 }
 
+// pass 1b: one thread per (b, h, channel): fold the chunk statistics into (1/scale, mean) once, instead of once per
+// pass-2 CTA (a 16-deep dependent load chain in front of a 16 KB tile)
+template <typename T, int D>
+__global__ void v_stats_final_kernel(const VPartial* __restrict__ part, float2* __restrict__ tab,
+                                     float* __restrict__ v_scale, float* __restrict__ vm_out, int N, int nchunk,
+                                     float scale_max, int total) {
+  using A = typename SumAcc<T>::type;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*D
+  if (idx >= total) return;
+  const int d = idx % D;
+  const int64_t bh = idx / D;
+  const int n16 = (N + 15) / 16 * 16;
+  float mx = -INFINITY, mn = INFINITY;
+  A t = A(0);
+  for (int c = 0; c < nchunk; ++c) {
+    const VPartial q = part[(bh * nchunk + c) * D + d];
+    mx = fmaxf(mx, q.mx); mn = fminf(mn, q.mn);
+    t += *reinterpret_cast<const A*>(&q.sum_bits);
+  }
+  if (n16 > N) { mx = fmaxf(mx, 0.f); mn = fminf(mn, 0.f); }  // statistics run over the zero-padded 16-multiple (:336-337)
+  float vm = 0.f, amax;
+  if (vm_out != nullptr) {
+    vm = __fdiv_rn(SumAcc<T>::to_f32(t), (float)n16);         // mean divides by the padded count (:382)
+    amax = fmaxf(fabsf(__fsub_rn(mx, vm)), fabsf(__fsub_rn(mn, vm)));
+    vm_out[idx] = vm;
+  } else {
+    amax = fmaxf(fabsf(mx), fabsf(mn));
+  }
+  v_scale[idx] = __fdiv_rn(amax, scale_max);
+  tab[idx] = make_float2(amax > 0.f ? __fdiv_rn(scale_max, amax) : 0.f, vm);  // all-zero channel: codes 0 instead of 0/0
+}
+
 // pass 2: every row-group of TPR threads owns one quad of OUTPUT positions, i.e. the four tokens
-// {2w, 2w+1, 8+2w, 9+2w} of a 16-group (fused.cu:290-292 inverted), loads their rows (4 x 16 B in flight), scales,
-// packs the four e4m3 codes of every channel into one word, and the CTA writes [channel][position] rows through a
-// padded shared-memory transpose.
+// {2w, 2w+1, 8+2w, 9+2w} of a 16-group (fused.cu:290-292 inverted), loads their rows, scales, packs the four e4m3
+// codes of every channel into one word, and the CTA writes [channel][position] rows through a padded shared-memory
+// transpose.  A CTA takes kVTiles consecutive tiles and issues all their row loads first (8 x 16 B in flight/thread).
+constexpr int kVTiles = 2;
 template <int D> struct VQuantCfg {
-  static constexpr int TPR = D / 8, G = 256 / TPR, TT = G * 4;  // tokens per CTA: 128 (D=64) / 64 (D=128)
+  static constexpr int TPR = D / 8, G = 256 / TPR, TT = G * 4;  // tokens per tile: 128 (D=64) / 64 (D=128)
 };
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
-v_fp8_quant_kernel(const T* __restrict__ v, const VPartial* __restrict__ part, uint8_t* __restrict__ v8,
-                   float* __restrict__ v_scale, float* __restrict__ vm_out, int N, int npad, int nchunk, int64_t sb,
-                   int64_t sh, int64_t sn, int64_t osb, int64_t osh, int64_t osd, float scale_max, int H) {
-  using A = typename SumAcc<T>::type;
+v_fp8_quant_kernel(const T* __restrict__ v, const float2* __restrict__ tab, uint8_t* __restrict__ v8, int N, int npad,
+                   int64_t sb, int64_t sh, int64_t sn, int64_t osb, int64_t osh, int64_t osd, int H) {
   using C = VQuantCfg<D>;
-  constexpr int TPR = C::TPR, TT = C::TT, WPR = TT / 4;  // words per channel row of the tile
+  constexpr int TPR = C::TPR, TT = C::TT, WPR = TT / 4;  // words per channel row of a tile
   const int tid = threadIdx.x, c8 = (tid % TPR) * 8, g = tid / TPR;
-  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.y, b = blockIdx.z;
   __shared__ float s_r[D], s_vm[D];
-  __shared__ uint32_t s_t[D][WPR + 1];
-  const int n16 = (N + 15) / 16 * 16;
-  // issue the four row loads before the statistics reduction so their latency overlaps it
-  const int tok0 = tile * TT + (g / 4) * 16 + 2 * (g % 4);
-  const int toks[4] = {tok0, tok0 + 1, tok0 + 8, tok0 + 9};
+  __shared__ uint32_t s_t[kVTiles][D][WPR + 1];
   const T* src = v + b * sb + h * sh + c8;
-  uint4 raw[4];
+  uint4 raw[kVTiles][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    raw[j] = make_uint4(0, 0, 0, 0);
-    if (toks[j] < N) raw[j] = ld_stream_v4(src + (int64_t)toks[j] * sn);
+  for (int tt = 0; tt < kVTiles; ++tt) {
+    const int tok0 = (blockIdx.x * kVTiles + tt) * TT + (g / 4) * 16 + 2 * (g % 4);
+    const int toks[4] = {tok0, tok0 + 1, tok0 + 8, tok0 + 9};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      raw[tt][j] = make_uint4(0, 0, 0, 0);
+      if (toks[j] < N) raw[tt][j] = ld_stream_v4(src + (int64_t)toks[j] * sn);
+    }
   }
   if (tid < D) {
-    float mx = -INFINITY, mn = INFINITY;
-    A t = A(0);
-    for (int c = 0; c < nchunk; ++c) {
-      const VPartial q = part[(((int64_t)b * H + h) * nchunk + c) * D + tid];
-      mx = fmaxf(mx, q.mx); mn = fminf(mn, q.mn);
-      t += *reinterpret_cast<const A*>(&q.sum_bits);
-    }
-    if (n16 > N) { mx = fmaxf(mx, 0.f); mn = fminf(mn, 0.f); }  // statistics run over the zero-padded 16-multiple (:336-337)
-    float vm = 0.f, amax;
-    if (vm_out != nullptr) {
-      vm = __fdiv_rn(SumAcc<T>::to_f32(t), (float)n16);         // mean divides by the padded count (:382)
-      amax = fmaxf(fabsf(__fsub_rn(mx, vm)), fabsf(__fsub_rn(mn, vm)));
-    } else {
-      amax = fmaxf(fabsf(mx), fabsf(mn));
-    }
-    s_vm[tid] = vm;
-    s_r[tid] = amax > 0.f ? __fdiv_rn(scale_max, amax) : 0.f;   // all-zero channel: codes 0 instead of 0/0
-    if (tile == 0) {
-      v_scale[((int64_t)b * H + h) * D + tid] = __fdiv_rn(amax, scale_max);
-      if (vm_out != nullptr) vm_out[((int64_t)b * H + h) * D + tid] = vm;
+    const float2 t = tab[((int64_t)b * H + h) * D + tid];
+    s_r[tid] = t.x;
+    s_vm[tid] = t.y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int tt = 0; tt < kVTiles; ++tt) {
+    float f[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack8<T>(raw[tt][j], f[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float vm = s_vm[c8 + i], r = s_r[c8 + i];
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = __fmul_rn(__fsub_rn(f[j][i], vm), r);
+      uint16_t lo, hi;
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(y[1]), "f"(y[0]));
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(y[3]), "f"(y[2]));
+      s_t[tt][c8 + i][g] = (uint32_t)lo | ((uint32_t)hi << 16);
     }
   }
   __syncthreads();
-  float f[4][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) unpack8<T>(raw[j], f[j]);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float vm = s_vm[c8 + i], r = s_r[c8 + i];
-    float y[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = __fmul_rn(__fsub_rn(f[j][i], vm), r);
-    uint16_t lo, hi;
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(y[1]), "f"(y[0]));
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(y[3]), "f"(y[2]));
-    s_t[c8 + i][g] = (uint32_t)lo | ((uint32_t)hi << 16);
-  }
-  __syncthreads();
-  // channel rows of the tile: TT contiguous output bytes each, written one word per thread (coalesced)
-  uint8_t* dst = v8 + b * osb + h * osh + (int64_t)tile * TT;
-  for (int idx = tid; idx < D * WPR; idx += 256) {
-    const int d = idx / WPR, w = idx % WPR;
-    if (tile * TT + 4 * w < npad) *reinterpret_cast<uint32_t*>(dst + (int64_t)d * osd + 4 * w) = s_t[d][w];
+  // channel rows of the tiles: kVTiles * TT contiguous output bytes each, one word per thread (coalesced)
+  uint8_t* dst = v8 + b * osb + h * osh + (int64_t)blockIdx.x * kVTiles * TT;
+  for (int idx = tid; idx < D * kVTiles * WPR; idx += 256) {
+    const int d = idx / (kVTiles * WPR), w = idx % (kVTiles * WPR);
+    if ((int64_t)blockIdx.x * kVTiles * TT + 4 * w < npad)
+      *reinterpret_cast<uint32_t*>(dst + (int64_t)d * osd + 4 * w) = s_t[w / WPR][d][w % WPR];
   }
 }
 
@@ -342,7 +360,7 @@ int lowbit_quant_pack_lastdim(const void* data, void* code, void* scale, void* m
 
 int64_t lowbit_v_fp8_workspace_bytes(int B, int H, int N, int D) {
   (void)N;
-  return (int64_t)B * H * kVChunks * D * (int64_t)sizeof(VPartial);
+  return (int64_t)B * H * kVChunks * D * (int64_t)sizeof(VPartial) + (int64_t)B * H * D * 8;  // chunk statistics + (1/scale, mean) table
 }
 
 int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm, void* workspace, int B, int H, int N,
@@ -360,11 +378,14 @@ int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
   const int nchunk = (N + chunk - 1) / chunk;
   const int npad = (N + 63) / 64 * 64;
   dim3 g1(nchunk, H, B);
+  const int total = B * H * D;
+  float2* tab = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(workspace) + (int64_t)B * H * nchunk * D * sizeof(VPartial));
 #define LAUNCH(T, DD)                                                                                               \
   if (vm != nullptr) v_stats_partial_kernel<T, DD, true><<<g1, 256, 0, st>>>((const T*)v, (VPartial*)workspace, N, chunk, nchunk, sb, sh, sn, H); \
   else v_stats_partial_kernel<T, DD, false><<<g1, 256, 0, st>>>((const T*)v, (VPartial*)workspace, N, chunk, nchunk, sb, sh, sn, H); \
-  v_fp8_quant_kernel<T, DD><<<dim3((N + VQuantCfg<DD>::TT - 1) / VQuantCfg<DD>::TT, H, B), 256, 0, st>>>(           \
-      (const T*)v, (const VPartial*)workspace, (uint8_t*)v8, v_scale, vm, N, npad, nchunk, sb, sh, sn, osb, osh, osd, scale_max, H);
+  v_stats_final_kernel<T, DD><<<(total + 255) / 256, 256, 0, st>>>((const VPartial*)workspace, tab, v_scale, vm, N, nchunk, scale_max, total); \
+  v_fp8_quant_kernel<T, DD><<<dim3((N + kVTiles * VQuantCfg<DD>::TT - 1) / (kVTiles * VQuantCfg<DD>::TT), H, B), 256, 0, st>>>( \
+      (const T*)v, tab, (uint8_t*)v8, N, npad, sb, sh, sn, osb, osh, osd, H);
   if (dtype == LOWBIT_F16) {
     if (D == 64) { LAUNCH(__half, 64) } else { LAUNCH(__half, 128) }
   } else if (dtype == LOWBIT_BF16) {
