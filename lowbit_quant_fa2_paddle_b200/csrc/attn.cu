@@ -326,6 +326,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int BNH = BN / SP;                                // score columns per softmax thread and step
   constexpr int PCH = PCOLS / SP;                             // P columns per softmax thread and step
   constexpr int DH = D / SP;                                  // O columns per softmax thread (rescale, epilogue)
+  __shared__ float s_vs[PV == PV_E4M3 ? D : 1], s_vm[PV == PV_E4M3 ? D : 1];  // FP8 P.V: v_scale / v_mean of this (b, kv head)
   __shared__ int s_flag[4][2];                                // SP = 2: "rescale wanted at step j" token per warp pair
   __shared__ float s_mx[2][kBM], s_l[2][kBM];                 // SP = 2: row-max / row-sum exchange between the halves
   extern __shared__ uint8_t smem_raw[];
@@ -396,6 +397,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
     if constexpr (KM == KM_MIX) { ptx::prefetch_tmap(&tmK8); ptx::prefetch_tmap(&tmK2); }
+  }
+  if constexpr (PV == PV_E4M3) {
+    if (tid < D) {
+      s_vs[tid] = p.v_scale[((int64_t)b * p.Hkv + hkv) * D + tid];
+      s_vm[tid] = p.v_mean ? p.v_mean[((int64_t)b * p.Hkv + hkv) * D + tid] : 0.f;
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -655,8 +662,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_wait(bar_final, 0, 32);
     ptx::tc_fence_after();
     const bool live_row = row < p.Nq;
-    const float* vsc = (PV == PV_E4M3) ? p.v_scale + ((int64_t)b * p.Hkv + hkv) * D : nullptr;
-    const float* vmn = (PV == PV_E4M3 && p.v_mean) ? p.v_mean + ((int64_t)b * p.Hkv + hkv) * D : nullptr;
+    // per-channel V scale / mean of this (b, kv head): staged in shared memory at kernel start -- read straight from
+    // global memory here, every element's load sat behind the previous store to the (possibly aliasing) fp32 state and
+    // cost the ring merge epilogue 0.76 ms per 8K x 8K launch
+    const float* vsc = (PV == PV_E4M3) ? s_vs : nullptr;
+    const float* vmn = (PV == PV_E4M3 && p.v_mean) ? s_vm : nullptr;
     const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
     float m_prev = -INFINITY, l_prev = 0.f;  // ring step: running state, read before the pair barrier below
     if (p.oacc_io != nullptr && !p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }

@@ -14,7 +14,7 @@ from lowbit_quant_fa2_paddle_b200 import attention as A  # noqa: E402
 shapes = {"c2": (4, 32, 4096, 64, False), "c2c": (4, 32, 4096, 64, True), "d128": (4, 32, 4096, 128, False),
           "d128c8k": (4, 32, 8192, 128, True), "d128c16k": (2, 32, 16384, 128, True),
           "d128c32k": (1, 32, 32768, 128, True), "c2_16k": (1, 32, 16384, 64, False),
-          "c4": (2, 48, 17776, 64, False)}
+          "c4": (2, 48, 17776, 64, False), "d128_8k": (1, 32, 8192, 128, False)}
 dev = torch.device("cuda:0")
 for spec in (sys.argv[1:] or ["c2", "c2c", "d128", "d128c8k"]):
     name, _, mode = spec.partition(":")
