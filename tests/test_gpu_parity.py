@@ -844,3 +844,19 @@ def test_dynamic_k_api_vs_oracle_and_sdpa(L, cuda_dev, d, causal, pv):
     # loose floor, not asserted at the INT8 level
     sd = OA.sdpa_fp32(q, k, v, "HND", causal)
     assert cos_sim(o.cpu(), sd) >= 0.98
+
+
+# ------------------------------------------------------------------------------------------------ development variant
+def test_column_split_softmax_variant_passes_the_attention_suite(cuda_dev):
+    """LOWBIT_ATTN_VARIANT=16 selects the column-split softmax (two threads per query row) for every
+    mode of the kernel; it is read once per process, so the attention tests are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LOWBIT_ATTN_VARIANT="16")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "golden or api_vs_oracle or fp8_pv or packed_int4 or ring_partial or mixed_k_attention",
+                        "--deselect", "tests/test_gpu_parity.py::test_column_split_softmax_variant_passes_the_attention_suite"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
