@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LOWBIT_ABI_VERSION 3
+#define LOWBIT_ABI_VERSION 4
 
 /* element types of the floating-point inputs / outputs */
 enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
@@ -68,6 +68,27 @@ enum {
 
 int lowbit_version(void);
 const char* lowbit_last_error(void);
+
+/* Varlen (packed [T,H,D] tensors + cu_seqlens, src/core.py:356-491) -- no host synchronisation: like the reference's
+ * kernels (quant_per_block_varlen.py:120, attn_qk_int8_block_varlen.py:126-128) the grids are sized from max_seqlen and a
+ * CTA past its sequence's end exits.  cu_seqlens / cu_scale: int32 [nseq+1] on the device; cu_scale[b] = number of
+ * scale blocks of the sequences before b (cumsum of ceil(len/blk)).  Scales are head-major: scale[h][cu_scale[b] + j]
+ * with `scale_stride` entries per head (>= cu_scale[nseq]; T/blk + nseq always suffices).  km: [H,D] (ONE mean over all
+ * packed tokens, core.py:448) or NULL.  Strides in elements of (head, token). */
+int lowbit_quant_per_block_varlen(const void* in, const void* km, void* codes, float* scale, const int32_t* cu_seqlens,
+                                  const int32_t* cu_scale, int nseq, int H, int max_seqlen, int D, int64_t ish,
+                                  int64_t isn, int64_t osh, int64_t osn, int scale_stride, int blk, int bits, int pack,
+                                  float sm_scale_arg, int mode, int dtype, void* stream);
+/* Attention over packed codes: sequence b attends q rows cu_seqlens_q[b].. to k/v rows cu_seqlens_k[b]..; FP16 P.V;
+ * tail keys are masked (LOWBIT_ATTN_COMPAT_TAIL is rejected: the rows after a sequence belong to the next one);
+ * causal needs q_len == k_len per sequence (not checked: that would need a device->host read).  A sequence without
+ * keys gets zeros (attn_qk_int8_block_varlen.py:168-189).  o: packed [Tq,Hq,D]. */
+int lowbit_attn_fwd_varlen(const void* q_codes, const void* k_codes, const void* v, const float* q_scale,
+                           const float* k_scale, const int32_t* kbits, const int32_t* cu_seqlens_q,
+                           const int32_t* cu_seqlens_k, const int32_t* cu_q_scale, const int32_t* cu_k_scale, void* o,
+                           int nseq, int Hq, int Hkv, int Tq, int Tk, int max_seqlen_q, int D, int64_t qsh, int64_t qsn,
+                           int64_t ksh, int64_t ksn, int64_t vsh, int64_t vsn, int64_t osh, int64_t osn,
+                           int q_scale_stride, int k_scale_stride, int qk_mode, int out_dtype, int flags, void* stream);
 
 /* Dynamic K bit allocation (the reference has thresholds, core.py:1055-1061, and harnesses but no kernel;
  * semantics stated here, parity unpinned): every 64-row block of (k - km) is quantized symmetrically to INT8, INT4 or

@@ -25,6 +25,8 @@ _P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 SIGNATURES = {
     "lowbit_version": (_I, []),
     "lowbit_last_error": (_c.c_char_p, []),
+    "lowbit_quant_per_block_varlen": (_I, [_P] * 6 + [_I] * 4 + [_L] * 4 + [_I] * 4 + [_F, _I, _I, _P]),
+    "lowbit_attn_fwd_varlen": (_I, [_P] * 11 + [_I] * 7 + [_L] * 8 + [_I] * 5 + [_P]),
     "lowbit_quant_k_mixed": (_I, [_P] * 6 + [_I] * 4 + [_L] * 6 + [_F, _F, _I, _I, _P]),
     "lowbit_prep_qk_workspace_bytes": (_L, [_I] * 4),
     "lowbit_prep_qk": (_I, [_P] * 8 + [_I] * 7 + [_L] * 12 + [_F] + [_I] * 6 + [_P]),
@@ -62,7 +64,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.lowbit_version() != 3:
+        if handle.lowbit_version() != 4:
             raise LowbitNativeError("liblowbit_fa_b200.so ABI version mismatch")
         _lib = handle
     return _lib

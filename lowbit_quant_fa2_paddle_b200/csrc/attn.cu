@@ -42,6 +42,9 @@ struct AttnParams {
   const float* v_scale;  // PV e4m3: [B,Hkv,D]
   const float* v_mean;   // PV e4m3: [B,Hkv,D] or null
   const int32_t* kbits;  // mixed-width K: [B,Hkv,nkb] in {8,4,2}
+  // varlen (packed [T,H,D] tensors): sequence b owns rows cu_q[b]..cu_q[b+1] (queries) / cu_k[b].. (keys); its scale
+  // blocks start at cu_qs[b] / cu_ks[b] inside the head-major scale arrays [H][nqb] / [Hkv][nkb] (nqb, nkb = strides)
+  const int32_t *cu_q, *cu_k, *cu_qs, *cu_ks;
   void* o;
   float* lse;
   float* m_io;           // partial (ring) state: [B,Hq,Nq]; oacc_io != null selects the merge epilogue
@@ -354,9 +357,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (p.Hq / p.Hkv);
 
+  // this CTA's view of the problem: the padded tensors' (b, h) slice, or -- varlen -- sequence b of the packed tensors
+  int Nq = p.Nq, Nk = p.Nk, nkb = p.nkb;
+  int q_row0 = 0, k_row0 = 0, tb = b;  // row offsets into the packed tensors; batch coordinate of the tensor maps
+  int64_t qs_idx = ((int64_t)b * p.Hq + hq) * p.nqb + qt;   // my q_scale entry
+  int64_t ks_base = ((int64_t)b * p.Hkv + hkv) * p.nkb;    // first k_scale / kbits entry of my (b, kv head)
+  int64_t orow_base = (int64_t)b * p.osb;                  // element offset of my first output row (head added later)
+  if (p.cu_q != nullptr) {
+    q_row0 = p.cu_q[b];
+    Nq = p.cu_q[b + 1] - q_row0;
+    k_row0 = p.cu_k[b];
+    Nk = p.cu_k[b + 1] - k_row0;
+    if (qt * kBM >= Nq) return;  // the grid is sized for the longest sequence (attn_qk_int8_block_varlen.py:126-128)
+    nkb = (Nk + kScaleBlk - 1) / kScaleBlk;
+    qs_idx = (int64_t)hq * p.nqb + p.cu_qs[b] + qt;
+    ks_base = (int64_t)hkv * p.nkb + p.cu_ks[b];
+    orow_base = (int64_t)q_row0 * p.osn;
+    tb = 0;
+    if (Nk == 0) {  // no keys: the reference divides a zero accumulator by l = 1 (attn_qk_int8_block_varlen.py:168-189)
+      if (tid < kBM && qt * kBM + tid < Nq) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.o) +
+                                              (orow_base + (int64_t)hq * p.osh + (int64_t)(qt * kBM + tid) * p.osn) * 2);
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+      }
+      return;
+    }
+  }
+
   // key-block range of this Q tile.  compat_tail walks the reference's whole 64-key blocks (phantom zero keys).
   const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
-  const int nk_eff = compat ? p.nkb * kScaleBlk : p.Nk;
+  const int nk_eff = compat ? nkb * kScaleBlk : Nk;
   int nblk = (nk_eff + BN - 1) / BN;
   // causal: key (global k_off + c) is visible to row (global q_off + r) iff c <= delta + r
   const int dq = p.delta + qt * kBM;  // delta + first row of the tile
@@ -365,8 +396,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ring step whose K/V shard lies wholly in this tile's future: the running state is unchanged
     if (p.oacc_io != nullptr && p.first && tid < kBM) {
       const int row = qt * kBM + tid;
-      if (row < p.Nq) {
-        const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
+      if (row < Nq) {
+        const int64_t idx = ((int64_t)b * p.Hq + hq) * Nq + row;
         p.m_io[idx] = -INFINITY;
         p.l_io[idx] = 0.f;
         float4* od = reinterpret_cast<float4*>(p.oacc_io + idx * D);
@@ -424,15 +455,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
         if constexpr (KM == KM_I8) {
           ptx::mbar_expect_tx(kfull + ks, SM::kK);
-          ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, j * BN, hkv, b);
+          ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
         } else if constexpr (KM == KM_K4) {
           ptx::mbar_expect_tx(kfull + ks, SM::kKp);
-          ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, j * BN, hkv, b);
+          ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
         } else {  // mixed width: the block's bit width picks the box (first D*bits/8 bytes of every container row)
-          const int bits = p.kbits[((int64_t)b * p.Hkv + hkv) * p.nkb + min(j * BN / kScaleBlk, p.nkb - 1)];
+          const int bits = p.kbits[ks_base + min(j * BN / kScaleBlk, nkb - 1)];
           const CUtensorMap* tm = (bits == 8) ? &tmK8 : (bits == 4 ? &tmK : &tmK2);
           ptx::mbar_expect_tx(kfull + ks, BN * D * bits / 8);
-          ptx::tma_load_4d(sKp + ks * SM::kKp, tm, kfull + ks, 0, j * BN, hkv, b);
+          ptx::tma_load_4d(sKp + ks * SM::kKp, tm, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
         }
       };
       auto load_v = [&](int j) {
@@ -440,8 +471,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
         ptx::mbar_expect_tx(vfull + vs, SM::kV);
         if constexpr (PV == PV_F16) {
-          ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, j * BN, hkv, b);
-          if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + BN * 128, &tmV, vfull + vs, 64, j * BN, hkv, b);
+          ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, k_row0 + j * BN, hkv, tb);
+          if (D == 128) ptx::tma_load_4d(sV + vs * SM::kV + BN * 128, &tmV, vfull + vs, 64, k_row0 + j * BN, hkv, tb);
         } else {
           ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, j * BN, 0, hkv, b);  // [d][key] tile, keys contiguous
         }
@@ -462,7 +493,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if constexpr (!KX) ptx::umma_commit(kfree + ks);  // K stage may be refilled
       };
       ptx::mbar_expect_tx(bar_q, SM::kQ);
-      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, qt * kBM, hq, b);
+      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
       for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
       for (int j = 0; j < min(2, nblk); ++j) load_v(j);
       if constexpr (!KX) {
@@ -516,20 +547,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int wq = warp & 3;                      // TMEM lane quadrant (and warp-pair index for SP = 2)
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     const int row = qt * kBM + r;  // query row owned by this thread
-    float qs = p.q_scale[((int64_t)b * p.Hq + hq) * p.nqb + qt];
+    float qs = p.q_scale[qs_idx];
     if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
-    const float* ks_ptr = p.k_scale + ((int64_t)b * p.Hkv + hkv) * p.nkb;
-    const int32_t* kb_ptr = (KM == KM_MIX) ? p.kbits + ((int64_t)b * p.Hkv + hkv) * p.nkb : nullptr;
+    const float* ks_ptr = p.k_scale + ks_base;
+    const int32_t* kb_ptr = (KM == KM_MIX) ? p.kbits + ks_base : nullptr;
     auto kb = [&](int jj) -> int {  // bit width of key block jj
-      if constexpr (KM == KM_MIX) return kb_ptr[min(jj * BN / kScaleBlk, p.nkb - 1)];
+      if constexpr (KM == KM_MIX) return kb_ptr[min(jj * BN / kScaleBlk, nkb - 1)];
       else return 4;
     };
     auto kfac = [&](int jj) -> float {  // the expanded operand holds code, code*16 or code*64
       if constexpr (KM == KM_MIX) { const int bb = kb(jj); return bb == 8 ? 1.f : (bb == 4 ? 0.0625f : 0.015625f); }
       else return 1.f;
     };
-    const bool mask_tail = !compat && (p.Nk % BN != 0);
-    const int last_kblk = (p.Nk + BN - 1) / BN - 1;
+    const bool mask_tail = !compat && (Nk % BN != 0);
+    const int last_kblk = (Nk + BN - 1) / BN - 1;
     const uint32_t tS0 = tmem_base + lane_off + half * BNH, tS1 = tS0 + BN;  // my score columns in S buffer 0 / 1
     const uint32_t tP0 = tmem_base + lane_off + half * PCH, tP1 = tP0 + BN;  // my P columns (P aliases S)
     const uint32_t tOl = tO + lane_off;
@@ -641,18 +672,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float sc0 = qs * ks_cur;
       float sc1 = sc0;
       if (kPerScale == 1) sc1 = qs * ks_ptr[j + 1];
-      const float ks_nxt = ks_ptr[min((j + 2) / kPerScale, p.nkb - 1)];  // prefetch for the next pair
+      const float ks_nxt = ks_ptr[min((j + 2) / kPerScale, nkb - 1)];  // prefetch for the next pair
       step(std::false_type{}, tS0, tP0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
       step(std::false_type{}, tS1, tP1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
       ks_cur = ks_nxt;
     }
     // remaining blocks (odd leftover, causal diagonal band, masked tail): generic path
     for (; j < nblk; ++j) {
-      const float sc = qs * ks_ptr[min(j / kPerScale, p.nkb - 1)];
+      const float sc = qs * ks_ptr[min(j / kPerScale, nkb - 1)];
       const int c0 = j * BN;
       int lim = BN;  // columns [0, lim] are live
       if (causal) lim = min(lim, p.delta + row - c0);
-      if (mask_tail && j == last_kblk) lim = min(lim, p.Nk - 1 - c0);
+      if (mask_tail && j == last_kblk) lim = min(lim, Nk - 1 - c0);
       step(std::true_type{}, (j & 1) ? tS1 : tS0, (j & 1) ? tP1 : tP0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc,
            lim);
     }
@@ -661,13 +692,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---- epilogue ------------------------------------------------------------------------------------
     ptx::mbar_wait(bar_final, 0, 32);
     ptx::tc_fence_after();
-    const bool live_row = row < p.Nq;
+    const bool live_row = row < Nq;
     // per-channel V scale / mean of this (b, kv head): staged in shared memory at kernel start -- read straight from
     // global memory here, every element's load sat behind the previous store to the (possibly aliasing) fp32 state and
     // cost the ring merge epilogue 0.76 ms per 8K x 8K launch
     const float* vsc = (PV == PV_E4M3) ? s_vs : nullptr;
     const float* vmn = (PV == PV_E4M3 && p.v_mean) ? s_vm : nullptr;
-    const int64_t idx = ((int64_t)b * p.Hq + hq) * p.Nq + row;
+    const int64_t idx = ((int64_t)b * p.Hq + hq) * Nq + row;
     float m_prev = -INFINITY, l_prev = 0.f;  // ring step: running state, read before the pair barrier below
     if (p.oacc_io != nullptr && !p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }
     if constexpr (SP == 2) {  // row sum = the two halves' partial sums
@@ -679,7 +710,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (p.oacc_io == nullptr) {
       // O / l (* v_scale + v_mean) -> out dtype, lse2 = log2(l) + m - OFF
       const float inv_l = 1.0f / l;
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + ((int64_t)b * p.osb + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
+      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (orow_base + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
 #pragma unroll
       for (int cc = 0; cc < DH; cc += 32) {
         const int c = cbeg + cc;
@@ -869,6 +900,9 @@ struct AttnArgs {
   int B, Hq, Hkv, Nq, Nk, D;
   int64_t qsb, qsh, qsn, ksb, ksh, ksn, vsb, vsh, vsn;
   int qk_mode, pv_mode, flags;
+  // varlen: B = 1, Nq / Nk = packed token counts; the grid covers nseq sequences of at most max_q query rows
+  const int32_t *cu_q = nullptr, *cu_k = nullptr, *cu_qs = nullptr, *cu_ks = nullptr;
+  int nseq = 0, max_q = 0, nqb_stride = 0, nkb_stride = 0;
 };
 
 static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStream_t st) {
@@ -916,10 +950,16 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   p.Hq = a.Hq; p.Hkv = a.Hkv; p.Nq = a.Nq; p.Nk = a.Nk;
   p.nqb = (a.Nq + 127) / 128; p.nkb = (a.Nk + 63) / 64;
   p.flags = a.flags;
+  int grid_b = a.B;
+  if (a.cu_q != nullptr) {  // varlen: the kernel takes per-sequence lengths from cu_*; p.Nq only sizes the grid
+    p.cu_q = a.cu_q; p.cu_k = a.cu_k; p.cu_qs = a.cu_qs; p.cu_ks = a.cu_ks;
+    p.Nq = a.max_q; p.nqb = a.nqb_stride; p.nkb = a.nkb_stride;
+    grid_b = a.nseq;
+  }
   const CUtensorMap* p8 = (km == KM_MIX) ? &tk8 : nullptr;
   const CUtensorMap* p2 = (km == KM_MIX) ? &tk2 : nullptr;
-  if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, a.B, km, pv, st, p8, p2);
-  return dispatch_attn<128>(tq, tk, tv, p, a.B, km, pv, st, p8, p2);
+  if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, grid_b, km, pv, st, p8, p2);
+  return dispatch_attn<128>(tq, tk, tv, p, grid_b, km, pv, st, p8, p2);
 }
 
 }  // namespace lowbit
@@ -947,6 +987,31 @@ extern "C" int lowbit_attn_fwd(const void* q_codes, const void* k_codes, const v
   p.out_dtype = out_dtype; p.delta = 0; p.first = 1;
   p.dbg = (qk_mode == LOWBIT_QK_I8 && pv_mode == LOWBIT_PV_F16 && !causal) ? g_attn_debug : nullptr;
   return run_attn("lowbit_attn_fwd", a, p, (cudaStream_t)stream);
+}
+
+extern "C" int lowbit_attn_fwd_varlen(const void* q_codes, const void* k_codes, const void* v, const float* q_scale,
+                                      const float* k_scale, const int32_t* kbits, const int32_t* cu_seqlens_q,
+                                      const int32_t* cu_seqlens_k, const int32_t* cu_q_scale, const int32_t* cu_k_scale,
+                                      void* o, int nseq, int Hq, int Hkv, int Tq, int Tk, int max_seqlen_q, int D,
+                                      int64_t qsh, int64_t qsn, int64_t ksh, int64_t ksn, int64_t vsh, int64_t vsn,
+                                      int64_t osh, int64_t osn, int q_scale_stride, int k_scale_stride, int qk_mode,
+                                      int out_dtype, int flags, void* stream) {
+  LOWBIT_CHECK(o && cu_seqlens_q && cu_seqlens_k && cu_q_scale && cu_k_scale, "lowbit_attn_fwd_varlen: null pointer");
+  LOWBIT_CHECK(out_dtype == LOWBIT_F16 || out_dtype == LOWBIT_BF16, "lowbit_attn_fwd_varlen: bad out_dtype %d", out_dtype);
+  LOWBIT_CHECK(nseq > 0 && max_seqlen_q > 0, "lowbit_attn_fwd_varlen: empty batch");
+  LOWBIT_CHECK(!(flags & LOWBIT_ATTN_COMPAT_TAIL),
+               "lowbit_attn_fwd_varlen: compat_tail is not defined for packed sequences (the rows after a sequence are the next one's)");
+  LOWBIT_CHECK((osn % 8) == 0 && (osh % 8) == 0 && ((uintptr_t)o & 15) == 0,
+               "lowbit_attn_fwd_varlen: output must keep 16-byte row alignment");
+  // packed [T,H,D] tensors are one batch entry for the tensor maps; the batch stride is irrelevant
+  AttnArgs a{q_codes, k_codes, v, q_scale, k_scale, nullptr, nullptr, kbits, 1, Hq, Hkv, Tq, Tk, D,
+             qsn * Tq, qsh, qsn, ksn * Tk, ksh, ksn, vsn * Tk, vsh, vsn, qk_mode, LOWBIT_PV_F16, flags};
+  a.cu_q = cu_seqlens_q; a.cu_k = cu_seqlens_k; a.cu_qs = cu_q_scale; a.cu_ks = cu_k_scale;
+  a.nseq = nseq; a.max_q = max_seqlen_q; a.nqb_stride = q_scale_stride; a.nkb_stride = k_scale_stride;
+  AttnParams p{};
+  p.o = o; p.lse = nullptr; p.osb = 0; p.osh = osh; p.osn = osn;
+  p.out_dtype = out_dtype; p.delta = 0; p.first = 1;
+  return run_attn("lowbit_attn_fwd_varlen", a, p, (cudaStream_t)stream);
 }
 
 extern "C" int lowbit_attn_fwd_partial(const void* q_codes, const void* k_codes, const void* v, const float* q_scale,

@@ -271,6 +271,27 @@ static int launch_qpb(const void* in, const void* km, void* codes, float* scale,
 
 
 // ------------------------------------------------------------------------------------------------
+// varlen (packed [T,H,D], cu_seqlens) per-block quantizer: quant_per_block_varlen.py:22-72
+// ------------------------------------------------------------------------------------------------
+// Grid (ceil(max_seqlen / BLK), H, sequences) like the reference (:120); a CTA whose block lies past its sequence's end
+// exits (:44-45).  Blocks restart at every sequence; scales are written head-major, scale[h][cu_scale[b] + jb] with
+// `scale_stride` entries per head (the attention kernel's varlen layout), km is one [H,D] row set for all sequences
+// (core.py:448: `k.mean(dim=0)`).
+template <typename T, int D, int BLK>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_per_block_varlen_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_t* __restrict__ out,
+                              float* __restrict__ scale, const int32_t* __restrict__ cu, const int32_t* __restrict__ cu_scale,
+                              int64_t ish, int64_t isn, int64_t osh, int64_t osn, int scale_stride, float sm, int bits,
+                              int pack, int mode, int H) {
+  __shared__ float s_w[kQuantThreads / 32];
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int start = cu[b], len = cu[b + 1] - start;
+  if (jb * BLK >= len) return;
+  quant_block_body<T, D, BLK>(in + (int64_t)start * isn, km, out + (int64_t)start * osn, scale + cu_scale[b], len,
+                              scale_stride, 0, ish, isn, 0, osh, osn, sm, bits, pack, mode, H, jb, h, 0, s_w);
+}
+
+// ------------------------------------------------------------------------------------------------
 // mixed-width K: dynamic INT8 / INT4 / INT2 per 64-row block (thresholds of core.py:1055-1061)
 // ------------------------------------------------------------------------------------------------
 // Container: D bytes per row; a block of width `bits` uses the first D*bits/8 bytes of each of its rows, in the byte
@@ -796,6 +817,40 @@ extern "C" {
 
 int lowbit_version(void) { return LOWBIT_ABI_VERSION; }
 const char* lowbit_last_error(void) { return last_error().c_str(); }
+
+int lowbit_quant_per_block_varlen(const void* in, const void* km, void* codes, float* scale, const int32_t* cu_seqlens,
+                                  const int32_t* cu_scale, int nseq, int H, int max_seqlen, int D, int64_t ish,
+                                  int64_t isn, int64_t osh, int64_t osn, int scale_stride, int blk, int bits, int pack,
+                                  float sm, int mode, int dtype, void* stream) {
+  LOWBIT_CHECK(D == 64 || D == 128, "lowbit_quant_per_block_varlen: head_dim must be 64 or 128 (got %d)", D);
+  LOWBIT_CHECK(in && codes && scale && cu_seqlens && cu_scale, "lowbit_quant_per_block_varlen: null pointer");
+  LOWBIT_CHECK(nseq > 0 && H > 0 && max_seqlen > 0, "lowbit_quant_per_block_varlen: empty batch");
+  LOWBIT_CHECK(blk == 64 || blk == 128, "lowbit_quant_per_block_varlen: block size must be 64 or 128 (got %d)", blk);
+  LOWBIT_CHECK(bits == 8 || bits == 4 || bits == 2, "lowbit_quant_per_block_varlen: bits must be 8, 4 or 2 (got %d)", bits);
+  LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_quant_per_block_varlen: bad mode %d", mode);
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0, "lowbit_quant_per_block_varlen: input strides must keep 16-byte alignment");
+  const int div = pack ? 8 / bits : 1;
+  LOWBIT_CHECK((osn * div) % 8 == 0, "lowbit_quant_per_block_varlen: code rows must keep 8-byte alignment");
+  dim3 grid((max_seqlen + blk - 1) / blk, H, nseq);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_VL(T, DD, BB)                                                                                        \
+  quant_per_block_varlen_kernel<T, DD, BB><<<grid, kQuantThreads, 0, st>>>((const T*)in, (const T*)km, (int8_t*)codes, \
+      scale, cu_seqlens, cu_scale, ish, isn, osh, osn, scale_stride, sm, bits, pack, mode, H)
+#define LAUNCH_VL_T(T)                                                                      \
+  do {                                                                                      \
+    if (D == 64 && blk == 64) LAUNCH_VL(T, 64, 64);                                         \
+    else if (D == 64) LAUNCH_VL(T, 64, 128);                                                \
+    else if (blk == 64) LAUNCH_VL(T, 128, 64);                                              \
+    else LAUNCH_VL(T, 128, 128);                                                            \
+  } while (0)
+  if (dtype == LOWBIT_F16) LAUNCH_VL_T(__half);
+  else if (dtype == LOWBIT_BF16) LAUNCH_VL_T(__nv_bfloat16);
+  else return lowbit::fail("lowbit_quant_per_block_varlen: bad dtype %d", dtype);
+#undef LAUNCH_VL_T
+#undef LAUNCH_VL
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int lowbit_quant_k_mixed(const void* k, const void* km, const int32_t* kbits_in, void* codes, float* scale,
                          int32_t* kbits_out, int B, int H, int N, int D, int64_t isb, int64_t ish, int64_t isn,
