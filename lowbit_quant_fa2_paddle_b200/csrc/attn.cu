@@ -82,6 +82,15 @@ enum { PV_F16 = 0, PV_E4M3 = 1 };
 // Per-head-dim tiling.  D=64 is exp2(MUFU)-bound: small 32-key steps keep the register footprint under 96 so that
 // four CTAs (16 softmax warps) share an SM and hide each other's latencies.  D=128 has twice the tensor work per
 // exp2 and runs 64-key steps with two CTAs per SM.
+// K tiles that need expansion (packed INT4 / mixed width): at D = 128 (two CTAs per SM, registers to spare) a dedicated
+// expander warp does it, so the softmax warps -- the critical path -- carry no unpack instructions and the expansion
+// runs ahead of them; at D = 64 (four CTAs per SM, 96 registers per thread) there is no room for another warp and
+// the softmax threads expand K_{j+2} at the end of step j.
+template <int D, int KM, int VAR> struct AttnRoles {
+  static constexpr bool kExpander = (KM != 0) && (D == 128) && ((VAR & 16) == 0);
+  static constexpr int kThreads = AttnSP<D, VAR>::kThreads + (kExpander ? 32 : 0);
+};
+
 template <int D> struct AttnCfg;
 template <> struct AttnCfg<64> {
   static constexpr int BN = 32, CTAS = 4, KS = 4, VS = 3, TMEM_COLS = 128;
@@ -311,7 +320,7 @@ __device__ __forceinline__ void permute_q_tile(uint8_t* sQ, int tid) {
 // P.V of the previous one run on the tensor pipe while the softmax warps work on block j; K/V stages are refilled
 // by the same thread as soon as the MMAs that read them have committed.
 template <int D, int KM, int PV, int VAR, bool DBG>
-__global__ void __launch_bounds__((AttnSP<D, VAR>::kThreads), AttnCfg<D>::CTAS)
+__global__ void __launch_bounds__((AttnRoles<D, KM, VAR>::kThreads), AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK8,
                 const __grid_constant__ CUtensorMap tmK2, const AttnParams p) {
@@ -326,6 +335,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int SP = AttnSP<D, VAR>::value;                   // softmax warpgroups (threads per query row)
   constexpr int kSoftmaxThreads = AttnSP<D, VAR>::kSoftmaxThreads;
   constexpr int HW = 4 * SP;                                  // index of the helper warp
+  constexpr bool EXW = AttnRoles<D, KM, VAR>::kExpander;      // warp HW + 1 expands the K tiles
+  constexpr int kExpThreads = EXW ? 32 : kSoftmaxThreads;     // threads that expand K tiles (and arrive on kfree)
   constexpr int BNH = BN / SP;                                // score columns per softmax thread and step
   constexpr int PCH = PCOLS / SP;                             // P columns per softmax thread and step
   constexpr int DH = D / SP;                                  // O columns per softmax thread (rescale, epilogue)
@@ -348,8 +359,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_ready = bar_s + 2;     // [2] 128 softmax threads wrote P into buffer b (INT4: and expanded K_{j+2})
   uint64_t* bar_o = p_ready + 2;     // PV_j done (one phase per key block)
   uint64_t* bar_final = bar_o + 1;   // last PV done (single phase: parity waits must never lag 2 phases)
-  uint64_t* bar_k01 = bar_final + 1; // INT4: Q permuted and K_0, K_1 expanded
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_k01 + 1);
+  uint64_t* bar_k01 = bar_final + 1; // INT4: Q permuted and K_0, K_1 expanded (expander warp: Q permuted)
+  uint64_t* kready = bar_k01 + 1;    // [2] expander warp: operand stage holds the expanded K tile
+  uint64_t* kopfree = kready + 2;    // [2] QK on an operand stage complete: the expander may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kopfree + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
@@ -416,13 +429,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(bar_q, 1);
     for (int i = 0; i < KPS; ++i) {
       ptx::mbar_init(kfull + i, 1);
-      ptx::mbar_init(kfree + i, KX ? kSoftmaxThreads : 1);
+      ptx::mbar_init(kfree + i, KX ? kExpThreads : 1);
     }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kSoftmaxThreads); }
     ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_final, 1);
-    ptx::mbar_init(bar_k01, kSoftmaxThreads);
+    ptx::mbar_init(bar_k01, kExpThreads);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(kready + i, 32); ptx::mbar_init(kopfree + i, 1); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
@@ -440,6 +454,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tO = tmem_base + 2 * BN;  // fp32 output accumulator, D columns
+  const int32_t* kb_ptr = (KM == KM_MIX) ? p.kbits + ks_base : nullptr;
+  auto kb = [&](int jj) -> int {  // bit width of key block jj
+    if constexpr (KM == KM_MIX) return kb_ptr[min(jj * BN / kScaleBlk, nkb - 1)];
+    else return 4;
+  };
 
   if (warp == HW) {
     // ================================ helper: TMA producer + tcgen05 issuer ================================
@@ -480,6 +499,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto issue_qk = [&](int j) {
         const int ks = j % KS;
         if constexpr (!KX) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+        if constexpr (EXW) {
+          ptx::mbar_wait(kready + ks, (j / KS) & 1, 24);  // expanded by the expander warp; its packed stage is free
+          if (j + KPS < nblk) load_k(j + KPS);
+        }
         ptx::tc_fence_after();
         const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
         const uint32_t tS = tmem_base + (j & 1) * BN;
@@ -491,6 +514,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
         if constexpr (!KX) ptx::umma_commit(kfree + ks);  // K stage may be refilled
+        if constexpr (EXW) ptx::umma_commit(kopfree + ks);  // operand stage may be overwritten
       };
       ptx::mbar_expect_tx(bar_q, SM::kQ);
       ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
@@ -499,9 +523,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (!KX) {
         ptx::mbar_wait(bar_q, 0, 21);
       } else {
-        ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted, K_0 / K_1 expanded (their packed stages are free again)
-        if (KPS < nblk) load_k(KPS);
-        if (KPS + 1 < nblk) load_k(KPS + 1);
+        ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted (softmax-thread expansion: and K_0 / K_1 expanded, stages free)
+        if constexpr (!EXW) {
+          if (KPS < nblk) load_k(KPS);
+          if (KPS + 1 < nblk) load_k(KPS + 1);
+        }
       }
       issue_qk(0);
       if (nblk > 1) issue_qk(1);
@@ -534,11 +560,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // refill: the K stage consumed longest ago and the V stage of PV_{j-1} (complete in steady state)
         if constexpr (!KX) {
           if (j + KPS < nblk) load_k(j + KPS);
-        } else {
+        } else if constexpr (!EXW) {
           if (j + 2 + KPS < nblk) load_k(j + 2 + KPS);  // softmax step j expanded K_{j+2}: its packed stage is free
         }
         if (j + 2 < nblk) load_v(j + 2);
       }
+    }
+  } else if (EXW && warp == HW + 1) {
+    // ================================ expander warp: packed K tiles -> int8 operand stages ================================
+    const int et = tid & 31;
+    ptx::mbar_wait(bar_q, 0, 33);
+    permute_q_tile<D, 32>(sQ, et);
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive(bar_k01);
+    for (int j = 0; j < nblk; ++j) {
+      const int ks = j % KS, kps = j % KPS;
+      if (j >= KS) ptx::mbar_wait(kopfree + ks, ((j / KS) - 1) & 1, 36);  // QK_{j-KS} has read this operand stage
+      ptx::mbar_wait(kfull + kps, (j / KPS) & 1, 34);
+      expand_k_tile<D, BN, 32, KM>(sKp + kps * SM::kKp, sK + ks * SM::kK, et, kb(j));
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(kfree + kps);
+      ptx::mbar_arrive(kready + ks);
     }
   } else {
     // ================================ softmax warps ================================
@@ -550,11 +592,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float qs = p.q_scale[qs_idx];
     if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
     const float* ks_ptr = p.k_scale + ks_base;
-    const int32_t* kb_ptr = (KM == KM_MIX) ? p.kbits + ks_base : nullptr;
-    auto kb = [&](int jj) -> int {  // bit width of key block jj
-      if constexpr (KM == KM_MIX) return kb_ptr[min(jj * BN / kScaleBlk, nkb - 1)];
-      else return 4;
-    };
     auto kfac = [&](int jj) -> float {  // the expanded operand holds code, code*16 or code*64
       if constexpr (KM == KM_MIX) { const int bb = kb(jj); return bb == 8 ? 1.f : (bb == 4 ? 0.0625f : 0.015625f); }
       else return 1.f;
@@ -566,7 +603,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
 
-    if constexpr (KX) {
+    if constexpr (KX && !EXW) {
       ptx::mbar_wait(bar_q, 0, 33);
       permute_q_tile<D, kSoftmaxThreads>(sQ, tid);
 #pragma unroll
@@ -644,7 +681,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (PV == PV_F16) l += softmax_block_f16<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
       else l += softmax_block_e4m3<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
       tmem_st_n<PCH>(tPb, pk);  // P aliases the first columns of its S buffer
-      if constexpr (KX) {
+      if constexpr (KX && !EXW) {
         // expand K_{j+2} into the operand stage QK_j just released (S_j ready => QK_j complete)
         if (j + 2 < nblk) {
           const int kps = (j + 2) % KPS;
@@ -858,7 +895,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, AttnSP<D, VAR>::kThreads, SM::kBytes, st>>>(tq, tk, tv, tk8 ? *tk8 : tk, tk2 ? *tk2 : tk, p);
+  kern<<<grid, AttnRoles<D, KM, VAR>::kThreads, SM::kBytes, st>>>(tq, tk, tv, tk8 ? *tk8 : tk, tk2 ? *tk2 : tk, p);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
