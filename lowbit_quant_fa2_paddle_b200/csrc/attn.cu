@@ -82,12 +82,14 @@ enum { PV_F16 = 0, PV_E4M3 = 1 };
 // Per-head-dim tiling.  D=64 is exp2(MUFU)-bound: small 32-key steps keep the register footprint under 96 so that
 // four CTAs (16 softmax warps) share an SM and hide each other's latencies.  D=128 has twice the tensor work per
 // exp2 and runs 64-key steps with two CTAs per SM.
-// K tiles that need expansion (packed INT4 / mixed width): at D = 128 (two CTAs per SM, registers to spare) a dedicated
-// expander warp does it, so the softmax warps -- the critical path -- carry no unpack instructions and the expansion
-// runs ahead of them; at D = 64 (four CTAs per SM, 96 registers per thread) there is no room for another warp and
-// the softmax threads expand K_{j+2} at the end of step j.
+// K tiles that need expansion (packed INT4 / mixed width): a dedicated expander warp does it, so the softmax warps --
+// the critical path -- carry no unpack instructions and the expansion runs ahead of them (D = 128: 1194 -> 1340 TOPS
+// at 8K non-causal).  At D = 64 the sixth warp lowers the register cap of four CTAs per SM from 96 to 80 (132 bytes
+// of spill in the softmax) and still wins, 717 -> 745 TOPS; handing registers over with setmaxnreg does not work out
+// (the helper path needs > 32 registers, and a two-warp trailing warpgroup hangs on it).  The column-split variant
+// (VAR bit 4) keeps the softmax threads expanding K_{j+2} at the end of step j.
 template <int D, int KM, int VAR> struct AttnRoles {
-  static constexpr bool kExpander = (KM != 0) && (D == 128) && ((VAR & 16) == 0);
+  static constexpr bool kExpander = (KM != 0) && ((VAR & 16) == 0);
   static constexpr int kThreads = AttnSP<D, VAR>::kThreads + (kExpander ? 32 : 0);
 };
 
