@@ -125,3 +125,25 @@ def test_varlen_api_glue_vs_sdpa(name):
         a, b, c, e = cu_q[i], cu_q[i + 1], cu_k[i], cu_k[i + 1]
         ref = A.sdpa_fp32(g["q"][a:b].unsqueeze(0), g["k"][c:e].unsqueeze(0), g["v"][c:e].unsqueeze(0), "NHD", causal)
         assert cos_sim(o[a:b], ref[0]) > 0.999
+
+
+def test_mixed_container_pack_unpack_roundtrip():
+    """oracle.quant.pack_mixed / unpack_mixed (the D-byte mixed-width K container of lowbit_quant_k_mixed) are inverse
+    for every width class, both layouts and head dims, and a block of width w only touches the first D*w/8 bytes."""
+    g = torch.Generator().manual_seed(5)
+    for layout in ("HND", "NHD"):
+        for d in (64, 128):
+            n = 200
+            kb = torch.tensor([2, 4, 8], dtype=torch.int32)[torch.randint(0, 3, (1, 2, (n + 63) // 64), generator=g)]
+            lim = torch.tensor([0, 0, 1, 0, 7, 0, 0, 0, 127])[kb.long()].repeat_interleave(64, dim=2)[:, :, :n]
+            c = (torch.rand(1, 2, n, d, generator=g) * 2 - 1) * lim[..., None]
+            c = c.round().to(torch.int8)
+            if layout == "NHD":
+                c = c.permute(0, 2, 1, 3).contiguous()
+            p = Q.pack_mixed(c, kb, 64, layout)
+            assert torch.equal(Q.unpack_mixed(p, kb, 64, layout), c)
+            ph = p if layout == "HND" else p.permute(0, 2, 1, 3)
+            rows = kb.repeat_interleave(64, dim=2)[:, :, :n]
+            for w in (2, 4):
+                tail = ph[..., d * w // 8:][rows == w]
+                assert int(tail.abs().sum()) == 0
