@@ -518,12 +518,17 @@ def test_ring_attention_world1_cuda_backend(L, cuda_dev):
     dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda_dev)
     try:
         for layout, causal, qk, pv, d in (("HND", True, "int4", "fp16", 64), ("NHD", False, "int8", "fp16", 128),
-                                          ("HND", True, "int4", "fp8", 128)):
+                                          ("HND", True, "int4", "fp8", 128), ("HND", True, "mixed", "fp16", 128),
+                                          ("NHD", False, "mixed", "fp16", 64)):
             q = mk(1, 4, 1024, d, layout, torch.float16, 91).to(cuda_dev)
             k = mk(1, 2, 1024, d, layout, torch.float16, 92, bias=2.0).to(cuda_dev)
+            if qk == "mixed":
+                k = _mixed_k(1, 2, 1024, d, layout, torch.float16, 92).to(cuda_dev)
             v = mk(1, 2, 1024, d, layout, torch.float16, 93).to(cuda_dev)
             o, lse = P.ring_attention(q, k, v, tensor_layout=layout, is_causal=causal, qk=qk, pv=pv, return_lse=True)
-            if pv == "fp8":
+            if qk == "mixed":
+                fn = L.lowbit_fa_q_int8_k_dynamic
+            elif pv == "fp8":
                 fn = L.lowbit_fa_qk_int4_pv_fp8
             else:
                 fn = L.lowbit_fa_qk_int4_pv_fp16_triton if qk == "int4" else L.lowbit_fa_qk_int8_pv_fp16_triton
@@ -860,3 +865,25 @@ def test_column_split_softmax_variant_passes_the_attention_suite(cuda_dev):
                         "--deselect", "tests/test_gpu_parity.py::test_column_split_softmax_variant_passes_the_attention_suite"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [1, 31, 64, 65, 129])
+@pytest.mark.parametrize("d", [64, 128])
+def test_tiny_sequences_every_k_format(L, cuda_dev, n, d):
+    """One to a few key blocks (prologue-only pipelines: expander warp, K stage ring, masked tail) for the packed INT4,
+    mixed-width and FP8-PV operators, causal and not, against the CPU oracle."""
+    from oracle import attention as OA
+    q = mk(1, 2, n, d, "HND", torch.float16, 101)
+    k = mk(1, 2, n, d, "HND", torch.float16, 102, bias=1.0)
+    v = mk(1, 2, n, d, "HND", torch.float16, 103)
+    dq, dk, dv = q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev)
+    for causal in (False, True):
+        o = L.lowbit_fa_qk_int4_pv_fp16_triton(dq, dk, dv, is_causal=causal)
+        ref = OA.lowbit_fa_api(q, k, v, "HND", causal, compat_tail=False, pv_accum="fp32", qk="int4")
+        assert (o.cpu().float() - ref.float()).abs().max().item() <= 4e-3
+        o = L.lowbit_fa_q_int8_k_dynamic(dq, dk, dv, is_causal=causal)
+        ref = OA.lowbit_fa_api(q, k, v, "HND", causal, compat_tail=False, pv_accum="fp32", qk="mixed")
+        assert (o.cpu().float() - ref.float()).abs().max().item() <= 4e-3
+        o = L.lowbit_fa_qk_int4_pv_fp8(dq, dk, dv, is_causal=causal)
+        ref = OA.lowbit_fa_api(q, k, v, "HND", causal, compat_tail=False, pv_accum="fp32", qk="int4", pv="fp8")
+        assert (o.cpu().float() - ref.float()).abs().max().item() <= 0.125 * float(v.abs().max())

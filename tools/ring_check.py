@@ -26,6 +26,7 @@ def main():
         ("NHD", True, "int4", "fp16", 64, 2, 4, 2, 4096),
         ("HND", True, "int4", "fp8", 128, 1, 4, 4, 4096),
         ("HND", True, "int4", "fp16", 128, 1, 8, 8, 16384),
+        ("HND", True, "mixed", "fp16", 128, 1, 4, 4, 8192),   # dynamic INT8/INT4/INT2 K blocks
     ]
     for layout, causal, qk, pv, d, b, hq, hkv, n in cfgs:
         torch.manual_seed(7)
@@ -34,13 +35,19 @@ def main():
         q = torch.randn(shp(hq), dtype=torch.float16, device=dev)
         k = torch.randn(shp(hkv), dtype=torch.float16, device=dev) + 1.5
         v = torch.randn(shp(hkv), dtype=torch.float16, device=dev)
+        if qk == "mixed":  # block magnitudes over the three width classes (around the common mean)
+            w = torch.tensor([0.1, 1.0, 3.0], device=dev)[torch.arange(n, device=dev) // 64 % 3]
+            w = w.view(1, 1, n, 1) if layout == "HND" else w.view(1, n, 1, 1)
+            k = ((k.float() - 1.5) * w + 1.5).half()
         zig = causal
         chunks = P.seq_chunks(n, world, rank, zig)
         take = lambda x: torch.cat([x.narrow(seq, c.offset, c.length) for c in chunks], dim=seq).contiguous()
         o, lse = P.ring_attention(take(q), take(k), take(v), tensor_layout=layout, is_causal=causal, qk=qk, pv=pv,
                                   return_lse=True)
         # reference: the single-GPU entry point on the full tensors
-        if pv == "fp8":
+        if qk == "mixed":
+            fn = L.lowbit_fa_q_int8_k_dynamic
+        elif pv == "fp8":
             fn = L.lowbit_fa_qk_int4_pv_fp8 if qk == "int4" else L.lowbit_fa_qk_int8_pv_fp8_cuda
         else:
             fn = L.lowbit_fa_qk_int4_pv_fp16_triton if qk == "int4" else L.lowbit_fa_qk_int8_pv_fp16_triton
