@@ -68,6 +68,15 @@ def ncu_traffic_bytes():
         return None
 
 
+def mufu_bound(B, Hq, N, causal, attn_ms, sm_mhz, sms=148):
+    """exp2 evaluations per attention launch against the XU pipe's 16 MUFU.EX2 per clock per SM at the SM clock sampled
+    during the run (1965 MHz when the sample is missing)."""
+    exps = float(B) * Hq * N * N / (2 if causal else 1)
+    rate = sms * 16 * (sm_mhz or 1965) * 1e6
+    floor_ms = exps / rate * 1e3
+    return {"exp2_per_launch": exps, "peak_exp2_per_s": rate, "floor_ms": floor_ms, "frac": floor_ms / attn_ms}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -467,7 +476,10 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": ncu_traffic_bytes() if args.workload == "c2" else None, "peak_source": peak_src,
-                         "algorithmic_flop_per_launch": ops, "ms_per_launch": attn_ms},
+                         "algorithmic_flop_per_launch": ops, "ms_per_launch": attn_ms,
+                         # the co-bound that actually binds at D=64: one MUFU.EX2 per score,
+                         # 16 per clock per SM
+                         "mufu_co_bound": mufu_bound(B, Hq, N, causal, attn_ms, (sampler.summary() or {}).get("sm_mhz"))},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
