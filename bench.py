@@ -467,7 +467,7 @@ def main():
                        "vs_baseline_note": "BASELINE.md 199.5 TFLOP/s is attention-kernel-only on unstated hardware; value includes quantization"},
             "attn_only": {"value": world * ops / (attn_alone_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": attn_alone_ms},
             "e2e": {"value": world * ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": e2e_ms,
-                    "api": "lowbit_fa_host (pinned host q,k,v -> pinned host o; 8 chunks on 3 streams)",
+                    "api": "lowbit_fa_host (pinned host q,k,v -> pinned host o; 9 chunks on 3 streams, replayed as one CUDA graph)",
                     "serial_ms": e2e_serial_ms, "statistic": "median of per-step CUDA-event times", "mean_ms": e2e_mean_ms,
                     "max_ms": e2e_max_ms, "steps": KE, "host_cpus_bound": affinity,
                     "h2d_bytes_per_step": int(hq_.numel() * 2 + hk_.numel() * 2 + hv_.numel() * 2),

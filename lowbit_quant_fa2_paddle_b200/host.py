@@ -35,19 +35,14 @@ _stage_cache = {}
 
 
 def _staging(dev: torch.device, dtype, shapes):
-    """Persistent device staging buffers (q, k, v chunk + a "slot free" event) x _NSLOT, cached per chunk geometry, so
-    the pipelined loop never goes to the allocator (a cudaMalloc in the loop shows up as a multi-millisecond stall)."""
+    """Persistent device staging buffers (q, k, v chunk) x _NSLOT, cached per chunk geometry, so the pipelined loop
+    never goes to the allocator (a cudaMalloc in the loop shows up as a multi-millisecond stall)."""
     key = (dev.index, dtype, shapes)
     slots = _stage_cache.get(key)
     if slots is None:
         if len(_stage_cache) >= 4:  # a handful of geometries at most: drop the oldest
             _stage_cache.pop(next(iter(_stage_cache)))
-        slots = []
-        for _ in range(_NSLOT):
-            bufs = [torch.empty(sh, dtype=dtype, device=dev) for sh in shapes]
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            slots.append((bufs[0], bufs[1], bufs[2], ev))
+        slots = [tuple(torch.empty(sh, dtype=dtype, device=dev) for sh in shapes) for _ in range(_NSLOT)]
         _stage_cache[key] = slots
     return slots
 
@@ -56,7 +51,10 @@ def plan_chunks(B: int, Hq: int, Hkv: int, tensor_layout: str, chunks: Optional[
     """Cut the (batch, kv-head) units into chunks whose host memory is ONE contiguous range per tensor (a strided
     host slice would need a CPU-side gather before the DMA).  Returns [(b, kv_head_begin, kv_head_end), ...].
     HND `[B,H,N,D]`: any head range of one batch entry is contiguous.  NHD `[B,N,H,D]`: only whole batch entries are.
-    `chunks` is a target count (default 8); q heads follow their kv head (GQA groups are never split)."""
+    `chunks` is a target count (default 8); q heads follow their kv head (GQA groups are never split).
+    The pipeline is bound by the copy-in (PCIe), so what is left exposed is the tail: the last chunk's kernels and
+    copy-out start only when its last input byte has arrived.  The last chunk is therefore cut once more into a large
+    and a small part (a quarter), which shortens that tail without making the other chunks too small to fill the GPU."""
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
     if Hq % Hkv != 0:
@@ -68,16 +66,90 @@ def plan_chunks(B: int, Hq: int, Hkv: int, tensor_layout: str, chunks: Optional[
         while Hkv % per_b:  # equal head groups
             per_b -= 1
     step = Hkv // per_b
-    return [(b, h0, h0 + step) for b in range(B) for h0 in range(0, Hkv, step)]
+    plan = [(b, h0, h0 + step) for b in range(B) for h0 in range(0, Hkv, step)]
+    if tensor_layout == "HND" and step >= 4 and len(plan) > 1:
+        b, h0, h1 = plan.pop()
+        cut = h1 - max(1, step // 4)
+        plan += [(b, h0, cut), (b, cut, h1)]
+    return plan
+
+
+def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=None):
+    """Enqueue the three-stream pipeline on the caller's current stream of `dev` (eagerly, or into a CUDA graph that
+    is being captured on that stream: every event waited on is recorded inside this call and both side streams
+    fork from and re-join the current stream, which is what stream capture requires).  `keep`: a list that receives
+    the per-chunk outputs, so that under capture no chunk's memory is handed to a later chunk."""
+    def view(t, b, h0, h1):
+        return t[b:b + 1, h0:h1] if tensor_layout == "HND" else t[b:b + 1, :, h0:h1]
+
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = _side_streams(dev)
+    # everything enqueued so far on the caller's stream -- including an earlier call's kernels that read the staging
+    # slots -- is ordered before the first copy of this call
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    hmax = max(h1 - h0 for _, h0, h1 in plan)  # staging slots take the largest chunk; smaller ones use a leading view
+    b0 = plan[0][0]
+    shapes = tuple(tuple(view(t, b0, 0, e).shape) for t, e in ((qt, hmax * grp), (kt, hmax), (vt, hmax)))
+    slots = _staging(dev, qt.dtype, shapes)
+
+    def lead(t, nh):  # the first nh heads of a staging buffer (contiguous: HND slots hold one batch entry)
+        return t if tensor_layout != "HND" or t.shape[1] == nh else t[:, :nh]
+    free = [None] * _NSLOT  # "the kernels that read this slot are done", recorded on the caller's stream
+
+    def stage(i):
+        """H2D of chunk i into staging slot i % NSLOT, after the kernels that last read that slot."""
+        b, h0, h1 = plan[i]
+        sq, sk, sv = slots[i % _NSLOT]
+        dq, dk, dv = lead(sq, (h1 - h0) * grp), lead(sk, h1 - h0), lead(sv, h1 - h0)
+        with torch.cuda.stream(s_in):
+            if free[i % _NSLOT] is not None:
+                s_in.wait_event(free[i % _NSLOT])
+            dk.copy_(view(kt, b, h0, h1), non_blocking=True)  # K first: its mean + codes head the chunk
+            dq.copy_(view(qt, b, h0 * grp, h1 * grp), non_blocking=True)
+            dv.copy_(view(vt, b, h0, h1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return dq, dk, dv, ev
+
+    staged = stage(0)
+    for i, (b, h0, h1) in enumerate(plan):
+        dq, dk, dv, ev = staged
+        if i + 1 < len(plan):
+            staged = stage(i + 1)  # enqueue the next H2D before this chunk's kernels
+        cur.wait_event(ev)
+        o = op(dq, dk, dv, tensor_layout=tensor_layout, **op_kwargs)
+        done = torch.cuda.Event()
+        done.record(cur)  # the slot may be overwritten once these kernels are done
+        free[i % _NSLOT] = done
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            view(out, b, h0 * grp, h1 * grp).copy_(o, non_blocking=True)
+        if keep is not None:
+            keep.append(o)
+        else:
+            o.record_stream(s_out)
+    cur.wait_stream(s_in)
+    cur.wait_stream(s_out)
+
+
+_graphs = {}  # call signature -> [times seen, CUDAGraph | None, kept tensors]
+_GRAPH_CACHE = 4
 
 
 def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, tensor_layout: str = "HND",
-                   chunks: Optional[int] = None, device=None, **op_kwargs: Any):
+                   chunks: Optional[int] = None, device=None, graph: Optional[bool] = None, **op_kwargs: Any):
     """Run `op` (default `lowbit_fa_qk_int8_pv_fp16_triton`) on HOST tensors q, k, v (pinned memory for asynchronous
     DMA) and return the HOST tensor `out` (allocated pinned when not given), overlapping the copies with the kernels.
     Work is ordered on the caller's current stream of `device`: when this returns, everything is enqueued and the
     current stream has been made to wait for the last copy-out -- synchronize it (or an event on it) before reading
-    `out` on the host.  `return_lse` is not supported on this entry point."""
+    `out` on the host.  `return_lse` is not supported on this entry point.
+
+    `graph` (default: automatic): a caller that comes back with the SAME pinned buffers (a serving loop that refills
+    them in place) gets the whole pipeline -- every copy, kernel and cross-stream dependency of every chunk -- as
+    one CUDA graph, captured the second time that call signature is seen and replayed from then on.  The host then
+    spends microseconds per call instead of ~0.2 ms per chunk, which is what lets the call be cut into more, smaller
+    chunks (less exposed first copy-in and last copy-out).  `graph=False` always enqueues eagerly."""
     from . import core
     op = op or core.lowbit_fa_qk_int8_pv_fp16_triton
     if op_kwargs.get("return_lse"):
@@ -102,42 +174,39 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
     grp = Hq // Hkv
     plan = plan_chunks(B, Hq, Hkv, tensor_layout, chunks)
 
-    def view(t, b, h0, h1):
-        return t[b:b + 1, h0:h1] if tensor_layout == "HND" else t[b:b + 1, :, h0:h1]
-
+    key = None
+    if graph is not False and all(t.is_pinned() for t in (qt, kt, vt, out)):
+        try:
+            key = (dev.index, qt.data_ptr(), kt.data_ptr(), vt.data_ptr(), out.data_ptr(), tuple(qt.shape),
+                   tuple(kt.shape), tuple(vt.shape), qt.dtype, tensor_layout, len(plan), op,
+                   tuple(sorted(op_kwargs.items())))
+            hash(key)
+        except TypeError:
+            key = None  # an unhashable operator argument: enqueue eagerly
     with torch.cuda.device(dev):
-        cur = torch.cuda.current_stream(dev)
-        s_in, s_out = _side_streams(dev)
-        s_in.wait_stream(cur)
-        s_out.wait_stream(cur)
-        b0, h0, h1 = plan[0]
-        shapes = tuple(tuple(view(t, b0, a, e).shape) for t, a, e in ((qt, h0 * grp, h1 * grp), (kt, h0, h1), (vt, h0, h1)))
-        slots = _staging(dev, qt.dtype, shapes)
-
-        def stage(i):
-            """H2D of chunk i into staging slot i % NSLOT, after the kernels that last read that slot."""
-            b, h0, h1 = plan[i]
-            dq, dk, dv, free = slots[i % _NSLOT]
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(free)
-                dk.copy_(view(kt, b, h0, h1), non_blocking=True)  # K first: its mean + codes head the chunk
-                dq.copy_(view(qt, b, h0 * grp, h1 * grp), non_blocking=True)
-                dv.copy_(view(vt, b, h0, h1), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(s_in)
-            return dq, dk, dv, ev, free
-
-        staged = stage(0)
-        for i, (b, h0, h1) in enumerate(plan):
-            dq, dk, dv, ev, free = staged
-            if i + 1 < len(plan):
-                staged = stage(i + 1)  # enqueue the next H2D before this chunk's kernels
-            cur.wait_event(ev)
-            o = op(dq, dk, dv, tensor_layout=tensor_layout, **op_kwargs)
-            free.record(cur)  # the slot may be overwritten once these kernels are done
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(free)
-                view(out, b, h0 * grp, h1 * grp).copy_(o, non_blocking=True)
-            o.record_stream(s_out)
-        cur.wait_stream(s_out)
+        if key is None:
+            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)
+            return out
+        entry = _graphs.get(key)
+        if entry is None:
+            if len(_graphs) >= _GRAPH_CACHE:
+                _graphs.pop(next(iter(_graphs)))
+            _graphs[key] = [1, None, None]
+            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)  # first sighting: eager (warms the kernels)
+            return out
+        if entry[1] is None:
+            cur = torch.cuda.current_stream(dev)
+            cap = torch.cuda.Stream(dev)
+            cap.wait_stream(cur)
+            g, keep = torch.cuda.CUDAGraph(), []
+            with torch.cuda.graph(g, stream=cap):
+                _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=keep)
+            entry[1], entry[2] = g, keep
+        entry[0] += 1
+        entry[1].replay()
     return out
+
+
+def drop_graphs() -> None:
+    """Forget the captured pipelines (and release the device memory their private pools hold)."""
+    _graphs.clear()

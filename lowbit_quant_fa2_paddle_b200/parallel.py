@@ -226,6 +226,16 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
     if backend is None and not on_cuda:
         raise N.LowbitNativeError("ring_attention: tensors must live on a CUDA device (no CPU fallback)")
 
+    import os
+    marks = [] if (on_cuda and os.environ.get("LOWBIT_RING_TIMING")) else None  # (label, event) on the compute stream
+
+    def mark(label):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(q.device))
+            marks.append((label, ev))
+
+    mark("start")
     my_chunks = seq_chunks(n_total, world, rank, zigzag)
     assert sum(c.length for c in my_chunks) == n_local, "local shard length does not match N / world"
 
@@ -243,6 +253,7 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
         dist.all_reduce(ksum, group=group)
         km = (ksum.to(torch.float32) / torch.tensor(float(n_total), dtype=torch.float32, device=k.device)).to(k.dtype)
         km = km.contiguous()  # [B,Hkv,D] (seq dim reduced away in either layout)
+    mark("k mean (sum + all-reduce)")
 
     # quantize once: Q chunks stay resident, the K/V shard goes into the flat ring message
     q_packs = [be.quantize_q(x) for x in local_views(q)]
@@ -250,6 +261,7 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
     for i, (kx, vx) in enumerate(zip(local_views(k), local_views(v))):
         be.quantize_kv(kx, vx.to(torch.float16) if (pv == "fp16" and vx.dtype != torch.float16) else vx, km, msg, i)
     bufs = [msg, msg.like()]
+    mark("quantize q, k, v")
 
     compute_stream = torch.cuda.current_stream(q.device) if on_cuda else None
     comm_stream = torch.cuda.Stream(q.device) if on_cuda else None
@@ -280,6 +292,7 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
                 for w in works:
                     w.wait()
         cur ^= 1
+        mark(f"step {step}")
 
     outs, lses = [], []
     for qi in range(len(my_chunks)):
@@ -287,6 +300,12 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
         outs.append(o_i)
         lses.append(lse_i)
     o = outs[0] if len(outs) == 1 else torch.cat(outs, dim=seq)
+    mark("finalize")
+    if marks is not None:
+        torch.cuda.synchronize(q.device)
+        if rank == 0:
+            print("ring timing (ms): " + ", ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.3f}" for a, b in zip(marks, marks[1:])),
+                  flush=True)
     if not return_lse:
         return o
     lse2 = lses[0] if len(lses) == 1 else torch.cat(lses, dim=2)

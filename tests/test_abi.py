@@ -155,7 +155,12 @@ def test_more_error_conventions():
         L.lowbit_fa_varlen(p.float(), p.float(), p.float(), cu, cu, 6, 6)
     with pytest.raises(LowbitNativeError):
         L.lowbit_fa_host(h, h, h, device="cpu")
-    assert L.plan_chunks(4, 32, 32, "HND", None) == [(b, h0, h0 + 16) for b in range(4) for h0 in (0, 16)]
+    # equal head groups, the last one cut once more (large + small) to shorten the exposed tail of the pipeline
+    assert L.plan_chunks(4, 32, 32, "HND", None) == \
+        [(b, h0, h0 + 16) for b in range(4) for h0 in (0, 16)][:-1] + [(3, 16, 28), (3, 28, 32)]
+    for args in ((4, 32, 32, "HND", None), (2, 8, 2, "HND", 8), (1, 6, 6, "HND", 3), (3, 4, 4, "HND", 1), (2, 4, 4, "NHD", 8)):
+        units = [(b, h) for b, h0, h1 in L.plan_chunks(*args) for h in range(h0, h1)]
+        assert units == [(b, h) for b in range(args[0]) for h in range(args[2])]  # every (batch, kv head) once, in order
     assert L.plan_chunks(2, 8, 2, "NHD", 8) == [(0, 0, 2), (1, 0, 2)]
     with pytest.raises(ValueError):
         L.plan_chunks(1, 3, 2, "HND", 4)

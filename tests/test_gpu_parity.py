@@ -615,6 +615,41 @@ def test_host_streaming_matches_device_call(L, cuda_dev, layout, b, hq, hkv, n, 
     assert torch.equal(out4, ref4.cpu())
 
 
+@pytest.mark.parametrize("layout,b,hq,hkv,n,d,causal,chunks", [
+    ("HND", 2, 4, 4, 700, 64, False, 8),
+    ("HND", 1, 8, 2, 512, 128, True, 4),
+    ("NHD", 3, 4, 4, 300, 64, False, None),
+])
+def test_host_streaming_replays_a_captured_graph(L, cuda_dev, layout, b, hq, hkv, n, d, causal, chunks):
+    """A caller that returns with the same pinned buffers gets the pipeline as one CUDA graph (captured at the second
+    call, replayed afterwards).  The buffers are refilled in place between calls: every replay must read the new
+    contents and stay bit-identical to the plain operator call; graph=False never captures."""
+    from lowbit_quant_fa2_paddle_b200 import host as H
+    H.drop_graphs()
+    q = mk(b, hq, n, d, layout, torch.float16, 31).pin_memory()
+    k = mk(b, hkv, n, d, layout, torch.float16, 32, bias=2.0).pin_memory()
+    v = mk(b, hkv, n, d, layout, torch.float16, 33).pin_memory()
+    out = torch.empty(q.shape, dtype=q.dtype).pin_memory()
+    for it in range(4):
+        if it:  # refill in place: same addresses, new values
+            q.copy_(mk(b, hq, n, d, layout, torch.float16, 40 + it))
+            k.copy_(mk(b, hkv, n, d, layout, torch.float16, 50 + it, bias=1.0))
+            v.copy_(mk(b, hkv, n, d, layout, torch.float16, 60 + it))
+        out.zero_()
+        got = L.lowbit_fa_host(q, k, v, out=out, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev)
+        ref = L.lowbit_fa_qk_int8_pv_fp16_triton(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout,
+                                                 is_causal=causal)
+        torch.cuda.synchronize()
+        assert got is out and torch.equal(out, ref.cpu()), f"call {it}"
+    entries = [e for e in H._graphs.values()]
+    assert len(entries) == 1 and entries[0][1] is not None and entries[0][0] == 4  # seen 4 times, graph captured
+    out.zero_()
+    L.lowbit_fa_host(q, k, v, out=out, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev, graph=False)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref.cpu()) and entries[0][0] == 4
+    H.drop_graphs()
+
+
 # ------------------------------------------------------------------------------------------------ triton_gpu rounding
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("bits", [8, 4])
