@@ -55,6 +55,39 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = to_f32<T>(h[i]);
 }
 
+// fp32 pair -> the input dtype (one packed conversion, round to nearest even) -> fp32 pair: `k - km` as the framework
+// computes it in the tensor's dtype (quant_per_block.py:186-187)
+template <typename T> __device__ __forceinline__ float2 round_trip2(float2 v);
+template <> __device__ __forceinline__ float2 round_trip2<__half>(float2 v) { return __half22float2(__float22half2_rn(v)); }
+template <> __device__ __forceinline__ float2 round_trip2<__nv_bfloat16>(float2 v) {
+  return __bfloat1622float2(__float22bfloat162_rn(v));
+}
+
+// Load side of the per-block quantizers for one 8-element row chunk, on packed fp32 pairs (FADD2 / FMUL2: one issue
+// slot per two elements -- these kernels are instruction-issue bound, not HBM bound, at 15-30 us per launch):
+//   x = f32(in) [- f32(km)] [rounded to the input dtype] * sm,  amax = max(amax, |x|)
+// A row that is out of range must contribute exact zeros: without km that is what the zero-filled load gives
+// (0 * sm); with km the caller substitutes km's own bits for the row (km - km = 0), which is cheaper than a select
+// per element.  Same IEEE operations per lane as the scalar form, so the same bits.
+template <typename T, bool HAS_KM, bool ROUND_KM>
+__device__ __forceinline__ void prep_row8(const uint4& raw, const float (&kmf)[8], float sm, float (&x)[8], float& amax) {
+  float f[8];
+  unpack8<T>(raw, f);
+  const float2 sm2 = make_float2(sm, sm);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 v = make_float2(f[2 * i], f[2 * i + 1]);
+    if constexpr (HAS_KM) {
+      v = __fadd2_rn(v, make_float2(-kmf[2 * i], -kmf[2 * i + 1]));  // x - km == x + (-km), bit for bit
+      if constexpr (ROUND_KM) v = round_trip2<T>(v);
+    }
+    v = __fmul2_rn(v, sm2);
+    x[2 * i] = v.x;
+    x[2 * i + 1] = v.y;
+    amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));
+  }
+}
+
 // Exact per-thread accumulation.  fp16: every value is an integer X = x * 2^24 with |X| < 2^40; it is split
 // without any conversion instruction into hi = RN(16 x) and lo = X - hi * 2^20 (|lo| <= 2^19) by two magic-constant
 // FMAs (1.5 * 2^23: the integer lands in the low mantissa bits), and the RAW float bits are summed in two int32

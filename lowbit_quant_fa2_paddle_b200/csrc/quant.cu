@@ -51,6 +51,12 @@ __device__ __forceinline__ int q1_code_fast(float x, float sc, float rcp) {
   y = __fadd_rn(y, __uint_as_float(0x3f000000u | (__float_as_uint(y) & 0x80000000u)));
   return __float2int_rz(y);
 }
+// copysign(0.5f, y) in one LOP3: (bits(y) & 0x80000000) | 0x3f000000
+__device__ __forceinline__ float half_with_sign_of(float y) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, 0x80000000, 0x3f000000, 0xEA;" : "=r"(r) : "r"(__float_as_uint(y)));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ int q1_code_ieee(float x, float sc) {
   float y = __fdiv_rn(x, sc);
   y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
@@ -103,8 +109,18 @@ __device__ __forceinline__ void codes8(const float (&x)[8], int (&c)[8], float s
 #pragma unroll
     for (int i = 0; i < 8; ++i) c[i] = q1_code_divfull(x[i], sc);
   } else if (triton && !slow_div) {
+    // q1_code_fast on packed fp32 pairs (FMUL2 / FFMA2 / FADD2); fma(q0, -sc, x) == fma(-q0, sc, x) bit for bit
+    const float2 rcp2 = make_float2(rcp, rcp), nsc2 = make_float2(-sc, -sc);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) c[i] = q1_code_fast(x[i], sc, rcp);
+    for (int i = 0; i < 4; ++i) {
+      const float2 xv = make_float2(x[2 * i], x[2 * i + 1]);
+      const float2 q0 = __fmul2_rn(xv, rcp2);
+      const float2 rem = __ffma2_rn(q0, nsc2, xv);
+      float2 y = __ffma2_rn(rem, rcp2, q0);
+      y = __fadd2_rn(y, make_float2(half_with_sign_of(y.x), half_with_sign_of(y.y)));
+      c[2 * i] = __float2int_rz(y.x);
+      c[2 * i + 1] = __float2int_rz(y.y);
+    }
   } else if (triton) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) c[i] = q1_code_ieee(x[i], sc);
@@ -183,9 +199,10 @@ __device__ __forceinline__ void quant_block_body(const T* __restrict__ in, const
 
   float kmf[8];
   const bool has_km = km != nullptr;
+  uint4 km_raw = make_uint4(0, 0, 0, 0);
   if (has_km) {  // L2 load: in the fused kernel km was written by another CTA of the same launch
-    uint4 raw = __ldcg(reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8));
-    unpack8<T>(raw, kmf);
+    km_raw = __ldcg(reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8));
+    unpack8<T>(km_raw, kmf);
   }
 
   float x[NP][8];
@@ -194,30 +211,20 @@ __device__ __forceinline__ void quant_block_body(const T* __restrict__ in, const
   for (int p = 0; p < NP; ++p) {
     const int rl = (p % NPS) * RPP + r0;  // row inside its block
     const int row = row_base + (p / NPS) * BLK + rl;
-    raw[p] = make_uint4(0, 0, 0, 0);
+    raw[p] = km_raw;  // rows >= N contribute 0 (masked load): zeros without km, km - km with it
     if (rl < BLK && row < N) raw[p] = ld_stream_v4(src + (int64_t)row * isn);
   }
   float amax[NSUB];
 #pragma unroll
   for (int u = 0; u < NSUB; ++u) amax[u] = 0.f;
+  auto prep = [&](auto has_km_tag, auto round_tag) {  // block-uniform choice made once, not per element
 #pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    unpack8<T>(raw[p], x[p]);
-    const int rl = (p % NPS) * RPP + r0;
-    const bool live = (rl < BLK) && (row_base + (p / NPS) * BLK + rl < N);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = x[p][i];
-      if (has_km) {
-        v = __fsub_rn(v, kmf[i]);
-        if ((mode & 0xff) == LOWBIT_QMODE_TRITON) v = to_f32<T>(from_f32<T>(v));  // `k - km` in the input dtype
-      }
-      v = __fmul_rn(v, sm);
-      v = live ? v : 0.f;  // rows >= N contribute 0 (masked load), even when km != 0
-      x[p][i] = v;
-      amax[p / NPS] = fmaxf(amax[p / NPS], fabsf(v));
-    }
-  }
+    for (int p = 0; p < NP; ++p)
+      prep_row8<T, decltype(has_km_tag)::value, decltype(round_tag)::value>(raw[p], kmf, sm, x[p], amax[p / NPS]);
+  };
+  if (!has_km) prep(std::false_type{}, std::false_type{});
+  else if ((mode & 0xff) == LOWBIT_QMODE_TRITON) prep(std::true_type{}, std::true_type{});  // `k - km` in the input dtype
+  else prep(std::true_type{}, std::false_type{});
   // block abs-max: warp redux + smem
 #pragma unroll
   for (int u = 0; u < NSUB; ++u) {
@@ -435,54 +442,68 @@ quant_per_block_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const T* __
     ptx::prefetch_tmap(&tmIn);
   }
   __syncthreads();
-  auto issue = [&](int t, int stage) {  // thread 0: fetch tile t (linear over b, h, block) into `stage`
-    const int j = t % nblk, h = (t / nblk) % H, b = t / (nblk * H);
-    ptx::mbar_expect_tx(full + stage, C::kTileBytes);
-    ptx::tma_load_4d(smem + stage * C::kTileBytes, &tmIn, full + stage, 0, j * BLK, h, b);
-  };
+  // Tile t = (b * H + h) * nblk + j.  The coordinates of the tile being quantized and of the tile being fetched
+  // advance by a fixed stride per iteration: carried along with two compare-and-wrap steps instead of three integer
+  // divisions per tile (which were a sixth of the instructions of this issue-bound kernel).
+  struct Coord { int j, h, b; };
   const int first = blockIdx.x, stride = gridDim.x;
+  const int dj = stride % nblk, dh = (stride / nblk) % H, db = stride / (nblk * H);
+  auto coord_of = [&](int t) { return Coord{t % nblk, (t / nblk) % H, t / (nblk * H)}; };
+  auto advance = [&](Coord& c) {
+    c.j += dj; c.h += dh; c.b += db;
+    if (c.j >= nblk) { c.j -= nblk; c.h += 1; }
+    if (c.h >= H) { c.h -= H; c.b += 1; }
+  };
+  auto issue = [&](const Coord& c, int stage) {  // thread 0: fetch one tile into `stage`
+    ptx::mbar_expect_tx(full + stage, C::kTileBytes);
+    ptx::tma_load_4d(smem + stage * C::kTileBytes, &tmIn, full + stage, 0, c.j * BLK, c.h, c.b);
+  };
+  Coord cur = coord_of(first), nxt = cur;  // nxt: the tile S iterations ahead (thread 0's fetch cursor)
   if (tid == 0) {
-    for (int i = 0; i < S; ++i)
-      if (first + i * stride < total) issue(first + i * stride, i);
+    for (int i = 0; i < S; ++i) {
+      if (first + i * stride < total) issue(nxt, i);
+      advance(nxt);
+    }
   }
   int it = 0;
-  for (int t = first; t < total; t += stride, ++it) {
+  for (int t = first; t < total; t += stride, ++it, advance(cur)) {
     const int stage = it % S;
-    const int jb = t % nblk, h = (t / nblk) % H, b = t / (nblk * H);
+    const int jb = cur.j, h = cur.h, b = cur.b;
     float kmf[8];
     const bool has_km = km != nullptr;
+    uint4 km_raw = make_uint4(0, 0, 0, 0);
     if (has_km) {
-      uint4 raw = *reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8);
-      unpack8<T>(raw, kmf);
+      km_raw = *reinterpret_cast<const uint4*>(km + ((int64_t)b * H + h) * D + c8);
+      unpack8<T>(km_raw, kmf);
     }
     ptx::mbar_wait(full + stage, (it / S) & 1, 40);
     const uint8_t* tile = smem + stage * C::kTileBytes;
     float x[NP][8];
+    uint4 raw[NP];
     float amax = 0.f;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const int rl = p * RPP + r0;
       const bool live = (rl < BLK) && (jb * BLK + rl < N);
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (rl < BLK) raw = *reinterpret_cast<const uint4*>(tile + ((size_t)rl * D + c8) * 2);
-      unpack8<T>(raw, x[p]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v = x[p][i];
-        if (has_km) {
-          v = __fsub_rn(v, kmf[i]);
-          if (triton) v = to_f32<T>(from_f32<T>(v));  // `k - km` in the input dtype
-        }
-        v = __fmul_rn(v, sm);
-        v = live ? v : 0.f;  // rows >= N contribute 0 (masked load), even when km != 0
-        x[p][i] = v;
-        amax = fmaxf(amax, fabsf(v));
-      }
+      // rows >= N contribute 0 (the TMA zero fill is the masked load): zeros without km, km - km with it
+      raw[p] = km_raw;
+      if (live) raw[p] = *reinterpret_cast<const uint4*>(tile + ((size_t)rl * D + c8) * 2);
     }
+    auto prep = [&](auto has_km_tag, auto round_tag) {  // block-uniform choice made once, not per element
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+        prep_row8<T, decltype(has_km_tag)::value, decltype(round_tag)::value>(raw[p], kmf, sm, x[p], amax);
+    };
+    if (!has_km) prep(std::false_type{}, std::false_type{});
+    else if (triton) prep(std::true_type{}, std::true_type{});  // `k - km` in the input dtype
+    else prep(std::true_type{}, std::false_type{});
     amax = warp_max(amax);
     if ((tid & 31) == 0) s_w[it & 1][tid >> 5] = amax;
     __syncthreads();  // every thread has finished reading this stage
-    if (tid == 0 && t + S * stride < total) issue(t + S * stride, stage);
+    if (tid == 0) {
+      if (t + S * stride < total) issue(nxt, stage);
+      advance(nxt);
+    }
     float bmax = s_w[it & 1][0];
 #pragma unroll
     for (int w = 1; w < kQuantThreads / 32; ++w) bmax = fmaxf(bmax, s_w[it & 1][w]);

@@ -194,16 +194,23 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
             _graphs[key] = [1, None, None]
             _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)  # first sighting: eager (warms the kernels)
             return out
+        entry[0] += 1
         if entry[1] is None:
             cur = torch.cuda.current_stream(dev)
             cap = torch.cuda.Stream(dev)
             cap.wait_stream(cur)
             g, keep = torch.cuda.CUDAGraph(), []
-            with torch.cuda.graph(g, stream=cap):
-                _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=keep)
-            entry[1], entry[2] = g, keep
-        entry[0] += 1
-        entry[1].replay()
+            try:
+                # thread_local: CUDA calls of other threads (e.g. a NCCL watchdog polling events) do not break the capture
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                    _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=keep)
+                entry[1], entry[2] = g, keep
+            except RuntimeError:
+                entry[1] = False  # this operator cannot be captured (it synchronises): same kernels, enqueued eagerly
+        if entry[1] is False:
+            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)
+        else:
+            entry[1].replay()
     return out
 
 
