@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LOWBIT_ABI_VERSION 4
+#define LOWBIT_ABI_VERSION 5
 
 /* element types of the floating-point inputs / outputs */
 enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
@@ -130,6 +130,18 @@ int lowbit_prep_qk(const void* q, const void* k, void* km_out, void* q_codes, fl
 int64_t lowbit_k_mean_workspace_bytes(int B, int H, int N, int D);
 int lowbit_k_mean(const void* k, void* km_out, void* workspace, int B, int H, int N, int D,
                   int64_t stride_b, int64_t stride_h, int64_t stride_n, int dtype, void* stream);
+
+/* S1 + Q1/Q2/Q4 for K in ONE launch and ONE pass over HBM: K mean over the sequence (src/core.py:293), `k - km` and the
+ * per-64-row-block codes of the smoothed K (quant_per_block.py:181-248 with km / src/quant.py:70-98).  A thread-block
+ * cluster of 8 CTAs holds one (batch, kv-head) slice in shared memory, reduces the exact column sums over distributed
+ * shared memory and quantizes from there.  km_out [B,H,D] (input dtype), codes / scale as lowbit_quant_per_block with
+ * blk = 64: bit-identical to lowbit_k_mean followed by lowbit_quant_per_block(k, km, blk=64, sm=1).
+ * fp16 only, and a slice has to fit the cluster (N * D * 2 bytes <= ~1.6 MB): lowbit_k_smooth_quant_supported() says
+ * so; otherwise call the two separate entry points. */
+int lowbit_k_smooth_quant_supported(int N, int D, int dtype);
+int lowbit_k_smooth_quant(const void* k, void* km_out, void* codes, float* scale, int B, int H, int N, int D,
+                          int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
+                          int bits, int pack, int mode, int dtype, void* stream);
 
 /* Q1/Q2/Q4 (+INT2) -- symmetric per-block quantizer.
  * Replaces: quant_per_block_int8_kernel / quant_per_block_int4_unpack_kernel

@@ -24,6 +24,8 @@ from .core import (  # noqa: F401
 )
 from .quant import (  # noqa: F401
     k_mean,
+    k_smooth_quant,
+    k_smooth_quant_supported,
     prep_qk,
     per_block_int8,
     per_block_int8_cuda,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "lowbit_prep_qk": (_I, [_P] * 8 + [_I] * 7 + [_L] * 12 + [_F] + [_I] * 6 + [_P]),
     "lowbit_k_mean_workspace_bytes": (_L, [_I] * 4),
     "lowbit_k_mean": (_I, [_P, _P, _P] + [_I] * 4 + [_L] * 3 + [_I, _P]),
+    "lowbit_k_smooth_quant_supported": (_I, [_I, _I, _I]),
+    "lowbit_k_smooth_quant": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I, _I, _I, _I, _P]),
     "lowbit_quant_per_block": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I, _I, _I, _F, _I, _I, _P]),
     "lowbit_quant_per_thread": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I] * 5 + [_P]),
     "lowbit_quant_pack_lastdim": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
@@ -64,7 +66,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.lowbit_version() != 4:
+        if handle.lowbit_version() != 5:
             raise LowbitNativeError("liblowbit_fa_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 namespace lowbit {
 
 std::string& last_error() {
@@ -830,6 +832,172 @@ __global__ void lse_fixup_kernel(float* __restrict__ lse, const T* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K smoothing + K codes in ONE launch with ONE pass over HBM (src/core.py:291-306 + quant_per_block.py:181-248)
+// ------------------------------------------------------------------------------------------------
+// The separate path runs three dependent launches (column-sum chunks -> mean -> quantizer) and reads K twice.  Here a
+// thread-block cluster of kKsqCluster CTAs owns one (batch, kv-head) slice: every CTA parks its share of the rows in
+// shared memory while it adds them up (the same exact, order-independent fixed-point sum as k_mean_partial_kernel),
+// the per-CTA column sums meet through distributed shared memory, every CTA forms the same mean (bit-identical to
+// lowbit_k_mean: exact sum -> fp32 -> / N -> fp16), and the 64-row blocks are then quantized straight out of shared
+// memory with the arithmetic of quant_block_body.  fp16 only (the bf16 mean is defined by a summation order).
+constexpr int kKsqCluster = 8;                 // portable cluster size
+constexpr int kKsqMaxTileBytes = 200 * 1024;   // rows of one CTA held in shared memory
+
+__host__ __device__ inline int ksq_rows_per_cta(int N) {
+  const int nblk = (N + 63) / 64;
+  return (nblk + kKsqCluster - 1) / kKsqCluster * 64;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kQuantThreads, (D == 64 ? 3 : 2))
+k_smooth_quant_cluster_kernel(const T* __restrict__ k, T* __restrict__ km_out, int8_t* __restrict__ out,
+                              float* __restrict__ scale, int N, int nblk, int rows_cta, int64_t isb, int64_t ish,
+                              int64_t isn, int64_t osb, int64_t osh, int64_t osn, int bits, int pack, int mode, int H) {
+  namespace cg = cooperative_groups;
+  using A = typename MeanAcc<T>::type;
+  constexpr int TPR = D / 8, RPP = kQuantThreads / TPR, NW = kQuantThreads / 32;
+  constexpr int NPS = 64 / RPP;  // passes per 64-row block
+  extern __shared__ uint8_t ksq_smem_raw[];
+  uint4* tile = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(ksq_smem_raw) + 15) & ~uintptr_t(15));
+  __shared__ A s_part[NW][D];      // per-warp column sums
+  __shared__ A s_sum[D];           // this CTA's column sums (read by the whole cluster)
+  __shared__ __align__(16) T s_km[D];
+  __shared__ float s_w[2][NW];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int slice = blockIdx.x / kKsqCluster, h = slice % H, b = slice / H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cq = tid % TPR, c8 = cq * 8, r0 = tid / TPR;
+  const int row_begin = rank * rows_cta;
+  const T* src = k + b * isb + h * ish + c8;
+
+  // (a) rows -> shared memory, exact column sums on the way
+  {
+    A acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = A(0);
+    RowAcc<T> ra;
+    ra.clear();
+    int since_flush = 0;
+    // every row of this CTA's share is requested at once with 16-byte asynchronous copies straight into shared
+    // memory (no registers held while the ~64 KB per CTA are in flight); a thread then sums the chunks it copied
+    // itself, so its own wait_group is all the ordering the sum needs
+    for (int r = r0; r < rows_cta; r += RPP) {
+      if (row_begin + r < N) {
+        const uint32_t daddr = (uint32_t)__cvta_generic_to_shared(&tile[r * TPR + cq]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(daddr), "l"(src + (int64_t)(row_begin + r) * isn) : "memory");
+      } else {
+        tile[r * TPR + cq] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int r = r0; r < rows_cta; r += RPP) {
+      ra.add(tile[r * TPR + cq]);  // absent rows add exact zeros
+      if (++since_flush >= 240) { ra.flush(acc); since_flush = 0; }
+    }
+    ra.flush(acc);
+    // lanes that share lane % TPR hold the same columns: fold them, then one row of sums per warp
+#pragma unroll
+    for (int off = TPR; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    }
+    if (lane < TPR) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_part[warp][c8 + i] = acc[i];
+    }
+  }
+  __syncthreads();
+  if (tid < D) {
+    A t = A(0);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += s_part[w][tid];
+    s_sum[tid] = t;
+  }
+  // (b) the cluster's column sums -> the slice mean (every CTA computes the same value)
+  cluster.sync();
+  if (tid < D) {
+    A t = A(0);
+    for (int rr = 0; rr < kKsqCluster; ++rr) t += cluster.map_shared_rank(s_sum, rr)[tid];
+    const T kmv = from_f32<T>(__fdiv_rn(MeanAcc<T>::to_sum_f32(t), (float)N));
+    s_km[tid] = kmv;
+    if (rank == 0) km_out[((int64_t)b * H + h) * D + tid] = kmv;
+  }
+  cluster.sync();  // s_km visible to the CTA; nobody leaves while its s_sum may still be read
+
+  // (c) 64-row blocks out of shared memory
+  const uint4 km_raw = *reinterpret_cast<const uint4*>(&s_km[c8]);
+  float kmf[8];
+  unpack8<T>(km_raw, kmf);
+  const bool triton = (mode & 0xff) == LOWBIT_QMODE_TRITON;
+  int8_t* dst = out + b * osb + h * osh;
+  const int nloc = rows_cta / 64;
+  for (int bl = 0; bl < nloc; ++bl) {
+    const int jb = rank * nloc + bl;
+    if (jb >= nblk) break;  // uniform over the CTA
+    float x[NPS][8];
+    uint4 raw[NPS];
+    float amax = 0.f;
+#pragma unroll
+    for (int p = 0; p < NPS; ++p) {
+      const int rl = p * RPP + r0;
+      raw[p] = km_raw;  // rows >= N contribute 0 (masked load): km - km
+      if (jb * 64 + rl < N) raw[p] = tile[(bl * 64 + rl) * TPR + cq];
+    }
+    if (triton) {
+#pragma unroll
+      for (int p = 0; p < NPS; ++p) prep_row8<T, true, true>(raw[p], kmf, 1.0f, x[p], amax);
+    } else {
+#pragma unroll
+      for (int p = 0; p < NPS; ++p) prep_row8<T, true, false>(raw[p], kmf, 1.0f, x[p], amax);
+    }
+    amax = warp_max(amax);
+    if (lane == 0) s_w[bl & 1][warp] = amax;
+    __syncthreads();
+    float bmax = s_w[bl & 1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) bmax = fmaxf(bmax, s_w[bl & 1][w]);
+    const BlockScale bs = block_scale(bmax, bits, mode);
+    if (tid == 0) scale[((int64_t)b * H + h) * nblk + jb] = bs.sc;
+    quantize_rows<NPS>(x, dst, osn, jb * 64, RPP, r0, c8, 64, N, bs.sc, bs.rcp, triton, bs.slow_div, bits, pack,
+                       bs.gpu_div);
+  }
+}
+
+template <typename T, int D>
+static int launch_ksq(const void* k, void* km_out, void* codes, float* scale, int B, int H, int N, int64_t isb,
+                      int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn, int bits, int pack, int mode,
+                      cudaStream_t st) {
+  const int rows_cta = ksq_rows_per_cta(N);
+  const int smem = rows_cta * D * 2 + 16;
+  auto kern = k_smooth_quant_cluster_kernel<T, D>;
+  static int configured = 0;
+  if (configured < smem) {
+    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsqMaxTileBytes + 16));
+    configured = kKsqMaxTileBytes + 16;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((int64_t)B * H * kKsqCluster), 1, 1);
+  cfg.blockDim = dim3(kQuantThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kKsqCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int nblk = (N + 63) / 64;
+  LOWBIT_CUDA(cudaLaunchKernelEx(&cfg, kern, (const T*)k, (T*)km_out, (int8_t*)codes, scale, N, nblk, rows_cta, isb, ish,
+                                 isn, osb, osh, osn, bits, pack, mode, H));
+  return 0;
+}
+
 }  // namespace lowbit
 
 using namespace lowbit;
@@ -992,6 +1160,31 @@ int lowbit_k_mean(const void* k, void* km_out, void* workspace, int B, int H, in
 #undef LAUNCH
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
+}
+
+
+int lowbit_k_smooth_quant_supported(int N, int D, int dtype) {
+  if (dtype != LOWBIT_F16 || (D != 64 && D != 128) || N <= 0) return 0;
+  return (int64_t)ksq_rows_per_cta(N) * D * 2 <= kKsqMaxTileBytes ? 1 : 0;
+}
+
+int lowbit_k_smooth_quant(const void* k, void* km_out, void* codes, float* scale, int B, int H, int N, int D,
+                          int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
+                          int bits, int pack, int mode, int dtype, void* stream) {
+  LOWBIT_CHECK(k && km_out && codes && scale, "lowbit_k_smooth_quant: null pointer");
+  LOWBIT_CHECK(lowbit_k_smooth_quant_supported(N, D, dtype),
+               "lowbit_k_smooth_quant: unsupported (N=%d, D=%d, dtype=%d): fp16, head_dim 64/128, a (b,h) slice must fit "
+               "the cluster's shared memory -- use lowbit_k_mean + lowbit_quant_per_block", N, D, dtype);
+  LOWBIT_CHECK(bits == 8 || bits == 4 || bits == 2, "lowbit_k_smooth_quant: bits must be 8, 4 or 2 (got %d)", bits);
+  LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_k_smooth_quant: bad mode %d", mode);
+  LOWBIT_CHECK(B > 0 && H > 0 && (int64_t)B * H * kKsqCluster < (1ll << 31), "lowbit_k_smooth_quant: bad batch / head count");
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0 && ((uintptr_t)k & 15) == 0,
+               "lowbit_k_smooth_quant: input must keep 16-byte alignment");
+  const int ob = (pack && bits < 8) ? bits : 8;  // bytes of 8 codes
+  LOWBIT_CHECK(osn % ob == 0 && osh % ob == 0 && osb % ob == 0, "lowbit_k_smooth_quant: output strides misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 64) return launch_ksq<__half, 64>(k, km_out, codes, scale, B, H, N, isb, ish, isn, osb, osh, osn, bits, pack, mode, st);
+  return launch_ksq<__half, 128>(k, km_out, codes, scale, B, H, N, isb, ish, isn, osb, osh, osn, bits, pack, mode, st);
 }
 
 int lowbit_quant_per_block(const void* in, const void* km, void* codes, float* scale, int B, int H, int N, int D,

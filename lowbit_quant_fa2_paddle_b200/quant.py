@@ -72,6 +72,51 @@ def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout, out=None):
     return T.like(codes, x), T.like(scale, x)
 
 
+def k_smooth_quant_supported(k, tensor_layout="HND"):
+    """True when `k_smooth_quant` takes this tensor: fp16, head_dim 64 / 128, and a (batch, head) slice of K
+    (N * D * 2 bytes) fits the shared memory of one 8-CTA cluster (~1.6 MB)."""
+    kt = T.as_torch(k)
+    if kt.dtype != torch.float16 or kt.dim() != 4 or kt.shape[-1] not in (64, 128):
+        return False
+    n = kt.shape[2] if tensor_layout == "HND" else kt.shape[1]
+    return bool(N.lib().lowbit_k_smooth_quant_supported(int(n), int(kt.shape[-1]), N.F16))
+
+
+def k_smooth_quant(k, bits=8, pack=False, tensor_layout="HND", backend="triton"):
+    """`km = k.mean(seq)`, `k - km` and its per-64-row-block codes (core.py:291-306 + quant_per_block.py:181-248) in
+    ONE launch that reads K from HBM once: a thread-block cluster per (batch, head) slice keeps the slice in shared
+    memory between the exact column sum and the quantizer.  -> (km keepdim, k_codes, k_scale), bit-identical to
+    `k_mean` followed by the per-block quantizer with that km."""
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if backend not in _MODES:
+        raise ValueError(f"Unsupported quantization backend: {backend}")
+    kt = T.as_torch(k)
+    dev = T.require_cuda(kt)
+    b, h, n, d, sb, sh, sn = T.bhnd(kt, tensor_layout)
+    km = torch.empty((b, h, d), dtype=kt.dtype, device=dev)
+    shape = list(kt.shape)
+    shape[-1] = d * bits // 8 if (pack and bits < 8) else d
+    codes = torch.empty(shape, dtype=torch.int8, device=dev)
+    scale = torch.empty((b, h, (n + 63) // 64), dtype=torch.float32, device=dev)
+    _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
+    N.call("lowbit_k_smooth_quant", kt.data_ptr(), km.data_ptr(), codes.data_ptr(), scale.data_ptr(), b, h, n, d,
+           sb, sh, sn, osb, osh, osn, bits, int(bool(pack)), _MODES[backend], T.dtype_code(kt.dtype), T.stream_ptr(dev))
+    km = km.unsqueeze(2) if tensor_layout == "HND" else km.unsqueeze(1)
+    return T.like(km, k), T.like(codes, k), T.like(scale, k)
+
+
+def _smooth_k_codes(kt, smooth_k, kbits, kpack, mode_name, tensor_layout):
+    """K side of the preparation step: (km | None, k_codes, k_scale).  One cluster launch when the slice fits
+    and LOWBIT_K_FUSED=1 asks for it, else k_mean + the per-block quantizer (the default: see DESIGN.md 4.1)."""
+    import os
+    if smooth_k and os.environ.get("LOWBIT_K_FUSED", "0") == "1" and k_smooth_quant_supported(kt, tensor_layout):
+        return k_smooth_quant(kt, kbits, kpack, tensor_layout, mode_name)
+    km = k_mean(kt, tensor_layout) if smooth_k else None
+    k_c, k_s = _quant_one(kt, km, 64, kbits, kpack, 1.0, _MODES[mode_name], tensor_layout)
+    return km, k_c, k_s
+
+
 def _per_block(q, k, km, BLKQ, BLKK, sm_scale, tensor_layout, qbits, kbits, kpack, backend):
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
@@ -108,8 +153,7 @@ def smooth_and_quantize(q, k, smooth_k, sm_scale, tensor_layout, qbits, kbits, k
     if overlap is None:
         overlap = os.environ.get("LOWBIT_QUANT_OVERLAP", "1") != "0"
     if not overlap:
-        km = k_mean(kt, tensor_layout) if smooth_k else None
-        k_c, k_s = _quant_one(kt, km, 64, kbits, kpack, 1.0, mode, tensor_layout)
+        km, k_c, k_s = _smooth_k_codes(kt, smooth_k, kbits, kpack, backend, tensor_layout)
         q_c, q_s = _quant_one(qt, None, 128, qbits, False, sm_scale * LOG2E, mode, tensor_layout)
         return q_c, q_s, k_c, k_s, km
     b, h, n, d, _, _, _ = T.bhnd(qt, tensor_layout)
@@ -125,8 +169,7 @@ def smooth_and_quantize(q, k, smooth_k, sm_scale, tensor_layout, qbits, kbits, k
     with torch.cuda.stream(side):
         _quant_one(qt, None, 128, qbits, False, sm_scale * LOG2E, mode, tensor_layout, out=(q_c, q_s))
         join.record(side)
-    km = k_mean(kt, tensor_layout) if smooth_k else None
-    k_c, k_s = _quant_one(kt, km, 64, kbits, kpack, 1.0, mode, tensor_layout)
+    km, k_c, k_s = _smooth_k_codes(kt, smooth_k, kbits, kpack, backend, tensor_layout)
     cur.wait_event(join)
     return q_c, q_s, k_c, k_s, km
 

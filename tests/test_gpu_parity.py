@@ -587,6 +587,49 @@ def test_k_mean_exact_on_all_fp16_values(L, cuda_dev):
     assert torch.equal(km.view(-1)[:60], torch.zeros(60).half())
 
 
+# ------------------------------------------------------------------------------------------------ fused K smoothing
+@pytest.mark.parametrize("layout", ["HND", "NHD"])
+@pytest.mark.parametrize("b,h,n,d", [(1, 2, 1, 64), (2, 3, 63, 64), (1, 2, 64, 128), (2, 2, 65, 64), (1, 3, 512, 64),
+                                     (2, 2, 700, 128), (1, 4, 4096, 64), (1, 2, 5000, 128), (1, 1, 12000, 64)])
+def test_k_smooth_quant_cluster_kernel_is_bit_identical(L, cuda_dev, layout, b, h, n, d):
+    """lowbit_k_smooth_quant (one cluster launch, K read once, slice parked in shared memory, column sums over DSMEM)
+    against lowbit_k_mean + lowbit_quant_per_block: km, codes and scales bit for bit, for int8 / packed INT4 / INT2 and
+    both rounding conventions; and against the CPU oracle for the default mode."""
+    from oracle import quant as OQ
+    k = mk(b, h, n, d, layout, torch.float16, 71, bias=2.5)
+    dk = k.to(cuda_dev)
+    assert L.k_smooth_quant_supported(dk, layout)
+    km_ref = L.k_mean(dk, layout)
+    for bits, pack, backend in ((8, False, "triton"), (4, True, "triton"), (2, True, "triton"), (8, False, "cuda"),
+                                (4, False, "triton_gpu")):
+        km, kc, ks = L.k_smooth_quant(dk, bits=bits, pack=pack, tensor_layout=layout, backend=backend)
+        from lowbit_quant_fa2_paddle_b200 import quant as Qz
+        kc_ref, ks_ref = Qz._quant_one(dk, km_ref, 64, bits, pack, 1.0, Qz._MODES[backend], layout)
+        assert torch.equal(km, km_ref), (bits, pack, backend)
+        assert torch.equal(kc, kc_ref), (bits, pack, backend)
+        assert torch.equal(ks.view(torch.int32), ks_ref.view(torch.int32)), (bits, pack, backend)
+    km, kc, ks = L.k_smooth_quant(dk, tensor_layout=layout)
+    km_o = OQ.k_mean(k, layout)
+    _, _, kc_o, ks_o = OQ.per_block_int8_q1(k, k, km_o, tensor_layout=layout)
+    assert torch.equal(km.cpu(), km_o) and torch.equal(kc.cpu(), kc_o) and torch.equal(ks.cpu(), ks_o)
+
+
+def test_k_smooth_quant_unsupported_shapes_fall_back(L, cuda_dev):
+    """bf16 and slices larger than a cluster's shared memory are not taken by the fused kernel: the C entry point says
+    so, and the operator then runs the separate launches (same result as with LOWBIT_K_FUSED=0)."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    k16 = mk(1, 1, 256, 64, "HND", torch.bfloat16, 72).to(cuda_dev)
+    assert not L.k_smooth_quant_supported(k16)
+    with pytest.raises(NV.LowbitNativeError):
+        L.k_smooth_quant(k16)
+    assert not NV.lib().lowbit_k_smooth_quant_supported(13000, 64, NV.F16)
+    assert NV.lib().lowbit_k_smooth_quant_supported(12800, 64, NV.F16)
+    assert not NV.lib().lowbit_k_smooth_quant_supported(6464, 128, NV.F16)
+    q = mk(1, 2, 300, 64, "HND", torch.bfloat16, 73).to(cuda_dev)
+    o = L.lowbit_fa_qk_int8_pv_fp16_triton(q, q, q)
+    assert o.dtype == torch.bfloat16 and torch.isfinite(o.float()).all()
+
+
 # ------------------------------------------------------------------------------------------------ host streaming
 @pytest.mark.parametrize("layout,b,hq,hkv,n,d,causal,chunks", [
     ("HND", 2, 4, 4, 700, 64, False, None),
