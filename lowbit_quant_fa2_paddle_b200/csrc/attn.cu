@@ -342,6 +342,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int BNH = BN / SP;                                // score columns per softmax thread and step
   constexpr int PCH = PCOLS / SP;                             // P columns per softmax thread and step
   constexpr int DH = D / SP;                                  // O columns per softmax thread (rescale, epilogue)
+  constexpr bool kWarpArrive = (SP == 1);                     // p_ready counts warps, not threads
   __shared__ float s_vs[PV == PV_E4M3 ? D : 1], s_vm[PV == PV_E4M3 ? D : 1];  // FP8 P.V: v_scale / v_mean of this (b, kv head)
   __shared__ int s_flag[4][2];                                // SP = 2: "rescale wanted at step j" token per warp pair
   __shared__ float s_mx[2][kBM], s_l[2][kBM];                 // SP = 2: row-max / row-sum exchange between the halves
@@ -434,7 +435,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_init(kfree + i, KX ? kExpThreads : 1);
     }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kSoftmaxThreads); }
+    // p_ready: one arrival per softmax warp (tcgen05.wait::st is a warp collective, so lane 0 can speak for the warp);
+    // the column-split / softmax-thread-expansion variant keeps one arrival per thread (each orders its own writes)
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kWarpArrive ? 4 : kSoftmaxThreads); }
     ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_final, 1);
     ptx::mbar_init(bar_k01, kExpThreads);
@@ -695,7 +698,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(pr);
+      if constexpr (kWarpArrive) {
+        if ((tid & 31) == 0) ptx::mbar_arrive(pr);
+      } else {
+        ptx::mbar_arrive(pr);
+      }
     };
 
     constexpr int kPerScale = kScaleBlk / BN;  // key blocks per k_scale entry (2 for BN=32, 1 for BN=64)
