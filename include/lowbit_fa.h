@@ -173,6 +173,25 @@ int lowbit_quant_per_thread(const void* in, const void* km, void* codes, float* 
 int lowbit_quant_pack_lastdim(const void* data, void* code, void* scale, void* mn,
                               int64_t rows, int T, int group, int bits, int dtype, void* stream);
 
+/* KV-cache attention over KIVI-packed low-bit K / V -- fp16 queries against a cache quantized by
+ * lowbit_quant_pack_lastdim (new_pack.py:247-300; the prototype's driver attn_4bit_per_block.py:637-665):
+ * replaces _quantized_flash_attn_forward / _fwd_kernel (src/triton/quantization/attn_4bit_per_block.py:28-553).
+ *   q      fp16 [B,Nq,H,D], element strides (q_stride_b, q_stride_n, q_stride_h), last dim contiguous
+ *   kcode  [B,D,H,N*bits/8] bytes (K packed along the sequence, per channel), kscale / kmn fp16 [B,D,H,N/group]
+ *   vcode  [B,N,H,D*bits/8] bytes (V packed along the channels, per token),   vscale / vmn fp16 [B,N,H,D/group]
+ *          all six contiguous; code i of a byte sits at bits [i*bits, (i+1)*bits)
+ *   o      fp16, addressed like q; lse (may be NULL) f32 [B,H,lse_stride], natural log (m + log l, :372)
+ * K^ = fma(code, scale, mn), V^ likewise, S = q.K^ in fp32, softmax(S * softmax_scale), o = P.V^ (:260-262, :330-372).
+ * D in {64, 128}, bits in {4, 2}, group_size 32, N a multiple of 32; non-causal, no bias (the prototype's driver).
+ * HBM-bound decode path: the cache is read once, key splits are merged through `workspace`
+ * (>= lowbit_kv_attn_workspace_bytes()). */
+int64_t lowbit_kv_attn_workspace_bytes(int B, int H, int Nq, int N, int D);
+int lowbit_kv_attn_fwd(const void* q, const void* kcode, const void* kscale, const void* kmn, const void* vcode,
+                       const void* vscale, const void* vmn, void* o, float* lse, void* workspace, int B, int H, int Nq,
+                       int N, int D, int group_size, int bits, float softmax_scale, int64_t q_stride_b,
+                       int64_t q_stride_n, int64_t q_stride_h, int64_t o_stride_b, int64_t o_stride_n,
+                       int64_t o_stride_h, int lse_stride, void* stream);
+
 /* Q6 -- V -> FP8 e4m3 per channel, transposed, padded, token-permuted
  * (src/quant.py:210-291; TransposePadPermuteKernel + MeanScaleKernel csrc/fused/fused.cu:263-428).
  * v8: e4m3 bytes addressed as [b][h][d][pos], pos contiguous in [0, Npad64), with byte strides

@@ -48,6 +48,7 @@ from .varlen import (  # noqa: F401
     k_mean_varlen,
 )
 from .host import lowbit_fa_host, plan_chunks  # noqa: F401
+from .kv_cache import quantized_flash_attn_forward, quant_and_pack_kv  # noqa: F401
 from .attention import forward, forward_causal, forward_partial, finalize, PartialState  # noqa: F401
 
 __version__ = "0.1.0"

@@ -37,6 +37,8 @@ SIGNATURES = {
     "lowbit_quant_per_block": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I, _I, _I, _F, _I, _I, _P]),
     "lowbit_quant_per_thread": (_I, [_P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I] * 5 + [_P]),
     "lowbit_quant_pack_lastdim": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "lowbit_kv_attn_workspace_bytes": (_L, [_I] * 5),
+    "lowbit_kv_attn_fwd": (_I, [_P] * 10 + [_I] * 7 + [_F] + [_L] * 6 + [_I, _P]),
     "lowbit_v_fp8_workspace_bytes": (_L, [_I] * 4),
     "lowbit_v_fp8_per_channel": (_I, [_P, _P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_F, _I, _P]),
     "lowbit_abs_max": (_I, [_P, _P] + [_I] * 4 + [_L] * 3 + [_I, _P]),

@@ -1,0 +1,94 @@
+"""KV-cache attention over KIVI-packed low-bit K / V: oracle consistency on CPU, kernel parity on
+the GPU.  Parity is unpinned for the attention itself (the reference's prototype kernel does not run as written, see
+oracle/kv_attn.py); the cache format underneath is pinned bit-exactly by tests/golden/kivi_*.npz."""
+import math
+
+import pytest
+import torch
+
+from oracle import kv_attn as OKV
+from oracle import quant as OQ
+
+
+def make_cache(B, N, H, D, bits, seed):
+    g = torch.Generator().manual_seed(seed)
+    k = (torch.randn(B, N, H, D, generator=g) + 0.5 * torch.randn(1, 1, H, D, generator=g)).half()
+    v = torch.randn(B, N, H, D, generator=g).half()
+    kc, ks, km = OQ.kivi_quantize_and_pack(k.transpose(1, 3).contiguous(), 32, bits)
+    vc, vs, vm = OQ.kivi_quantize_and_pack(v, 32, bits)
+    return k, v, (kc, ks, km, vc, vs, vm)
+
+
+@pytest.mark.parametrize("bits", [4, 2])
+def test_oracle_matches_dequantize_then_sdpa(bits):
+    """The oracle equals fp32 attention over the cache dequantized the reference's way (`unpack_and_dequant_*`,
+    new_pack.py:69-144: fp16 `code * scale + mn`) up to that fp16 rounding, and tracks unquantized attention."""
+    B, Nq, N, H, D = 2, 3, 160, 2, 64
+    k, v, cache = make_cache(B, N, H, D, bits, 1)
+    q = torch.randn(B, Nq, H, D, generator=torch.Generator().manual_seed(2)).half()
+    o, lse, sc = OKV.quantized_flash_attn_forward(q, *cache, group_size=32, bits=bits)
+    assert sc == 1.0 / math.sqrt(D) and o.shape == q.shape and lse.shape == (B, H, Nq)
+    khat = OQ.kivi_unpack_and_dequant(cache[0], cache[1], cache[2], 32, bits).float()   # [B,D,H,N]
+    vhat = OQ.kivi_unpack_and_dequant(cache[3], cache[4], cache[5], 32, bits).float()   # [B,N,H,D]
+    s = torch.einsum("bqhd,bdhn->bhqn", q.float(), khat) * sc
+    ref = torch.einsum("bhqn,bnhd->bqhd", torch.softmax(s, dim=-1), vhat)
+    assert (o.float() - ref).abs().max().item() < 4e-3
+    assert (lse - torch.logsumexp(s, dim=-1)).abs().max().item() < 2e-2
+    full = torch.einsum("bhqn,bnhd->bqhd",
+                        torch.softmax(torch.einsum("bqhd,bnhd->bhqn", q.float(), k.float()) * sc, dim=-1), v.float())
+    cos = torch.nn.functional.cosine_similarity(o.float().flatten(), full.flatten(), dim=0).item()
+    assert cos > (0.99 if bits == 4 else 0.85)
+
+
+def test_unpack_codes_bit_order():
+    """code i of a byte sits at bits [i*bits, (i+1)*bits) (new_pack.py:198-219)."""
+    b = torch.tensor([[0x21, 0xF0]], dtype=torch.uint8).view(torch.int8)
+    assert OKV.unpack_codes(b, 4).tolist() == [[1, 2, 0, 15]]
+    b = torch.tensor([[0b11100100]], dtype=torch.uint8).view(torch.int8)
+    assert OKV.unpack_codes(b, 2).tolist() == [[0, 1, 2, 3]]
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [4, 2])
+@pytest.mark.parametrize("B,Nq,N,H,D", [(1, 1, 32, 1, 64), (2, 1, 160, 3, 64), (1, 1, 4128, 2, 128), (2, 3, 128, 2, 128),
+                                        (1, 4, 1056, 2, 64), (1, 9, 288, 1, 128), (3, 1, 8192, 4, 64)])
+def test_kv_cache_attention_matches_oracle(bits, B, Nq, N, H, D):
+    """csrc/kv_attn.cu through the Python mirror of `_quantized_flash_attn_forward`, cache packed on the GPU by the
+    bit-exact KIVI quantizer: o within 2e-3 (fp16 output), lse within 1e-3 of the CPU oracle; one and several key
+    splits, partial last tile, 1 / several query rows."""
+    import lowbit_quant_fa2_paddle_b200 as L
+    from lowbit_quant_fa2_paddle_b200 import kv_cache as KV
+    dev = torch.device("cuda:0")
+    k, v, cache_cpu = make_cache(B, N, H, D, bits, 10 + N)
+    q = torch.randn(B, Nq, H, D, generator=torch.Generator().manual_seed(3)).half()
+    cache = KV.quant_and_pack_kv(k.to(dev), v.to(dev), 32, bits)
+    for got, ref in zip(cache, cache_cpu):
+        assert torch.equal(got.cpu(), ref), "cache format differs from the pinned oracle"
+    o, lse, sc = KV.quantized_flash_attn_forward(q.to(dev), *cache, group_size=32, bits=bits)
+    o_ref, lse_ref, sc_ref = OKV.quantized_flash_attn_forward(q, *cache_cpu, group_size=32, bits=bits)
+    torch.cuda.synchronize()
+    assert sc == sc_ref and o.shape == q.shape and lse.shape == (B, H, (Nq + 127) // 128 * 128)
+    assert (o.cpu().float() - o_ref.float()).abs().max().item() <= 2e-3
+    assert (lse.cpu()[:, :, :Nq] - lse_ref).abs().max().item() <= 1e-3
+    assert L.quantized_flash_attn_forward is KV.quantized_flash_attn_forward
+
+
+@pytest.mark.gpu
+def test_kv_cache_attention_argument_checks():
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    from lowbit_quant_fa2_paddle_b200 import kv_cache as KV
+    dev = torch.device("cuda:0")
+    k, v, _ = make_cache(1, 64, 1, 64, 4, 5)
+    cache = KV.quant_and_pack_kv(k.to(dev), v.to(dev))
+    q = torch.randn(1, 1, 1, 64).half().to(dev)
+    with pytest.raises(NotImplementedError):
+        KV.quantized_flash_attn_forward(q, *cache, group_size=32, bits=4, causal=True)
+    with pytest.raises(NotImplementedError):
+        KV.quantized_flash_attn_forward(q, *cache, group_size=32, bits=4, bias=q)
+    with pytest.raises(AssertionError):
+        KV.quantized_flash_attn_forward(q, *cache, group_size=32, bits=2)      # shapes say 4 bits
+    with pytest.raises(NV.LowbitNativeError):
+        KV.quantized_flash_attn_forward(q.cpu(), *[c.cpu() for c in cache], group_size=32, bits=4)  # no CPU fallback
+    o, lse, _ = KV.quantized_flash_attn_forward(q, *cache, softmax_scale=0.2)   # defaults: group 32, 4 bits
+    assert torch.isfinite(o.float()).all()
