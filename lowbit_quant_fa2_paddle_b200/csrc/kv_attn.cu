@@ -32,6 +32,16 @@ __device__ __forceinline__ float kv_ex2(float x) {
 }
 
 // R query rows per CTA.  Workspace layout per (b, h, row, split): [m, l, o[D]] fp32.
+//
+// Both contractions walk the packed words as they are: one 32-bit word holds 8 (4-bit) or 16 (2-bit) codes that share
+// their scale group, so a thread takes 8 codes per shared-memory load and the affine part is factored out,
+//   S[n]  = sum_d (q[d] sc[d,g]) code[d,n]  +  sum_d q[d] mn[d,g]          (g = group of key n)
+//   o[c]  = sum_n (p[n] vs[n,g]) code[n,c]  +  sum_n p[n] vm[n,g]          (g = group of channel c)
+// which leaves one conversion and one FMA per code in the inner loops (the first version dequantized every element
+// with its own loads: 9 instructions per code, 1.0 TB/s).
+//   scores : thread (ko, ds) <-> key octet ko of the tile x channel slice {d = 8 j + ds}; the 8 slices of an octet are
+//            adjacent lanes and meet by three xor-shuffles
+//   P.V    : thread (co, ks) <-> channel octet co x key slice ks; the slices meet once per CTA, at the end
 template <int D, int BITS, int R>
 __global__ void __launch_bounds__(kKvThreads)
 kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__ kcode,
@@ -39,21 +49,24 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
                        const uint8_t* __restrict__ vcode, const __half* __restrict__ vscale,
                        const __half* __restrict__ vmn, float* __restrict__ ws, int H, int Nq, int N, int nsplit,
                        int keys_per_split, float scale_log2e, int64_t qsb, int64_t qsn, int64_t qsh) {
-  constexpr int KB = kKvTile * BITS / 8;        // bytes of one channel row of a K tile
   constexpr int VB = D * BITS / 8;              // bytes of one token row of V
-  constexpr int CPB = 8 / BITS;                 // codes per byte
   constexpr uint32_t CM = (1u << BITS) - 1u;
   constexpr int KG = kKvTile / kKvGroup;        // K scale groups per tile (4)
   constexpr int VG = D / kKvGroup;              // V scale groups per token
-  constexpr int NH = kKvThreads / D;            // key halves in the P.V phase (D = 64: 2, D = 128: 1)
+  constexpr int KW = kKvTile * BITS / 32;       // words per channel row of a K tile
+  constexpr int VW = D * BITS / 32;             // words per token row of V
+  constexpr int KWP = KW + 4, VWP = VW + 1;     // padded row strides: the access patterns below are conflict-free
+  constexpr int DS = D / 8;                     // channels per score thread
+  constexpr int NCO = D / 8;                    // channel octets
+  constexpr int KPS = kKvTile / (kKvThreads / NCO);  // keys per P.V thread and tile
+  static_assert(kKvThreads == 128 && kKvTile == 128, "thread <-> (octet, slice) maps assume 128 x 128");
   __shared__ __align__(16) float sQ[R][D];
-  __shared__ __align__(16) uint8_t sK[D][KB];
-  __shared__ __half2 sKs[D][KG];                // (scale, mn)
-  __shared__ __align__(16) uint8_t sV[kKvTile][VB];
-  __shared__ __half2 sVs[kKvTile][VG];
-  __shared__ float sP[R][kKvTile];
-  __shared__ float sRed[R][4];
-  __shared__ float sO[NH > 1 ? R : 1][NH > 1 ? D : 1];
+  __shared__ uint32_t sK[D][KWP];
+  __shared__ float2 sKs[D][KG];                 // (scale, mn)
+  __shared__ uint32_t sV[kKvTile][VWP];
+  __shared__ float2 sVs[kKvTile][VG];           // (scale, mn)
+  __shared__ float2 sPV[R][kKvTile][VG];        // (p * scale, p * mn); reused for the final cross-warp fold
+  __shared__ float sRedM[R][4], sRedL[R][4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int split = blockIdx.x % nsplit, qtile = blockIdx.x / nsplit;
@@ -78,133 +91,213 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
   const __half* vs_base = vscale + ((int64_t)b * N * H + h) * VG;
   const __half* vm_base = vmn + ((int64_t)b * N * H + h) * VG;
 
-  float m_run[R], l_run[R], o_acc[R];
+  // thread maps
+  const int ko = tid >> 3, ds = tid & 7;        // scores: key octet (a warp = 4 octets = one scale group), channel slice
+  const int kwidx = (ko * 8 * BITS) / 32, kwsh = (ko * 8 * BITS) % 32;
+  const int co = tid % NCO, ks = tid / NCO;     // P.V: channel octet, key slice
+  const int vwidx = (co * 8 * BITS) / 32, vwsh = (co * 8 * BITS) % 32;
+  const int gch = co / 4;                       // scale group of my channels (32 channels = 4 octets)
+
+  float m_run[R], l_run[R], o_acc[R][8];
 #pragma unroll
-  for (int r = 0; r < R; ++r) { m_run[r] = -INFINITY; l_run[r] = 0.f; o_acc[r] = 0.f; }
-  const int c = tid % D;         // my channel in the P.V phase
-  const int khalf = tid / D;     // my half of the tile's keys in the P.V phase (D = 64)
+  for (int r = 0; r < R; ++r) {
+    m_run[r] = -INFINITY;
+    l_run[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o_acc[r][i] = 0.f;
+  }
 
   for (int n0 = n_begin; n0 < n_end; n0 += kKvTile) {
     __syncthreads();  // previous tile fully consumed (also orders the sQ fill before its first use)
-    // ---- stage the tile: 4-byte words, consecutive threads on consecutive words of a row ----
+    // ---- stage the tile: 4-byte words, consecutive threads on consecutive words of a row; every thread keeps its
+    //      column and walks the rows with a constant pointer stride (no per-element index arithmetic) ----
     {
-      constexpr int KW = KB / 4;  // words per channel row of the K tile
-      for (int i = tid; i < D * KW; i += kKvThreads) {
-        const int d = i / KW, w = i % KW;
-        const int n = n0 + w * 4 * CPB;  // first key of this word
-        uint32_t v = 0;
-        if (n < N) v = *reinterpret_cast<const uint32_t*>(kc_base + (int64_t)d * H * krow_bytes + (int64_t)n0 * BITS / 8 + w * 4);
-        *reinterpret_cast<uint32_t*>(&sK[d][w * 4]) = v;
-      }
-      for (int i = tid; i < D * KG; i += kKvThreads) {
-        const int d = i / KG, g = i % KG;
-        const int gi = n0 / kKvGroup + g;
-        __half2 v = __floats2half2_rn(0.f, 0.f);
-        if (gi < kgroups) v = __halves2half2(ks_base[(int64_t)d * H * kgroups + gi], km_base[(int64_t)d * H * kgroups + gi]);
-        sKs[d][g] = v;
-      }
-      constexpr int VW = VB / 4;  // words per token row of V
-      for (int i = tid; i < kKvTile * VW; i += kKvThreads) {
-        const int nl = i / VW, w = i % VW;
-        uint32_t v = 0;
-        if (n0 + nl < N) v = *reinterpret_cast<const uint32_t*>(vc_base + (int64_t)(n0 + nl) * H * VB + w * 4);
-        *reinterpret_cast<uint32_t*>(&sV[nl][w * 4]) = v;
-      }
-      for (int i = tid; i < kKvTile * VG; i += kKvThreads) {
-        const int nl = i / VG, g = i % VG;
-        __half2 v = __floats2half2_rn(0.f, 0.f);
-        if (n0 + nl < N) v = __halves2half2(vs_base[(int64_t)(n0 + nl) * H * VG + g], vm_base[(int64_t)(n0 + nl) * H * VG + g]);
-        sVs[nl][g] = v;
-      }
+      constexpr int KRS = kKvThreads / KW;  // K rows covered per pass
+      const int kw = tid % KW, kd0 = tid / KW;
+      const bool k_ok = (n0 + kw * (32 / BITS)) < N;  // N is a multiple of 32: a word never straddles the end
+      const uint8_t* kp = kc_base + (int64_t)kd0 * H * krow_bytes + (int64_t)n0 * BITS / 8 + kw * 4;
+      const int64_t kstep = (int64_t)KRS * H * krow_bytes;
+#pragma unroll 4
+      for (int d = kd0; d < D; d += KRS, kp += kstep) sK[d][kw] = k_ok ? *reinterpret_cast<const uint32_t*>(kp) : 0u;
+
+      constexpr int SRS = kKvThreads / KG;  // K scale rows per pass
+      const int sg = tid % KG, sd0 = tid / KG;
+      const int gi = n0 / kKvGroup + sg;
+      const bool s_ok = gi < kgroups;
+      const __half* sp = ks_base + (int64_t)sd0 * H * kgroups + gi;
+      const __half* mp = km_base + (int64_t)sd0 * H * kgroups + gi;
+      const int64_t sstep = (int64_t)SRS * H * kgroups;
+#pragma unroll 4
+      for (int d = sd0; d < D; d += SRS, sp += sstep, mp += sstep)
+        sKs[d][sg] = s_ok ? make_float2(__half2float(*sp), __half2float(*mp)) : make_float2(0.f, 0.f);
+
+      constexpr int VRS = kKvThreads / VW;  // V rows covered per pass
+      const int vw = tid % VW, vn0 = tid / VW;
+      const uint8_t* vp = vc_base + (int64_t)(n0 + vn0) * H * VB + vw * 4;
+      const int64_t vstep = (int64_t)VRS * H * VB;
+#pragma unroll 4
+      for (int nl = vn0; nl < kKvTile; nl += VRS, vp += vstep)
+        sV[nl][vw] = (n0 + nl < N) ? *reinterpret_cast<const uint32_t*>(vp) : 0u;
+
+      constexpr int TRS = kKvThreads / VG;  // V scale rows per pass
+      const int tg = tid % VG, tn0 = tid / VG;
+      const __half* tsp = vs_base + (int64_t)(n0 + tn0) * H * VG + tg;
+      const __half* tmp_ = vm_base + (int64_t)(n0 + tn0) * H * VG + tg;
+      const int64_t tstep = (int64_t)TRS * H * VG;
+#pragma unroll 4
+      for (int nl = tn0; nl < kKvTile; nl += TRS, tsp += tstep, tmp_ += tstep)
+        sVs[nl][tg] = (n0 + nl < N) ? make_float2(__half2float(*tsp), __half2float(*tmp_)) : make_float2(0.f, 0.f);
     }
     __syncthreads();
 
-    // ---- scores: thread <-> key tid of the tile ----
-    float s[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) s[r] = 0.f;
-    {
-      const int byte = tid / CPB, sh = (tid % CPB) * BITS, g = tid / kKvGroup;
-#pragma unroll 4
-      for (int d = 0; d < D; ++d) {
-        const float code = (float)((sK[d][byte] >> sh) & CM);
-        const float2 sm = __half22float2(sKs[d][g]);
-        const float kd = fmaf(code, sm.x, sm.y);
-#pragma unroll
-        for (int r = 0; r < R; ++r) s[r] = fmaf(sQ[r][d], kd, s[r]);
-      }
-    }
-    const bool live = (n0 + tid) < n_end;
-    // ---- online softmax (base 2) ----
-    float p[R];
+    // ---- scores of my key octet over my channel slice, then the 8 slices meet ----
+    float s[R][8], cst[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float v = live ? s[r] : -INFINITY;
+      cst[r] = 0.f;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-      if (lane == 0) sRed[r][warp] = v;
+      for (int i = 0; i < 8; ++i) s[r][i] = 0.f;
+    }
+#pragma unroll 2
+    for (int j = 0; j < DS; ++j) {
+      const int d = j * 8 + ds;
+      const uint32_t codes = sK[d][kwidx] >> kwsh;
+      const float2 sm = sKs[d][warp];  // the warp's keys share one scale group
+      float qs[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float qv = sQ[r][d];
+        qs[r] = qv * sm.x;
+        cst[r] = fmaf(qv, sm.y, cst[r]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float cf = (float)((codes >> (i * BITS)) & CM);
+#pragma unroll
+        for (int r = 0; r < R; ++r) s[r][i] = fmaf(qs[r], cf, s[r][i]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        cst[r] += __shfl_xor_sync(0xffffffffu, cst[r], off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[r][i] += __shfl_xor_sync(0xffffffffu, s[r][i], off);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[r][i] += cst[r];
+    }
+    // ---- online softmax (base 2); every lane of an octet holds the same 8 scores ----
+    const int nk = n0 + ko * 8;  // first key of my octet
+    float mloc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v = fmaxf(v, (nk + i < n_end) ? s[r][i] : -INFINITY);
+      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+      mloc[r] = v;
+      if (lane == 0) sRedM[r][warp] = v;
     }
     __syncthreads();
     float alpha[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float mt = fmaxf(fmaxf(sRed[r][0], sRed[r][1]), fmaxf(sRed[r][2], sRed[r][3]));
+      const float mt = fmaxf(fmaxf(sRedM[r][0], sRedM[r][1]), fmaxf(sRedM[r][2], sRedM[r][3]));
       const float m_new = fmaxf(m_run[r], mt);   // finite: every tile holds at least one live key
       alpha[r] = kv_ex2(m_run[r] - m_new);       // first tile: exp2(-inf) = 0
-      p[r] = live ? kv_ex2(s[r] - m_new) : 0.f;
       m_run[r] = m_new;
-      sP[r][tid] = p[r];
-    }
-    __syncthreads();  // sRed read by everyone before it is reused for the sums; sP complete
+      float lsum = 0.f, pmine = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float v = p[r];
+      for (int i = 0; i < 8; ++i) {
+        const float pi = (nk + i < n_end) ? kv_ex2(s[r][i] - m_new) : 0.f;
+        lsum += pi;
+        pmine = (i == ds) ? pi : pmine;  // lane ds of the octet publishes key ds
+      }
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+      if (lane == 0) sRedL[r][warp] = lsum;
+      const int nl = ko * 8 + ds;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0) sRed[r][warp] = v;
+      for (int g = 0; g < VG; ++g) {
+        const float2 vsm = sVs[nl][g];
+        sPV[r][nl][g] = make_float2(pmine * vsm.x, pmine * vsm.y);
+      }
     }
+    (void)mloc;
     __syncthreads();
+    // ---- P.V over my channel octet and key slice ----
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      l_run[r] = l_run[r] * alpha[r] + ((sRed[r][0] + sRed[r][1]) + (sRed[r][2] + sRed[r][3]));
-      o_acc[r] *= alpha[r];
-    }
-    // ---- P.V: thread <-> channel c (and key half khalf when D = 64) ----
-    {
-      const int byte = c / CPB, sh = (c % CPB) * BITS, g = c / kKvGroup;
-      constexpr int KPH = kKvTile / NH;  // keys per half
-      const int nb = khalf * KPH;
-#pragma unroll 4
-      for (int nl = nb; nl < nb + KPH; ++nl) {
-        const float code = (float)((sV[nl][byte] >> sh) & CM);
-        const float2 sm = __half22float2(sVs[nl][g]);
-        const float vd = fmaf(code, sm.x, sm.y);
+      l_run[r] = l_run[r] * alpha[r] + ((sRedL[r][0] + sRedL[r][1]) + (sRedL[r][2] + sRedL[r][3]));
 #pragma unroll
-        for (int r = 0; r < R; ++r) o_acc[r] = fmaf(sP[r][nl], vd, o_acc[r]);
+      for (int i = 0; i < 8; ++i) o_acc[r][i] *= alpha[r];
+    }
+    {
+      float cv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) cv[r] = 0.f;
+#pragma unroll 2
+      for (int nn = 0; nn < KPS; ++nn) {
+        const int nl = ks * KPS + nn;
+        const uint32_t codes = sV[nl][vwidx] >> vwsh;
+        float pv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float2 t = sPV[r][nl][gch];
+          pv[r] = t.x;
+          cv[r] += t.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float cf = (float)((codes >> (i * BITS)) & CM);
+#pragma unroll
+          for (int r = 0; r < R; ++r) o_acc[r][i] = fmaf(pv[r], cf, o_acc[r][i]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o_acc[r][i] += cv[r];
       }
     }
   }
 
-  // ---- partial result of this split ----
-  if constexpr (NH > 1) {  // fold the two key halves (same channel, threads c and c + D)
-    __syncthreads();
-    if (khalf == 1) {
+  // ---- partial result of this split: fold the key slices (lanes, then warps) ----
 #pragma unroll
-      for (int r = 0; r < R; ++r) sO[r][c] = o_acc[r];
-    }
-    __syncthreads();
-    if (khalf == 0) {
+  for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) o_acc[r] += sO[r][c];
+    for (int off = NCO; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o_acc[r][i] += __shfl_xor_sync(0xffffffffu, o_acc[r][i], off);
     }
   }
-  if (khalf == 0) {
+  __syncthreads();  // sPV is free
+  float* sO = reinterpret_cast<float*>(&sPV[0][0][0]);  // [4 warps][R][D]
+  if (lane < NCO) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sO[(warp * R + r) * D + co * 8 + i] = o_acc[r][i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < R * D; i += kKvThreads) {
+    const int r = i / D, c = i % D;
+    if (row0 + r >= Nq) continue;
+    const float v = (sO[(0 * R + r) * D + c] + sO[(1 * R + r) * D + c]) + (sO[(2 * R + r) * D + c] + sO[(3 * R + r) * D + c]);
+    float* dst = ws + ((((int64_t)b * H + h) * Nq + (row0 + r)) * nsplit + split) * (D + 2);
+    dst[2 + c] = v;
+  }
+  if (tid == 0) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (row0 + r >= Nq) continue;
       float* dst = ws + ((((int64_t)b * H + h) * Nq + (row0 + r)) * nsplit + split) * (D + 2);
-      if (c == 0) { dst[0] = m_run[r]; dst[1] = l_run[r]; }
-      dst[2 + c] = o_acc[r];
+      dst[0] = m_run[r];
+      dst[1] = l_run[r];
     }
   }
 }
@@ -228,10 +321,12 @@ __global__ void kv_attn_merge_kernel(const float* __restrict__ ws, __half* __res
 }
 
 static int kv_splits(int B, int H, int Nq, int N, int R, int* keys_per_split) {
-  // enough CTAs to fill the GPU a few times over, splits of whole tiles, none of them empty
+  // splits of whole tiles, none of them empty; about four waves of the resident capacity (148 SMs x 6-7 CTAs) so
+  // that the partial last wave costs little (the first version's 10 splits made 1.24 waves: 38 % of the run at a
+  // quarter of the occupancy)
   const int tiles = (N + kKvTile - 1) / kKvTile;
   const int64_t base = (int64_t)B * H * ((Nq + R - 1) / R);
-  int want = (int)((148 * 8 + base - 1) / base);
+  int want = (int)((148 * 6 * 4) / base);
   want = want < 1 ? 1 : (want > tiles ? tiles : want);
   const int tps = (tiles + want - 1) / want;  // tiles per split
   *keys_per_split = tps * kKvTile;
