@@ -107,48 +107,67 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
     for (int i = 0; i < 8; ++i) o_acc[r][i] = 0.f;
   }
 
+  // ---- tile staging, split in two halves: `fetch` issues the global loads of a tile into registers (4-byte words,
+  //      consecutive threads on consecutive words of a row, every thread keeps its column and walks the rows with a
+  //      constant pointer stride), `commit` parks them in shared memory.  The loads of tile i+1 are issued before
+  //      the arithmetic of tile i, so their latency hides behind it. ----
+  constexpr int KRS = kKvThreads / KW, NKW = D / KRS;        // K rows per pass, K words per thread
+  constexpr int SRS = kKvThreads / KG, NKS = D / SRS;        // K scale rows per pass, entries per thread
+  constexpr int VRS = kKvThreads / VW, NVW = kKvTile / VRS;  // V rows per pass, V words per thread
+  constexpr int TRS = kKvThreads / VG, NVS = kKvTile / TRS;  // V scale rows per pass, entries per thread
+  const int kw = tid % KW, kd0 = tid / KW;
+  const int sg = tid % KG, sd0 = tid / KG;
+  const int vw = tid % VW, vn0 = tid / VW;
+  const int tg = tid % VG, tn0 = tid / VG;
+  uint32_t rk[NKW], rv[NVW];
+  __half rks[NKS], rkm[NKS], rvs[NVS], rvm[NVS];
+  auto fetch = [&](int n0) {
+    const bool k_ok = (n0 + kw * (32 / BITS)) < N;  // N is a multiple of 32: a word never straddles the end
+    const uint8_t* kp = kc_base + (int64_t)kd0 * H * krow_bytes + (int64_t)n0 * BITS / 8 + kw * 4;
+    const int64_t kstep = (int64_t)KRS * H * krow_bytes;
+#pragma unroll
+    for (int i = 0; i < NKW; ++i, kp += kstep) rk[i] = k_ok ? *reinterpret_cast<const uint32_t*>(kp) : 0u;
+    const int gi = n0 / kKvGroup + sg;
+    const bool s_ok = gi < kgroups;
+    const __half* sp = ks_base + (int64_t)sd0 * H * kgroups + gi;
+    const __half* mp = km_base + (int64_t)sd0 * H * kgroups + gi;
+    const int64_t sstep = (int64_t)SRS * H * kgroups;
+#pragma unroll
+    for (int i = 0; i < NKS; ++i, sp += sstep, mp += sstep) {
+      rks[i] = s_ok ? *sp : __float2half_rn(0.f);
+      rkm[i] = s_ok ? *mp : __float2half_rn(0.f);
+    }
+    const uint8_t* vp = vc_base + (int64_t)(n0 + vn0) * H * VB + vw * 4;
+    const int64_t vstep = (int64_t)VRS * H * VB;
+#pragma unroll
+    for (int i = 0; i < NVW; ++i, vp += vstep) rv[i] = (n0 + vn0 + i * VRS < N) ? *reinterpret_cast<const uint32_t*>(vp) : 0u;
+    const __half* tsp = vs_base + (int64_t)(n0 + tn0) * H * VG + tg;
+    const __half* tmp_ = vm_base + (int64_t)(n0 + tn0) * H * VG + tg;
+    const int64_t tstep = (int64_t)TRS * H * VG;
+#pragma unroll
+    for (int i = 0; i < NVS; ++i, tsp += tstep, tmp_ += tstep) {
+      const bool ok = (n0 + tn0 + i * TRS) < N;
+      rvs[i] = ok ? *tsp : __float2half_rn(0.f);
+      rvm[i] = ok ? *tmp_ : __float2half_rn(0.f);
+    }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int i = 0; i < NKW; ++i) sK[kd0 + i * KRS][kw] = rk[i];
+#pragma unroll
+    for (int i = 0; i < NKS; ++i) sKs[sd0 + i * SRS][sg] = make_float2(__half2float(rks[i]), __half2float(rkm[i]));
+#pragma unroll
+    for (int i = 0; i < NVW; ++i) sV[vn0 + i * VRS][vw] = rv[i];
+#pragma unroll
+    for (int i = 0; i < NVS; ++i) sVs[tn0 + i * TRS][tg] = make_float2(__half2float(rvs[i]), __half2float(rvm[i]));
+  };
+
+  fetch(n_begin);
   for (int n0 = n_begin; n0 < n_end; n0 += kKvTile) {
     __syncthreads();  // previous tile fully consumed (also orders the sQ fill before its first use)
-    // ---- stage the tile: 4-byte words, consecutive threads on consecutive words of a row; every thread keeps its
-    //      column and walks the rows with a constant pointer stride (no per-element index arithmetic) ----
-    {
-      constexpr int KRS = kKvThreads / KW;  // K rows covered per pass
-      const int kw = tid % KW, kd0 = tid / KW;
-      const bool k_ok = (n0 + kw * (32 / BITS)) < N;  // N is a multiple of 32: a word never straddles the end
-      const uint8_t* kp = kc_base + (int64_t)kd0 * H * krow_bytes + (int64_t)n0 * BITS / 8 + kw * 4;
-      const int64_t kstep = (int64_t)KRS * H * krow_bytes;
-#pragma unroll 4
-      for (int d = kd0; d < D; d += KRS, kp += kstep) sK[d][kw] = k_ok ? *reinterpret_cast<const uint32_t*>(kp) : 0u;
-
-      constexpr int SRS = kKvThreads / KG;  // K scale rows per pass
-      const int sg = tid % KG, sd0 = tid / KG;
-      const int gi = n0 / kKvGroup + sg;
-      const bool s_ok = gi < kgroups;
-      const __half* sp = ks_base + (int64_t)sd0 * H * kgroups + gi;
-      const __half* mp = km_base + (int64_t)sd0 * H * kgroups + gi;
-      const int64_t sstep = (int64_t)SRS * H * kgroups;
-#pragma unroll 4
-      for (int d = sd0; d < D; d += SRS, sp += sstep, mp += sstep)
-        sKs[d][sg] = s_ok ? make_float2(__half2float(*sp), __half2float(*mp)) : make_float2(0.f, 0.f);
-
-      constexpr int VRS = kKvThreads / VW;  // V rows covered per pass
-      const int vw = tid % VW, vn0 = tid / VW;
-      const uint8_t* vp = vc_base + (int64_t)(n0 + vn0) * H * VB + vw * 4;
-      const int64_t vstep = (int64_t)VRS * H * VB;
-#pragma unroll 4
-      for (int nl = vn0; nl < kKvTile; nl += VRS, vp += vstep)
-        sV[nl][vw] = (n0 + nl < N) ? *reinterpret_cast<const uint32_t*>(vp) : 0u;
-
-      constexpr int TRS = kKvThreads / VG;  // V scale rows per pass
-      const int tg = tid % VG, tn0 = tid / VG;
-      const __half* tsp = vs_base + (int64_t)(n0 + tn0) * H * VG + tg;
-      const __half* tmp_ = vm_base + (int64_t)(n0 + tn0) * H * VG + tg;
-      const int64_t tstep = (int64_t)TRS * H * VG;
-#pragma unroll 4
-      for (int nl = tn0; nl < kKvTile; nl += TRS, tsp += tstep, tmp_ += tstep)
-        sVs[nl][tg] = (n0 + nl < N) ? make_float2(__half2float(*tsp), __half2float(*tmp_)) : make_float2(0.f, 0.f);
-    }
+    commit();
     __syncthreads();
+    if (n0 + kKvTile < n_end) fetch(n0 + kKvTile);  // in flight during this tile's arithmetic
 
     // ---- scores of my key octet over my channel slice, then the 8 slices meet ----
     float s[R][8], cst[R];
