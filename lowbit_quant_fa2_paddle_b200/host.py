@@ -92,6 +92,9 @@ def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, kee
     b0 = plan[0][0]
     shapes = tuple(tuple(view(t, b0, 0, e).shape) for t, e in ((qt, hmax * grp), (kt, hmax), (vt, hmax)))
     slots = _staging(dev, qt.dtype, shapes)
+    if keep is not None:
+        keep.append(slots)  # a captured graph writes into these buffers on every replay: it must own a reference,
+        #                     or an eviction from the staging cache would hand their memory to someone else
 
     def lead(t, nh):  # the first nh heads of a staging buffer (contiguous: HND slots hold one batch entry)
         return t if tensor_layout != "HND" or t.shape[1] == nh else t[:, :nh]
