@@ -16,7 +16,7 @@ QMODE_FLAG_DIV_FULL = 0x200  # Q1 with PTX div.full.f32: the reference kernels a
 QMODE_FLAG_IEEE_DIV = 0x100  # validation: Q1 quotient by IEEE division instead of the 3-instruction exact sequence
 QK_I8, QK_Q8K4, QK_Q8KMIX = 0, 1, 2
 PV_F16, PV_E4M3 = 0, 1
-ATTN_CAUSAL, ATTN_COMPAT_TAIL = 1, 2
+ATTN_CAUSAL, ATTN_COMPAT_TAIL, ATTN_NARROW = 1, 2, 4
 
 _c = ctypes
 _P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float

@@ -67,7 +67,8 @@ def _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale,
 
 
 def _forward(q, k, v, q_scale, k_scale, tensor_layout, output_dtype, return_lse, causal,
-             qk_mode=N.QK_I8, pv_mode=N.PV_F16, compat_tail=False, v_scale=None, v_mean=None, kbits=None, out=None):
+             qk_mode=N.QK_I8, pv_mode=N.PV_F16, compat_tail=False, v_scale=None, v_mean=None, kbits=None, out=None,
+             narrow=False):
     dev, qt, ptrs, dims, keep = _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale, v_mean, kbits)
     b, hq, hkv, nq, nk, d = dims[:6]
     if causal:
@@ -80,7 +81,7 @@ def _forward(q, k, v, q_scale, k_scale, tensor_layout, output_dtype, return_lse,
         assert o.shape == qt.shape and o.dtype == odt and o.device == dev and o.stride(-1) == 1
     _, _, _, _, osb, osh, osn = T.bhnd(o, tensor_layout)
     lse = torch.empty((b, hq, nq), dtype=torch.float32, device=dev) if return_lse else None
-    flags = (N.ATTN_CAUSAL if causal else 0) | (N.ATTN_COMPAT_TAIL if compat_tail else 0)
+    flags = (N.ATTN_CAUSAL if causal else 0) | (N.ATTN_COMPAT_TAIL if compat_tail else 0) | (N.ATTN_NARROW if narrow else 0)
     N.call("lowbit_attn_fwd", *ptrs, o.data_ptr(), lse.data_ptr() if lse is not None else None,
            *dims, osb, osh, osn, qk_mode, pv_mode, T.dtype_code(odt), flags, T.stream_ptr(dev))
     if lse is None:
@@ -132,7 +133,8 @@ def finalize(state, like_q, tensor_layout="HND", output_dtype=torch.float16, ret
 def forward(q, k, v, q_scale, k_scale, tensor_layout="HND", output_dtype=torch.float16, return_lse=False,
             compat_tail=False, **modes):
     """Non-causal INT8-QK / FP16-PV attention over pre-quantized codes.  `modes` (qk_mode, pv_mode, v_scale,
-    v_mean) select packed INT4 K codes and the FP8 P.V path."""
+    v_mean) select packed INT4 K codes and the FP8 P.V path; narrow=True forces the 32-key-step kernel at
+    head_dim 64 (LOWBIT_ATTN_NARROW)."""
     return _forward(q, k, v, q_scale, k_scale, tensor_layout, output_dtype, return_lse, False,
                     compat_tail=compat_tail, **modes)
 

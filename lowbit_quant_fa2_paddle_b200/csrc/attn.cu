@@ -28,6 +28,7 @@
 // writes 8- and 2-bit rows in the byte order that makes those expansions land in that layout (quant.cu).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "softmax_wide.cuh"
 
 #include <cuda.h>
 #include <limits.h>
@@ -60,37 +61,25 @@ struct AttnParams {
 
 static int32_t* g_attn_debug = nullptr;
 
+
 constexpr int kBM = 128;      // Q rows per CTA (= TMEM lanes)
 constexpr int kScaleBlk = 64; // k_scale granularity of the reference quantizer (BLKK)
-// Softmax warpgroups per CTA.  SP = 1: thread t owns query row t (one TMEM lane, all BN score columns of a step).
-// SP = 2: threads t and t+128 own the two column halves of row t, which doubles the warps that hide each other's
-// TMEM / barrier / MUFU latencies where TMEM (not registers) caps the CTAs per SM (D = 128: 256 columns per CTA).
-// The two warps of a pair share one reference maximum per row: they agree on the (rare) rescale with a 64-thread
-// named barrier per step, keep partial row sums, and split the columns of O in the rescale and the epilogue.
-// Measured on B200 (profiles/r1_attn_d128_ncu_summary.json): the duplicated per-step overhead (+20 % instructions)
-// outweighs the extra warps -- D=128 1288 vs 1341 TOPS, D=64 635 vs 818 -- so SP = 1 is the default and VAR bit 4
-// selects SP = 2 (development A/B; parity-tested the same way).
-template <int D, int VAR> struct AttnSP {
-  static constexpr int value = (VAR & 16) ? 2 : 1;
-  static constexpr int kSoftmaxThreads = 128 * value;
-  static constexpr int kThreads = kSoftmaxThreads + 32;  // + one helper warp (TMA producer + tcgen05 issuer, one elected lane)
-};
 
 enum { KM_I8 = 0, KM_K4 = 1, KM_MIX = 2 };  // KM_K4 / KM_MIX: K tiles are expanded in shared memory
 enum { PV_F16 = 0, PV_E4M3 = 1 };
 
-// Per-head-dim tiling.  D=64 is exp2(MUFU)-bound: small 32-key steps keep the register footprint under 96 so that
-// four CTAs (16 softmax warps) share an SM and hide each other's latencies.  D=128 has twice the tensor work per
-// exp2 and runs 64-key steps with two CTAs per SM.
+// Two kernels share this file:
+//   attn_fwd_wide_kernel  head_dim 64, INT8 / packed-INT4 K, FP16 or FP8 P.V -- 128-key steps (the default there)
+//   attn_fwd_kernel       head_dim 128 (64-key steps), and head_dim 64 with the mixed-width K container (32-key steps)
+//
+// Per-head-dim tiling of attn_fwd_kernel.  D=64: 32-key steps keep the register footprint under 96 so that four CTAs
+// (16 softmax warps) share an SM.  D=128 has twice the tensor work per exp2 and runs 64-key steps, two CTAs per SM
+// (TMEM: 2 x 64 score columns + 128 output columns = 256 per CTA).
 // K tiles that need expansion (packed INT4 / mixed width): a dedicated expander warp does it, so the softmax warps --
-// the critical path -- carry no unpack instructions and the expansion runs ahead of them (D = 128: 1194 -> 1340 TOPS
-// at 8K non-causal).  At D = 64 the sixth warp lowers the register cap of four CTAs per SM from 96 to 80 (132 bytes
-// of spill in the softmax) and still wins, 717 -> 745 TOPS; handing registers over with setmaxnreg does not work out
-// (the helper path needs > 32 registers, and a two-warp trailing warpgroup hangs on it).  The column-split variant
-// (VAR bit 4) keeps the softmax threads expanding K_{j+2} at the end of step j.
-template <int D, int KM, int VAR> struct AttnRoles {
-  static constexpr bool kExpander = (KM != 0) && ((VAR & 16) == 0);
-  static constexpr int kThreads = AttnSP<D, VAR>::kThreads + (kExpander ? 32 : 0);
+// the critical path -- carry no unpack instructions and the expansion runs ahead of them.
+template <int D, int KM> struct AttnRoles {
+  static constexpr bool kExpander = (KM != KM_I8);
+  static constexpr int kThreads = 128 + 32 + (kExpander ? 32 : 0);  // softmax warps + helper warp (+ expander warp)
 };
 
 template <int D> struct AttnCfg;
@@ -120,73 +109,40 @@ struct AttnSmem {
   static constexpr int kBytes = kQ + kKStages * kK + C::VS * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
 };
 
-template <int VAR>
-__device__ __forceinline__ float score_to_f32(uint32_t v) {
-  return (VAR & 1) ? ptx::i2f_small((int)v) : __int2float_rn((int)v);
-}
-
-// One softmax step over a BN-key block for one query row: p = exp2(S*sc + nm), packed to fp16 pairs, row sum in fp32.
+// One softmax step over a BN-key block for one query row: p = exp2(S*sc + nm), packed to fp16 pairs, row sum in fp32
+// (packed fp32x2 arithmetic, FFMA2 / FADD2: one instruction scales, or accumulates, two scores).
 // MASKED: columns > lim contribute 0 (causal diagonal band / masked tail keys).
-// VAR bit 2: one pair in every four goes through the FMA-pipe polynomial instead of MUFU.EX2.
-template <int BN, bool MASKED, int VAR>
+template <int BN, bool MASKED>
 __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ s, float sc, float nm, int lim,
                                                    uint32_t* __restrict__ pk) {
-  if constexpr ((VAR & 2) == 0) {
-    // packed fp32x2 arithmetic (FFMA2 / FADD2): one instruction scales, or accumulates, two scores
-    const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
-    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-    float2 acc2 = make_float2(0.f, 0.f), acc3 = make_float2(0.f, 0.f);  // VAR bit 6: four independent sum chains
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < BN; c += 4) {
-      const float2 x0 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c]), score_to_f32<VAR>(s[c + 1])), sc2, nm2);
-      const float2 x1 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c + 2]), score_to_f32<VAR>(s[c + 3])), sc2, nm2);
-      float2 p0, p1;
-      if ((VAR & 4) && (c % 8 == 4)) p0 = ptx::ex2_poly2(x0);
-      else p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
-      if ((VAR & 8) && (c % 8 == 0)) p1 = ptx::ex2_poly2(x1);
-      else p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
-      if (MASKED) {
-        p0.x = (c <= lim) ? p0.x : 0.f;
-        p0.y = (c + 1 <= lim) ? p0.y : 0.f;
-        p1.x = (c + 2 <= lim) ? p1.x : 0.f;
-        p1.y = (c + 3 <= lim) ? p1.y : 0.f;
-      }
-      if ((VAR & 64) && (c % 8 == 4)) {
-        acc2 = __fadd2_rn(acc2, p0);
-        acc3 = __fadd2_rn(acc3, p1);
-      } else {
-        acc0 = __fadd2_rn(acc0, p0);
-        acc1 = __fadd2_rn(acc1, p1);
-      }
-      pk[c / 2] = ptx::pack_f16x2(p0.x, p0.y);
-      pk[c / 2 + 1] = ptx::pack_f16x2(p1.x, p1.y);
+  for (int c = 0; c < BN; c += 4) {
+    const float2 x0 = __ffma2_rn(make_float2(__int2float_rn((int)s[c]), __int2float_rn((int)s[c + 1])), sc2, nm2);
+    const float2 x1 = __ffma2_rn(make_float2(__int2float_rn((int)s[c + 2]), __int2float_rn((int)s[c + 3])), sc2, nm2);
+    float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
+    float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
+    if (MASKED) {
+      p0.x = (c <= lim) ? p0.x : 0.f;
+      p0.y = (c + 1 <= lim) ? p0.y : 0.f;
+      p1.x = (c + 2 <= lim) ? p1.x : 0.f;
+      p1.y = (c + 3 <= lim) ? p1.y : 0.f;
     }
-    float2 t = __fadd2_rn(acc0, acc1);
-    if (VAR & 64) t = __fadd2_rn(t, __fadd2_rn(acc2, acc3));
-    return t.x + t.y;
-  } else {
-    float lsum0 = 0.f, lsum1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < BN; c += 2) {
-      float p0 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c]), sc, nm));
-      float p1 = ptx::ex2(fmaf(score_to_f32<VAR>(s[c + 1]), sc, nm));
-      if (MASKED) {
-        p0 = (c <= lim) ? p0 : 0.f;
-        p1 = (c + 1 <= lim) ? p1 : 0.f;
-      }
-      lsum0 += p0;
-      lsum1 += p1;
-      pk[c / 2] = ptx::pack_f16x2(p0, p1);
-    }
-    return lsum0 + lsum1;
+    acc0 = __fadd2_rn(acc0, p0);
+    acc1 = __fadd2_rn(acc1, p1);
+    pk[c / 2] = ptx::pack_f16x2(p0.x, p0.y);
+    pk[c / 2 + 1] = ptx::pack_f16x2(p1.x, p1.y);
   }
+  const float2 t = __fadd2_rn(acc0, acc1);
+  return t.x + t.y;
 }
 
 // FP8 variant: p~ = e4m3_rn_satfinite(exp2(S*sc + nm)) (nm carries -m + OFF), four codes per TMEM word.  The row sum
 // is taken over the ROUNDED values (accumulate_d_f8, attn_utils.cuh:550-562), here through exact e4m3 -> f16
 // conversion and short f16x2 partial sums.  Key c of an aligned 16-group sits at the K index the reference's V layout
 // expects (fused.cu:290-292): word w of a group = keys {2w, 2w+1, 8+2w, 9+2w}.
-template <int BN, bool MASKED, int VAR>
+template <int BN, bool MASKED>
 __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__ s, float sc, float nm, int lim,
                                                     uint32_t* __restrict__ pk) {
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
@@ -197,8 +153,8 @@ __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int c0 = 16 * g + 2 * w, c1 = c0 + 8;
-      const float2 x0 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c0]), score_to_f32<VAR>(s[c0 + 1])), sc2, nm2);
-      const float2 x1 = __ffma2_rn(make_float2(score_to_f32<VAR>(s[c1]), score_to_f32<VAR>(s[c1 + 1])), sc2, nm2);
+      const float2 x0 = __ffma2_rn(make_float2(__int2float_rn((int)s[c0]), __int2float_rn((int)s[c0 + 1])), sc2, nm2);
+      const float2 x1 = __ffma2_rn(make_float2(__int2float_rn((int)s[c1]), __int2float_rn((int)s[c1 + 1])), sc2, nm2);
       float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
       float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
       if (MASKED) {
@@ -220,13 +176,6 @@ __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__
   return t;
 }
 
-template <int BN, bool MASKED>
-__device__ __forceinline__ int row_max(const uint32_t* __restrict__ s, int lim) {
-  int m4[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};  // 4 independent chains (latency, not throughput, bound)
-#pragma unroll
-  for (int c = 0; c < BN; ++c) m4[c & 3] = max(m4[c & 3], (!MASKED || c <= lim) ? (int)s[c] : INT_MIN);
-  return max(max(m4[0], m4[1]), max(m4[2], m4[3]));
-}
 template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
   if constexpr (N == 16) ptx::tmem_ld_x16(taddr, r);
   else if constexpr (N == 32) ptx::tmem_ld_x32(taddr, r);
@@ -314,15 +263,161 @@ __device__ __forceinline__ void permute_q_tile(uint8_t* sQ, int tid) {
   }
 }
 
-// Warp roles:  warps 0-3  softmax (thread t <-> query row t <-> TMEM lane t); in INT4-K mode they also expand K tiles
+
+// Row epilogue of both kernels (thread <-> query row <-> TMEM lane; tOl = this warp's lanes of the fp32 accumulator):
+//   O / l (* v_scale + v_mean) -> fp16 / bf16, lse2 = log2(l) + m - OFF;
+//   or, ring steps (oacc_io != null): merge (m_ref, l, O) of this K/V shard into the running fp32 state in HBM.
+// vsc / vmn: per-channel V scale / mean of this (b, kv head), staged in SHARED memory at kernel start -- read straight
+// from global memory here, every element's load sat behind the previous store to the (possibly aliasing) fp32 state
+// and cost the ring merge epilogue 0.76 ms per 8K x 8K launch.
+template <int D, int PV>
+__device__ __forceinline__ void attn_epilogue(const AttnParams& p, const uint32_t tOl, const float l, const float m_ref,
+                                              const int row, const int Nq, const int b, const int hq,
+                                              const int64_t orow_base, const float* vsc, const float* vmn) {
+  using PC = PvCfg<PV>;
+  const bool live_row = row < Nq;
+  const int64_t idx = ((int64_t)b * p.Hq + hq) * Nq + row;
+  if (p.oacc_io == nullptr) {
+    const float inv_l = 1.0f / l;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (orow_base + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
+#pragma unroll
+    for (int c = 0; c < D; c += 32) {
+      uint32_t o[32];
+      ptx::tmem_ld_x32(tOl + c, o);  // warp collective: every lane executes it
+      ptx::tmem_wait_ld();
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(o[2 * i]) * inv_l, bb = __uint_as_float(o[2 * i + 1]) * inv_l;
+        if constexpr (PV == PV_E4M3) {
+          a *= vsc[c + 2 * i];
+          bb *= vsc[c + 2 * i + 1];
+          if (vmn) { a += vmn[c + 2 * i]; bb += vmn[c + 2 * i + 1]; }
+        }
+        w[i] = (p.out_dtype == LOWBIT_F16) ? ptx::pack_f16x2(a, bb) : ptx::pack_bf16x2(a, bb);
+      }
+      if (live_row) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      }
+    }
+    if (live_row && p.lse) p.lse[idx] = ptx::lg2(l) + m_ref - PC::OFF;
+  } else {
+    // in true (dequantized) units
+    float m_prev = -INFINITY, l_prev = 0.f;
+    if (!p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }
+    const float m_cur = (l > 0.f) ? m_ref : -INFINITY;  // a row that saw only masked keys contributes nothing
+    const float m_new = fmaxf(m_prev, m_cur);
+    const float wa = (m_prev == -INFINITY) ? 0.f : ptx::ex2(m_prev - m_new);
+    const float wb0 = (m_cur == -INFINITY) ? 0.f : ptx::ex2(m_cur - m_new);
+    const float wb = wb0 * ((PV == PV_E4M3) ? exp2f(-PC::OFF) : 1.f);  // stored P carries 2^OFF
+    const float l_cur = l * wb;
+    float* od = p.oacc_io + idx * D;
+#pragma unroll
+    for (int c = 0; c < D; c += 16) {
+      uint32_t o[16];
+      ptx::tmem_ld_x16(tOl + c, o);
+      ptx::tmem_wait_ld();
+      if (live_row) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!p.first) prev = *reinterpret_cast<const float4*>(od + c + i);
+          float v[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float cur = __uint_as_float(o[i + t]) * wb;
+            if constexpr (PV == PV_E4M3) {
+              cur *= vsc[c + i + t];
+              if (vmn) cur += vmn[c + i + t] * l_cur;
+            }
+            v[t] = cur;
+          }
+          prev.x = prev.x * wa + v[0]; prev.y = prev.y * wa + v[1];
+          prev.z = prev.z * wa + v[2]; prev.w = prev.w * wa + v[3];
+          *reinterpret_cast<float4*>(od + c + i) = prev;
+        }
+      }
+    }
+    if (live_row) {
+      p.m_io[idx] = m_new;
+      p.l_io[idx] = l_prev * wa + l_cur;
+    }
+  }
+}
+
+// What one CTA works on: the padded tensors' (b, h) slice, or -- varlen -- sequence b of the packed tensors.
+struct TileView {
+  int Nq, Nk, nkb;          // rows of this (b, h) / sequence; k_scale blocks
+  int q_row0, k_row0, tb;   // row offsets into the packed tensors; batch coordinate of the tensor maps
+  int64_t qs_idx, ks_base;  // my q_scale entry; first k_scale / kbits entry of my (b, kv head)
+  int64_t orow_base;        // element offset of my first output row (head added later)
+  bool done;                // nothing left to do for this CTA
+};
+
+// Resolves the CTA's view and handles the degenerate tiles (past the end of a varlen sequence; a sequence without keys).
+template <int D>
+__device__ __forceinline__ TileView tile_view(const AttnParams& p, const int qt, const int hq, const int hkv, const int b,
+                                              const int tid) {
+  TileView t;
+  t.Nq = p.Nq; t.Nk = p.Nk; t.nkb = p.nkb;
+  t.q_row0 = 0; t.k_row0 = 0; t.tb = b;
+  t.qs_idx = ((int64_t)b * p.Hq + hq) * p.nqb + qt;
+  t.ks_base = ((int64_t)b * p.Hkv + hkv) * p.nkb;
+  t.orow_base = (int64_t)b * p.osb;
+  t.done = false;
+  if (p.cu_q != nullptr) {
+    t.q_row0 = p.cu_q[b];
+    t.Nq = p.cu_q[b + 1] - t.q_row0;
+    t.k_row0 = p.cu_k[b];
+    t.Nk = p.cu_k[b + 1] - t.k_row0;
+    if (qt * kBM >= t.Nq) { t.done = true; return t; }  // the grid is sized for the longest sequence (attn_qk_int8_block_varlen.py:126-128)
+    t.nkb = (t.Nk + kScaleBlk - 1) / kScaleBlk;
+    t.qs_idx = (int64_t)hq * p.nqb + p.cu_qs[b] + qt;
+    t.ks_base = (int64_t)hkv * p.nkb + p.cu_ks[b];
+    t.orow_base = (int64_t)t.q_row0 * p.osn;
+    t.tb = 0;
+    if (t.Nk == 0) {  // no keys: the reference divides a zero accumulator by l = 1 (attn_qk_int8_block_varlen.py:168-189)
+      if (tid < kBM && qt * kBM + tid < t.Nq) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.o) +
+                                              (t.orow_base + (int64_t)hq * p.osh + (int64_t)(qt * kBM + tid) * p.osn) * 2);
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+      }
+      t.done = true;
+    }
+  }
+  return t;
+}
+
+// ring step whose K/V shard lies wholly in this tile's future: the running state is unchanged (initialised when first)
+template <int D>
+__device__ __forceinline__ void empty_ring_step(const AttnParams& p, const int qt, const int hq, const int b,
+                                                const int Nq, const int tid) {
+  if (p.oacc_io != nullptr && p.first && tid < kBM) {
+    const int row = qt * kBM + tid;
+    if (row < Nq) {
+      const int64_t idx = ((int64_t)b * p.Hq + hq) * Nq + row;
+      p.m_io[idx] = -INFINITY;
+      p.l_io[idx] = 0.f;
+      float4* od = reinterpret_cast<float4*>(p.oacc_io + idx * D);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) od[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// Warp roles:  warps 0-3  softmax (thread t <-> query row t <-> TMEM lane t)
 //              warp 4     helper: one elected lane is both the TMA producer and the tcgen05 issuer; the warp also
 //                         owns the TMEM allocation
+//              warp 5     (packed / mixed-width K) expander: packed K tiles -> int8 operand stages
 // TMEM columns: S/P buffer 0 [0,BN)  S/P buffer 1 [BN,2BN)  O [2BN, 2BN+D)
 // Pipeline: QK_{j+2} is issued right after PV_j, so the int8 contraction of the next two key blocks and the
 // P.V of the previous one run on the tensor pipe while the softmax warps work on block j; K/V stages are refilled
 // by the same thread as soon as the MMAs that read them have committed.
-template <int D, int KM, int PV, int VAR, bool DBG>
-__global__ void __launch_bounds__((AttnRoles<D, KM, VAR>::kThreads), AttnCfg<D>::CTAS)
+template <int D, int KM, int PV, bool DBG>
+__global__ void __launch_bounds__((AttnRoles<D, KM>::kThreads), AttnCfg<D>::CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK8,
                 const __grid_constant__ CUtensorMap tmK2, const AttnParams p) {
@@ -330,24 +425,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   using SM = AttnSmem<D, KM, PV>;
   using PC = PvCfg<PV>;
   constexpr int BN = C::BN, VS = C::VS;
-  constexpr int KS = SM::kKStages;                   // int8 operand stages (INT4 mode: 2, indexed like the S buffers)
-  constexpr bool KX = (KM != KM_I8);                          // K tiles are expanded by the softmax threads
+  constexpr int KS = SM::kKStages;                   // int8 operand stages (expanded K: 2, indexed like the S buffers)
+  constexpr bool KX = (KM != KM_I8);                          // K tiles are expanded by the expander warp
   constexpr int KPS = KX ? SM::kKpStages : C::KS;             // TMA-filled K stages
   constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;     // TMEM columns of one P tile
-  constexpr int SP = AttnSP<D, VAR>::value;                   // softmax warpgroups (threads per query row)
-  constexpr int kSoftmaxThreads = AttnSP<D, VAR>::kSoftmaxThreads;
-  constexpr int HW = 4 * SP;                                  // index of the helper warp
-  constexpr bool EXW = AttnRoles<D, KM, VAR>::kExpander;      // warp HW + 1 expands the K tiles
-  constexpr int kExpThreads = EXW ? 32 : kSoftmaxThreads;     // threads that expand K tiles (and arrive on kfree)
-  constexpr int BNH = BN / SP;                                // score columns per softmax thread and step
-  constexpr int PCH = PCOLS / SP;                             // P columns per softmax thread and step
-  constexpr int DH = D / SP;                                  // O columns per softmax thread (rescale, epilogue)
+  constexpr int HW = 4;                                       // index of the helper warp
   // p_ready counts warps, not threads (measured: D=128 causal +3 %, D=64 INT8 K unchanged, but -1.8 % on the D=64
   // expander-warp kernels, which keep per-thread arrivals)
-  constexpr bool kWarpArrive = (SP == 1) && !(D == 64 && AttnRoles<D, KM, VAR>::kExpander);
+  constexpr bool kWarpArrive = !(D == 64 && KX);
   __shared__ float s_vs[PV == PV_E4M3 ? D : 1], s_vm[PV == PV_E4M3 ? D : 1];  // FP8 P.V: v_scale / v_mean of this (b, kv head)
-  __shared__ int s_flag[4][2];                                // SP = 2: "rescale wanted at step j" token per warp pair
-  __shared__ float s_mx[2][kBM], s_l[2][kBM];                 // SP = 2: row-max / row-sum exchange between the halves
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -356,15 +442,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sKp = sV + VS * SM::kV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + SM::kKpStages * SM::kKp);
   uint64_t* bar_q = bars + 0;
-  uint64_t* kfull = bars + 1;        // [KPS] TMA -> consumer (MMA issuer, or the expanding softmax threads)
+  uint64_t* kfull = bars + 1;        // [KPS] TMA -> consumer (MMA issuer, or the expander warp)
   uint64_t* kfree = kfull + KPS;     // [KPS] consumer -> TMA
   uint64_t* vfull = kfree + KPS;     // [VS]
   uint64_t* vfree = vfull + VS;      // [VS]
   uint64_t* bar_s = vfree + VS;      // [2] QK done: S buffer b holds scores
-  uint64_t* p_ready = bar_s + 2;     // [2] 128 softmax threads wrote P into buffer b (INT4: and expanded K_{j+2})
+  uint64_t* p_ready = bar_s + 2;     // [2] the softmax warps wrote P into buffer b
   uint64_t* bar_o = p_ready + 2;     // PV_j done (one phase per key block)
   uint64_t* bar_final = bar_o + 1;   // last PV done (single phase: parity waits must never lag 2 phases)
-  uint64_t* bar_k01 = bar_final + 1; // INT4: Q permuted and K_0, K_1 expanded (expander warp: Q permuted)
+  uint64_t* bar_k01 = bar_final + 1; // expander warp: Q permuted
   uint64_t* kready = bar_k01 + 1;    // [2] expander warp: operand stage holds the expanded K tile
   uint64_t* kopfree = kready + 2;    // [2] QK on an operand stage complete: the expander may overwrite it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kopfree + 2);
@@ -375,33 +461,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (p.Hq / p.Hkv);
 
-  // this CTA's view of the problem: the padded tensors' (b, h) slice, or -- varlen -- sequence b of the packed tensors
-  int Nq = p.Nq, Nk = p.Nk, nkb = p.nkb;
-  int q_row0 = 0, k_row0 = 0, tb = b;  // row offsets into the packed tensors; batch coordinate of the tensor maps
-  int64_t qs_idx = ((int64_t)b * p.Hq + hq) * p.nqb + qt;   // my q_scale entry
-  int64_t ks_base = ((int64_t)b * p.Hkv + hkv) * p.nkb;    // first k_scale / kbits entry of my (b, kv head)
-  int64_t orow_base = (int64_t)b * p.osb;                  // element offset of my first output row (head added later)
-  if (p.cu_q != nullptr) {
-    q_row0 = p.cu_q[b];
-    Nq = p.cu_q[b + 1] - q_row0;
-    k_row0 = p.cu_k[b];
-    Nk = p.cu_k[b + 1] - k_row0;
-    if (qt * kBM >= Nq) return;  // the grid is sized for the longest sequence (attn_qk_int8_block_varlen.py:126-128)
-    nkb = (Nk + kScaleBlk - 1) / kScaleBlk;
-    qs_idx = (int64_t)hq * p.nqb + p.cu_qs[b] + qt;
-    ks_base = (int64_t)hkv * p.nkb + p.cu_ks[b];
-    orow_base = (int64_t)q_row0 * p.osn;
-    tb = 0;
-    if (Nk == 0) {  // no keys: the reference divides a zero accumulator by l = 1 (attn_qk_int8_block_varlen.py:168-189)
-      if (tid < kBM && qt * kBM + tid < Nq) {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.o) +
-                                              (orow_base + (int64_t)hq * p.osh + (int64_t)(qt * kBM + tid) * p.osn) * 2);
-#pragma unroll
-        for (int i = 0; i < D / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
-      }
-      return;
-    }
-  }
+  const TileView tv = tile_view<D>(p, qt, hq, hkv, b, tid);
+  if (tv.done) return;
+  const int Nq = tv.Nq, Nk = tv.Nk, nkb = tv.nkb, q_row0 = tv.q_row0, k_row0 = tv.k_row0, tb = tv.tb;
+  const int64_t qs_idx = tv.qs_idx, ks_base = tv.ks_base, orow_base = tv.orow_base;
 
   // key-block range of this Q tile.  compat_tail walks the reference's whole 64-key blocks (phantom zero keys).
   const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
@@ -411,18 +474,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int dq = p.delta + qt * kBM;  // delta + first row of the tile
   if (causal) nblk = max(0, min(nblk, (dq + kBM + BN - 1) / BN));
   if (nblk == 0) {
-    // ring step whose K/V shard lies wholly in this tile's future: the running state is unchanged
-    if (p.oacc_io != nullptr && p.first && tid < kBM) {
-      const int row = qt * kBM + tid;
-      if (row < Nq) {
-        const int64_t idx = ((int64_t)b * p.Hq + hq) * Nq + row;
-        p.m_io[idx] = -INFINITY;
-        p.l_io[idx] = 0.f;
-        float4* od = reinterpret_cast<float4*>(p.oacc_io + idx * D);
-#pragma unroll
-        for (int i = 0; i < D / 4; ++i) od[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+    empty_ring_step<D>(p, qt, hq, b, Nq, tid);
     return;
   }
 
@@ -434,15 +486,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(bar_q, 1);
     for (int i = 0; i < KPS; ++i) {
       ptx::mbar_init(kfull + i, 1);
-      ptx::mbar_init(kfree + i, KX ? kExpThreads : 1);
+      ptx::mbar_init(kfree + i, KX ? 32 : 1);
     }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
-    // p_ready: one arrival per softmax warp (tcgen05.wait::st is a warp collective, so lane 0 can speak for the warp);
-    // the column-split / softmax-thread-expansion variant keeps one arrival per thread (each orders its own writes)
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kWarpArrive ? 4 : kSoftmaxThreads); }
+    // p_ready: one arrival per softmax warp (tcgen05.wait::st is a warp collective, so lane 0 can speak for the warp)
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_s + i, 1); ptx::mbar_init(p_ready + i, kWarpArrive ? 4 : 128); }
     ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_final, 1);
-    ptx::mbar_init(bar_k01, kExpThreads);
+    ptx::mbar_init(bar_k01, 32);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(kready + i, 32); ptx::mbar_init(kopfree + i, 1); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmQ);
@@ -476,7 +527,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_pv = (PV == PV_F16) ? ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D)
                                                    : ptx::make_idesc(ptx::kCF32, ptx::kE4M3, ptx::kE4M3, 0, 0, kBM, D);
       const uint32_t aq = ptx::smem_u32(sQ);
-      auto load_k = [&](int j) {  // int8 tile (swizzled) or packed INT4 tile (linear) into TMA stage j % KPS
+      auto load_k = [&](int j) {  // int8 tile (swizzled) or packed tile (linear) into TMA stage j % KPS
         const int ks = j % KPS;
         ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
         if constexpr (KM == KM_I8) {
@@ -505,8 +556,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       auto issue_qk = [&](int j) {
         const int ks = j % KS;
-        if constexpr (!KX) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
-        if constexpr (EXW) {
+        if constexpr (!KX) {
+          ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+        } else {
           ptx::mbar_wait(kready + ks, (j / KS) & 1, 24);  // expanded by the expander warp; its packed stage is free
           if (j + KPS < nblk) load_k(j + KPS);
         }
@@ -521,21 +573,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
         if constexpr (!KX) ptx::umma_commit(kfree + ks);  // K stage may be refilled
-        if constexpr (EXW) ptx::umma_commit(kopfree + ks);  // operand stage may be overwritten
+        else ptx::umma_commit(kopfree + ks);               // operand stage may be overwritten
       };
       ptx::mbar_expect_tx(bar_q, SM::kQ);
       ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
       for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
       for (int j = 0; j < min(2, nblk); ++j) load_v(j);
-      if constexpr (!KX) {
-        ptx::mbar_wait(bar_q, 0, 21);
-      } else {
-        ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted (softmax-thread expansion: and K_0 / K_1 expanded, stages free)
-        if constexpr (!EXW) {
-          if (KPS < nblk) load_k(KPS);
-          if (KPS + 1 < nblk) load_k(KPS + 1);
-        }
-      }
+      if constexpr (!KX) ptx::mbar_wait(bar_q, 0, 21);
+      else ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted
       issue_qk(0);
       if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
@@ -567,13 +612,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // refill: the K stage consumed longest ago and the V stage of PV_{j-1} (complete in steady state)
         if constexpr (!KX) {
           if (j + KPS < nblk) load_k(j + KPS);
-        } else if constexpr (!EXW) {
-          if (j + 2 + KPS < nblk) load_k(j + 2 + KPS);  // softmax step j expanded K_{j+2}: its packed stage is free
         }
         if (j + 2 < nblk) load_v(j + 2);
       }
     }
-  } else if (EXW && warp == HW + 1) {
+  } else if (KX && warp == HW + 1) {
     // ================================ expander warp: packed K tiles -> int8 operand stages ================================
     const int et = tid & 31;
     ptx::mbar_wait(bar_q, 0, 33);
@@ -591,10 +634,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ================================ softmax warps ================================
-    const int half = (SP == 2) ? (tid >> 7) : 0;  // which column half of the score tile this thread owns
     const int r = tid & (kBM - 1);                // query row inside the tile = TMEM lane
-    const int wq = warp & 3;                      // TMEM lane quadrant (and warp-pair index for SP = 2)
-    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;  // TMEM lane quadrant of this warp
     const int row = qt * kBM + r;  // query row owned by this thread
     float qs = p.q_scale[qs_idx];
     if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
@@ -605,64 +646,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     const bool mask_tail = !compat && (Nk % BN != 0);
     const int last_kblk = (Nk + BN - 1) / BN - 1;
-    const uint32_t tS0 = tmem_base + lane_off + half * BNH, tS1 = tS0 + BN;  // my score columns in S buffer 0 / 1
-    const uint32_t tP0 = tmem_base + lane_off + half * PCH, tP1 = tP0 + BN;  // my P columns (P aliases S)
+    const uint32_t tS0 = tmem_base + lane_off, tS1 = tS0 + BN;  // my score columns in S buffer 0 / 1 (P aliases S)
     const uint32_t tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
 
-    if constexpr (KX && !EXW) {
-      ptx::mbar_wait(bar_q, 0, 33);
-      permute_q_tile<D, kSoftmaxThreads>(sQ, tid);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (j < nblk) {
-          ptx::mbar_wait(kfull + j, 0, 34);
-          expand_k_tile<D, BN, kSoftmaxThreads, KM>(sKp + j * SM::kKp, sK + j * SM::kK, tid, kb(j));
-          ptx::mbar_arrive(kfree + j);
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(bar_k01);
-    }
-
     // one key block: wait for S, row max, (rare) rescale of O, P = exp2(S*sc - m) -> TMEM, signal the issuer
-    auto step = [&](auto masked_tag, const uint32_t tSb, const uint32_t tPb, uint64_t* bs, uint64_t* pr,
-                    const uint32_t ph, const int j, const float sc_in, const int lim_tile) {
+    auto step = [&](auto masked_tag, const uint32_t tSb, uint64_t* bs, uint64_t* pr, const uint32_t ph, const int j,
+                    const float sc_in, const int lim) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const float sc = sc_in * kfac(j);
-      const int lim = lim_tile - half * BNH;  // live columns of my half: [0, lim]
       ptx::mbar_wait(bs, ph, 30);
       ptx::tc_fence_after();
-      uint32_t s[BNH];
-      tmem_ld_n<BNH>(tSb, s);
+      uint32_t s[BN];
+      tmem_ld_n<BN>(tSb, s);
       ptx::tmem_wait_ld();
       if constexpr (DBG) {
         if (p.dbg != nullptr && j * BN < 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-          for (int c = 0; c < BNH; ++c) p.dbg[r * 64 + j * BN + half * BNH + c] = (int)s[c];
+          for (int c = 0; c < BN; ++c) p.dbg[r * 64 + j * BN + c] = (int)s[c];
         }
       }
-      const int imax = row_max<BNH, MASKED>(s, lim);
+      const int imax = wide::row_max_i<BN, MASKED>(s, lim);
       const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
       // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision,
-      // tcgen05.ld/st are warp collectives; pair-uniform for SP = 2)
-      bool want = __any_sync(0xffffffffu, mblk > m_ref + PC::THR);
-      if constexpr (SP == 2) {
-        // The pair barrier also orders the P store below after the partner's score load above: P of the upper half
-        // lands on TMEM columns that hold the lower half's scores.
-        volatile int* flag = &s_flag[wq][j & 1];
-        if (want && (tid & 31) == 0) *flag = j + 1;  // token = step index: never needs clearing
-        ptx::bar_sync(1 + wq, 64);
-        want = (*flag == j + 1);
-      }
-      if (want) {
-        float mb = mblk;
-        if constexpr (SP == 2) {
-          s_mx[half][r] = mblk;
-          ptx::bar_sync(1 + wq, 64);
-          mb = fmaxf(mblk, s_mx[half ^ 1][r]);
-        }
-        const float m_new = fmaxf(m_ref, mb);
+      // tcgen05.ld/st are warp collectives)
+      if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
+        const float m_new = fmaxf(m_ref, mblk);
         const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
         l *= alpha;
         m_ref = m_new;
@@ -672,8 +681,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::mbar_wait(bar_o, (j - 1) & 1, 31);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int cc = 0; cc < DH; cc += 16) {
-            const int c = half * DH + cc;
+          for (int c = 0; c < D; c += 16) {
             uint32_t o[16];
             ptx::tmem_ld_x16(tOl + c, o);
             ptx::tmem_wait_ld();
@@ -683,21 +691,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      uint32_t pk[PCH];
+      uint32_t pk[PCOLS];
       const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-      if constexpr (PV == PV_F16) l += softmax_block_f16<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
-      else l += softmax_block_e4m3<BNH, MASKED, VAR>(s, sc, nm, lim, pk);
-      tmem_st_n<PCH>(tPb, pk);  // P aliases the first columns of its S buffer
-      if constexpr (KX && !EXW) {
-        // expand K_{j+2} into the operand stage QK_j just released (S_j ready => QK_j complete)
-        if (j + 2 < nblk) {
-          const int kps = (j + 2) % KPS;
-          ptx::mbar_wait(kfull + kps, ((j + 2) / KPS) & 1, 35);
-          expand_k_tile<D, BN, kSoftmaxThreads, KM>(sKp + kps * SM::kKp, sK + (j & 1) * SM::kK, tid, kb(j + 2));
-          ptx::mbar_arrive(kfree + kps);
-          ptx::fence_proxy_async_smem();
-        }
-      }
+      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED>(s, sc, nm, lim, pk);
+      else l += softmax_block_e4m3<BN, MASKED>(s, sc, nm, lim, pk);
+      tmem_st_n<PCOLS>(tSb, pk);  // P aliases the first columns of its S buffer
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       if constexpr (kWarpArrive) {
@@ -721,8 +719,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float sc1 = sc0;
       if (kPerScale == 1) sc1 = qs * ks_ptr[j + 1];
       const float ks_nxt = ks_ptr[min((j + 2) / kPerScale, nkb - 1)];  // prefetch for the next pair
-      step(std::false_type{}, tS0, tP0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
-      step(std::false_type{}, tS1, tP1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
+      step(std::false_type{}, tS0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
+      step(std::false_type{}, tS1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
       ks_cur = ks_nxt;
     }
     // remaining blocks (odd leftover, causal diagonal band, masked tail): generic path
@@ -732,102 +730,384 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int lim = BN;  // columns [0, lim] are live
       if (causal) lim = min(lim, p.delta + row - c0);
       if (mask_tail && j == last_kblk) lim = min(lim, Nk - 1 - c0);
-      step(std::true_type{}, (j & 1) ? tS1 : tS0, (j & 1) ? tP1 : tP0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc,
-           lim);
+      step(std::true_type{}, (j & 1) ? tS1 : tS0, bar_s + (j & 1), p_ready + (j & 1), (j >> 1) & 1, j, sc, lim);
     }
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------
     ptx::mbar_wait(bar_final, 0, 32);
     ptx::tc_fence_after();
-    const bool live_row = row < Nq;
-    // per-channel V scale / mean of this (b, kv head): staged in shared memory at kernel start -- read straight from
-    // global memory here, every element's load sat behind the previous store to the (possibly aliasing) fp32 state and
-    // cost the ring merge epilogue 0.76 ms per 8K x 8K launch
-    const float* vsc = (PV == PV_E4M3) ? s_vs : nullptr;
-    const float* vmn = (PV == PV_E4M3 && p.v_mean) ? s_vm : nullptr;
-    const int64_t idx = ((int64_t)b * p.Hq + hq) * Nq + row;
-    float m_prev = -INFINITY, l_prev = 0.f;  // ring step: running state, read before the pair barrier below
-    if (p.oacc_io != nullptr && !p.first && live_row) { m_prev = p.m_io[idx]; l_prev = p.l_io[idx]; }
-    if constexpr (SP == 2) {  // row sum = the two halves' partial sums
-      s_l[half][r] = l;
-      ptx::bar_sync(1 + wq, 64);
-      l += s_l[half ^ 1][r];
-    }
-    const int cbeg = half * DH;  // my share of the D output columns
-    if (p.oacc_io == nullptr) {
-      // O / l (* v_scale + v_mean) -> out dtype, lse2 = log2(l) + m - OFF
-      const float inv_l = 1.0f / l;
-      uint8_t* orow = reinterpret_cast<uint8_t*>(p.o) + (orow_base + (int64_t)hq * p.osh + (int64_t)row * p.osn) * 2;
-#pragma unroll
-      for (int cc = 0; cc < DH; cc += 32) {
-        const int c = cbeg + cc;
-        uint32_t o[32];
-        ptx::tmem_ld_x32(tOl + c, o);  // warp collective: every lane executes it
-        ptx::tmem_wait_ld();
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a = __uint_as_float(o[2 * i]) * inv_l, bb = __uint_as_float(o[2 * i + 1]) * inv_l;
-          if constexpr (PV == PV_E4M3) {
-            a *= vsc[c + 2 * i];
-            bb *= vsc[c + 2 * i + 1];
-            if (vmn) { a += vmn[c + 2 * i]; bb += vmn[c + 2 * i + 1]; }
-          }
-          w[i] = (p.out_dtype == LOWBIT_F16) ? ptx::pack_f16x2(a, bb) : ptx::pack_bf16x2(a, bb);
-        }
-        if (live_row) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 2);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-        }
-      }
-      if (live_row && p.lse && half == 0) p.lse[idx] = ptx::lg2(l) + m_ref - PC::OFF;
-    } else {
-      // ring step: merge (m_ref, l, O) of this K/V shard into the running fp32 state, in true (dequantized) units
-      const float m_cur = (l > 0.f) ? m_ref : -INFINITY;  // a row that saw only masked keys contributes nothing
-      const float m_new = fmaxf(m_prev, m_cur);
-      const float wa = (m_prev == -INFINITY) ? 0.f : ptx::ex2(m_prev - m_new);
-      const float wb0 = (m_cur == -INFINITY) ? 0.f : ptx::ex2(m_cur - m_new);
-      const float wb = wb0 * ((PV == PV_E4M3) ? exp2f(-PC::OFF) : 1.f);  // stored P carries 2^OFF
-      const float l_cur = l * wb;
-      float* od = p.oacc_io + idx * D;
-#pragma unroll
-      for (int cc = 0; cc < DH; cc += 16) {
-        const int c = cbeg + cc;
-        uint32_t o[16];
-        ptx::tmem_ld_x16(tOl + c, o);
-        ptx::tmem_wait_ld();
-        if (live_row) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!p.first) prev = *reinterpret_cast<const float4*>(od + c + i);
-            float v[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float cur = __uint_as_float(o[i + t]) * wb;
-              if constexpr (PV == PV_E4M3) {
-                cur *= vsc[c + i + t];
-                if (vmn) cur += vmn[c + i + t] * l_cur;
-              }
-              v[t] = cur;
-            }
-            prev.x = prev.x * wa + v[0]; prev.y = prev.y * wa + v[1];
-            prev.z = prev.z * wa + v[2]; prev.w = prev.w * wa + v[3];
-            *reinterpret_cast<float4*>(od + c + i) = prev;
-          }
-        }
-      }
-      if (live_row && half == 0) {  // the partner read m_io / l_io before the pair barrier above
-        p.m_io[idx] = m_new;
-        p.l_io[idx] = l_prev * wa + l_cur;
-      }
-    }
+    attn_epilogue<D, PV>(p, tOl, l, m_ref, row, Nq, b, hq, orow_base, (PV == PV_E4M3) ? s_vs : nullptr,
+                         (PV == PV_E4M3 && p.v_mean) ? s_vm : nullptr);
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == HW) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ================================================================================================================
+// attn_fwd_wide_kernel -- head_dim 64, 128-key steps.
+//
+// At head_dim 64 the kernel is bound by the softmax, not by the tensor pipe (one exp2 per 128 tensor MACs; MUFU floor
+// 2.7x the tensor floor), and round 1's 32-key steps spent 38 % of the softmax warps' instructions on per-step
+// overhead (barrier waits, TMEM round trips, votes, address arithmetic: 6.5 warp instructions per score of which 4.0
+// are the arithmetic itself).  This kernel cuts that overhead four-fold and takes work off the MUFU pipe:
+//
+//   * one step = 128 keys = four 32-key chunks: a thread (= query row = TMEM lane) streams its scores out of TMEM chunk
+//     by chunk (the tcgen05.ld of chunk c+1 in flight while chunk c is computed: 2 x 32 score registers) and writes P
+//     chunk by chunk into its own TMEM columns (P does not alias S); one barrier round, one vote, one scale lookup
+//     per 128 keys instead of per 32;
+//   * TMEM: S [0,128) int32 | P [128,192) fp16 (or 32 columns e4m3) | O [192,256) fp32 -- 256 columns, two CTAs per SM,
+//     which take turns on the MUFU pipe: while one waits for its next score tile the other computes;
+//   * optimistic maximum (fp16 P.V): after its first block a row keeps its reference maximum and computes P at once; only
+//     when the block's row sum reaches 2^15 (some p could overflow fp16) is the exact block maximum taken and the
+//     block redone from the scores still in TMEM (S is released to QK_{j+1} after that check) -- softmax is
+//     invariant under the choice of the reference maximum, P.V and l accumulate in fp32, and the integer-max pass
+//     (0.5 instruction per score on the ALU pipe, and a second trip through TMEM) disappears from the common path;
+//   * PF of every 8 score pairs take the FMA-pipe exp2 (softmax_wide.cuh) instead of MUFU.EX2;
+//   * warp roles: warps 0-3 softmax, warp 4 helper (one elected lane: TMA producer + tcgen05 issuer; TMEM owner),
+//     warp 5 K expander (packed INT4 K).
+// ================================================================================================================
+template <int KM, int PV>
+struct WideSmem {
+  static constexpr int D = 64, BN = 128, VS = 3;
+  static constexpr int kQ = kBM * D;                            // int8
+  static constexpr int kK = BN * D;                             // int8 operand stage
+  static constexpr int kKStages = (KM == KM_I8) ? 3 : 2;
+  static constexpr int kKp = BN * D / 2;                        // packed INT4 staging stage
+  static constexpr int kKpStages = (KM == KM_K4) ? 4 : 0;
+  static constexpr int kV = (PV == PV_F16) ? BN * D * 2 : BN * D;  // fp16 [key][d] / e4m3 [d][key]
+  static constexpr int kBytes = kQ + kKStages * kK + VS * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
+};
+template <int KM> constexpr int wide_threads() { return 128 + 32 + (KM != KM_I8 ? 32 : 0); }
+
+template <int KM, int PV, int PF, bool DBG>
+__global__ void __launch_bounds__(wide_threads<KM>(), 2)
+attn_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  static_assert(KM == KM_I8 || KM == KM_K4, "mixed-width K runs on attn_fwd_kernel");
+  using SM = WideSmem<KM, PV>;
+  using PC = PvCfg<PV>;
+  constexpr int D = 64, BN = 128, VS = 3;
+  constexpr bool KX = (KM != KM_I8);
+  constexpr int KS = SM::kKStages;                           // int8 operand stages
+  constexpr int KPS = KX ? SM::kKpStages : KS;               // TMA-filled K stages
+  constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;    // TMEM columns of one P tile
+  constexpr int PCH = PCOLS / 4;                             // ... of one 32-key chunk
+  constexpr uint32_t kTmemCols = 256, kColP = BN, kColO = BN + 64;
+  __shared__ float s_vs[PV == PV_E4M3 ? D : 1], s_vm[PV == PV_E4M3 ? D : 1];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + SM::kQ;
+  uint8_t* sV = sK + KS * SM::kK;
+  uint8_t* sKp = sV + VS * SM::kV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + SM::kKpStages * SM::kKp);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* kfull = bars + 1;        // [KPS] TMA -> consumer (issuer, or the expander warp)
+  uint64_t* kfree = kfull + KPS;     // [KPS] consumer -> TMA
+  uint64_t* vfull = kfree + KPS;     // [VS]
+  uint64_t* vfree = vfull + VS;      // [VS]
+  uint64_t* bar_s = vfree + VS;      // QK_j done: S holds the scores of block j            (phase j)
+  uint64_t* s_free = bar_s + 1;      // 4 softmax warps are done with S_j: QK_{j+1} may overwrite it  (phase j)
+  uint64_t* p_ready = s_free + 1;    // 4 softmax warps wrote P_j                             (phase j)
+  uint64_t* bar_o = p_ready + 1;     // PV_j done: O updated, P may be overwritten            (phase j)
+  uint64_t* bar_final = bar_o + 1;   // last PV done
+  uint64_t* bar_qperm = bar_final + 1;  // expander warp: Q permuted
+  uint64_t* kready = bar_qperm + 1;  // [2] expander warp: operand stage holds the expanded K tile
+  uint64_t* kopfree = kready + 2;    // [2] QK on an operand stage complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kopfree + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
+  const int qt = causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
+  const int hq = blockIdx.y, b = blockIdx.z;
+  const int hkv = hq / (p.Hq / p.Hkv);
+
+  const TileView tv = tile_view<D>(p, qt, hq, hkv, b, tid);
+  if (tv.done) return;
+  const int Nq = tv.Nq, Nk = tv.Nk, nkb = tv.nkb, q_row0 = tv.q_row0, k_row0 = tv.k_row0, tb = tv.tb;
+  const int64_t qs_idx = tv.qs_idx, ks_base = tv.ks_base, orow_base = tv.orow_base;
+
+  // keys [0, nk_lim) take part; compat_tail walks the reference's whole 64-key blocks (phantom zero keys)
+  const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
+  const int nk_lim = compat ? nkb * kScaleBlk : Nk;
+  int nblk = (nk_lim + BN - 1) / BN;
+  const int dq = p.delta + qt * kBM;  // causal: key c is visible to tile row r iff c <= dq + r
+  if (causal) nblk = max(0, min(nblk, (dq + kBM + BN - 1) / BN));
+  if (nblk == 0) {
+    empty_ring_step<D>(p, qt, hq, b, Nq, tid);
+    return;
+  }
+
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  if (tid == 0) {
+    ptx::mbar_init(bar_q, 1);
+    for (int i = 0; i < KPS; ++i) {
+      ptx::mbar_init(kfull + i, 1);
+      ptx::mbar_init(kfree + i, KX ? 32 : 1);
+    }
+    for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(s_free, 4);
+    ptx::mbar_init(p_ready, 4);
+    ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(bar_final, 1);
+    ptx::mbar_init(bar_qperm, 32);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(kready + i, 32); ptx::mbar_init(kopfree + i, 1); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if constexpr (PV == PV_E4M3) {
+    if (tid < D) {
+      s_vs[tid] = p.v_scale[((int64_t)b * p.Hkv + hkv) * D + tid];
+      s_vm[tid] = p.v_mean ? p.v_mean[((int64_t)b * p.Hkv + hkv) * D + tid] : 0.f;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================ helper: TMA producer + tcgen05 issuer (one elected lane) ================================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
+      constexpr uint32_t idesc_pv = (PV == PV_F16) ? ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D)
+                                                   : ptx::make_idesc(ptx::kCF32, ptx::kE4M3, ptx::kE4M3, 0, 0, kBM, D);
+      const uint32_t aq = ptx::smem_u32(sQ);
+      const uint32_t tS = tmem_base, tP = tmem_base + kColP, tO = tmem_base + kColO;
+      auto load_k = [&](int j) {  // int8 tile (swizzled) or packed INT4 tile (linear) into TMA stage j % KPS
+        const int ks = j % KPS;
+        ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
+        if constexpr (KM == KM_I8) {
+          ptx::mbar_expect_tx(kfull + ks, SM::kK);
+          ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
+        } else {
+          ptx::mbar_expect_tx(kfull + ks, SM::kKp);
+          ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
+        }
+      };
+      auto load_v = [&](int j) {
+        const int vs = j % VS;
+        ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
+        ptx::mbar_expect_tx(vfull + vs, SM::kV);
+        if constexpr (PV == PV_F16) ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, k_row0 + j * BN, hkv, tb);
+        else ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, j * BN, 0, hkv, b);  // [d][key] tile
+      };
+      auto issue_qk = [&](int j) {
+        const int ks = j % KS;
+        if constexpr (!KX) {
+          ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+        } else {
+          ptx::mbar_wait(kready + ks, (j / KS) & 1, 24);  // expanded by the expander warp; its packed stage is free
+          if (j + KPS < nblk) load_k(j + KPS);
+        }
+        ptx::tc_fence_after();
+        const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
+#pragma unroll
+        for (int kk = 0; kk < D / 32; ++kk) {  // K-major operands, rows of 64 bytes, 64B swizzle, 8 rows = 512 B (SBO)
+          const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, 8 * D, ptx::kSwz64);
+          const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, 8 * D, ptx::kSwz64);
+          ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+        }
+        ptx::umma_commit(bar_s);
+        ptx::umma_commit(KX ? kopfree + ks : kfree + ks);
+      };
+      ptx::mbar_expect_tx(bar_q, SM::kQ);
+      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
+      for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
+      for (int j = 0; j < min(VS - 1, nblk); ++j) load_v(j);
+      ptx::mbar_wait(KX ? bar_qperm : bar_q, 0, 21);
+      issue_qk(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          ptx::mbar_wait(s_free, j & 1, 25);  // the softmax warps are done with S_j
+          issue_qk(j + 1);
+        }
+        const int vs = j % VS;
+        ptx::mbar_wait(p_ready, j & 1, 22);
+        ptx::mbar_wait(vfull + vs, (j / VS) & 1, 23);
+        ptx::tc_fence_after();
+        const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
+        if constexpr (PV == PV_F16) {
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); one 64-wide d atom
+            const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
+            ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < BN / 32; ++kk) {
+            // V^T tile: K-major (keys contiguous), rows of 128 bytes, 128B swizzle, 8 channel rows = 1024 B (SBO)
+            const uint64_t db = ptx::make_smem_desc(av + kk * 32, 16, 8 * BN, ptx::kSwz128);
+            ptx::umma_f8_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+          }
+        }
+        ptx::umma_commit(vfree + vs);
+        ptx::umma_commit(bar_o);
+        if (j == nblk - 1) ptx::umma_commit(bar_final);
+        // refill: the K stage of QK_j (complete: S_j has been consumed) and the V stage of PV_{j-1} (complete: the
+        // softmax warps waited for it before they wrote P_j)
+        if constexpr (!KX) {
+          if (j + KPS < nblk) load_k(j + KPS);
+        }
+        if (j + VS - 1 < nblk) load_v(j + VS - 1);
+      }
+    }
+  } else if (KX && warp == 5) {
+    // ================================ expander warp: packed INT4 K tiles -> int8 operand stages ================================
+    const int et = tid & 31;
+    ptx::mbar_wait(bar_q, 0, 33);
+    permute_q_tile<D, 32>(sQ, et);
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive(bar_qperm);
+    for (int j = 0; j < nblk; ++j) {
+      const int ks = j % KS, kps = j % KPS;
+      if (j >= KS) ptx::mbar_wait(kopfree + ks, ((j / KS) - 1) & 1, 36);  // QK_{j-KS} has read this operand stage
+      ptx::mbar_wait(kfull + kps, (j / KPS) & 1, 34);
+      unpack_k4_tile<D, BN, 32>(sKp + kps * SM::kKp, sK + ks * SM::kK, et);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(kfree + kps);
+      ptx::mbar_arrive(kready + ks);
+    }
+  } else {
+    // ================================ softmax warps ================================
+    const int lane = tid & 31;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;  // TMEM lane quadrant of this warp
+    const int row = qt * kBM + tid;                         // query row owned by this thread (tid < 128)
+    float qs = p.q_scale[qs_idx];
+    if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
+    const float* ks_ptr = p.k_scale + ks_base;
+    const bool mask_tail = (nk_lim % BN) != 0;
+    const int last_kblk = (nk_lim + BN - 1) / BN - 1;
+    const uint32_t tSl = tmem_base + lane_off, tPl = tSl + kColP, tOl = tSl + kColO;
+    float m_ref = -INFINITY, l = 0.f;
+
+    // one 128-key block; sc_a / sc_b: dequantization factors of its two 64-key scale blocks; columns > lim are masked
+    auto step = [&](auto masked_tag, const int j, const float sc_a, const float sc_b, const int lim) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      ptx::mbar_wait(bar_s, j & 1, 30);
+      ptx::tc_fence_after();
+      uint32_t sa[32], sb[32];  // chunk double buffer
+      ptx::tmem_ld_x32(tSl, sa);
+      // exact: take the block maximum first (first block of a row, masked blocks, e4m3 P); otherwise optimistic
+      bool exact = MASKED || (PV == PV_E4M3);
+      if (!exact) exact = __any_sync(0xffffffffu, m_ref == -INFINITY);
+      float lsum;
+      for (;;) {
+        if (exact) {
+          // pass over the four chunks for the block maximum (chunk 0 is already on its way into sa)
+          ptx::tmem_wait_ld();
+          ptx::tmem_ld_x32(tSl + 32, sb);
+          int ia = wide::row_max_i<32, MASKED>(sa, lim);
+          ptx::tmem_wait_ld();
+          ptx::tmem_ld_x32(tSl + 64, sa);
+          ia = max(ia, wide::row_max_i<32, MASKED>(sb, lim - 32));
+          ptx::tmem_wait_ld();
+          ptx::tmem_ld_x32(tSl + 96, sb);
+          int ib = wide::row_max_i<32, MASKED>(sa, lim - 64);
+          ptx::tmem_wait_ld();
+          ptx::tmem_ld_x32(tSl, sa);  // chunk 0 again, for the exp pass below
+          ib = max(ib, wide::row_max_i<32, MASKED>(sb, lim - 96));
+          const float ma = (MASKED && ia == INT_MIN) ? -INFINITY : (float)ia * sc_a;
+          const float mb = (MASKED && ib == INT_MIN) ? -INFINITY : (float)ib * sc_b;
+          const float mblk = fmaxf(ma, mb);
+          // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision)
+          if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
+            const float m_new = fmaxf(m_ref, mblk);
+            const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
+            l *= alpha;
+            m_ref = m_new;
+            if (j > 0) {
+              ptx::mbar_wait(bar_o, (j - 1) & 1, 31);  // PV_{j-1} has landed in O (phase j-1 or j: unambiguous)
+              ptx::tc_fence_after();
+#pragma unroll
+              for (int c = 0; c < D; c += 16) {
+                uint32_t o[16];
+                ptx::tmem_ld_x16(tOl + c, o);
+                ptx::tmem_wait_ld();  // (also completes the chunk-0 load above)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                ptx::tmem_st_x16(tOl + c, o);
+              }
+            }
+          }
+        }
+        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
+        lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t* cur = (c & 1) ? sb : sa;
+          uint32_t* nxt = (c & 1) ? sa : sb;
+          ptx::tmem_wait_ld();                                          // chunk c has arrived
+          if (c < 3) ptx::tmem_ld_x32(tSl + 32 * (c + 1), nxt);         // chunk c+1 on its way while c is computed
+          uint32_t pk[PCH];
+          const float sc = (c < 2) ? sc_a : sc_b;
+          if constexpr (DBG) {
+            if (p.dbg != nullptr && j == 0 && c < 2 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) p.dbg[tid * 64 + 32 * c + i] = (int)cur[i];
+            }
+          }
+          if constexpr (PV == PV_F16) lsum += wide::chunk_f16<MASKED, PF>(cur, sc, nm, lim - 32 * c, pk);
+          else lsum += softmax_block_e4m3<32, MASKED>(cur, sc, nm, lim - 32 * c, pk);
+          if (c == 0 && j > 0) {  // P_{j-1} has been consumed by PV_{j-1}: its columns may be overwritten
+            ptx::mbar_wait(bar_o, (j - 1) & 1, 37);
+            ptx::tc_fence_after();
+          }
+          tmem_st_n<PCH>(tPl + c * PCH, pk);
+        }
+        if (exact) break;
+        if (!__any_sync(0xffffffffu, !(lsum < 32768.f))) break;  // every p < 2^15: finite in fp16
+        // some score outgrew the row's reference maximum by 2^15: redo the block with the exact maximum
+        ptx::tmem_wait_st();
+        ptx::tmem_ld_x32(tSl, sa);
+        exact = true;
+      }
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(s_free);  // S_j is no longer needed: QK_{j+1} may overwrite it
+      l += lsum;
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(p_ready);
+    };
+
+    int n_full = nblk;  // blocks [0, n_full) need no mask
+    if (causal) n_full = max(0, min(n_full, (dq + 1) / BN));
+    if (mask_tail) n_full = min(n_full, last_kblk);
+    int j = 0;
+    float ka = ks_ptr[0], kb2 = ks_ptr[min(1, nkb - 1)];
+    for (; j < nblk; ++j) {
+      const float sc_a = qs * ka, sc_b = qs * kb2;
+      ka = ks_ptr[min(2 * j + 2, nkb - 1)];  // prefetch for the next block
+      kb2 = ks_ptr[min(2 * j + 3, nkb - 1)];
+      if (j < n_full) {
+        step(std::false_type{}, j, sc_a, sc_b, 0);
+      } else {
+        const int c0 = j * BN;
+        int lim = BN;  // columns [0, lim] are live
+        if (causal) lim = min(lim, dq + tid - c0);
+        if (mask_tail && j == last_kblk) lim = min(lim, nk_lim - 1 - c0);
+        step(std::true_type{}, j, sc_a, sc_b, lim);
+      }
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------------
+    ptx::mbar_wait(bar_final, 0, 32);
+    ptx::tc_fence_after();
+    attn_epilogue<D, PV>(p, tOl, l, m_ref, row, Nq, b, hq, orow_base, (PV == PV_E4M3) ? s_vs : nullptr,
+                         (PV == PV_E4M3 && p.v_mean) ? s_vm : nullptr);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // o = O_acc / l, lse2 = log2(l) + m  (end of a ring / sequence-parallel pass)
@@ -895,50 +1175,103 @@ int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize,
   return 0;
 }
 
-template <int D, int KM, int PV, int VAR, bool DBG = false>
+// (ptr, geometry) -> encoded tensor map.  cuTensorMapEncodeTiled costs 1-2 us per map and an attention call needs 3-5
+// of them; serving loops come back with the same buffers (allocator reuse, CUDA-graph replays), so a small
+// per-thread cache removes that from the launch path.  A map encodes nothing but its arguments: an entry can never
+// be stale, whatever the buffer holds.
+struct MapKey {
+  const void* ptr;
+  int64_t dim[4], str[3];
+  int dt, esize, box0, box1, swz;
+  bool operator==(const MapKey& o) const {
+    if (ptr != o.ptr || dt != o.dt || esize != o.esize || box0 != o.box0 || box1 != o.box1 || swz != o.swz) return false;
+    for (int i = 0; i < 4; ++i) if (dim[i] != o.dim[i]) return false;
+    for (int i = 0; i < 3; ++i) if (str[i] != o.str[i]) return false;
+    return true;
+  }
+};
+static int cached_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, const int64_t (&dim)[4],
+                      const int64_t (&stride_elems)[3], int box0, int box1, CUtensorMapSwizzle swz) {
+  constexpr int kSlots = 32;
+  struct Slot { MapKey key; CUtensorMap map; bool used; };
+  thread_local Slot slots[kSlots];
+  thread_local int next = 0;
+  MapKey k{ptr, {dim[0], dim[1], dim[2], dim[3]}, {stride_elems[0], stride_elems[1], stride_elems[2]},
+           (int)dt, esize, box0, box1, (int)swz};
+  for (int i = 0; i < kSlots; ++i)
+    if (slots[i].used && slots[i].key == k) { *m = slots[i].map; return 0; }
+  if (make_map(m, ptr, dt, esize, dim, stride_elems, box0, box1, swz)) return 1;
+  slots[next].key = k; slots[next].map = *m; slots[next].used = true;
+  next = (next + 1) % kSlots;
+  return 0;
+}
+
+// The opt-in for > 48 KB of dynamic shared memory is a per-DEVICE function attribute: set it on every launch (it is a
+// cheap host-side call) instead of once per process, so that a process driving several GPUs works on all of them.
+template <int D, int KM, int PV, bool DBG = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                        cudaStream_t st, const CUtensorMap* tk8 = nullptr, const CUtensorMap* tk2 = nullptr) {
-  auto kern = attn_fwd_kernel<D, KM, PV, VAR, DBG>;
+  auto kern = attn_fwd_kernel<D, KM, PV, DBG>;
   using SM = AttnSmem<D, KM, PV>;
-  static bool configured = false;
-  if (!configured) {
-    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
-  }
+  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
   dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, AttnRoles<D, KM, VAR>::kThreads, SM::kBytes, st>>>(tq, tk, tv, tk8 ? *tk8 : tk, tk2 ? *tk2 : tk, p);
+  kern<<<grid, AttnRoles<D, KM>::kThreads, SM::kBytes, st>>>(tq, tk, tv, tk8 ? *tk8 : tk, tk2 ? *tk2 : tk, p);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int KM, int PV, int PF, bool DBG = false>
+static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                       cudaStream_t st) {
+  auto kern = attn_fwd_wide_kernel<KM, PV, PF, DBG>;
+  using SM = WideSmem<KM, PV>;
+  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
+  kern<<<grid, wide_threads<KM>(), SM::kBytes, st>>>(tq, tk, tv, p);
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Development switches (read once): LOWBIT_ATTN_WIDE=0 sends head_dim 64 back to the 32-key-step kernel;
+// LOWBIT_ATTN_PF=n (0..3) sets how many of every 8 score pairs take the FMA-pipe exp2 in the wide kernel.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+constexpr int kDefaultPF = 2;
+static bool use_wide(int D, int km, int pv, int flags) {
+  static const int wide = env_int("LOWBIT_ATTN_WIDE", 1);
+  return wide != 0 && !(flags & LOWBIT_ATTN_NARROW) && D == 64 && km != KM_MIX && (pv == PV_F16 || wide >= 2);
+}
+
+template <int KM>
+static int dispatch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                         int pv, cudaStream_t st) {
+  static const int pf = env_int("LOWBIT_ATTN_PF", kDefaultPF);
+  if (pv == PV_E4M3) return launch_wide<KM, PV_E4M3, 0>(tq, tk, tv, p, B, st);
+  if (KM == KM_I8 && p.dbg != nullptr) return launch_wide<KM_I8, PV_F16, kDefaultPF, true>(tq, tk, tv, p, B, st);
+  switch (pf) {
+    case 0: return launch_wide<KM, PV_F16, 0>(tq, tk, tv, p, B, st);
+    case 1: return launch_wide<KM, PV_F16, 1>(tq, tk, tv, p, B, st);
+    case 3: return launch_wide<KM, PV_F16, 3>(tq, tk, tv, p, B, st);
+    default: return launch_wide<KM, PV_F16, 2>(tq, tk, tv, p, B, st);
+  }
 }
 
 template <int D>
 static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                          int B, int km, int pv, cudaStream_t st, const CUtensorMap* tk8, const CUtensorMap* tk2) {
   if (km == KM_MIX) {
-    if (pv == PV_F16) return launch_attn<D, KM_MIX, PV_F16, 0>(tq, tk, tv, p, B, st, tk8, tk2);
-    return launch_attn<D, KM_MIX, PV_E4M3, 0>(tq, tk, tv, p, B, st, tk8, tk2);
+    if (pv == PV_F16) return launch_attn<D, KM_MIX, PV_F16>(tq, tk, tv, p, B, st, tk8, tk2);
+    return launch_attn<D, KM_MIX, PV_E4M3>(tq, tk, tv, p, B, st, tk8, tk2);
   }
-  static int variant = -1;  // development switch (LOWBIT_ATTN_VARIANT): A/B of softmax instruction selection
-  if (variant < 0) { const char* e = getenv("LOWBIT_ATTN_VARIANT"); variant = e ? atoi(e) : 0; }
   if (km == KM_I8 && pv == PV_F16) {
-    if (p.dbg != nullptr) return launch_attn<D, KM_I8, PV_F16, 0, true>(tq, tk, tv, p, B, st);
-    switch (variant) {
-      case 1: return launch_attn<D, KM_I8, PV_F16, 1>(tq, tk, tv, p, B, st);
-      case 4: return launch_attn<D, KM_I8, PV_F16, 4>(tq, tk, tv, p, B, st);
-      case 12: return launch_attn<D, KM_I8, PV_F16, 12>(tq, tk, tv, p, B, st);
-      case 16: return launch_attn<D, KM_I8, PV_F16, 16>(tq, tk, tv, p, B, st);
-      case 64: return launch_attn<D, KM_I8, PV_F16, 64>(tq, tk, tv, p, B, st);
-      default: return launch_attn<D, KM_I8, PV_F16, 0>(tq, tk, tv, p, B, st);
-    }
+    if (p.dbg != nullptr) return launch_attn<D, KM_I8, PV_F16, true>(tq, tk, tv, p, B, st);
+    return launch_attn<D, KM_I8, PV_F16>(tq, tk, tv, p, B, st);
   }
-  if (variant == 16) {  // column-split softmax (SP = 2), every mode: parity-tested through LOWBIT_ATTN_VARIANT=16
-    if (km == KM_K4 && pv == PV_F16) return launch_attn<D, KM_K4, PV_F16, 16>(tq, tk, tv, p, B, st);
-    if (km == KM_I8 && pv == PV_E4M3) return launch_attn<D, KM_I8, PV_E4M3, 16>(tq, tk, tv, p, B, st);
-    return launch_attn<D, KM_K4, PV_E4M3, 16>(tq, tk, tv, p, B, st);
-  }
-  if (km == KM_K4 && pv == PV_F16) return launch_attn<D, KM_K4, PV_F16, 0>(tq, tk, tv, p, B, st);
-  if (km == KM_I8 && pv == PV_E4M3) return launch_attn<D, KM_I8, PV_E4M3, 0>(tq, tk, tv, p, B, st);
-  return launch_attn<D, KM_K4, PV_E4M3, 0>(tq, tk, tv, p, B, st);
+  if (km == KM_K4 && pv == PV_F16) return launch_attn<D, KM_K4, PV_F16>(tq, tk, tv, p, B, st);
+  if (km == KM_I8 && pv == PV_E4M3) return launch_attn<D, KM_I8, PV_E4M3>(tq, tk, tv, p, B, st);
+  return launch_attn<D, KM_K4, PV_E4M3>(tq, tk, tv, p, B, st);
 }
 
 struct AttnArgs {
@@ -963,36 +1296,39 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   LOWBIT_CHECK(a.qk_mode != LOWBIT_QK_Q8KMIX || a.kbits != nullptr, "%s: mixed-width K needs kbits", who);
   LOWBIT_CHECK(a.pv_mode == LOWBIT_PV_F16 || a.pv_mode == LOWBIT_PV_E4M3, "%s: bad pv_mode %d", who, a.pv_mode);
   LOWBIT_CHECK(a.pv_mode != LOWBIT_PV_E4M3 || a.v_scale != nullptr, "%s: the FP8 P.V path needs v_scale", who);
-  const int D = a.D, BN = (D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN;
+  const int D = a.D;
   const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : (a.qk_mode == LOWBIT_QK_Q8KMIX ? KM_MIX : KM_I8);
   const int pv = (a.pv_mode == LOWBIT_PV_E4M3) ? PV_E4M3 : PV_F16;
+  const bool wide = use_wide(D, km, pv, a.flags);
+  const int BN = wide ? 128 : ((D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN);  // keys per step = rows of a K / V box
 
   CUtensorMap tq, tk, tv, tk8, tk2;
   const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   {
     const int64_t dim[4] = {D, a.Nq, a.Hq, a.B}, str[3] = {a.qsn, a.qsh, a.qsb};
-    if (make_map(&tq, a.q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, kBM, swz_qk)) return 1;
+    if (cached_map(&tq, a.q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, kBM, swz_qk)) return 1;
   }
   if (km == KM_I8) {
     const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
-    if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, swz_qk)) return 1;
+    if (cached_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, swz_qk)) return 1;
   } else if (km == KM_K4) {  // packed INT4: rows of D/2 bytes, landed linearly (no swizzle) for the in-kernel expansion
     const int64_t dim[4] = {D / 2, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
-    if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (cached_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   } else {  // mixed width: container rows of D bytes; one map per bit width, the box takes the row prefix in use
     const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
-    if (make_map(&tk8, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-    if (make_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-    if (make_map(&tk2, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 4, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (cached_map(&tk8, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (cached_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 2, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+    if (cached_map(&tk2, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D / 4, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   }
   if (pv == PV_F16) {
     const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.vsn, a.vsh, a.vsb};
-    if (make_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dim, str, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (cached_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dim, str, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   } else {  // e4m3 [b][h][d][pos]: (vsb, vsh, vsn) are the byte strides of (b, h, d); positions contiguous
     const int64_t npad = (a.Nk + 63) / 64 * 64;
     const int64_t dim[4] = {npad, D, a.Hkv, a.B}, str[3] = {a.vsn, a.vsh, a.vsb};
-    if (make_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, BN, D,
-                 BN == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (cached_map(&tv, a.v, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, BN, D,
+                   BN == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (BN == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)))
+      return 1;
   }
   p.q_scale = a.q_scale; p.k_scale = a.k_scale; p.v_scale = a.v_scale; p.v_mean = a.v_mean; p.kbits = a.kbits;
   p.Hq = a.Hq; p.Hkv = a.Hkv; p.Nq = a.Nq; p.Nk = a.Nk;
@@ -1006,6 +1342,10 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   }
   const CUtensorMap* p8 = (km == KM_MIX) ? &tk8 : nullptr;
   const CUtensorMap* p2 = (km == KM_MIX) ? &tk2 : nullptr;
+  if (wide) {
+    if (km == KM_I8) return dispatch_wide<KM_I8>(tq, tk, tv, p, grid_b, pv, st);
+    return dispatch_wide<KM_K4>(tq, tk, tv, p, grid_b, pv, st);
+  }
   if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, grid_b, km, pv, st, p8, p2);
   return dispatch_attn<128>(tq, tk, tv, p, grid_b, km, pv, st, p8, p2);
 }
@@ -1097,3 +1437,4 @@ extern "C" int lowbit_attn_finalize(const float* m, const float* l, const float*
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
+

@@ -232,6 +232,14 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// register hand-over between the warpgroups of a CTA (every warp of the warpgroup executes it; N multiple of 8)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---------------------------------------------------------------- math
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -276,27 +284,4 @@ __device__ __forceinline__ float f16x2_sum(uint32_t v) {
   asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo), "=f"(hi) : "r"(v));
   return lo + hi;
 }
-// exp2 on the FMA/ALU pipes (no MUFU): Cody-Waite range reduction with the 1.5*2^23 magic constant, degree-3
-// minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5), exponent inserted by an integer multiply-add.
-// Valid for x <= 126; x is clamped below at -126.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  const float kMagic = 12582912.0f;
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 mg = make_float2(kMagic, kMagic);
-  const float2 r = __fadd2_rn(x, mg);                          // low mantissa bits = round(x)
-  const float2 t = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
-  const float2 f = __fadd2_rn(x, make_float2(-t.x, -t.y));     // f in [-0.5, 0.5]
-  float2 p = __ffma2_rn(make_float2(0.05517103523015976f, 0.05517103523015976f), f,
-                        make_float2(0.24260984361171722f, 0.24260984361171722f));
-  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = __ffma2_rn(p, f, make_float2(0.9999281764030457f, 0.9999281764030457f));
-  float2 y;
-  y.x = __int_as_float(__float_as_int(r.x) * 0x00800000 + __float_as_int(p.x));
-  y.y = __int_as_float(__float_as_int(r.y) * 0x00800000 + __float_as_int(p.y));
-  return y;
-}
-// exact int32 -> fp32 for |v| < 2^22 without the conversion pipe (IADD + FADD)
-__device__ __forceinline__ float i2f_small(int v) { return __int_as_float(v + 0x4B400000) - 12582912.0f; }
-
 }  // namespace ptx
