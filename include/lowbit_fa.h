@@ -64,7 +64,7 @@ enum {
   LOWBIT_ATTN_CAUSAL = 1,      /* attn_qk_int8_per_block_causal.py:24-79 (requires Nq == Nk)          */
   LOWBIT_ATTN_COMPAT_TAIL = 2, /* reproduce the reference's unmasked tail keys when Nk % 64 != 0
                                   (attn_qk_int8_per_block.py:48-49)                  */
-  LOWBIT_ATTN_NARROW = 4       /* head_dim 64: run the 32-key-step kernel instead of the default 128-key-step one
+  LOWBIT_ATTN_NARROW = 4       /* head_dim 64: run the 32-key-step kernel instead of the default 64-key-step one
                                   (A/B and bit-identity checks against the mixed-width K path, which always
                                   runs 32-key steps); same results within the documented tolerance        */
 };

@@ -28,7 +28,7 @@
 // writes 8- and 2-bit rows in the byte order that makes those expansions land in that layout (quant.cu).
 #include "common.cuh"
 #include "ptx.cuh"
-#include "softmax_wide.cuh"
+#include "softmax_chunk.cuh"
 
 #include <cuda.h>
 #include <limits.h>
@@ -69,8 +69,8 @@ enum { KM_I8 = 0, KM_K4 = 1, KM_MIX = 2 };  // KM_K4 / KM_MIX: K tiles are expan
 enum { PV_F16 = 0, PV_E4M3 = 1 };
 
 // Two kernels share this file:
-//   attn_fwd_wide_kernel  head_dim 64, INT8 / packed-INT4 K, FP16 or FP8 P.V -- 128-key steps (the default there)
-//   attn_fwd_kernel       head_dim 128 (64-key steps), and head_dim 64 with the mixed-width K container (32-key steps)
+//   attn_fwd_n64_kernel   head_dim 64, INT8 / packed-INT4 K, fp16 P.V -- 64-key steps, four CTAs per SM (the default there)
+//   attn_fwd_kernel       head_dim 128 (64-key steps); head_dim 64 with the mixed-width K container or FP8 P.V (32-key steps)
 //
 // Per-head-dim tiling of attn_fwd_kernel.  D=64: 32-key steps keep the register footprint under 96 so that four CTAs
 // (16 softmax warps) share an SM.  D=128 has twice the tensor work per exp2 and runs 64-key steps, two CTAs per SM
@@ -666,7 +666,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < BN; ++c) p.dbg[r * 64 + j * BN + c] = (int)s[c];
         }
       }
-      const int imax = wide::row_max_i<BN, MASKED>(s, lim);
+      const int imax = chunk::row_max_i<BN, MASKED>(s, lim);
       const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
       // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision,
       // tcgen05.ld/st are warp collectives)
@@ -746,77 +746,54 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ================================================================================================================
-// attn_fwd_wide_kernel -- head_dim 64, 128-key steps.
+// attn_fwd_n64_kernel -- head_dim 64, INT8 K, fp16 P.V: 64-key steps at FOUR CTAs per SM.
 //
-// At head_dim 64 the kernel is bound by the softmax, not by the tensor pipe (one exp2 per 128 tensor MACs; MUFU floor
-// 2.7x the tensor floor), and round 1's 32-key steps spent 38 % of the softmax warps' instructions on per-step
-// overhead (barrier waits, TMEM round trips, votes, address arithmetic: 6.5 warp instructions per score of which 4.0
-// are the arithmetic itself).  This kernel cuts that overhead four-fold and takes work off the MUFU pipe:
-//
-//   * one step = 128 keys = four 32-key chunks: a thread (= query row = TMEM lane) streams its scores out of TMEM chunk
-//     by chunk (the tcgen05.ld of chunk c+1 in flight while chunk c is computed: 2 x 32 score registers) and writes P
-//     chunk by chunk into its own TMEM columns (P does not alias S); one barrier round, one vote, one scale lookup
-//     per 128 keys instead of per 32;
-//   * TMEM: S [0,128) int32 | P [128,192) fp16 (or 32 columns e4m3) | O [192,256) fp32 -- 256 columns, two CTAs per SM,
-//     which take turns on the MUFU pipe: while one waits for its next score tile the other computes;
-//   * optimistic maximum (fp16 P.V): after its first block a row keeps its reference maximum and computes P at once; only
-//     when the block's row sum reaches 2^15 (some p could overflow fp16) is the exact block maximum taken and the
-//     block redone from the scores still in TMEM (S is released to QK_{j+1} after that check) -- softmax is
-//     invariant under the choice of the reference maximum, P.V and l accumulate in fp32, and the integer-max pass
-//     (0.5 instruction per score on the ALU pipe, and a second trip through TMEM) disappears from the common path;
-//   * PF of every 8 score pairs take the FMA-pipe exp2 (softmax_wide.cuh) instead of MUFU.EX2;
-//   * warp roles: warps 0-3 softmax, warp 4 helper (one elected lane: TMA producer + tcgen05 issuer; TMEM owner),
-//     warp 5 K expander (packed INT4 K).
+// Keeps what makes attn_fwd_kernel fast at head_dim 64 -- 16 softmax warps per SM, 96 registers, exact lazy maximum --
+// and halves its per-step overhead (barrier round, TMEM round trip, vote, scale lookup, loop control: 2.5 of its 6.5
+// warp instructions per score).  TMEM per CTA stays at 128 columns: S [0,64) single-buffered | O [64,128); P_j (32
+// columns fp16) aliases the UPPER half of S.  A thread streams its row through registers 32 scores at a time:
+//   pass 1  ld S[0,32) -> max;  ld S[32,64) -> max           (the upper chunk stays in registers)
+//   pass 2  exp(upper chunk) -> P[16,32) -> TMEM cols [48,64)  (its own, consumed columns)
+//           ld S[0,32) again; exp -> P[0,16) -> TMEM cols [32,48)
+// so that at most 32 scores + 16 packed P words are live.  With one S buffer, QK_{j+1} follows PV_j on the tensor
+// pipe (same issuing thread: in order) and a CTA waits for its next scores once per step; four resident CTAs cover
+// that.
 // ================================================================================================================
-template <int KM, int PV>
-struct WideSmem {
-  static constexpr int D = 64, BN = 128, VS = 3;
-  static constexpr int kQ = kBM * D;                            // int8
-  static constexpr int kK = BN * D;                             // int8 operand stage
-  static constexpr int kKStages = (KM == KM_I8) ? 3 : 2;
-  static constexpr int kKp = BN * D / 2;                        // packed INT4 staging stage
-  static constexpr int kKpStages = (KM == KM_K4) ? 4 : 0;
-  static constexpr int kV = (PV == PV_F16) ? BN * D * 2 : BN * D;  // fp16 [key][d] / e4m3 [d][key]
-  static constexpr int kBytes = kQ + kKStages * kK + VS * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
+template <int KM>
+struct N64Smem {
+  static constexpr int D = 64, BN = 64, VS = 3;
+  static constexpr int KS = (KM == KM_I8) ? 3 : 2;              // int8 operand stages
+  static constexpr int KPS = (KM == KM_I8) ? KS : 4;            // TMA-filled stages (packed INT4: staging ring)
+  static constexpr int kQ = kBM * D, kK = BN * D, kKp = BN * D / 2, kV = BN * D * 2;
+  static constexpr int kBytes = kQ + KS * kK + VS * kV + (KM == KM_I8 ? 0 : KPS * kKp) + 256 /*barriers*/ + 1024 /*align*/;
 };
-template <int KM> constexpr int wide_threads() { return 128 + 32 + (KM != KM_I8 ? 32 : 0); }
 
-template <int KM, int PV, int PF, bool DBG>
-__global__ void __launch_bounds__(wide_threads<KM>(), 2)
-attn_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+template <int KM, int PF, bool DBG>
+__global__ void __launch_bounds__(160, 4)
+attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   static_assert(KM == KM_I8 || KM == KM_K4, "mixed-width K runs on attn_fwd_kernel");
-  using SM = WideSmem<KM, PV>;
-  using PC = PvCfg<PV>;
-  constexpr int D = 64, BN = 128, VS = 3;
+  using SM = N64Smem<KM>;
+  using PC = PvCfg<PV_F16>;
+  constexpr int D = 64, BN = 64, KS = SM::KS, KPS = SM::KPS, VS = SM::VS;
   constexpr bool KX = (KM != KM_I8);
-  constexpr int KS = SM::kKStages;                           // int8 operand stages
-  constexpr int KPS = KX ? SM::kKpStages : KS;               // TMA-filled K stages
-  constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;    // TMEM columns of one P tile
-  constexpr int PCH = PCOLS / 4;                             // ... of one 32-key chunk
-  constexpr uint32_t kTmemCols = 256, kColP = BN, kColO = BN + 64;
-  __shared__ float s_vs[PV == PV_E4M3 ? D : 1], s_vm[PV == PV_E4M3 ? D : 1];
+  constexpr uint32_t kTmemCols = 128, kColP = 32, kColO = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + SM::kQ;
   uint8_t* sV = sK + KS * SM::kK;
-  uint8_t* sKp = sV + VS * SM::kV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + SM::kKpStages * SM::kKp);
+  uint8_t* sKp = sV + VS * SM::kV;   // packed INT4 staging ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + (KX ? KPS * SM::kKp : 0));
   uint64_t* bar_q = bars + 0;
-  uint64_t* kfull = bars + 1;        // [KPS] TMA -> consumer (issuer, or the expander warp)
-  uint64_t* kfree = kfull + KPS;     // [KPS] consumer -> TMA
+  uint64_t* kfull = bars + 1;        // [KPS]
+  uint64_t* kfree = kfull + KPS;     // [KPS]
   uint64_t* vfull = kfree + KPS;     // [VS]
   uint64_t* vfree = vfull + VS;      // [VS]
-  uint64_t* bar_s = vfree + VS;      // QK_j done: S holds the scores of block j            (phase j)
-  uint64_t* s_free = bar_s + 1;      // 4 softmax warps are done with S_j: QK_{j+1} may overwrite it  (phase j)
-  uint64_t* p_ready = s_free + 1;    // 4 softmax warps wrote P_j                             (phase j)
-  uint64_t* bar_o = p_ready + 1;     // PV_j done: O updated, P may be overwritten            (phase j)
-  uint64_t* bar_final = bar_o + 1;   // last PV done
-  uint64_t* bar_qperm = bar_final + 1;  // expander warp: Q permuted
-  uint64_t* kready = bar_qperm + 1;  // [2] expander warp: operand stage holds the expanded K tile
-  uint64_t* kopfree = kready + 2;    // [2] QK on an operand stage complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kopfree + 2);
+  uint64_t* bar_s = vfree + VS;      // QK_j done                         (phase j)
+  uint64_t* p_ready = bar_s + 1;     // 4 softmax warps wrote P_j         (phase j)
+  uint64_t* bar_final = p_ready + 1; // last PV done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
@@ -829,9 +806,8 @@ attn_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int Nq = tv.Nq, Nk = tv.Nk, nkb = tv.nkb, q_row0 = tv.q_row0, k_row0 = tv.k_row0, tb = tv.tb;
   const int64_t qs_idx = tv.qs_idx, ks_base = tv.ks_base, orow_base = tv.orow_base;
 
-  // keys [0, nk_lim) take part; compat_tail walks the reference's whole 64-key blocks (phantom zero keys)
   const bool compat = (p.flags & LOWBIT_ATTN_COMPAT_TAIL) != 0;
-  const int nk_lim = compat ? nkb * kScaleBlk : Nk;
+  const int nk_lim = compat ? nkb * kScaleBlk : Nk;  // keys [0, nk_lim) take part
   int nblk = (nk_lim + BN - 1) / BN;
   const int dq = p.delta + qt * kBM;  // causal: key c is visible to tile row r iff c <= dq + r
   if (causal) nblk = max(0, min(nblk, (dq + kBM + BN - 1) / BN));
@@ -846,28 +822,15 @@ attn_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   if (tid == 0) {
     ptx::mbar_init(bar_q, 1);
-    for (int i = 0; i < KPS; ++i) {
-      ptx::mbar_init(kfull + i, 1);
-      ptx::mbar_init(kfree + i, KX ? 32 : 1);
-    }
+    for (int i = 0; i < KPS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
     ptx::mbar_init(bar_s, 1);
-    ptx::mbar_init(s_free, 4);
     ptx::mbar_init(p_ready, 4);
-    ptx::mbar_init(bar_o, 1);
     ptx::mbar_init(bar_final, 1);
-    ptx::mbar_init(bar_qperm, 32);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(kready + i, 32); ptx::mbar_init(kopfree + i, 1); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
-  }
-  if constexpr (PV == PV_E4M3) {
-    if (tid < D) {
-      s_vs[tid] = p.v_scale[((int64_t)b * p.Hkv + hkv) * D + tid];
-      s_vm[tid] = p.v_mean ? p.v_mean[((int64_t)b * p.Hkv + hkv) * D + tid] : 0.f;
-    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -875,205 +838,194 @@ attn_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ================================ helper: TMA producer + tcgen05 issuer (one elected lane) ================================
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
-      constexpr uint32_t idesc_pv = (PV == PV_F16) ? ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D)
-                                                   : ptx::make_idesc(ptx::kCF32, ptx::kE4M3, ptx::kE4M3, 0, 0, kBM, D);
-      const uint32_t aq = ptx::smem_u32(sQ);
-      const uint32_t tS = tmem_base, tP = tmem_base + kColP, tO = tmem_base + kColO;
-      auto load_k = [&](int j) {  // int8 tile (swizzled) or packed INT4 tile (linear) into TMA stage j % KPS
-        const int ks = j % KPS;
-        ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
-        if constexpr (KM == KM_I8) {
-          ptx::mbar_expect_tx(kfull + ks, SM::kK);
-          ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
-        } else {
-          ptx::mbar_expect_tx(kfull + ks, SM::kKp);
-          ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
-        }
-      };
-      auto load_v = [&](int j) {
-        const int vs = j % VS;
-        ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
-        ptx::mbar_expect_tx(vfull + vs, SM::kV);
-        if constexpr (PV == PV_F16) ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, k_row0 + j * BN, hkv, tb);
-        else ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, j * BN, 0, hkv, b);  // [d][key] tile
-      };
-      auto issue_qk = [&](int j) {
-        const int ks = j % KS;
-        if constexpr (!KX) {
-          ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
-        } else {
-          ptx::mbar_wait(kready + ks, (j / KS) & 1, 24);  // expanded by the expander warp; its packed stage is free
-          if (j + KPS < nblk) load_k(j + KPS);
-        }
-        ptx::tc_fence_after();
-        const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
+    // ================================ helper warp ================================
+    // one elected lane: TMA producer + tcgen05 issuer.  Packed INT4 K: all 32 lanes also expand the K tiles into the
+    // int8 operand stages, two blocks ahead of their QK (right after QK_{j+1} is issued, K_{j+2} goes into the stage
+    // QK_j read -- complete, since S_j has been consumed).
+    const int lane = tid & 31;
+    auto run = [&](auto whole_warp_tag) {
+      constexpr bool WW = decltype(whole_warp_tag)::value;  // every lane runs this; single-lane work is elected
+    constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
+    constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
+    const uint32_t aq = ptx::smem_u32(sQ);
+    const uint32_t tS = tmem_base, tP = tmem_base + kColP, tO = tmem_base + kColO;
+    auto load_k = [&](int j) {  // lead lane: int8 tile (swizzled) or packed INT4 tile (linear) into TMA stage j % KPS
+      const int ks = j % KPS;
+      ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
+      if constexpr (!KX) {
+        ptx::mbar_expect_tx(kfull + ks, SM::kK);
+        ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
+      } else {
+        ptx::mbar_expect_tx(kfull + ks, SM::kKp);
+        ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
+      }
+    };
+    auto load_v = [&](int j) {
+      const int vs = j % VS;
+      ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
+      ptx::mbar_expect_tx(vfull + vs, SM::kV);
+      ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, k_row0 + j * BN, hkv, tb);
+    };
+    auto expand = [&](int j) {  // whole warp: packed K_j -> operand stage j % KS; frees and refills its staging stage
+      const int kps = j % KPS;
+      ptx::mbar_wait(kfull + kps, (j / KPS) & 1, 34);
+      unpack_k4_tile<D, BN, 32>(sKp + kps * SM::kKp, sK + (j % KS) * SM::kK, lane);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (!WW || ptx::elect_one()) {
+        ptx::mbar_arrive(kfree + kps);
+        if (j + KPS < nblk) load_k(j + KPS);
+      }
+    };
+    auto issue_qk = [&](int j) {  // lead lane
+      const int ks = j % KS;
+      if constexpr (!KX) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+      ptx::tc_fence_after();
+      const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
 #pragma unroll
-        for (int kk = 0; kk < D / 32; ++kk) {  // K-major operands, rows of 64 bytes, 64B swizzle, 8 rows = 512 B (SBO)
-          const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, 8 * D, ptx::kSwz64);
-          const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, 8 * D, ptx::kSwz64);
-          ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
-        }
-        ptx::umma_commit(bar_s);
-        ptx::umma_commit(KX ? kopfree + ks : kfree + ks);
-      };
+      for (int kk = 0; kk < D / 32; ++kk) {  // K-major operands, rows of 64 bytes, 64B swizzle, 8 rows = 512 B (SBO)
+        const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, 8 * D, ptx::kSwz64);
+        const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, 8 * D, ptx::kSwz64);
+        ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+      }
+      ptx::umma_commit(bar_s);
+      if constexpr (!KX) ptx::umma_commit(kfree + ks);
+    };
+    if (!WW || ptx::elect_one()) {
       ptx::mbar_expect_tx(bar_q, SM::kQ);
       ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
       for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
       for (int j = 0; j < min(VS - 1, nblk); ++j) load_v(j);
-      ptx::mbar_wait(KX ? bar_qperm : bar_q, 0, 21);
+    }
+    if constexpr (KX) {
+      __syncwarp();
+      ptx::mbar_wait(bar_q, 0, 33);
+      permute_q_tile<D, 32>(sQ, lane);
+      ptx::fence_proxy_async_smem();
+      expand(0);
+      if (nblk > 1) expand(1);
+      __syncwarp();
+    }
+    if (!WW || ptx::elect_one()) {
+      if constexpr (!KX) ptx::mbar_wait(bar_q, 0, 21);
       issue_qk(0);
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          ptx::mbar_wait(s_free, j & 1, 25);  // the softmax warps are done with S_j
-          issue_qk(j + 1);
-        }
+    }
+    for (int j = 0; j < nblk; ++j) {
+      if (!WW || ptx::elect_one()) {
         const int vs = j % VS;
-        ptx::mbar_wait(p_ready, j & 1, 22);
         ptx::mbar_wait(vfull + vs, (j / VS) & 1, 23);
+        ptx::mbar_wait_spin(p_ready, j & 1, 22);  // latency critical: the next scores wait behind this
         ptx::tc_fence_after();
         const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
-        if constexpr (PV == PV_F16) {
 #pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); one 64-wide d atom
-            const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
-            ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
-          }
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < BN / 32; ++kk) {
-            // V^T tile: K-major (keys contiguous), rows of 128 bytes, 128B swizzle, 8 channel rows = 1024 B (SBO)
-            const uint64_t db = ptx::make_smem_desc(av + kk * 32, 16, 8 * BN, ptx::kSwz128);
-            ptx::umma_f8_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
-          }
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); one 64-wide d atom
+          const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
+          ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
         }
         ptx::umma_commit(vfree + vs);
-        ptx::umma_commit(bar_o);
         if (j == nblk - 1) ptx::umma_commit(bar_final);
-        // refill: the K stage of QK_j (complete: S_j has been consumed) and the V stage of PV_{j-1} (complete: the
-        // softmax warps waited for it before they wrote P_j)
+        if (j + 1 < nblk) issue_qk(j + 1);  // overwrites S / P_j: ordered after PV_j on the tensor pipe
         if constexpr (!KX) {
-          if (j + KPS < nblk) load_k(j + KPS);
+          if (j + KPS < nblk) load_k(j + KPS);  // the stage of QK_j (complete: S_j was consumed)
         }
-        if (j + VS - 1 < nblk) load_v(j + VS - 1);
+        if (j + VS - 1 < nblk) load_v(j + VS - 1);  // the stage of PV_{j-1} (complete: QK_j's commit followed it)
+      }
+      if constexpr (KX) {
+        __syncwarp();
+        if (j + 2 < nblk) expand(j + 2);
+        __syncwarp();
       }
     }
-  } else if (KX && warp == 5) {
-    // ================================ expander warp: packed INT4 K tiles -> int8 operand stages ================================
-    const int et = tid & 31;
-    ptx::mbar_wait(bar_q, 0, 33);
-    permute_q_tile<D, 32>(sQ, et);
-    ptx::fence_proxy_async_smem();
-    ptx::mbar_arrive(bar_qperm);
-    for (int j = 0; j < nblk; ++j) {
-      const int ks = j % KS, kps = j % KPS;
-      if (j >= KS) ptx::mbar_wait(kopfree + ks, ((j / KS) - 1) & 1, 36);  // QK_{j-KS} has read this operand stage
-      ptx::mbar_wait(kfull + kps, (j / KPS) & 1, 34);
-      unpack_k4_tile<D, BN, 32>(sKp + kps * SM::kKp, sK + ks * SM::kK, et);
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(kfree + kps);
-      ptx::mbar_arrive(kready + ks);
-    }
+    };
+    // INT8 K: only the elected lane has work (the other lanes wait at the reconvergence point and cost no issue slots)
+    if constexpr (KX) run(std::true_type{});
+    else if (ptx::elect_one()) run(std::false_type{});
   } else {
     // ================================ softmax warps ================================
     const int lane = tid & 31;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;  // TMEM lane quadrant of this warp
-    const int row = qt * kBM + tid;                         // query row owned by this thread (tid < 128)
-    float qs = p.q_scale[qs_idx];
-    if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
+    const int row = qt * kBM + tid;
+    const float qs = p.q_scale[qs_idx] * (KX ? 0.0625f : 1.f);  // packed INT4 K: the operand holds code*16
     const float* ks_ptr = p.k_scale + ks_base;
     const bool mask_tail = (nk_lim % BN) != 0;
     const int last_kblk = (nk_lim + BN - 1) / BN - 1;
     const uint32_t tSl = tmem_base + lane_off, tPl = tSl + kColP, tOl = tSl + kColO;
     float m_ref = -INFINITY, l = 0.f;
 
-    // one 128-key block; sc_a / sc_b: dequantization factors of its two 64-key scale blocks; columns > lim are masked
-    auto step = [&](auto masked_tag, const int j, const float sc_a, const float sc_b, const int lim) {
+    auto step = [&](auto masked_tag, const int j, const float sc, const int lim) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       ptx::mbar_wait(bar_s, j & 1, 30);
       ptx::tc_fence_after();
-      uint32_t sa[32], sb[32];  // chunk double buffer
-      ptx::tmem_ld_x32(tSl, sa);
-      // exact: take the block maximum first (first block of a row, masked blocks, e4m3 P); otherwise optimistic
-      bool exact = MASKED || (PV == PV_E4M3);
+      uint32_t s[32], pk[16];
+      auto dump = [&](int half) {
+        if constexpr (DBG) {
+          if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) p.dbg[tid * 64 + 32 * half + c] = (int)s[c];
+          }
+        }
+      };
+      // Optimistic step (every unmasked block after a row's first): keep the reference maximum, P at once, two TMEM
+      // loads.  Nothing is stored before the block's row sum has shown that no p reached 2^15 (finite in fp16);
+      // otherwise the exact step below redoes the block from the scores, which are still intact in TMEM.
+      bool exact = MASKED;
       if (!exact) exact = __any_sync(0xffffffffu, m_ref == -INFINITY);
-      float lsum;
-      for (;;) {
-        if (exact) {
-          // pass over the four chunks for the block maximum (chunk 0 is already on its way into sa)
-          ptx::tmem_wait_ld();
-          ptx::tmem_ld_x32(tSl + 32, sb);
-          int ia = wide::row_max_i<32, MASKED>(sa, lim);
-          ptx::tmem_wait_ld();
-          ptx::tmem_ld_x32(tSl + 64, sa);
-          ia = max(ia, wide::row_max_i<32, MASKED>(sb, lim - 32));
-          ptx::tmem_wait_ld();
-          ptx::tmem_ld_x32(tSl + 96, sb);
-          int ib = wide::row_max_i<32, MASKED>(sa, lim - 64);
-          ptx::tmem_wait_ld();
-          ptx::tmem_ld_x32(tSl, sa);  // chunk 0 again, for the exp pass below
-          ib = max(ib, wide::row_max_i<32, MASKED>(sb, lim - 96));
-          const float ma = (MASKED && ia == INT_MIN) ? -INFINITY : (float)ia * sc_a;
-          const float mb = (MASKED && ib == INT_MIN) ? -INFINITY : (float)ib * sc_b;
-          const float mblk = fmaxf(ma, mb);
-          // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision)
-          if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
-            const float m_new = fmaxf(m_ref, mblk);
-            const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
-            l *= alpha;
-            m_ref = m_new;
-            if (j > 0) {
-              ptx::mbar_wait(bar_o, (j - 1) & 1, 31);  // PV_{j-1} has landed in O (phase j-1 or j: unambiguous)
-              ptx::tc_fence_after();
-#pragma unroll
-              for (int c = 0; c < D; c += 16) {
-                uint32_t o[16];
-                ptx::tmem_ld_x16(tOl + c, o);
-                ptx::tmem_wait_ld();  // (also completes the chunk-0 load above)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                ptx::tmem_st_x16(tOl + c, o);
-              }
-            }
-          }
+      if (!exact) {
+        uint32_t ph[16];
+        const float nm = PC::OFF - m_ref;
+        ptx::tmem_ld_x32(tSl + 32, s);
+        ptx::tmem_wait_ld();
+        float lsum = chunk::chunk_f16<false, PF>(s, sc, nm, 0, ph);
+        ptx::tmem_ld_x32(tSl, s);
+        ptx::tmem_wait_ld();
+        lsum += chunk::chunk_f16<false, PF>(s, sc, nm, 0, pk);
+        exact = __any_sync(0xffffffffu, !(lsum < 32768.f));
+        if (!exact) {
+          l += lsum;
+          ptx::tmem_st_x16(tPl + 16, ph);
+          ptx::tmem_st_x16(tPl, pk);
         }
-        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-        lsum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t* cur = (c & 1) ? sb : sa;
-          uint32_t* nxt = (c & 1) ? sa : sb;
-          ptx::tmem_wait_ld();                                          // chunk c has arrived
-          if (c < 3) ptx::tmem_ld_x32(tSl + 32 * (c + 1), nxt);         // chunk c+1 on its way while c is computed
-          uint32_t pk[PCH];
-          const float sc = (c < 2) ? sc_a : sc_b;
-          if constexpr (DBG) {
-            if (p.dbg != nullptr && j == 0 && c < 2 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) p.dbg[tid * 64 + 32 * c + i] = (int)cur[i];
-            }
-          }
-          if constexpr (PV == PV_F16) lsum += wide::chunk_f16<MASKED, PF>(cur, sc, nm, lim - 32 * c, pk);
-          else lsum += softmax_block_e4m3<32, MASKED>(cur, sc, nm, lim - 32 * c, pk);
-          if (c == 0 && j > 0) {  // P_{j-1} has been consumed by PV_{j-1}: its columns may be overwritten
-            ptx::mbar_wait(bar_o, (j - 1) & 1, 37);
-            ptx::tc_fence_after();
-          }
-          tmem_st_n<PCH>(tPl + c * PCH, pk);
-        }
-        if (exact) break;
-        if (!__any_sync(0xffffffffu, !(lsum < 32768.f))) break;  // every p < 2^15: finite in fp16
-        // some score outgrew the row's reference maximum by 2^15: redo the block with the exact maximum
-        ptx::tmem_wait_st();
-        ptx::tmem_ld_x32(tSl, sa);
-        exact = true;
       }
-      ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(s_free);  // S_j is no longer needed: QK_{j+1} may overwrite it
-      l += lsum;
+      if (exact) {
+      // pass 1: block maximum.  lower chunk, then the upper chunk, which stays in registers
+      ptx::tmem_ld_x32(tSl, s);
+      ptx::tmem_wait_ld();
+      dump(0);
+      int imax = chunk::row_max_i<32, MASKED>(s, lim);
+      ptx::tmem_ld_x32(tSl + 32, s);
+      ptx::tmem_wait_ld();
+      dump(1);
+      imax = max(imax, chunk::row_max_i<32, MASKED>(s, lim - 32));
+      const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+      // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision)
+      if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
+        const float m_new = fmaxf(m_ref, mblk);
+        const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
+        l *= alpha;
+        m_ref = m_new;
+        if (j > 0) {
+          // S_j being ready implies PV_{j-1} completed (QK_j follows it on the tensor pipe): O is up to date
+#pragma unroll
+          for (int c = 0; c < D; c += 16) {
+            uint32_t o[16];
+            ptx::tmem_ld_x16(tOl + c, o);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st_x16(tOl + c, o);
+          }
+        }
+      }
+      const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
+      // pass 2: upper chunk (in registers) -> P[16,32) over its own columns; lower chunk re-read -> P[0,16)
+      l += softmax_block_f16<32, MASKED>(s, sc, nm, lim - 32, pk);
+      ptx::tmem_ld_x32(tSl, s);
+      ptx::tmem_st_x16(tPl + 16, pk);
+      ptx::tmem_wait_ld();
+      l += softmax_block_f16<32, MASKED>(s, sc, nm, lim, pk);
+      ptx::tmem_st_x16(tPl, pk);
+      }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       if (lane == 0) ptx::mbar_arrive(p_ready);
@@ -1082,28 +1034,25 @@ attn_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     int n_full = nblk;  // blocks [0, n_full) need no mask
     if (causal) n_full = max(0, min(n_full, (dq + 1) / BN));
     if (mask_tail) n_full = min(n_full, last_kblk);
-    int j = 0;
-    float ka = ks_ptr[0], kb2 = ks_ptr[min(1, nkb - 1)];
-    for (; j < nblk; ++j) {
-      const float sc_a = qs * ka, sc_b = qs * kb2;
-      ka = ks_ptr[min(2 * j + 2, nkb - 1)];  // prefetch for the next block
-      kb2 = ks_ptr[min(2 * j + 3, nkb - 1)];
+    float kcur = ks_ptr[0];
+    for (int j = 0; j < nblk; ++j) {
+      const float sc = qs * kcur;
+      kcur = ks_ptr[min(j + 1, nkb - 1)];  // prefetch for the next block
       if (j < n_full) {
-        step(std::false_type{}, j, sc_a, sc_b, 0);
+        step(std::false_type{}, j, sc, 0);
       } else {
         const int c0 = j * BN;
         int lim = BN;  // columns [0, lim] are live
         if (causal) lim = min(lim, dq + tid - c0);
         if (mask_tail && j == last_kblk) lim = min(lim, nk_lim - 1 - c0);
-        step(std::true_type{}, j, sc_a, sc_b, lim);
+        step(std::true_type{}, j, sc, lim);
       }
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------
     ptx::mbar_wait(bar_final, 0, 32);
     ptx::tc_fence_after();
-    attn_epilogue<D, PV>(p, tOl, l, m_ref, row, Nq, b, hq, orow_base, (PV == PV_E4M3) ? s_vs : nullptr,
-                         (PV == PV_E4M3 && p.v_mean) ? s_vm : nullptr);
+    attn_epilogue<D, PV_F16>(p, tOl, l, m_ref, row, Nq, b, hq, orow_base, nullptr, nullptr);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1220,42 +1169,40 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   return 0;
 }
 
-template <int KM, int PV, int PF, bool DBG = false>
-static int launch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
-                       cudaStream_t st) {
-  auto kern = attn_fwd_wide_kernel<KM, PV, PF, DBG>;
-  using SM = WideSmem<KM, PV>;
-  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-  dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
-  kern<<<grid, wide_threads<KM>(), SM::kBytes, st>>>(tq, tk, tv, p);
-  LOWBIT_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// Development switches (read once): LOWBIT_ATTN_WIDE=0 sends head_dim 64 back to the 32-key-step kernel;
-// LOWBIT_ATTN_PF=n (0..3) sets how many of every 8 score pairs take the FMA-pipe exp2 in the wide kernel.
+// Development switches (read once): LOWBIT_ATTN_N64=0 sends head_dim 64 back to the 32-key-step kernel;
+// LOWBIT_ATTN_PF=n (0..3) sets how many of every 8 score pairs take the FMA-pipe exp2 in the 64-key-step kernel.
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 constexpr int kDefaultPF = 2;
-static bool use_wide(int D, int km, int pv, int flags) {
-  static const int wide = env_int("LOWBIT_ATTN_WIDE", 1);
-  return wide != 0 && !(flags & LOWBIT_ATTN_NARROW) && D == 64 && km != KM_MIX && (pv == PV_F16 || wide >= 2);
-}
 
+template <int KM, int PF, bool DBG = false>
+static int launch_n64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                      cudaStream_t st) {
+  auto kern = attn_fwd_n64_kernel<KM, PF, DBG>;
+  using SM = N64Smem<KM>;
+  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  dim3 grid((p.Nq + kBM - 1) / kBM, p.Hq, B);
+  kern<<<grid, 160, SM::kBytes, st>>>(tq, tk, tv, p);
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
 template <int KM>
-static int dispatch_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
-                         int pv, cudaStream_t st) {
+static int dispatch_n64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                        cudaStream_t st) {
   static const int pf = env_int("LOWBIT_ATTN_PF", kDefaultPF);
-  if (pv == PV_E4M3) return launch_wide<KM, PV_E4M3, 0>(tq, tk, tv, p, B, st);
-  if (KM == KM_I8 && p.dbg != nullptr) return launch_wide<KM_I8, PV_F16, kDefaultPF, true>(tq, tk, tv, p, B, st);
+  if (KM == KM_I8 && p.dbg != nullptr) return launch_n64<KM_I8, kDefaultPF, true>(tq, tk, tv, p, B, st);
   switch (pf) {
-    case 0: return launch_wide<KM, PV_F16, 0>(tq, tk, tv, p, B, st);
-    case 1: return launch_wide<KM, PV_F16, 1>(tq, tk, tv, p, B, st);
-    case 3: return launch_wide<KM, PV_F16, 3>(tq, tk, tv, p, B, st);
-    default: return launch_wide<KM, PV_F16, 2>(tq, tk, tv, p, B, st);
+    case 0: return launch_n64<KM, 0>(tq, tk, tv, p, B, st);
+    case 1: return launch_n64<KM, 1>(tq, tk, tv, p, B, st);
+    case 3: return launch_n64<KM, 3>(tq, tk, tv, p, B, st);
+    default: return launch_n64<KM, 2>(tq, tk, tv, p, B, st);
   }
+}
+static bool use_n64(int D, int km, int pv, int flags) {
+  static const int on = env_int("LOWBIT_ATTN_N64", 1);
+  return on != 0 && !(flags & LOWBIT_ATTN_NARROW) && D == 64 && km != KM_MIX && pv == PV_F16;
 }
 
 template <int D>
@@ -1299,8 +1246,8 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   const int D = a.D;
   const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : (a.qk_mode == LOWBIT_QK_Q8KMIX ? KM_MIX : KM_I8);
   const int pv = (a.pv_mode == LOWBIT_PV_E4M3) ? PV_E4M3 : PV_F16;
-  const bool wide = use_wide(D, km, pv, a.flags);
-  const int BN = wide ? 128 : ((D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN);  // keys per step = rows of a K / V box
+  const bool n64 = use_n64(D, km, pv, a.flags);
+  const int BN = n64 ? 64 : ((D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN);  // keys per step = rows of a K / V box
 
   CUtensorMap tq, tk, tv, tk8, tk2;
   const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -1342,9 +1289,9 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   }
   const CUtensorMap* p8 = (km == KM_MIX) ? &tk8 : nullptr;
   const CUtensorMap* p2 = (km == KM_MIX) ? &tk2 : nullptr;
-  if (wide) {
-    if (km == KM_I8) return dispatch_wide<KM_I8>(tq, tk, tv, p, grid_b, pv, st);
-    return dispatch_wide<KM_K4>(tq, tk, tv, p, grid_b, pv, st);
+  if (n64) {
+    if (km == KM_I8) return dispatch_n64<KM_I8>(tq, tk, tv, p, grid_b, st);
+    return dispatch_n64<KM_K4>(tq, tk, tv, p, grid_b, st);
   }
   if (D == 64) return dispatch_attn<64>(tq, tk, tv, p, grid_b, km, pv, st, p8, p2);
   return dispatch_attn<128>(tq, tk, tv, p, grid_b, km, pv, st, p8, p2);

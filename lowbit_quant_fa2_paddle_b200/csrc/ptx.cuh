@@ -77,6 +77,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   mbar_wait_slow(bar, parity, tag);
 }
 
+// latency-critical waits (the tcgen05 issuer waiting for the softmax warps and vice versa): poll without suspending
+// for a while -- a suspended warp wakes up some hundred clocks after the completing arrive -- then fall back
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, int tag = 0) {
+#pragma unroll 1
+  for (int i = 0; i < 256; ++i)
+    if (mbar_test(bar, parity)) return;
+  mbar_wait(bar, parity, tag);
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -230,14 +239,6 @@ __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
 // named barrier among `nthreads` threads (whole warps); id 0 is __syncthreads
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// register hand-over between the warpgroups of a CTA (every warp of the warpgroup executes it; N multiple of 8)
-template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-}
-template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ---------------------------------------------------------------- math

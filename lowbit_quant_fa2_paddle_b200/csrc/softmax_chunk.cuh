@@ -1,8 +1,8 @@
-// softmax_wide.cuh -- register-level softmax building blocks of the 128-key-step attention kernel (csrc/attn.cu,
-// attn_fwd_wide_kernel) and of the instruction-mix microbenchmark tools/ubench_wide.cu (same code, no TMEM).
+// softmax_chunk.cuh -- register-level softmax building blocks of the head_dim-64 attention kernel (csrc/attn.cu,
+// attn_fwd_n64_kernel) and of the instruction-mix microbenchmark tools/ubench_softmax.cu (same code, no TMEM).
 //
-// One thread owns one query row.  A step hands it 128 int32 scores S (exact QK^T of the int8 codes); a chunk is 32
-// of them:  p = exp2(S * sc + nm)  ->  fp16 pairs (the A operand of the P.V MMA) + fp32 row sum.
+// One thread owns one query row.  A step hands it 64 int32 scores S (exact QK^T of the int8 codes) as two chunks of
+// 32:  p = exp2(S * sc + nm)  ->  fp16 pairs (the A operand of the P.V MMA) + fp32 row sum.
 //
 // exp2 runs on two pipes at once.  MUFU.EX2 does 16 results / clk / SM and is the binding unit at head_dim 64
 // (DESIGN.md 4.2); PF of every 8 score pairs therefore take the FMA pipe instead: Cody-Waite range reduction with
@@ -17,7 +17,7 @@
 #include <stdint.h>
 
 namespace lowbit {
-namespace wide {
+namespace chunk {
 
 __device__ __forceinline__ float ex2_mufu(float x) {
   float y;
@@ -110,5 +110,5 @@ __device__ __forceinline__ int row_max_i(const uint32_t* __restrict__ s, int lim
   return max(max(m4[0], m4[1]), max(m4[2], m4[3]));
 }
 
-}  // namespace wide
+}  // namespace chunk
 }  // namespace lowbit

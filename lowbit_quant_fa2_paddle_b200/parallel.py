@@ -198,13 +198,18 @@ def _exchange(dist, group, send_buf, recv_buf, world, rank):
 
 def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False, sm_scale: Optional[float] = None,
                    smooth_k: bool = True, qk: str = "int4", pv: str = "fp16", zigzag: Optional[bool] = None,
-                   return_lse: bool = False, group=None, backend=None, n_total: Optional[int] = None):
+                   return_lse: bool = False, group=None, backend=None, n_total: Optional[int] = None,
+                   timings: Optional[dict] = None):
     """Sequence-parallel low-bit attention over the ranks of `group` (default: the world).
 
     q, k, v: this rank's shard, [B,H,n_local,D] (HND) or [B,n_local,H,D] (NHD), n_local = N / world, holding the
     rank's chunks back to back in `seq_chunks` order (zig-zag by default for causal).  head_dim 64 or 128.
     Returns o for the local rows (same shape/dtype as q) and, with return_lse, lse [B,Hq,n_local] (natural log,
-    of the smoothed scores' softmax -- the (q . km) correction of core.py:344-350 is added like the API does)."""
+    of the smoothed scores' softmax -- the (q . km) correction of core.py:344-350 is added like the API does).
+    `timings`: a dict that receives this rank's phase times in ms (CUDA events on the compute stream; the call
+    synchronises the device to read them): "k_mean", "quantize", per ring step "compute" (attention kernels of the
+    resident shard) and "p2p_exposed" (what the step waited for the exchange beyond its own compute), "finalize",
+    and "p2p_bytes_per_step" (the flat K/V message one rank sends per step)."""
     import torch.distributed as dist
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
@@ -227,7 +232,7 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
         raise N.LowbitNativeError("ring_attention: tensors must live on a CUDA device (no CPU fallback)")
 
     import os
-    marks = [] if (on_cuda and os.environ.get("LOWBIT_RING_TIMING")) else None  # (label, event) on the compute stream
+    marks = [] if (on_cuda and (timings is not None or os.environ.get("LOWBIT_RING_TIMING"))) else None  # (label, event)
 
     def mark(label):
         if marks is not None:
@@ -282,6 +287,7 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
             for ki, kc in enumerate(src_chunks):
                 if pair_visible(qc, kc, is_causal):
                     states[qi] = be.partial(states[qi], q_packs[qi], bufs[cur], ki, qc.offset, kc.offset, bool(is_causal))
+        mark(f"compute {step}")
         if works is not None:
             if on_cuda:
                 with torch.cuda.stream(comm_stream):
@@ -303,9 +309,24 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
     mark("finalize")
     if marks is not None:
         torch.cuda.synchronize(q.device)
-        if rank == 0:
-            print("ring timing (ms): " + ", ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.3f}" for a, b in zip(marks, marks[1:])),
-                  flush=True)
+        spans = [(b_[0], a_[1].elapsed_time(b_[1])) for a_, b_ in zip(marks, marks[1:])]
+        if timings is not None:
+            timings.clear()
+            timings.update({"k_mean": 0.0, "quantize": 0.0, "compute": [], "p2p_exposed": [], "finalize": 0.0,
+                            "p2p_bytes_per_step": int(msg.nbytes), "steps": world})
+            for label, ms in spans:
+                if label.startswith("k mean"):
+                    timings["k_mean"] = ms
+                elif label.startswith("quantize"):
+                    timings["quantize"] = ms
+                elif label.startswith("compute"):
+                    timings["compute"].append(ms)
+                elif label.startswith("step"):
+                    timings["p2p_exposed"].append(ms)
+                elif label == "finalize":
+                    timings["finalize"] = ms
+        if rank == 0 and os.environ.get("LOWBIT_RING_TIMING"):
+            print("ring timing (ms): " + ", ".join(f"{lb} {ms:.3f}" for lb, ms in spans), flush=True)
     if not return_lse:
         return o
     lse2 = lses[0] if len(lses) == 1 else torch.cat(lses, dim=2)

@@ -909,7 +909,7 @@ def test_mixed_k_attention_identical_to_int8_path(L, cuda_dev, layout, hq, hkv, 
     # the mixed-width path runs 32-key steps: compare with the same kernel family (narrow=True)
     o_i8, lse_i8 = fn(qc, k_unp, v, qs, ks, tensor_layout=layout, return_lse=True, narrow=True, **kw)
     assert torch.equal(o_mix, o_i8) and torch.equal(lse_mix, lse_i8)
-    if d == 64:  # the default 128-key-step kernel: same softmax, different reference maxima / exp2 pipe
+    if d == 64:  # the default 64-key-step kernel: same softmax, different reference maxima / exp2 pipe
         o_w, lse_w = fn(qc, k_unp, v, qs, ks, tensor_layout=layout, return_lse=True, **kw)
         assert (o_w.float() - o_i8.float()).abs().max().item() <= (2e-3 if pv == "fp16" else 5e-2)
         assert (lse_w - lse_i8).abs().max().item() <= (1e-3 if pv == "fp16" else 3e-2)
@@ -935,13 +935,11 @@ def test_dynamic_k_api_vs_oracle_and_sdpa(L, cuda_dev, d, causal, pv):
 
 
 # ------------------------------------------------------------------------------------------------ kernel selection
-@pytest.mark.parametrize("env", [{"LOWBIT_ATTN_WIDE": "0"}, {"LOWBIT_ATTN_WIDE": "2"}, {"LOWBIT_ATTN_PF": "0"},
-                                 {"LOWBIT_ATTN_PF": "3"}])
+@pytest.mark.parametrize("env", [{"LOWBIT_ATTN_N64": "0"}, {"LOWBIT_ATTN_PF": "0"}, {"LOWBIT_ATTN_PF": "3"}])
 def test_attention_suite_under_every_kernel_selection(cuda_dev, env):
-    """head_dim 64 has two kernels and the 128-key-step one has a tunable share of FMA-pipe exp2: LOWBIT_ATTN_WIDE=0
-    (32-key steps everywhere), =2 (128-key steps for the FP8 P.V path too), LOWBIT_ATTN_PF=0 / 3 (none / 3 of 8 score
-    pairs off the MUFU pipe).  The switches are read once per process, so the attention tests are re-run in a child
-    process under each setting."""
+    """head_dim 64 has two kernels and the 64-key-step one has a tunable share of FMA-pipe exp2: LOWBIT_ATTN_N64=0
+    (32-key steps everywhere), LOWBIT_ATTN_PF=0 / 3 (none / 3 of every 8 score pairs off the MUFU pipe).  The switches
+    are read once per process, so the attention tests are re-run in a child process under each setting."""
     import os
     import subprocess
     import sys

@@ -25,6 +25,7 @@ def main():
         ("HND", False, "int8", "fp16", 64, 1, 4, 4, 2048),
         ("NHD", True, "int4", "fp16", 64, 2, 4, 2, 4096),
         ("HND", True, "int4", "fp8", 128, 1, 4, 4, 4096),
+        ("NHD", False, "int8", "fp8", 64, 1, 4, 2, 4096),
         ("HND", True, "int4", "fp16", 128, 1, 8, 8, 16384),
         ("HND", True, "mixed", "fp16", 128, 1, 4, 4, 8192),   # dynamic INT8/INT4/INT2 K blocks
     ]
@@ -55,14 +56,45 @@ def main():
         o_loc, lse_loc = take(o_ref), torch.cat([lse_ref[:, :, c.offset:c.offset + c.length] for c in chunks], dim=2)
         err = (o.float() - o_loc.float()).abs().max()
         lerr = (lse - lse_loc).abs().max()
-        stats = torch.stack([err, lerr])
+        # accuracy against exact attention (fp32 SDPA on the full tensors), ring and single pass side by side
+        hd = 1 if layout == "HND" else 2
+        to_h = (lambda x: x) if layout == "HND" else (lambda x: x.permute(0, 2, 1, 3))
+        kf, vf = to_h(k).float(), to_h(v).float()
+        if hq != hkv:
+            kf, vf = kf.repeat_interleave(hq // hkv, dim=1), vf.repeat_interleave(hq // hkv, dim=1)
+        sd = torch.nn.functional.scaled_dot_product_attention(to_h(q).float(), kf, vf, is_causal=causal)
+        sd = sd if layout == "HND" else sd.permute(0, 2, 1, 3)
+        sd_loc = take(sd.contiguous())
+        e_ring = (o.float() - sd_loc).abs()
+        e_one = (o_loc.float() - sd_loc).abs()
+        dots = torch.stack([(o.float() * sd_loc).sum(), (o.float() ** 2).sum(), (sd_loc ** 2).sum()]).double()
+        dist.all_reduce(dots)
+        cos = float(dots[0] / (dots[1].sqrt() * dots[2].sqrt()))
+        # rows that see fewer than 64 keys (the head of a causal sequence) carry un-averaged e4m3 rounding of P
+        # (2^-4 relative per element): report them apart from the bulk
+        pos = torch.cat([torch.arange(c.offset, c.offset + c.length, device=dev) for c in chunks])
+        few = (pos < 64) if causal else torch.zeros_like(pos, dtype=torch.bool)
+        few_b = few.view(1, 1, -1, 1) if layout == "HND" else few.view(1, -1, 1, 1)
+        zero = torch.zeros((), device=dev)
+        d_bulk = torch.where(few_b, zero, (o.float() - o_loc.float()).abs()).max()
+        stats = torch.stack([err, lerr, e_ring.max(), e_one.max(), d_bulk, e_ring.mean(), e_one.mean()])
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        tol = 4e-3 if pv == "fp16" else 0.125 * float(v.abs().max())
-        good = bool(stats[0] <= tol) and bool(stats[1] <= (1e-2 if pv == "fp16" else 5e-2))
+        if pv == "fp16":
+            good = bool(stats[0] <= 4e-3) and bool(stats[1] <= 1e-2) and cos >= 0.999
+        else:
+            # FP8 P.V: the ring rounds P~ to e4m3 against per-shard reference maxima, a single pass against one running
+            # maximum -- two different (equally valid) roundings of the same softmax, 2^-4 relative per element.  The bar
+            # is therefore accuracy against exact attention: cos-sim >= 0.999, the ring no worse than the single pass
+            # (max error within 1.25x, mean error within 1.1x), and the two within 0.05 of each other away from the
+            # first 64 causal rows.
+            good = (cos >= 0.999 and bool(stats[2] <= 1.25 * stats[3] + 1e-3) and bool(stats[5] <= 1.1 * stats[6] + 1e-4)
+                    and bool(stats[4] <= 0.05) and bool(stats[1] <= 5e-2))
         ok = ok and good
         if rank == 0:
             print(f"ring world={world} {layout} causal={causal} qk={qk} pv={pv} d={d} n={n}: max|o-o1|={float(stats[0]):.3e} "
-                  f"max|lse-lse1|={float(stats[1]):.3e} {'OK' if good else 'MISMATCH'}", flush=True)
+                  f"(rows>=64: {float(stats[4]):.3e}) max|lse-lse1|={float(stats[1]):.3e} | vs fp32 SDPA: cos={cos:.6f} "
+                  f"max err ring {float(stats[2]):.3e} / single {float(stats[3]):.3e}, mean err ring {float(stats[5]):.3e} / "
+                  f"single {float(stats[6]):.3e} {'OK' if good else 'MISMATCH'}", flush=True)
     # head sharding: each rank computes its head slice; gathered result == single-GPU result, bit for bit
     torch.manual_seed(9)
     b, n, h, d = 2, 1200, 8 * world, 64

@@ -47,5 +47,5 @@ for spec in (sys.argv[1:] or ["c2", "c2c", "d128", "d128c8k"]):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     ops = 4 * b * h * n * n * d / (2 if causal else 1)
-    print(f"{name}:{mode}: {ms:.3f} ms  {ops / ms / 1e9:.1f} TOPS  (WIDE={os.environ.get('LOWBIT_ATTN_WIDE', '1')} PF={os.environ.get('LOWBIT_ATTN_PF', 'default')})",
+    print(f"{name}:{mode}: {ms:.3f} ms  {ops / ms / 1e9:.1f} TOPS  (N64={os.environ.get('LOWBIT_ATTN_N64', '1')} PF={os.environ.get('LOWBIT_ATTN_PF', 'default')})",
           flush=True)

@@ -1,16 +1,18 @@
-// ubench_wide.cu -- instruction-mix microbenchmark of the 128-key softmax step of csrc/attn.cu (attn_fwd_wide_kernel):
-// the SAME device functions (csrc/softmax_wide.cuh), no TMEM / barriers, 8 softmax warps per SM like the kernel
+// ubench_softmax.cu -- instruction-mix microbenchmark of the softmax step of csrc/attn.cu (attn_fwd_n64_kernel): the
+// SAME device functions (csrc/softmax_chunk.cuh), no TMEM / barriers, 128 scores per iteration, 8 warps per SM
 // (2 CTAs of 128 threads, shared memory sized so that exactly two fit).  Development aid, not part of the library.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_wide tools/ubench_wide.cu
+// It gives the ceiling the instruction mix alone allows (profiles/r2_ubench_softmax.log): exact maximum + all MUFU
+// 13.9 exp2/clk/SM, optimistic maximum 15.5, optimistic + 1/8 on the FMA pipe 15.9 (MUFU alone: 16).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_softmax tools/ubench_softmax.cu
 // Prints exp2 results per clock per SM (peak of the MUFU pipe alone: 16).
 #include <cuda_runtime.h>
 #include <climits>
 #include <cstdint>
 #include <cstdio>
 
-#include "../lowbit_quant_fa2_paddle_b200/csrc/softmax_wide.cuh"
+#include "../lowbit_quant_fa2_paddle_b200/csrc/softmax_chunk.cuh"
 
-using namespace lowbit::wide;
+using namespace lowbit::chunk;
 
 // EXACT = 1: integer row max over the 128 scores first (the first / masked step of a row)
 // EXACT = 0: optimistic step (stale maximum, overflow check on the row sum)
