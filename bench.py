@@ -1,26 +1,41 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the low-bit attention hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch: K mean -> per-block INT8 quantize of Q and K (K smoothing
-fused) -> fused INT8-QK / FP16-PV attention, i.e. one call of lowbit_fa_qk_int8_pv_fp16_triton.
-Workload at N=1: BASELINE config 2 (B4 H32 N4096 D64 HND non-causal, randn fp16, seed 0).
-metric = attention TOPS = 4*B*H*Nq*Nk*D / latency (utils/benchmark.py:212-214 of the reference).
+metric = attention TOPS = 4*B*H*Nq*Nk*D / latency (/2 causal), utils/benchmark.py:212-214 of the reference.
+One "step" = one pass of the hot path over one batch: K mean -> per-block quantize of Q and K (K smoothing fused) ->
+fused low-bit attention, i.e. one call of the operator the workload names.
 
+Default workloads (what the driver runs):
+  N = 1   BASELINE config 2: INT8 QK + FP16 PV, HND, B4 H32 N4096 D64 non-causal (lowbit_fa_qk_int8_pv_fp16_triton);
+          the other single-GPU configs ride along as `other_configs` (one short timing each).
+  N > 1   BASELINE config 4, the north_star's head-sharded partition: q_int8 / k_int4, NHD, CogVideoX-5B shape B2 H48
+          N17776 D64, kv heads split over the ranks, NO collective on the data path, "scaling": "strong"
+          (value = ops of the whole workload / max-over-ranks step time); `strong_scaling.single_gpu` is the same
+          workload on ONE GPU measured in the same run (rank 0), so that the speed-up is self-contained.
+          `ring` carries BASELINE config 5 (B1 H32 N128K D128 causal, sequence-parallel NCCL P2P ring of quantized
+          K/V; INT4 K and dynamic INT4/INT2 K) with per-phase times and the bytes one rank sends per step.
+
+Keys of the JSON line:
   value          whole hot path (quantize + attention), inputs resident in HBM, CUDA events, max over ranks
   attn_only      the attention kernel alone (how the reference's published numbers are measured)
   e2e            the same operator from HOST pinned buffers through lowbit_fa_host: H2D of q,k,v + hot path + D2H of o
-                 inside the timed region, pipelined over (batch, head-group) chunks; serial_ms = the unpipelined time
-  roofline       dominant kernel (attention): algorithmic FLOP per launch / its mean CUDA-event duration inside the
-                 timed steps, against the measured dense bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline   oracle port of the reference's pure-Paddle quantize-and-attend math on the host cores, bounded sample
-N > 1: every rank runs the same workload on its own GPU (batch x head units are independent: no collective);
-value = units of all ranks / max-over-ranks time; "scaling": "weak".
+                 inside the timed region, pipelined over (batch, head-group) chunks; `h2d_gbs_per_rank` = every rank's
+                 plain pinned-host -> device copy rate with all ranks copying at once (what bounds e2e at N > 1)
+  roofline       dominant kernel (attention): algorithmic op per launch / its mean CUDA-event duration inside the timed
+                 steps.  `frac` is against the measured dense bf16 peak (MEASURED_PEAKS.json, the contract's number);
+                 `t_min` is SURVEY 8d's bound with every term measured: max(QK ops / INT8 peak + PV ops / FP16|FP8 peak,
+                 exp2 count / MUFU rate at the sampled SM clock, algorithmic bytes / HBM peak), `bound` names the binding
+                 term and `frac_of_t_min` = t_min / measured time.  `traffic` comes from the committed `ncu --set full`
+                 capture of the same kernel and shape (profiles/), not from this run.
+  cpu_baseline   oracle port of the reference's pure-Paddle quantize-and-attend math on the host cores (N = 1 only)
+  reference_gpu  the reference's own Triton kernels JIT-compiled for this GPU (staged under oracle/_ref), N = 1 only
 
---impl reference: the reference's CPU path (oracle port; Paddle/Triton cannot run the reference on this box's
-CPU other than through the interpreter) on a bounded sample with all host threads.
+--impl reference: the reference's CPU path (oracle port of its pure-Paddle math; Paddle is not installed and its Triton
+kernels have no CPU path other than the interpreter) with all host threads, on the same config as our arm at that N,
+each step a bounded sample of (batch, head) units scaled to the workload (`cpu_baseline.sample` says which).
 """
 import argparse
 import json
@@ -34,33 +49,54 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (B, Hq, Hkv, N, D, layout, causal, description)        -- INT8 QK + FP16 PV, every rank the same work (weak)
-    "c2": (4, 32, 32, 4096, 64, "HND", False, "BASELINE config 2: INT8 QK + FP16 PV, HND, B4 H32 N4096 D64 non-causal"),
-    "c2c": (4, 32, 32, 4096, 64, "HND", True, "config 2 shape, causal"),
-    "c3_8k": (4, 32, 32, 8192, 128, "HND", True, "config 3 shape (D128 causal 8K), INT8 QK + FP16 PV"),
-    "c4": (2, 48, 48, 17776, 64, "NHD", False, "config 4 shape: CogVideoX-5B B2 H48 N17776 D64 NHD"),
-}
-# the other BASELINE configs: (B, Hq, Hkv, N, D, layout, causal, qk, pv, partition, description)
+# name: B, Hq, Hkv, N, D, layout, causal, qk, pv, partition, description
 #   partition "replicate": every rank the whole workload (weak); "heads": kv-head slices, no collective (strong);
 #   "ring": sequence-parallel NCCL P2P ring of quantized K/V (strong)
-EXTRA = {
+WL = {
+    "c2": (4, 32, 32, 4096, 64, "HND", False, "int8", "fp16", "replicate", "BASELINE config 2: INT8 QK + FP16 PV, HND, B4 H32 N4096 D64 non-causal"),
+    "c2c": (4, 32, 32, 4096, 64, "HND", True, "int8", "fp16", "replicate", "config 2 shape, causal"),
+    "c3_8k": (4, 32, 32, 8192, 128, "HND", True, "int8", "fp16", "replicate", "config 3 shape (D128 causal 8K), INT8 QK + FP16 PV"),
     "c3q_8k": (4, 32, 32, 8192, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B4 H32 D128 causal N=8K"),
     "c3q_16k": (2, 32, 32, 16384, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B2 H32 D128 causal N=16K"),
     "c3q_32k": (1, 32, 32, 32768, 128, "HND", True, "int4", "fp8", "replicate", "BASELINE config 3: INT4 QK + FP8 PV, HND, B1 H32 D128 causal N=32K"),
+    "c4": (2, 48, 48, 17776, 64, "NHD", False, "int8", "fp16", "replicate", "config 4 shape, INT8 QK: CogVideoX-5B B2 H48 N17776 D64 NHD"),
     "c4s": (2, 48, 48, 17776, 64, "NHD", False, "q8k4", "fp16", "heads", "BASELINE config 4: q_int8/k_int4, NHD, CogVideoX-5B B2 H48 N17776 D64, head-sharded"),
     "c5": (1, 32, 32, 131072, 128, "HND", True, "int4", "fp16", "ring", "BASELINE config 5 (INT4 K): B1 H32 N128K D128 causal, sequence-parallel ring of quantized K/V"),
     "c5dyn": (1, 32, 32, 131072, 128, "HND", True, "mixed", "fp16", "ring", "BASELINE config 5: dynamic INT4/INT2 K bit allocation (per 64-key block), B1 H32 N128K D128 causal, sequence-parallel ring of quantized K/V"),
     "c5f8": (1, 32, 32, 131072, 128, "HND", True, "int4", "fp8", "ring", "BASELINE config 5 (INT4 K, FP8 V): B1 H32 N128K D128 causal, sequence-parallel ring"),
 }
 BASELINE_MD_TOPS = 199.5  # INT8 non-causal B4 H32 D64 N=4096, attention kernel only, hardware unstated
+METRIC = "attention TOPS (4*B*H*N^2*D / latency), quantize + attention"
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2_attn_c2_ncu_summary.json")
+
+
+# ------------------------------------------------------------------------------------------------ peaks and bounds
+def peaks():
+    """Measured denominators: MEASURED_PEAKS.json (driver: HBM copy, bf16 GEMM) and profiles/peaks_int8_fp8.json
+    (tools/measure_peaks.py on this pool's B200: INT8 / FP8 / FP16 library GEMMs, the same recipe)."""
+    p = {"bf16": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "int8": 4500.0, "fp8": 4500.0,
+         "fp16": 2250.0, "lowbit_source": "nominal dense (B200_PROFILING.md table)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update(bf16=float(m["bf16_tflops"]), hbm_gbs=float(m["hbm_gbs"]), source="measured (MEASURED_PEAKS.json bf16 burst)")
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "peaks_int8_fp8.json")) as f:
+            m = json.load(f)
+        p.update(int8=float(m["int8"]["burst_tops"]), fp8=float(m["fp8_e4m3"]["burst_tops"]), fp16=float(m["fp16"]["burst_tops"]),
+                 lowbit_source="measured (profiles/peaks_int8_fp8.json: cuBLASLt s8, e4m3 and fp16 GEMM 8192^3, burst)")
+    except Exception:
+        pass
+    return p
 
 
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the attention launch at C2 from the committed `ncu --set full`
-    summary (profiles/r1_attn_c2_ncu_summary.json, latest kernel version listed there)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the attention launch at config 2 from the committed
+    `ncu --set full` summary (latest kernel version listed there)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_attn_c2_ncu_summary.json")) as f:
+        with open(NCU_SUMMARY) as f:
             last = list(json.load(f).values())[-1]
         mb = lambda s: float(s.split()[0]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3}[s.split()[1]]
         return mb(last["dram__bytes_read.sum"]) + mb(last["dram__bytes_write.sum"])
@@ -68,24 +104,38 @@ def ncu_traffic_bytes():
         return None
 
 
-def mufu_bound(B, Hq, N, causal, attn_ms, sm_mhz, sms=148):
-    """exp2 evaluations per attention launch against the XU pipe's 16 MUFU.EX2 per clock per SM at the SM clock sampled
-    during the run (1965 MHz when the sample is missing)."""
-    exps = float(B) * Hq * N * N / (2 if causal else 1)
-    rate = sms * 16 * (sm_mhz or 1965) * 1e6
-    floor_ms = exps / rate * 1e3
-    return {"exp2_per_launch": exps, "peak_exp2_per_s": rate, "floor_ms": floor_ms, "frac": floor_ms / attn_ms}
+def roofline(kernel, B, Hq, Hkv, N, D, causal, qk, pv, attn_ms, sm_mhz, traffic=None, sms=148):
+    """The contract's roofline object plus SURVEY 8d's t_min with measured denominators."""
+    pk = peaks()
+    div = 2.0 if causal else 1.0
+    ops = 4.0 * B * Hq * N * N * D / div
+    exps = float(B) * Hq * N * N / div
+    kbytes = {"int8": 1.0, "int4": 0.5, "q8k4": 0.5, "mixed": 0.75}[qk]
+    vbytes = 2.0 if pv == "fp16" else 1.0
+    # algorithmic bytes of the attention launch: Q codes + K codes + V in, O out (scales are noise)
+    abytes = B * N * D * (Hq * 1.0 + Hkv * kbytes + Hkv * vbytes + Hq * 2.0)
+    t_tensor = (ops / 2) / (pk["int8"] * 1e12) + (ops / 2) / ((pk["fp16"] if pv == "fp16" else pk["fp8"]) * 1e12)
+    mufu_rate = sms * 16 * (sm_mhz or 1965) * 1e6
+    t_mufu = exps / mufu_rate
+    t_hbm = abytes / (pk["hbm_gbs"] * 1e9)
+    terms = {"tensor": t_tensor, "mufu": t_mufu, "hbm": t_hbm}
+    bound = max(terms, key=terms.get)
+    t_min = terms[bound]
+    achieved = ops / (attn_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16"], "traffic": traffic,
+            "traffic_source": (os.path.relpath(NCU_SUMMARY, ROOT) + " (ncu --set full capture of the same kernel and shape, not measured in this run)") if traffic else None,
+            "peak_source": pk["source"], "algorithmic_op_per_launch": ops, "algorithmic_bytes_per_launch": abytes,
+            "ms_per_launch": attn_ms,
+            "t_min": {"ms": t_min * 1e3, "binding": bound, "frac_of_t_min": t_min * 1e3 / attn_ms,
+                      "tensor_ms": t_tensor * 1e3, "mufu_ms": t_mufu * 1e3, "hbm_ms": t_hbm * 1e3,
+                      "int8_peak_tops": pk["int8"], "pv_peak_tops": pk["fp16"] if pv == "fp16" else pk["fp8"],
+                      "mufu_exp2_per_s": mufu_rate, "sm_mhz_used": sm_mhz or 1965, "hbm_gbs": pk["hbm_gbs"],
+                      "peaks_source": pk["lowbit_source"],
+                      "note": "a kernel that takes exp2 off the MUFU pipe (2 of 8 score pairs here) can beat mufu_ms"}}
 
 
-def peaks():
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            p = json.load(f)
-        return float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json bf16 burst)"
-    except Exception:
-        return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
-
-
+# ------------------------------------------------------------------------------------------------ plumbing
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML during the timed region."""
 
@@ -123,7 +173,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def summary(self):
         s = sorted(self.samples)
@@ -133,8 +183,7 @@ class ClockSampler(threading.Thread):
 
 def bind_near_gpu(index):
     """Pin this process to the CPU cores NVML reports as local to GPU `index` (same NUMA node / PCIe root), BEFORE the
-    pinned host buffers of the e2e leg are allocated, so that first-touch places them next to the GPU.  Without it the
-    H2D rate of the e2e leg varies 2x from run to run on the multi-socket GPU boxes."""
+    pinned host buffers of the e2e leg are allocated, so that first-touch places them next to the GPU."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -143,15 +192,20 @@ def bind_near_gpu(index):
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
         cpus &= set(os.sched_getaffinity(0))
+        numa = None
+        try:
+            numa = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            pass
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return len(cpus)
+            return {"cpus": len(cpus), "numa_node": numa}
     except Exception:
         pass
     return None
 
 
-def dist_setup(ngpus):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,149 +217,471 @@ def dist_setup(ngpus):
     return rank, world, local
 
 
-def cpu_baseline_run(wl, sample_heads=32, reps=1, causal=None):
-    """Time the oracle port (reference pure-Paddle math restated on torch-CPU) on (1 batch x sample_heads heads)
-    of the workload with all host threads.  Returns (tops, cores, sample description, seconds)."""
-    from oracle import attention as OA
-    B, Hq, Hkv, N, D, layout, caus, _ = WORKLOADS[wl]
-    causal = caus if causal is None else causal
-    torch.set_num_threads(os.cpu_count() or 1)
-    cores = torch.get_num_threads()
-    g = torch.Generator().manual_seed(0)
-    shp = (1, sample_heads, N, D) if layout == "HND" else (1, N, sample_heads, D)
-    q, k, v = (torch.randn(shp, generator=g).half() for _ in range(3))
-    OA.cpu_quantize_and_attend(q[:, :1] if layout == "HND" else q[:, :, :1], k[:, :1] if layout == "HND" else k[:, :, :1],
-                               v[:, :1] if layout == "HND" else v[:, :, :1], layout, causal)  # warm
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        for h0 in range(0, sample_heads, 4):  # 4 heads at a time bounds the fp32 score matrix to ~1 GiB
-            sl = (slice(None), slice(h0, h0 + 4)) if layout == "HND" else (slice(None), slice(None), slice(h0, h0 + 4))
-            OA.cpu_quantize_and_attend(q[sl], k[sl], v[sl], layout, causal)
-    dt = (time.perf_counter() - t0) / reps
-    ops = 4.0 * sample_heads * N * N * D / (2 if causal else 1)
-    return ops / dt / 1e12, cores, f"1 batch x {sample_heads} heads of {wl} (N={N}, D={D}), fp32 math, {reps} rep(s)", dt
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    wl = args.workload
-    B, Hq, Hkv, N, D, layout, causal, desc = WORKLOADS[wl]
-    heads = 32 if N <= 4096 else (8 if N <= 8192 else 4)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_baseline_run(wl, sample_heads=4)
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 5))):
-        tops, cores, sample, dt = cpu_baseline_run(wl, sample_heads=heads)
-        vals.append((tops, dt))
-        if time.perf_counter() - t0 > 120:
-            break
-    tops = sum(v[0] for v in vals) / len(vals)
-    ms = sum(v[1] for v in vals) / len(vals) * 1e3
-    line = {
-        "impl": "reference", "metric": "attention TOPS (4*B*H*N^2*D / latency), quantize + attention", "value": tops,
-        "unit": "TOPS", "n_gpus": args.gpus, "steps": len(vals), "warmup": 1, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 QK / fp16 PV (fp32 on CPU)",
-        "data": "synthetic randn fp16 seed 0",
-        "config": {"workload": desc, "sample": sample},
-        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
-
-
-
-def run_extra(args):
-    """BASELINE configs 3-5 (not the driver's default line): same metric, API-level step, CUDA events, max over ranks."""
-    rank, world, local = dist_setup(args.gpus)
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    import lowbit_quant_fa2_paddle_b200 as L
-    from lowbit_quant_fa2_paddle_b200 import parallel as P
-    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = EXTRA[args.workload]
-    W, K = max(args.warmup, 3), args.steps
-    torch.manual_seed(0)
-    seq = 2 if layout == "HND" else 1
-    shp = lambda h, n=N: (B, h, n, D) if layout == "HND" else (B, n, h, D)
-    ops_total = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
-    if qk == "mixed":
-        fn = L.lowbit_fa_q_int8_k_dynamic
-    elif pv == "fp8":
-        fn = L.lowbit_fa_qk_int4_pv_fp8 if qk != "int8" else L.lowbit_fa_qk_int8_pv_fp8_cuda
-    else:
-        fn = {"int8": L.lowbit_fa_qk_int8_pv_fp16_triton, "int4": L.lowbit_fa_qk_int4_pv_fp16_triton,
-              "q8k4": L.lowbit_fa_q_int8_k_int4_pv_fp16}[qk]
-
-    def dyn(k):
-        """dynamic-K workloads: every other 64-key block at 0.2x magnitude, so that the block statistic
-        max|k|/127 puts it in the INT2 class (<= 0.0125) and the rest in the INT4 class (randn: ~0.035)"""
-        if qk != "mixed":
-            return k
-        n = k.shape[seq]
-        w = torch.where((torch.arange(n, device=dev) // 64) % 2 == 1, 0.2, 1.0).to(k.dtype)
-        return k * (w.view(1, 1, n, 1) if layout == "HND" else w.view(1, n, 1, 1))
-    if part == "ring" and world > 1:
-        n_loc = N // world
-        q, k, v = (torch.randn(shp(h, n_loc), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
-        k = dyn(k)
-        step = lambda: P.ring_attention(q, k, v, tensor_layout=layout, is_causal=causal,
-                                        qk=qk if qk in ("int8", "mixed") else "int4", pv=pv)
-        scaling, units = "strong", ops_total
-    elif part == "heads" and world > 1:
-        q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
-        step = lambda: P.lowbit_fa_head_sharded(q, k, v, fn, world, rank, tensor_layout=layout, is_causal=causal)
-        scaling, units = "strong", ops_total
-    else:
-        q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
-        k = dyn(k)
-        step = lambda: fn(q, k, v, tensor_layout=layout, is_causal=causal)
-        scaling, units = ("strong", ops_total) if part != "replicate" else ("weak", ops_total * world)
-    stream = torch.cuda.current_stream(dev)
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(W):
-        step()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        step()
-    e1.record(stream)
-    barrier()
-    sampler.stop_flag = True
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / K
-    if rank == 0:
-        peak_tf, _, peak_src = peaks()
-        value = units / (ms * 1e-3) / 1e12
-        per_gpu = value / world
-        line = {"metric": "attention TOPS (4*B*H*N^2*D / latency), quantize + attention", "value": value, "unit": "TOPS",
-                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
-                "vs_baseline": None, "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)",
-                "data": "synthetic randn fp16 seed 0" + ("; every other 64-key block of K at 0.2x (INT2 class)" if qk == "mixed" else ""),
-                "config": {"workload": desc, "partition": part, "l2": "inputs larger than the 126 MB L2, no flush"},
-                "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel (whole step timed: quantize + attention"
-                             + (" + ring exchange" if part == "ring" else "") + ")", "achieved": per_gpu, "peak": peak_tf,
-                             "unit": "TFLOP/s", "frac": per_gpu / peak_tf, "traffic": None, "peak_source": peak_src},
-                "clocks": sampler.summary(), "gpu_launches": None}
-        print(json.dumps(line), flush=True)
+def barrier(world, dev):
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+    torch.cuda.synchronize(dev)
+
+
+def max_over_ranks(vals, world, dev):
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def gather_floats(val, world, dev):
+    t = torch.zeros(world, dtype=torch.float64, device=dev)
+    t[int(os.environ.get("RANK", "0"))] = val
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t)
+    return t.tolist()
+
+
+def api_fn(L, qk, pv):
+    if qk == "mixed":
+        return L.lowbit_fa_q_int8_k_dynamic
+    if pv == "fp8":
+        return L.lowbit_fa_qk_int4_pv_fp8 if qk != "int8" else L.lowbit_fa_qk_int8_pv_fp8_cuda
+    return {"int8": L.lowbit_fa_qk_int8_pv_fp16_triton, "int4": L.lowbit_fa_qk_int4_pv_fp16_triton,
+            "q8k4": L.lowbit_fa_q_int8_k_int4_pv_fp16}[qk]
+
+
+def make_inputs(B, Hq, Hkv, N, D, layout, qk, dev, seed=0):
+    torch.manual_seed(seed)
+    shp = lambda h: (B, h, N, D) if layout == "HND" else (B, N, h, D)
+    q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
+    if qk == "mixed":
+        # dynamic-K workloads: every other 64-key block at 0.2x magnitude, so that the block statistic max|k|/127 puts
+        # it in the INT2 class (<= 0.0125) and the rest in the INT4 class (randn: ~0.035)
+        w = torch.where((torch.arange(N, device=dev) // 64) % 2 == 1, 0.2, 1.0).to(k.dtype)
+        k = k * (w.view(1, 1, N, 1) if layout == "HND" else w.view(1, N, 1, 1))
+    return q, k, v
+
+
+def timed_steps(step, K, W, world, dev, local, with_clocks=True):
+    """W warm-up steps, then K steps between barrier + synchronize on both sides, CUDA events on the launching stream;
+    returns (ms per step on this rank, clock summary)."""
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(W):
+        step(None)
+    sampler = ClockSampler(local) if with_clocks else None
+    barrier(world, dev)
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step(i)
+    e1.record(stream)
+    barrier(world, dev)
+    if sampler:
+        sampler.stop_flag = True
+    return e0.elapsed_time(e1) / K, (sampler.summary() if sampler else None)
+
+
+def decomposed_step(q, k, v, layout, causal, qk, K, dev):
+    """The operator call cut at the attention launch so that CUDA events can bracket the dominant kernel inside the
+    timed steps: == lowbit_fa_qk_int8_pv_fp16_triton / lowbit_fa_q_int8_k_int4_pv_fp16 (checked bit for bit)."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    from lowbit_quant_fa2_paddle_b200 import attention as A
+    from lowbit_quant_fa2_paddle_b200 import quant as Qz
+    D = q.shape[-1]
+    sm_scale = 1.0 / D ** 0.5
+    kbits, packed = (8, False) if qk == "int8" else (4, True)
+    qk_mode = NV.QK_Q8K4 if packed else NV.QK_I8
+    stream = torch.cuda.current_stream(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+
+    def step(i=None):
+        qc, qs, kc, ks, _ = Qz.smooth_and_quantize(q, k, True, sm_scale, layout, 8, kbits, packed, "triton")
+        if i is not None:
+            ev[i][0].record(stream)
+        o, _ = A._forward(qc, kc, v, qs, ks, layout, torch.float16, False, causal, qk_mode=qk_mode)
+        if i is not None:
+            ev[i][1].record(stream)
+        return o
+
+    def attn_only(reps):
+        qc, qs, kc, ks, _ = Qz.smooth_and_quantize(q, k, True, sm_scale, layout, 8, kbits, packed, "triton")
+        f = lambda: A._forward(qc, kc, v, qs, ks, layout, torch.float16, False, causal, qk_mode=qk_mode)
+        for _ in range(3):
+            f()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            f()
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        return a0.elapsed_time(a1) / reps
+    return step, ev, attn_only
+
+
+def e2e_measure(L, fn, q, k, v, layout, causal, KE, world, dev):
+    """End to end from pinned host memory through lowbit_fa_host (H2D q,k,v + hot path + D2H o per step)."""
+    stream = torch.cuda.current_stream(dev)
+    hq_, hk_, hv_ = (t.contiguous().cpu().pin_memory() for t in (q, k, v))
+    ho = torch.empty(hq_.shape, dtype=torch.float16).pin_memory()
+
+    def serial():
+        dq, dk, dv = (t.to(dev, non_blocking=True) for t in (hq_, hk_, hv_))
+        ho.copy_(fn(dq, dk, dv, tensor_layout=layout, is_causal=causal), non_blocking=True)
+
+    serial()
+    torch.cuda.synchronize(dev)
+    ho_serial = ho.clone()
+    y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    y0.record(stream)
+    for _ in range(3):
+        serial()
+    y1.record(stream)
+    torch.cuda.synchronize(dev)
+    serial_ms = y0.elapsed_time(y1) / 3
+    ho.zero_()
+    run = lambda: L.lowbit_fa_host(hq_, hk_, hv_, out=ho, op=fn, tensor_layout=layout, is_causal=causal, graph=True)
+    for _ in range(3):
+        run()
+    barrier(world, dev)
+    xe = [torch.cuda.Event(enable_timing=True) for _ in range(KE + 1)]
+    xe[0].record(stream)
+    for i in range(KE):
+        run()
+        xe[i + 1].record(stream)  # lowbit_fa_host leaves the caller's stream waiting for the last copy-out
+    barrier(world, dev)
+    per = sorted(xe[i].elapsed_time(xe[i + 1]) for i in range(KE))
+    assert torch.equal(ho, ho_serial), "pipelined host entry point differs from the serial call"
+    # plain copy rate of this rank's inputs with every rank copying at the same time
+    dq = torch.empty(hq_.shape, dtype=hq_.dtype, device=dev)
+    barrier(world, dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(4):
+        dq.copy_(hq_, non_blocking=True)
+    c1.record(stream)
+    barrier(world, dev)
+    h2d_gbs = 4 * hq_.numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    return {"median_ms": per[KE // 2], "mean_ms": xe[0].elapsed_time(xe[KE]) / KE, "max_ms": per[-1], "serial_ms": serial_ms,
+            "steps": KE, "h2d": int(hq_.numel() * 2 + hk_.numel() * 2 + hv_.numel() * 2), "d2h": int(ho.numel() * 2),
+            "h2d_gbs": h2d_gbs}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_units(wl, units, reps=1):
+    """Time the oracle port (reference pure-Paddle math restated on torch-CPU) on `units` (batch, head) units of the
+    workload with all host threads; returns (TOPS, cores, sample description, seconds per rep)."""
+    from oracle import attention as OA
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(0)
+    shp = (1, units, N, D) if layout == "HND" else (1, N, units, D)
+    q, k, v = (torch.randn(shp, generator=g).half() for _ in range(3))
+    kbits = 4 if qk in ("q8k4", "int4") else 8
+    grp = 4 if N <= 4096 else (2 if N <= 8192 else 1)  # bounds the fp32 score matrix to ~1-1.3 GiB
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for h0 in range(0, units, grp):
+            sl = (slice(None), slice(h0, h0 + grp)) if layout == "HND" else (slice(None), slice(None), slice(h0, h0 + grp))
+            OA.cpu_quantize_and_attend(q[sl], k[sl], v[sl], layout, causal, kbits=kbits)
+    dt = (time.perf_counter() - t0) / reps
+    ops = 4.0 * units * N * N * D / (2 if causal else 1)
+    total = B * Hq
+    return ops / dt / 1e12, cores, (f"{units} of the {total} (batch, head) units of {wl} per step (N={N}, D={D}, fp32 math, "
+                                    f"all {cores} host threads); TOPS is a rate, so it needs no scaling"), dt
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return  # the other ranks of a torchrun launch exit 0 without work
+    wl = args.workload or ("c2" if args.gpus == 1 else "c4s")
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    if pv != "fp16" or qk not in ("int8", "q8k4"):
+        raise SystemExit("--impl reference is defined for the INT8-QK / q8k4, fp16-PV workloads")
+    units = B * Hq if N <= 4096 else (8 if N <= 8192 else 2)  # config 2 in full; a bounded sample of the long ones
+    for _ in range(args.warmup):
+        cpu_units(wl, min(units, 4))
+    vals = []
+    for _ in range(args.steps):
+        vals.append(cpu_units(wl, units))
+    tops = sum(v[0] for v in vals) / len(vals)
+    ms = sum(v[3] for v in vals) / len(vals) * 1e3
+    cores, sample = vals[0][1], vals[0][2]
+    line = {"impl": "reference", "metric": METRIC, "value": tops, "unit": "TOPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
+            "dtype": f"{qk} QK / {pv} PV codes, fp32 math on the CPU", "data": "synthetic randn fp16 seed 0",
+            "config": config_of(wl, args.gpus),
+            "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_of(wl, n_gpus):
+    """The `config` object: identical for our arm and the reference arm at the same N."""
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    part_txt = {"replicate": "every rank the whole workload" if n_gpus > 1 else "single GPU",
+                "heads": f"kv heads split over {n_gpus} rank(s), no collective on the data path",
+                "ring": f"sequence split over {n_gpus} rank(s), NCCL P2P ring of quantized K/V"}[part]
+    return {"workload": desc, "B": B, "Hq": Hq, "Hkv": Hkv, "N": N, "D": D, "layout": layout, "causal": causal,
+            "qk": qk, "pv": pv, "partition": part_txt, "smooth_k": True, "quantization_backend": "triton (Q1 rounding)",
+            "l2": "working set larger than the 126 MB L2, no flush"}
+
+
+# ------------------------------------------------------------------------------------------------ reference kernels on this GPU
+def reference_gpu(q, k, v, causal, ops):
+    """The reference's own Triton kernels (staged unmodified under oracle/_ref by oracle/stage_ref.sh), JIT-compiled for
+    this GPU: attention-only and quantize + attention TOPS at the bench workload."""
+    try:
+        os.environ["TRITON_INTERPRET"] = "0"
+        os.environ.setdefault("LOWBIT_REFERENCE_ROOT", os.path.join(ROOT, "oracle", "_ref", "reference"))
+        from oracle import ref_triton as RT
+        if not RT.available():
+            return {"unavailable": "reference kernels not staged under oracle/_ref (oracle/stage_ref.sh runs in the build container)"}
+        import lowbit_quant_fa2_paddle_b200 as L
+        stream = torch.cuda.current_stream(q.device)
+
+        def timed(f, reps=10, warm=3):
+            for _ in range(warm):
+                f()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                f()
+            b.record(stream)
+            torch.cuda.synchronize(q.device)
+            return a.elapsed_time(b) / reps
+        km = L.k_mean(k)
+        qi, qs, ki, ks = RT.per_block_int8(q, k, km=km)
+        t_attn = timed(lambda: RT.attn_forward(qi, ki, v, qs, ks, "HND", causal, torch.float16, False))
+
+        def op():
+            a, s1, c, s2 = RT.per_block_int8(q, k, km=k.mean(dim=2, keepdim=True))
+            return RT.attn_forward(a, c, v, s1, s2, "HND", causal, torch.float16, False)[0]
+        t_op = timed(op)
+        ours = L.lowbit_fa_qk_int8_pv_fp16_triton(q, k, v, is_causal=causal)
+        ref = op()
+        cos = float(torch.nn.functional.cosine_similarity(ours.float().flatten(), ref.float().flatten(), dim=0))
+        return {"kind": "reference Triton kernels (src/triton/quant_per_block.py, attn_qk_int8_per_block*.py) JIT-compiled for sm_100",
+                "attn_only_tops": ops / t_attn / 1e9, "value_tops": ops / t_op / 1e9, "attn_ms": t_attn, "op_ms": t_op,
+                "our_output_cos_vs_reference": cos,
+                "our_output_max_abs_vs_reference": float((ours.float() - ref.float()).abs().max())}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+# ------------------------------------------------------------------------------------------------ our arm, N = 1
+def quick_tops(L, wl, dev, reps=None):
+    """One short timing of another BASELINE config through its public operator (no decomposition)."""
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    q, k, v = make_inputs(B, Hq, Hkv, N, D, layout, qk, dev)
+    fn = api_fn(L, qk, pv)
+    f = lambda: fn(q, k, v, tensor_layout=layout, is_causal=causal)
+    ops = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
+    reps = reps or (10 if ops < 3e12 else 3)
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        f()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        f()
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / reps
+    del q, k, v
+    torch.cuda.empty_cache()
+    return {"workload": desc, "value": ops / ms / 1e9, "unit": "TOPS", "ms_per_step": ms, "steps": reps}
+
+
+def run_single(args, rank, world, local, dev):
+    """N = 1 (or --workload with partition "replicate" at N > 1: every rank the same work, weak scaling)."""
+    affinity = bind_near_gpu(local)
+    import lowbit_quant_fa2_paddle_b200 as L
+    from lowbit_quant_fa2_paddle_b200 import _native
+    _native.lib()
+    wl = args.workload or "c2"
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    W, K = max(args.warmup, 3), args.steps
+    q, k, v = make_inputs(B, Hq, Hkv, N, D, layout, qk, dev, seed=rank)
+    ops = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
+    fn = api_fn(L, qk, pv)
+    decomposable = pv == "fp16" and qk in ("int8", "q8k4", "int4")
+    attn_ev = attn_only = None
+    if decomposable:
+        step, attn_ev, attn_only = decomposed_step(q, k, v, layout, causal, qk, K, dev)
+        assert torch.equal(fn(q, k, v, tensor_layout=layout, is_causal=causal), step()), "bench step differs from the public API call"
+        launches = 5
+    else:
+        step = lambda i=None: fn(q, k, v, tensor_layout=layout, is_causal=causal)
+        launches = None
+    ms_local, clocks = timed_steps(step, K, W, world, dev, local)
+    attn_ms = (sum(a.elapsed_time(b) for a, b in attn_ev) / K) if attn_ev else None
+    attn_alone_ms = attn_only(max(10, min(K, 50))) if attn_only else None
+    e2e = None
+    if decomposable and wl in ("c2", "c2c", "c4s", "c4"):
+        e2e = e2e_measure(L, fn, q, k, v, layout, causal, max(3, min(K, 20)), world, dev)
+    ms_per_step, attn_ms_m, attn_alone_m, e2e_ms = max_over_ranks(
+        [ms_local, attn_ms or 0.0, attn_alone_ms or 0.0, e2e["median_ms"] if e2e else 0.0], world, dev)
+    h2d_rates = gather_floats(e2e["h2d_gbs"], world, dev) if e2e else None
+    if rank == 0:
+        value = world * ops / (ms_per_step * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": "TOPS", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": value / BASELINE_MD_TOPS if (wl == "c2" and world == 1) else None,
+                "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)", "data": "synthetic randn fp16 seed 0",
+                "config": config_of(wl, world), "gpu_launches": (launches * K) if launches else None, "clocks": clocks}
+        if wl == "c2":
+            line["vs_baseline_note"] = "BASELINE.md 199.5 TFLOP/s is attention-kernel-only on unstated hardware; value includes quantization"
+        if attn_alone_ms:
+            line["attn_only"] = {"value": world * ops / (attn_alone_m * 1e-3) / 1e12, "unit": "TOPS", "ms": attn_alone_m}
+            line["roofline"] = roofline("attn_fwd_n64_kernel" if D == 64 else "attn_fwd_kernel", B, Hq, Hkv, N, D, causal, qk, pv,
+                                        attn_ms_m, (clocks or {}).get("sm_mhz"), ncu_traffic_bytes() if wl == "c2" else None)
+        if e2e:
+            line["e2e"] = {"value": world * ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": e2e_ms,
+                           "api": "lowbit_fa_host(graph=True): pinned host q,k,v -> pinned host o; (batch, head-group) chunks on 3 streams, replayed as one CUDA graph",
+                           "serial_ms": e2e["serial_ms"], "statistic": "median of per-step CUDA-event times, max over ranks",
+                           "mean_ms": e2e["mean_ms"], "max_ms": e2e["max_ms"], "steps": e2e["steps"], "host_binding": affinity,
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "h2d_gbs_per_rank": h2d_rates}
+        if world == 1 and not args.workload:
+            # the other single-GPU configs of BASELINE.json, one short timing each (same process, after the headline)
+            line["other_configs"] = {n: quick_tops(L, n, dev) for n in ("c2c", "c3q_8k", "c4s")}
+            torch.manual_seed(0)
+            q0, k0, v0 = (torch.randn(B, Hq, N, D, dtype=torch.float16, device=dev) for _ in range(3))
+            line["reference_gpu"] = reference_gpu(q0, k0, v0, causal, ops)
+            if not args.no_cpu_baseline:
+                tops, cores, sample, _ = cpu_units(wl, 32 if N <= 4096 else 4)
+                line["cpu_baseline"] = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm, N > 1
+def run_ring(L, P, wl, world, rank, dev, steps=3, warm=2):
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    n_loc = N // world
+    torch.manual_seed(1000 + rank)
+    shp = lambda h: (B, h, n_loc, D) if layout == "HND" else (B, n_loc, h, D)
+    q, k, v = (torch.randn(shp(h), dtype=torch.float16, device=dev) for h in (Hq, Hkv, Hkv))
+    if qk == "mixed":
+        seq = 2 if layout == "HND" else 1
+        w = torch.where((torch.arange(n_loc, device=dev) // 64) % 2 == 1, 0.2, 1.0).to(k.dtype)
+        k = k * (w.view(1, 1, n_loc, 1) if seq == 2 else w.view(1, n_loc, 1, 1))
+    ring_qk = qk if qk in ("int8", "mixed") else "int4"
+    f = lambda t=None: P.ring_attention(q, k, v, tensor_layout=layout, is_causal=causal, qk=ring_qk, pv=pv, timings=t)
+    for _ in range(warm):
+        f()
+    stream = torch.cuda.current_stream(dev)
+    barrier(world, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        f()
+    e1.record(stream)
+    barrier(world, dev)
+    ms = max_over_ranks([e0.elapsed_time(e1) / steps], world, dev)[0]
+    tm = {}
+    f(tm)  # one more pass with phase events (it synchronises the device: outside the timed region)
+    comp, expo = sum(tm["compute"]), sum(tm["p2p_exposed"])
+    parts = max_over_ranks([tm["k_mean"], tm["quantize"], comp, expo, tm["finalize"]], world, dev)
+    ops = 4.0 * B * Hq * N * N * D / 2
+    del q, k, v
+    torch.cuda.empty_cache()
+    total = sum(parts)
+    limiter = max(zip(parts, ("K mean (sum + all-reduce)", "quantize", "attention of the resident shards",
+                              "P2P wait beyond the step's compute", "finalize")))[1]
+    return {"workload": desc, "value": ops / ms / 1e9, "unit": "TOPS", "ms_per_step": ms, "steps": steps, "scaling": "strong",
+            "phases_ms_max_over_ranks": {"k_mean_allreduce": parts[0], "quantize_q_k_v": parts[1], "attention_compute": parts[2],
+                                         "p2p_exposed": parts[3], "finalize": parts[4], "sum": total},
+            "per_step_ms_rank0": {"compute": tm["compute"], "p2p_exposed": tm["p2p_exposed"]},
+            "p2p_bytes_sent_per_rank_per_step": tm["p2p_bytes_per_step"], "ring_steps": world, "limiter": limiter}
+
+
+def run_multi(args, rank, world, local, dev):
+    """N > 1: BASELINE config 4, kv heads split over the ranks (no collective), strong scaling; config 5 ring as extras."""
+    affinity = bind_near_gpu(local)
+    import lowbit_quant_fa2_paddle_b200 as L
+    from lowbit_quant_fa2_paddle_b200 import _native
+    from lowbit_quant_fa2_paddle_b200 import parallel as P
+    _native.lib()
+    wl = args.workload or "c4s"
+    B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
+    W, K = max(args.warmup, 3), args.steps
+    ops_total = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
+    fn = api_fn(L, qk, pv)
+    if part == "ring":
+        r = run_ring(L, P, wl, world, rank, dev, steps=max(3, min(K, 10)), warm=W)
+        if rank == 0:
+            line = {"metric": METRIC, "value": r["value"], "unit": "TOPS", "n_gpus": world, "steps": r["steps"], "warmup": W,
+                    "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)", "data": "synthetic randn fp16", "config": config_of(wl, world),
+                    "ring": r, "gpu_launches": None}
+            print(json.dumps(line), flush=True)
+        return
+    # every rank holds the full tensors (same seed) and works on its kv-head slice as a strided view
+    q, k, v = make_inputs(B, Hq, Hkv, N, D, layout, qk, dev, seed=0)
+    hdim = 1 if layout == "HND" else 2
+    hq0, hq1, hkv0, hkv1 = P.head_shard(Hq, Hkv, world, rank)
+    qs_, ks_, vs_ = q.narrow(hdim, hq0, hq1 - hq0), k.narrow(hdim, hkv0, hkv1 - hkv0), v.narrow(hdim, hkv0, hkv1 - hkv0)
+    step, attn_ev, attn_only = decomposed_step(qs_, ks_, vs_, layout, causal, qk, K, dev)
+    o_api = P.lowbit_fa_head_sharded(q, k, v, fn, world, rank, tensor_layout=layout, is_causal=causal)
+    assert torch.equal(o_api, step()), "bench step differs from parallel.lowbit_fa_head_sharded"
+    del o_api
+    ms_local, clocks = timed_steps(step, K, W, world, dev, local)
+    attn_ms = sum(a.elapsed_time(b) for a, b in attn_ev) / K
+    attn_alone_ms = attn_only(max(10, min(K, 30)))
+    # the same workload on ONE GPU, in this run (rank 0; the other ranks wait at the barrier)
+    single_ms = 0.0
+    if rank == 0:
+        fs = lambda i=None: fn(q, k, v, tensor_layout=layout, is_causal=causal)
+        for _ in range(3):
+            fs()
+        stream = torch.cuda.current_stream(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        K1 = max(3, min(K, 10))
+        a0.record(stream)
+        for _ in range(K1):
+            fs()
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        single_ms = a0.elapsed_time(a1) / K1
+    barrier(world, dev)
+    e2e = e2e_measure(L, fn, qs_, ks_, vs_, layout, causal, max(3, min(K, 20)), world, dev)
+    ms_per_step, attn_ms_m, attn_alone_m, e2e_ms, single_ms = max_over_ranks(
+        [ms_local, attn_ms, attn_alone_ms, e2e["median_ms"], single_ms], world, dev)
+    h2d_rates = gather_floats(e2e["h2d_gbs"], world, dev)
+    h2d_tot, d2h_tot = (int(x) for x in max_over_ranks([e2e["h2d"] * 1.0, e2e["d2h"] * 1.0], world, dev))
+    del q, k, v, qs_, ks_, vs_
+    torch.cuda.empty_cache()
+    ring = {}
+    for name in ("c5", "c5dyn"):
+        try:
+            ring[name] = run_ring(L, P, name, world, rank, dev)
+        except Exception as e:  # noqa: BLE001
+            ring[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0:
+        value = ops_total / (ms_per_step * 1e-3) / 1e12
+        hq_loc = (hq1 - hq0)
+        line = {"metric": METRIC, "value": value, "unit": "TOPS", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": f"{qk} QK (int32 acc) / {pv} PV (fp32 acc)", "data": "synthetic randn fp16 seed 0",
+                "config": config_of(wl, world), "gpu_launches": 5 * K, "clocks": clocks,
+                "strong_scaling": {"single_gpu": {"value": ops_total / (single_ms * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": single_ms,
+                                                  "how": "the whole workload on rank 0's GPU, same run, same build"},
+                                   "speedup_vs_single_gpu": single_ms / ms_per_step, "ranks": world},
+                "attn_only": {"value": ops_total / (attn_alone_m * 1e-3) / 1e12, "unit": "TOPS", "ms": attn_alone_m},
+                "e2e": {"value": ops_total / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": e2e_ms,
+                        "api": "lowbit_fa_host(graph=True) per rank on its kv-head slice: pinned host q,k,v -> pinned host o",
+                        "statistic": "median of per-step CUDA-event times, max over ranks", "steps": e2e["steps"],
+                        "host_binding": affinity, "h2d_bytes_per_step": h2d_tot * world, "d2h_bytes_per_step": d2h_tot * world,
+                        "h2d_gbs_per_rank": h2d_rates,
+                        "note": "all ranks copy from one host memory system at once: the per-rank H2D rate above is what bounds e2e"},
+                "roofline": roofline("attn_fwd_n64_kernel", B, hq_loc, hkv1 - hkv0, N, D, causal, qk, pv, attn_ms_m,
+                                     (clocks or {}).get("sm_mhz")),
+                "ring": ring}
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -314,178 +690,19 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(EXTRA))
+    ap.add_argument("--workload", default=None, choices=sorted(WL))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.workload in EXTRA:
-        if args.impl == "reference":
-            raise SystemExit("--impl reference is defined for the INT8/FP16 workloads")
-        return run_extra(args)
     if args.impl == "reference":
         return run_reference(args)
-
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    affinity = bind_near_gpu(local)
-    import lowbit_quant_fa2_paddle_b200 as L
-    from lowbit_quant_fa2_paddle_b200 import _native
-    _native.lib()
-
-    B, Hq, Hkv, N, D, layout, causal, desc = WORKLOADS[args.workload]
-    W = max(args.warmup, 3)
-    K = args.steps
-    torch.manual_seed(rank)  # seed 0 on rank 0
-    shp = lambda h: (B, h, N, D) if layout == "HND" else (B, N, h, D)
-    q = torch.randn(shp(Hq), dtype=torch.float16, device=dev)
-    k = torch.randn(shp(Hkv), dtype=torch.float16, device=dev)
-    v = torch.randn(shp(Hkv), dtype=torch.float16, device=dev)
-    ops = 4.0 * B * Hq * N * N * D / (2 if causal else 1)
-    stream = torch.cuda.current_stream(dev)
-
-    # ---- the step, with CUDA events around the dominant kernel (attention) inside it ----
-    from lowbit_quant_fa2_paddle_b200 import attention as A
-    from lowbit_quant_fa2_paddle_b200 import quant as Qz
-    attn_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sm_scale = 1.0 / D ** 0.5
-
-    def step(i=None):
-        """== lowbit_fa_qk_int8_pv_fp16_triton(q,k,v,...) with event marks around the attention launch."""
-        qc, qs, kc, ks, _ = Qz.smooth_and_quantize(q, k, True, sm_scale, layout, 8, 8, False, "triton")
-        if i is not None:
-            attn_ev[i][0].record(stream)
-        o, _ = A._forward(qc, kc, v, qs, ks, layout, torch.float16, False, causal)
-        if i is not None:
-            attn_ev[i][1].record(stream)
-        return o
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(W):
-        step()
-    # parity spot-check of the public API against the step decomposition above (bit-identical)
-    o_api = L.lowbit_fa_qk_int8_pv_fp16_triton(q, k, v, tensor_layout=layout, is_causal=causal)
-    assert torch.equal(o_api, step()), "bench step differs from the public API call"
-    del o_api
-
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(K):
-        step(i)
-    e1.record(stream)
-    barrier()
-    sampler.stop_flag = True
-    total_ms = e0.elapsed_time(e1)
-    attn_ms = sum(a.elapsed_time(b) for a, b in attn_ev) / K
-
-    # ---- attention kernel alone (the reference's published style: quantization outside the timed region) ----
-    km = Qz.k_mean(k, layout)
-    qc, qs, kc, ks = Qz.per_block_int8(q, k, km=km, sm_scale=sm_scale, tensor_layout=layout)
-    for _ in range(3):
-        A._forward(qc, kc, v, qs, ks, layout, torch.float16, False, causal)
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    KA = max(10, min(K, 50))
-    a0.record(stream)
-    for _ in range(KA):
-        A._forward(qc, kc, v, qs, ks, layout, torch.float16, False, causal)
-    a1.record(stream)
-    torch.cuda.synchronize(dev)
-    attn_alone_ms = a0.elapsed_time(a1) / KA
-
-    # ---- end to end from host pinned memory (H2D q,k,v + hot path + D2H o) ----
-    hq_, hk_, hv_ = (t.cpu().pin_memory() for t in (q, k, v))
-    ho = torch.empty(q.shape, dtype=torch.float16).pin_memory()
-    KE = max(3, min(K, 20))
-
-    def e2e_step():
-        """The user-facing host entry point: pinned host q,k,v -> (H2D | quantize + attention | D2H, pipelined over
-        (batch, head-group) chunks on three streams) -> pinned host o."""
-        L.lowbit_fa_host(hq_, hk_, hv_, out=ho, tensor_layout=layout, is_causal=causal)
-
-    def e2e_serial_step():
-        """Same bytes, no overlap (copy in, one operator call, copy out): reported as e2e.serial_ms for context."""
-        dq = hq_.to(dev, non_blocking=True)
-        dk = hk_.to(dev, non_blocking=True)
-        dv = hv_.to(dev, non_blocking=True)
-        o = L.lowbit_fa_qk_int8_pv_fp16_triton(dq, dk, dv, tensor_layout=layout, is_causal=causal)
-        ho.copy_(o, non_blocking=True)
-
-    e2e_serial_step()
-    torch.cuda.synchronize(dev)
-    ho_serial = ho.clone()
-    y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    y0.record(stream)
-    for _ in range(3):
-        e2e_serial_step()
-    y1.record(stream)
-    torch.cuda.synchronize(dev)
-    e2e_serial_ms = y0.elapsed_time(y1) / 3
-    ho.zero_()
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    xe = [torch.cuda.Event(enable_timing=True) for _ in range(KE + 1)]
-    xe[0].record(stream)
-    for i in range(KE):
-        e2e_step()
-        xe[i + 1].record(stream)  # lowbit_fa_host leaves the caller's stream waiting for the last copy-out
-    barrier()
-    per = sorted(xe[i].elapsed_time(xe[i + 1]) for i in range(KE))
-    e2e_ms = xe[0].elapsed_time(xe[KE]) / KE
-    e2e_median_ms = per[KE // 2]
-    print("e2e per-step ms (sorted):", " ".join(f"{t:.2f}" for t in per), file=sys.stderr)
-    assert torch.equal(ho, ho_serial), "pipelined host entry point differs from the serial call"
-
-    # ---- max over ranks ----
-    e2e_mean_ms, e2e_max_ms = e2e_ms, per[-1]
-    e2e_ms = e2e_median_ms  # robust: 1 step in ~30 is hit by a 50-100 ms host/driver stall (see DESIGN.md section 6)
-    t = torch.tensor([total_ms, attn_ms, attn_alone_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, attn_ms, attn_alone_ms, e2e_ms = t.tolist()
-    ms_per_step = total_ms / K
-
-    if rank == 0:
-        peak_tf, peak_bw, peak_src = peaks()
-        value = world * ops / (ms_per_step * 1e-3) / 1e12
-        achieved = ops / (attn_ms * 1e-3) / 1e12
-        line = {
-            "metric": "attention TOPS (4*B*H*N^2*D / latency), quantize + attention", "value": value, "unit": "TOPS",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": value / BASELINE_MD_TOPS if args.workload == "c2" else None,
-            "dtype": "int8 QK (int32 acc) / fp16 PV (fp32 acc)", "data": "synthetic randn fp16 seed 0",
-            "config": {"workload": desc, "per_gpu": True, "l2": "working set ~320 MiB (q,k,v,codes,o) > 126 MB L2, no flush",
-                       "smooth_k": True, "quantization_backend": "triton (Q1 rounding)",
-                       "vs_baseline_note": "BASELINE.md 199.5 TFLOP/s is attention-kernel-only on unstated hardware; value includes quantization"},
-            "attn_only": {"value": world * ops / (attn_alone_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": attn_alone_ms},
-            "e2e": {"value": world * ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": e2e_ms,
-                    "api": "lowbit_fa_host (pinned host q,k,v -> pinned host o; 9 chunks on 3 streams, replayed as one CUDA graph)",
-                    "serial_ms": e2e_serial_ms, "statistic": "median of per-step CUDA-event times", "mean_ms": e2e_mean_ms,
-                    "max_ms": e2e_max_ms, "steps": KE, "host_cpus_bound": affinity,
-                    "h2d_bytes_per_step": int(hq_.numel() * 2 + hk_.numel() * 2 + hv_.numel() * 2),
-                    "d2h_bytes_per_step": int(ho.numel() * 2)},
-            "gpu_launches": 5 * K,
-            "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": ncu_traffic_bytes() if args.workload == "c2" else None, "peak_source": peak_src,
-                         "algorithmic_flop_per_launch": ops, "ms_per_launch": attn_ms,
-                         # the co-bound that actually binds at D=64 (DESIGN.md 4.2): one MUFU.EX2 per score,
-                         # 16 per clock per SM
-                         "mufu_co_bound": mufu_bound(B, Hq, N, causal, attn_ms, (sampler.summary() or {}).get("sm_mhz"))},
-            "clocks": sampler.summary(),
-        }
-        if not args.no_cpu_baseline:
-            tops, cores, sample, _ = cpu_baseline_run(args.workload, sample_heads=32 if N <= 4096 else (8 if N <= 8192 else 4))
-            line["cpu_baseline"] = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+    part = WL[args.workload][9] if args.workload else ("replicate" if world == 1 else "heads")
+    if world > 1 and part != "replicate":
+        run_multi(args, rank, world, local, dev)
+    else:
+        run_single(args, rank, world, local, dev)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LOWBIT_ABI_VERSION 5
+#define LOWBIT_ABI_VERSION 6
 
 /* element types of the floating-point inputs / outputs */
 enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
@@ -105,27 +105,6 @@ int lowbit_quant_k_mixed(const void* k, const void* km, const int32_t* kbits_in,
                          int32_t* kbits_out, int B, int H, int N, int D, int64_t isb, int64_t ish, int64_t isn,
                          int64_t osb, int64_t osh, int64_t osn, float thr8, float thr4, int mode, int dtype,
                          void* stream);
-
-/* S1 + Q1/Q2/Q4 fused -- everything the attention kernel needs from q and k in ONE launch: K mean over the sequence
- * (src/core.py:293), K smoothing `k - km` and per-64-row-block K codes, per-128-row-block Q codes scaled by
- * sm_scale_arg (= sm_scale * 1.44269504) (quant_per_block.py:181-248 / src/quant.py:21-98).  Results are bit-identical
- * to lowbit_k_mean + two lowbit_quant_per_block calls.  One persistent grid walks [K row-chunk sums | K blocks | Q
- * blocks] in stages: a (batch, kv-head) slice is summed, its mean published, and one stage later quantized while it
- * still sits in L2, so K crosses HBM once.  (Round-1 measurement on B200: 117 us vs 89 us for the three separate
- * kernels at B4 H32 N4096 D64 -- the item loop lacks the TMA prefetch ring of the stand-alone quantizer -- so the
- * Python operators still use the separate kernels; the entry point is parity-tested and kept for the next round.)
- * km_out [B,Hkv,D] in the input dtype (required when smooth_k); q_codes/k_codes addressed by the (o)strides like
- * lowbit_quant_per_block; q_scale [B,Hq,ceil(Nq/128)], k_scale [B,Hkv,ceil(Nk/64)] contiguous f32.
- * B * Hkv <= 8192.  workspace: >= lowbit_prep_qk_workspace_bytes(), 8-byte aligned, ZERO-FILLED once when allocated, then owned by
- * this entry point; epoch: positive, strictly increasing across calls that share a workspace (calls sharing a
- * workspace must be stream-ordered). */
-int64_t lowbit_prep_qk_workspace_bytes(int B, int Hkv, int Nk, int D);
-int lowbit_prep_qk(const void* q, const void* k, void* km_out, void* q_codes, float* q_scale, void* k_codes,
-                   float* k_scale, void* workspace, int epoch, int B, int Hq, int Hkv, int Nq, int Nk, int D,
-                   int64_t qsb, int64_t qsh, int64_t qsn, int64_t ksb, int64_t ksh, int64_t ksn,
-                   int64_t qosb, int64_t qosh, int64_t qosn, int64_t kosb, int64_t kosh, int64_t kosn,
-                   float sm_scale_arg, int qbits, int kbits, int kpack, int mode, int smooth_k, int dtype,
-                   void* stream);
 
 /* S1 -- K mean over the sequence (src/core.py:293 `k.mean(dim=seq_dim, keepdim=True)`).
  * km_out: [B, H, D] contiguous, same dtype as k.  workspace: >= lowbit_k_mean_workspace_bytes().
@@ -208,6 +187,13 @@ int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
                              int64_t stride_b, int64_t stride_h, int64_t stride_n,
                              int64_t v8_stride_b, int64_t v8_stride_h, int64_t v8_stride_d,
                              float scale_max, int dtype, void* stream);
+
+/* sub_mean (src/quant.py:175-207; SubMeanKernel csrc/fused/fused.cu:200-261): out = fp16(v - vm), the difference
+ * taken in the input dtype (__hsub2, :243) and then converted to fp16.  vm: [B,H,D] contiguous in v's dtype;
+ * out: fp16, addressed by (out_stride_b, out_stride_h, out_stride_n) like v; head_dim any multiple of 8. */
+int lowbit_sub_mean(const void* v, const void* vm, void* out, int B, int H, int N, int D,
+                    int64_t stride_b, int64_t stride_h, int64_t stride_n,
+                    int64_t out_stride_b, int64_t out_stride_h, int64_t out_stride_n, int dtype, void* stream);
 
 /* E4 -- global max|x| of a tensor (compute_scale, src/core.py:1039-1047).  out: one f32 (device). */
 int lowbit_abs_max(const void* x, float* out, int B, int H, int N, int D,

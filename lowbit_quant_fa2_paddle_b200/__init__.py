@@ -26,7 +26,6 @@ from .quant import (  # noqa: F401
     k_mean,
     k_smooth_quant,
     k_smooth_quant_supported,
-    prep_qk,
     per_block_int8,
     per_block_int8_cuda,
     per_block_int4_unpack,
@@ -38,6 +37,8 @@ from .quant import (  # noqa: F401
     per_thread_int4,
     per_warp_int8,
     per_channel_fp8,
+    sub_mean,
+    sub_mean_given,
     triton_quantize_and_pack_along_last_dim,
 )
 from .varlen import (  # noqa: F401
@@ -48,6 +49,7 @@ from .varlen import (  # noqa: F401
     k_mean_varlen,
 )
 from .host import lowbit_fa_host, plan_chunks  # noqa: F401
+from .plugin import as_sdpa, patch_sdpa  # noqa: F401
 from .kv_cache import quantized_flash_attn_forward, quant_and_pack_kv  # noqa: F401
 from .attention import forward, forward_causal, forward_partial, finalize, PartialState  # noqa: F401
 

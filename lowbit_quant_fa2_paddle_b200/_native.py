@@ -28,8 +28,7 @@ SIGNATURES = {
     "lowbit_quant_per_block_varlen": (_I, [_P] * 6 + [_I] * 4 + [_L] * 4 + [_I] * 4 + [_F, _I, _I, _P]),
     "lowbit_attn_fwd_varlen": (_I, [_P] * 11 + [_I] * 7 + [_L] * 8 + [_I] * 5 + [_P]),
     "lowbit_quant_k_mixed": (_I, [_P] * 6 + [_I] * 4 + [_L] * 6 + [_F, _F, _I, _I, _P]),
-    "lowbit_prep_qk_workspace_bytes": (_L, [_I] * 4),
-    "lowbit_prep_qk": (_I, [_P] * 8 + [_I] * 7 + [_L] * 12 + [_F] + [_I] * 6 + [_P]),
+    "lowbit_sub_mean": (_I, [_P, _P, _P] + [_I] * 4 + [_L] * 6 + [_I, _P]),
     "lowbit_k_mean_workspace_bytes": (_L, [_I] * 4),
     "lowbit_k_mean": (_I, [_P, _P, _P] + [_I] * 4 + [_L] * 3 + [_I, _P]),
     "lowbit_k_smooth_quant_supported": (_I, [_I, _I, _I]),
@@ -68,15 +67,22 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.lowbit_version() != 5:
+        if handle.lowbit_version() != 6:
             raise LowbitNativeError("liblowbit_fa_b200.so ABI version mismatch")
         _lib = handle
     return _lib
 
 
-def call(name, *args):
-    """Call an int-returning entry point; raise with the library's error text on failure."""
+def call(name, *args, device=None):
+    """Call an int-returning entry point; raise with the library's error text on failure.  `device`: the CUDA device
+    the tensors (and the stream argument) belong to -- made current for the call, so that a process that drives
+    several GPUs launches on the right one whatever torch's current device is."""
     L = lib()
-    rc = getattr(L, name)(*args)
+    if device is not None:
+        import torch
+        with torch.cuda.device(device):
+            rc = getattr(L, name)(*args)
+    else:
+        rc = getattr(L, name)(*args)
     if rc != 0:
         raise LowbitNativeError(f"{name} failed: {L.lowbit_last_error().decode()}")

@@ -83,7 +83,7 @@ def _forward(q, k, v, q_scale, k_scale, tensor_layout, output_dtype, return_lse,
     lse = torch.empty((b, hq, nq), dtype=torch.float32, device=dev) if return_lse else None
     flags = (N.ATTN_CAUSAL if causal else 0) | (N.ATTN_COMPAT_TAIL if compat_tail else 0) | (N.ATTN_NARROW if narrow else 0)
     N.call("lowbit_attn_fwd", *ptrs, o.data_ptr(), lse.data_ptr() if lse is not None else None,
-           *dims, osb, osh, osn, qk_mode, pv_mode, T.dtype_code(odt), flags, T.stream_ptr(dev))
+           *dims, osb, osh, osn, qk_mode, pv_mode, T.dtype_code(odt), flags, T.stream_ptr(dev), device=dev)
     if lse is None:
         lse = torch.empty([0], dtype=torch.float32)  # the reference returns an empty CPU tensor (:204)
     return T.like(o, q), T.like(lse, q)
@@ -110,7 +110,7 @@ def forward_partial(state, q, k, v, q_scale, k_scale, tensor_layout="HND", causa
         state = PartialState(b, hq, nq, d, dev)
     N.call("lowbit_attn_fwd_partial", *ptrs, state.m.data_ptr(), state.l.data_ptr(), state.o_acc.data_ptr(),
            *dims, int(q_offset), int(k_offset), qk_mode, pv_mode, N.ATTN_CAUSAL if causal else 0,
-           0 if state.started else 1, T.stream_ptr(dev))
+           0 if state.started else 1, T.stream_ptr(dev), device=dev)
     state.started = True
     return state
 
@@ -126,7 +126,7 @@ def finalize(state, like_q, tensor_layout="HND", output_dtype=torch.float16, ret
     lse = torch.empty((b, hq, nq), dtype=torch.float32, device=dev) if return_lse else None
     N.call("lowbit_attn_finalize", state.m.data_ptr(), state.l.data_ptr(), state.o_acc.data_ptr(), o.data_ptr(),
            lse.data_ptr() if lse is not None else None, b, hq, nq, d, osb, osh, osn, T.dtype_code(odt),
-           T.stream_ptr(dev))
+           T.stream_ptr(dev), device=dev)
     return o, lse
 
 

@@ -63,8 +63,7 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
             sm_scale = 1.0 / head_dim_og ** 0.5
         kbits = 8 if qk == "int8" else 4
         packed = (qk != "int8") and A.PACKED_K4_KERNEL
-        # K mean, then both quantizers with the K smoothing fused (core.py:291-319).  The single-launch form
-        # (Qz.prep_qk) is bit-identical but measured slower on B200 (117 vs 89 us at config 2), so it is not used here.
+        # K mean, then both quantizers with the K smoothing fused (core.py:291-319)
         kb = None
         if qk == "mixed":  # dynamic INT8 / INT4 / INT2 per 64-row K block
             km = Qz.k_mean(kt, tensor_layout) if smooth_k else None
@@ -85,7 +84,7 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
             hkv = T.bhnd(kt, tensor_layout)[1]
             kmp = Qz._km_bhd(km, b, hkv, d, tensor_layout) if smooth_k else None
             N.call("lowbit_lse_fixup", lse.data_ptr(), qt.data_ptr(), kmp.data_ptr() if kmp is not None else None,
-                   b, hq, hkv, nq, d, sb, sh, sn, float(sm_scale), T.dtype_code(dtype), T.stream_ptr(dev))
+                   b, hq, hkv, nq, d, sb, sh, sn, float(sm_scale), T.dtype_code(dtype), T.stream_ptr(dev), device=dev)
             return T.like(o, q), T.like(lse, q)
     return T.like(o, q)
 

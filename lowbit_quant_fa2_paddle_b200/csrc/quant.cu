@@ -531,14 +531,12 @@ quant_per_block_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const T* __
   }
 }
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device (a process may drive several GPUs: nothing device-specific is cached per process)
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
 }
 
 template <typename T, int D, int BLK>
@@ -553,11 +551,8 @@ static int launch_qpb_tma(const void* in, const void* km, void* codes, float* sc
   const int64_t dim[4] = {D, N, H, B}, str[3] = {isn, ish, isb};
   if (make_map(&tm, in, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dim, str, D, BLK, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
   auto kern = quant_per_block_tma_kernel<T, D, BLK>;
-  static bool configured = false;
-  if (!configured) {
-    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    configured = true;
-  }
+  // the > 48 KB opt-in is a per-device function attribute: set on every launch (cheap), not once per process
+  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
   int ctas_per_sm = (227 * 1024) / (C::kSmem + 1024);
   ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
   const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
@@ -653,137 +648,6 @@ __global__ void k_mean_final_kernel(const typename MeanAcc<T>::type* __restrict_
   for (int c = 0; c < nchunk; ++c) t += part[(bh * nchunk + c) * D + d];
   const float s32 = MeanAcc<T>::to_sum_f32(t);
   km[idx] = from_f32<T>(__fdiv_rn(s32, (float)N));
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused Q + K preparation: K column sums -> K mean -> K codes, and Q codes, in ONE persistent launch
-// (src/core.py:291-306 + quant_per_block.py:181-248: `km = k.mean`, `k - km`, two quantizer launches).
-//
-// The four launches of the unfused path are 15-30 us kernels that each ramp the whole chip up and down; here every
-// resident CTA walks one static list of work items, ordered in stages so that a (batch, kv-head) slice of K is summed
-// (A items), then -- one stage later, when its mean has been published -- quantized (K items) while it is still in
-// L2, with the independent Q blocks (Q items) spread evenly over the stages to keep HBM busy in between:
-//     stage s:  A(slices of group s)   K(slices of group s-1)   Q(share s)
-// Dependencies are forward only (K(g) waits for A(g), issued a whole stage earlier) and the grid never exceeds the
-// resident capacity, so the spin-wait cannot deadlock.  The mean is reduced in a fixed chunk order by the CTA that
-// finishes a slice last: bit-identical to lowbit_k_mean.  Arithmetic of the codes: the same device functions as the
-// stand-alone kernels.
-// ------------------------------------------------------------------------------------------------
-constexpr int kPrepMaxSlices = 8192;  // (batch x kv-head) slices one workspace serves: counters / flags sit at fixed offsets
-struct PrepParams {
-  const void *q, *k;
-  void* km;
-  int8_t *qc, *kc;
-  float *qs, *ks;
-  void* part;
-  int *counter, *ready;
-  int epoch;
-  int B, Hq, Hkv, Nq, Nk;
-  int64_t qsb, qsh, qsn, ksb, ksh, ksn, qosb, qosh, qosn, kosb, kosh, kosn;
-  float smq;
-  int qbits, kbits, kpack, mode, smooth;
-  int chunk, nchunk, nqb, nkb;  // K-sum rows per chunk / chunks per slice; Q blocks per (b,hq); K blocks per (b,hkv)
-  int nkb2;                     // K work items per slice (two blocks each)
-  int G, S, qps;                // slices per stage, stages that carry A work, Q items per stage
-  int total;
-};
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <typename T, int D>
-__global__ void __launch_bounds__(kQuantThreads)
-prep_qk_kernel(const PrepParams p) {
-  using A = typename MeanAcc<T>::type;
-  __shared__ float s_w[2 * kQuantThreads / 32];
-  __shared__ A s_sum[256 / (D / 8)][D + 1];
-  __shared__ int s_last;
-  const int tid = threadIdx.x;
-  const int nslice = p.B * p.Hkv;
-  const int nQ = p.B * p.Hq * p.nqb;
-  const T* kmp = p.smooth ? (const T*)p.km : nullptr;
-  for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
-    int i = item, s = 0, na, nk, nq;
-    for (;; ++s) {  // stage of this item (a handful of iterations: stages are thousands of items long)
-      const int a_sl = (p.smooth && s < p.S) ? min(p.G, nslice - s * p.G) : 0;
-      const int k_sl = (s >= 1) ? min(p.G, nslice - (s - 1) * p.G) : 0;
-      na = a_sl * p.nchunk;
-      nk = k_sl * p.nkb2;
-      nq = max(0, min(p.qps, nQ - s * p.qps));
-      if (i < na + nk + nq) break;
-      i -= na + nk + nq;
-    }
-    if (i < na) {
-      // ---- A: partial column sums of one K row chunk; the last chunk of a slice to finish publishes the mean
-      const int slice = s * p.G + i / p.nchunk, ch = i % p.nchunk;
-      ksum_chunk_body<T, D>((const T*)p.k, (A*)p.part, p.Nk, p.chunk, p.nchunk, p.ksb, p.ksh, p.ksn, p.Hkv, ch,
-                            slice % p.Hkv, slice / p.Hkv, s_sum);
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) s_last = (atomicAdd(p.counter + slice, 1) == p.nchunk - 1);
-      __syncthreads();
-      if (s_last) {
-        __threadfence();
-        if (tid < D) {
-          A t = A(0);
-          const A* part = (const A*)p.part + (int64_t)slice * p.nchunk * D + tid;
-          for (int c = 0; c < p.nchunk; ++c) t += __ldcg(part + (int64_t)c * D);
-          ((T*)p.km)[(int64_t)slice * D + tid] = from_f32<T>(__fdiv_rn(MeanAcc<T>::to_sum_f32(t), (float)p.Nk));
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-          p.counter[slice] = 0;  // ready for the next call on this workspace
-          st_release(p.ready + slice, p.epoch);
-        }
-      }
-    } else if (i < na + nk) {
-      // ---- K: two 64-row blocks (16-32 KB in flight) of a slice whose mean was published a stage ago
-      i -= na;
-      const int slice = (s - 1) * p.G + i / p.nkb2, jb = (i % p.nkb2) * 2;
-      if (p.smooth) {
-        if (tid == 0) {
-          // bounded (~2 s): a broken protocol (workspace not zero-filled, epoch reused) traps instead of hanging the GPU
-          int spins = 0;
-          while (ld_acquire(p.ready + slice) != p.epoch) {
-            __nanosleep(128);
-            if (++spins > (1 << 24)) __trap();
-          }
-        }
-        __syncthreads();
-      }
-      quant_block_body<T, D, 64, 2>((const T*)p.k, kmp, p.kc, p.ks, p.Nk, p.nkb, p.ksb, p.ksh, p.ksn, p.kosb, p.kosh,
-                                 p.kosn, 1.0f, p.kbits, p.kpack, p.mode, p.Hkv, jb, slice % p.Hkv, slice / p.Hkv, s_w);
-    } else {
-      // ---- Q: one 128-row block, scaled by sm_scale * log2(e)
-      const int qi = s * p.qps + (i - na - nk);
-      const int jb = qi % p.nqb, h = (qi / p.nqb) % p.Hq, b = qi / (p.nqb * p.Hq);
-      quant_block_body<T, D, 128>((const T*)p.q, nullptr, p.qc, p.qs, p.Nq, p.nqb, p.qsb, p.qsh, p.qsn, p.qosb, p.qosh,
-                                  p.qosn, p.smq, p.qbits, 0, p.mode, p.Hq, jb, h, b, s_w);
-    }
-    __syncthreads();  // shared scratch is reused by the next item
-  }
-}
-
-template <typename T, int D>
-static int launch_prep(PrepParams& p, cudaStream_t st) {
-  auto kern = prep_qk_kernel<T, D>;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    LOWBIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kQuantThreads, 0));
-    LOWBIT_CHECK(ctas_per_sm > 0, "lowbit_prep_qk: kernel does not fit an SM");
-  }
-  const int64_t cap = (int64_t)num_sms() * ctas_per_sm;  // all CTAs resident: the spin-wait on a mean cannot deadlock
-  const int grid = (int)(p.total < cap ? p.total : cap);
-  kern<<<grid, kQuantThreads, 0, st>>>(p);
-  LOWBIT_CUDA(cudaGetLastError());
-  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -975,11 +839,7 @@ static int launch_ksq(const void* k, void* km_out, void* codes, float* scale, in
   const int rows_cta = ksq_rows_per_cta(N);
   const int smem = rows_cta * D * 2 + 16;
   auto kern = k_smooth_quant_cluster_kernel<T, D>;
-  static int configured = 0;
-  if (configured < smem) {
-    LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsqMaxTileBytes + 16));
-    configured = kKsqMaxTileBytes + 16;
-  }
+  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kKsqMaxTileBytes + 16));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((int64_t)B * H * kKsqCluster), 1, 1);
   cfg.blockDim = dim3(kQuantThreads, 1, 1);
@@ -1064,68 +924,6 @@ int lowbit_quant_k_mixed(const void* k, const void* km, const int32_t* kbits_in,
 #undef LAUNCH_MIX
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
-}
-
-int64_t lowbit_prep_qk_workspace_bytes(int B, int Hkv, int Nk, int D) {
-  const int chunk = mean_chunk_rows(Nk);
-  const int nchunk = (Nk + chunk - 1) / chunk;
-  const int64_t part = (int64_t)B * Hkv * nchunk * D * 8;
-  return part + (int64_t)kPrepMaxSlices * 2 * 4;
-}
-
-int lowbit_prep_qk(const void* q, const void* k, void* km_out, void* q_codes, float* q_scale, void* k_codes,
-                   float* k_scale, void* workspace, int epoch, int B, int Hq, int Hkv, int Nq, int Nk, int D,
-                   int64_t qsb, int64_t qsh, int64_t qsn, int64_t ksb, int64_t ksh, int64_t ksn,
-                   int64_t qosb, int64_t qosh, int64_t qosn, int64_t kosb, int64_t kosh, int64_t kosn,
-                   float sm_scale_arg, int qbits, int kbits, int kpack, int mode, int smooth_k, int dtype,
-                   void* stream) {
-  LOWBIT_CHECK(D == 64 || D == 128, "lowbit_prep_qk: head_dim must be 64 or 128 (got %d)", D);
-  LOWBIT_CHECK(q && k && q_codes && q_scale && k_codes && k_scale && workspace, "lowbit_prep_qk: null pointer");
-  LOWBIT_CHECK(!smooth_k || km_out, "lowbit_prep_qk: smooth_k needs km_out");
-  LOWBIT_CHECK(B > 0 && Hq > 0 && Hkv > 0 && Nq > 0 && Nk > 0, "lowbit_prep_qk: empty tensor");
-  LOWBIT_CHECK(Hq % Hkv == 0, "lowbit_prep_qk: num_qo_heads (%d) must be divisible by num_kv_heads (%d)", Hq, Hkv);
-  LOWBIT_CHECK(qbits == 8 || qbits == 4, "lowbit_prep_qk: qbits must be 8 or 4");
-  LOWBIT_CHECK(kbits == 8 || kbits == 4 || kbits == 2, "lowbit_prep_qk: kbits must be 8, 4 or 2");
-  LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_prep_qk: bad mode %d", mode);
-  LOWBIT_CHECK(epoch > 0, "lowbit_prep_qk: epoch must be positive and grow with every call on a workspace");
-  LOWBIT_CHECK(qsn % 8 == 0 && qsh % 8 == 0 && qsb % 8 == 0 && ksn % 8 == 0 && ksh % 8 == 0 && ksb % 8 == 0,
-               "lowbit_prep_qk: input strides must keep 16-byte alignment");
-  LOWBIT_CHECK(((uintptr_t)workspace & 7) == 0, "lowbit_prep_qk: workspace must be 8-byte aligned");
-  const int kdiv = kpack ? 8 / kbits : 1;
-  LOWBIT_CHECK((kosn * kdiv) % 8 == 0 && qosn % 8 == 0, "lowbit_prep_qk: code rows must keep 8-byte alignment");
-  PrepParams p{};
-  p.q = q; p.k = k; p.km = km_out; p.qc = (int8_t*)q_codes; p.kc = (int8_t*)k_codes; p.qs = q_scale; p.ks = k_scale;
-  p.chunk = mean_chunk_rows(Nk);
-  p.nchunk = (Nk + p.chunk - 1) / p.chunk;
-  LOWBIT_CHECK((int64_t)B * Hkv <= kPrepMaxSlices, "lowbit_prep_qk: more than %d (batch x kv-head) slices", kPrepMaxSlices);
-  // fixed layout, independent of the shape, so one workspace serves calls of any shape: the counters are always left
-  // at zero and the flags only ever hold past epochs
-  p.counter = reinterpret_cast<int*>(workspace);
-  p.ready = p.counter + kPrepMaxSlices;
-  p.part = reinterpret_cast<uint8_t*>(workspace) + (int64_t)kPrepMaxSlices * 2 * 4;
-  p.epoch = epoch;
-  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
-  p.qsb = qsb; p.qsh = qsh; p.qsn = qsn; p.ksb = ksb; p.ksh = ksh; p.ksn = ksn;
-  p.qosb = qosb; p.qosh = qosh; p.qosn = qosn; p.kosb = kosb; p.kosh = kosh; p.kosn = kosn;
-  p.smq = sm_scale_arg; p.qbits = qbits; p.kbits = kbits; p.kpack = kpack; p.mode = mode; p.smooth = smooth_k ? 1 : 0;
-  p.nqb = (Nq + 127) / 128; p.nkb = (Nk + 63) / 64; p.nkb2 = (p.nkb + 1) / 2;
-  const int64_t nslice = (int64_t)B * Hkv, nQ = (int64_t)B * Hq * p.nqb;
-  const int64_t total = nslice * (p.smooth ? p.nchunk : 0) + nslice * p.nkb2 + nQ;
-  LOWBIT_CHECK(total < (1ll << 31), "lowbit_prep_qk: too many blocks");
-  // slices per stage: a group of K slices (summed, then quantized one stage later) should stay L2-resident (<= 8 MiB)
-  // and a stage should hold a few items per resident CTA
-  int64_t G = (8ll << 20) / ((int64_t)Nk * D * 2);
-  if (G < 1) G = 1;
-  if (G > 16) G = 16;
-  if (G > nslice) G = nslice;
-  p.G = (int)G;
-  p.S = (int)((nslice + G - 1) / G);
-  p.qps = (int)((nQ + p.S) / (p.S + 1));
-  p.total = (int)total;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LOWBIT_F16) return D == 64 ? launch_prep<__half, 64>(p, st) : launch_prep<__half, 128>(p, st);
-  if (dtype == LOWBIT_BF16) return D == 64 ? launch_prep<__nv_bfloat16, 64>(p, st) : launch_prep<__nv_bfloat16, 128>(p, st);
-  return lowbit::fail("lowbit_prep_qk: bad dtype %d", dtype);
 }
 
 int64_t lowbit_k_mean_workspace_bytes(int B, int H, int N, int D) {

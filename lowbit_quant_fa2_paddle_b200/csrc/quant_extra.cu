@@ -303,6 +303,39 @@ v_fp8_quant_kernel(const T* __restrict__ v, const float2* __restrict__ tab, uint
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// sub_mean (src/quant.py:175-207 -> SubMeanKernel, csrc/fused/fused.cu:200-261): v_smoothed = fp16(v - vm), the
+// difference taken IN THE INPUT DTYPE (__hsub2 on half2 / bfloat162, :243) and then converted to fp16 (:245-248).
+// One thread per 8 channels of one token; HBM-bound: 2 B read + 2 B written per element.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+sub_mean_kernel(const T* __restrict__ v, const T* __restrict__ vm, __half* __restrict__ out, int H, int N, int D,
+                int64_t sb, int64_t sh, int64_t sn, int64_t osb, int64_t osh, int64_t osn, int64_t total8) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int d8 = D / 8;
+  const int c = (int)(i % d8) * 8;
+  const int64_t t = i / d8;
+  const int n = (int)(t % N), h = (int)((t / N) % H), b = (int)(t / ((int64_t)N * H));
+  const uint4 raw = ld_stream_v4(v + b * sb + h * sh + (int64_t)n * sn + c);
+  const uint4 mraw = *reinterpret_cast<const uint4*>(vm + ((int64_t)b * H + h) * D + c);
+  float x[8], m[8];
+  unpack8<T>(raw, x);
+  unpack8<T>(mraw, m);
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // fp32 difference of two 16-bit values rounded once to T == the T-precision subtraction of the reference
+    const float2 dlt = round_trip2<T>(make_float2(x[2 * k] - m[2 * k], x[2 * k + 1] - m[2 * k + 1]));
+    const __half2 hh = __float22half2_rn(dlt);
+    ow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(out + b * osb + h * osh + (int64_t)n * osn + c) = o;
+}
+
 }  // namespace lowbit
 
 using namespace lowbit;
@@ -394,6 +427,29 @@ int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
     return fail("lowbit_v_fp8_per_channel: unsupported dtype %d", dtype);
   }
 #undef LAUNCH
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+int lowbit_sub_mean(const void* v, const void* vm, void* out, int B, int H, int N, int D, int64_t sb, int64_t sh,
+                    int64_t sn, int64_t osb, int64_t osh, int64_t osn, int dtype, void* stream) {
+  LOWBIT_CHECK(v && vm && out, "lowbit_sub_mean: null pointer");
+  LOWBIT_CHECK(D > 0 && D % 8 == 0, "lowbit_sub_mean: head_dim must be a multiple of 8 (got %d)", D);
+  LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_sub_mean: empty tensor");
+  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0 && osn % 8 == 0 && osh % 8 == 0 && osb % 8 == 0,
+               "lowbit_sub_mean: strides must keep 16-byte alignment");
+  LOWBIT_CHECK(((uintptr_t)v & 15) == 0 && ((uintptr_t)vm & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "lowbit_sub_mean: pointers must be 16-byte aligned");
+  const int64_t total8 = (int64_t)B * H * N * (D / 8);
+  const unsigned blocks = (unsigned)((total8 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LOWBIT_F16)
+    sub_mean_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)v, (const __half*)vm, (__half*)out, H, N, D, sb, sh, sn, osb, osh, osn, total8);
+  else if (dtype == LOWBIT_BF16)
+    sub_mean_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)vm, (__half*)out, H, N, D, sb, sh, sn, osb, osh, osn, total8);
+  else
+    return fail("lowbit_sub_mean: unsupported dtype %d", dtype);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }

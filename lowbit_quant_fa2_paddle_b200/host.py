@@ -13,6 +13,7 @@ into chunks of such units and overlaps the three stages on three CUDA streams:
 The result is bit-identical to one call on the whole tensors (tests/test_gpu_parity.py::test_host_streaming_*).
 This is what `bench.py` reports as `e2e`.
 """
+import threading
 from typing import Any, Callable, List, Optional, Tuple
 
 import torch
@@ -21,6 +22,7 @@ from . import _native as N
 from . import _tensor as T
 
 _streams = {}
+_lock = threading.RLock()  # guards the module-level caches (side streams, staging slots, captured graphs)
 
 
 def _side_streams(dev: torch.device):
@@ -141,18 +143,21 @@ _GRAPH_CACHE = 4
 
 
 def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, tensor_layout: str = "HND",
-                   chunks: Optional[int] = None, device=None, graph: Optional[bool] = None, **op_kwargs: Any):
+                   chunks: Optional[int] = None, device=None, graph: bool = False, **op_kwargs: Any):
     """Run `op` (default `lowbit_fa_qk_int8_pv_fp16_triton`) on HOST tensors q, k, v (pinned memory for asynchronous
     DMA) and return the HOST tensor `out` (allocated pinned when not given), overlapping the copies with the kernels.
     Work is ordered on the caller's current stream of `device`: when this returns, everything is enqueued and the
     current stream has been made to wait for the last copy-out -- synchronize it (or an event on it) before reading
     `out` on the host.  `return_lse` is not supported on this entry point.
 
-    `graph` (default: automatic): a caller that comes back with the SAME pinned buffers (a serving loop that refills
-    them in place) gets the whole pipeline -- every copy, kernel and cross-stream dependency of every chunk -- as
-    one CUDA graph, captured the second time that call signature is seen and replayed from then on.  The host then
-    spends microseconds per call instead of ~0.2 ms per chunk, which is what lets the call be cut into more, smaller
-    chunks (less exposed first copy-in and last copy-out).  `graph=False` always enqueues eagerly."""
+    `graph=True` (opt-in): a caller that comes back with the SAME pinned buffers (a serving loop that refills them in
+    place) gets the whole pipeline -- every copy, kernel and cross-stream dependency of every chunk -- as one CUDA
+    graph, captured the second time that call signature is seen and replayed from then on.  The host then spends
+    microseconds per call instead of ~0.2 ms per chunk.  What it costs, and why it is not the default: the capture
+    synchronises the device once; every cached graph (up to 4 signatures, `drop_graphs()` releases them) keeps its
+    staging slots, every chunk's output and all quantizer temporaries alive in a private pool (about one device copy
+    of q, k, v, o plus the codes); and an `op` whose host-side control flow depends on data or on the environment is
+    frozen as captured.  The default enqueues eagerly."""
     from . import core
     op = op or core.lowbit_fa_qk_int8_pv_fp16_triton
     if op_kwargs.get("return_lse"):
@@ -178,7 +183,7 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
     plan = plan_chunks(B, Hq, Hkv, tensor_layout, chunks)
 
     key = None
-    if graph is not False and all(t.is_pinned() for t in (qt, kt, vt, out)):
+    if graph and all(t.is_pinned() for t in (qt, kt, vt, out)):
         try:
             key = (dev.index, qt.data_ptr(), kt.data_ptr(), vt.data_ptr(), out.data_ptr(), tuple(qt.shape),
                    tuple(kt.shape), tuple(vt.shape), qt.dtype, tensor_layout, len(plan), op,
@@ -186,7 +191,7 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
             hash(key)
         except TypeError:
             key = None  # an unhashable operator argument: enqueue eagerly
-    with torch.cuda.device(dev):
+    with _lock, torch.cuda.device(dev):
         if key is None:
             _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)
             return out
@@ -219,4 +224,5 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
 
 def drop_graphs() -> None:
     """Forget the captured pipelines (and release the device memory their private pools hold)."""
-    _graphs.clear()
+    with _lock:
+        _graphs.clear()

@@ -66,5 +66,5 @@ def quantized_flash_attn_forward(q, kcode, kscale, kmn, vcode, vscale, vmn, grou
     N.call("lowbit_kv_attn_fwd", qt.data_ptr(), kc.data_ptr(), ks.data_ptr(), km.data_ptr(), vc.data_ptr(),
            vs.data_ptr(), vm.data_ptr(), o.data_ptr(), lse.data_ptr(), ws.data_ptr(), B, H, Nq, Nk, D, group_size, bits,
            float(softmax_scale), qt.stride(0), qt.stride(1), qt.stride(2), o.stride(0), o.stride(1), o.stride(2),
-           nq_round, T.stream_ptr(dev))
+           nq_round, T.stream_ptr(dev), device=dev)
     return T.like(o, q), T.like(lse, q), softmax_scale

@@ -27,7 +27,7 @@ def k_mean(k, tensor_layout="HND"):
     km = torch.empty((b, h, d), dtype=kt.dtype, device=dev)
     ws = torch.empty(N.lib().lowbit_k_mean_workspace_bytes(b, h, n, d), dtype=torch.uint8, device=dev)
     N.call("lowbit_k_mean", kt.data_ptr(), km.data_ptr(), ws.data_ptr(), b, h, n, d, sb, sh, sn,
-           T.dtype_code(kt.dtype), T.stream_ptr(dev))
+           T.dtype_code(kt.dtype), T.stream_ptr(dev), device=dev)
     km = km.unsqueeze(2) if tensor_layout == "HND" else km.unsqueeze(1)
     return T.like(km, k)
 
@@ -68,7 +68,7 @@ def _quant_one(x, km, blk, bits, pack, sm_arg, mode, tensor_layout, out=None):
     _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
     N.call("lowbit_quant_per_block", xt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
            codes.data_ptr(), scale.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osn,
-           blk, bits, int(bool(pack)), float(sm_arg), mode, T.dtype_code(xt.dtype), T.stream_ptr(dev))
+           blk, bits, int(bool(pack)), float(sm_arg), mode, T.dtype_code(xt.dtype), T.stream_ptr(dev), device=dev)
     return T.like(codes, x), T.like(scale, x)
 
 
@@ -101,7 +101,7 @@ def k_smooth_quant(k, bits=8, pack=False, tensor_layout="HND", backend="triton")
     scale = torch.empty((b, h, (n + 63) // 64), dtype=torch.float32, device=dev)
     _, _, _, _, osb, osh, osn = T.bhnd(codes, tensor_layout)
     N.call("lowbit_k_smooth_quant", kt.data_ptr(), km.data_ptr(), codes.data_ptr(), scale.data_ptr(), b, h, n, d,
-           sb, sh, sn, osb, osh, osn, bits, int(bool(pack)), _MODES[backend], T.dtype_code(kt.dtype), T.stream_ptr(dev))
+           sb, sh, sn, osb, osh, osn, bits, int(bool(pack)), _MODES[backend], T.dtype_code(kt.dtype), T.stream_ptr(dev), device=dev)
     km = km.unsqueeze(2) if tensor_layout == "HND" else km.unsqueeze(1)
     return T.like(km, k), T.like(codes, k), T.like(scale, k)
 
@@ -175,61 +175,6 @@ def smooth_and_quantize(q, k, smooth_k, sm_scale, tensor_layout, qbits, kbits, k
 
 
 _MODES = {"triton": N.QMODE_TRITON, "triton_gpu": N.QMODE_TRITON | N.QMODE_FLAG_DIV_FULL, "cuda": N.QMODE_CUDA}
-_prep_ws = {}  # (device index, stream handle) -> [workspace tensor (zero-filled once), epoch]
-
-
-def _prep_workspace(dev, nbytes):
-    """Workspace of the fused preparation kernel: partial K sums + per-slice counters / ready flags.  Owned per
-    (device, stream): calls that share one are stream-ordered.  Zero-filled when (re)allocated; the kernel leaves the
-    counters at zero and the flags hold the epoch of the last call, which only ever grows."""
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    ent = _prep_ws.get(key)
-    if ent is None or ent[0].numel() < nbytes:
-        ent = [torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev), 0]
-        _prep_ws[key] = ent
-    ent[1] += 1
-    if ent[1] >= (1 << 30):  # epoch wrap: start over on a clean workspace
-        ent[0].zero_()
-        ent[1] = 1
-    return ent[0], ent[1]
-
-
-def prep_qk(q, k, smooth_k=True, sm_scale=None, tensor_layout="HND", backend="triton", qbits=8, kbits=8, kpack=False):
-    """K mean + K smoothing + per-block Q / K quantization in ONE launch (lowbit_prep_qk): what
-    `km = k.mean(...)` + `per_block_int8(q, k, km=km, sm_scale=...)` compute (core.py:291-319), bit-identical.
-    -> (q_codes, q_scale, k_codes, k_scale, km [B,H,1,D] / [B,1,H,D] or None)."""
-    if tensor_layout not in ("HND", "NHD"):
-        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
-    if backend not in _MODES:
-        raise ValueError(f"Unsupported quantization backend: {backend}")
-    qt, kt = T.as_torch(q), T.as_torch(k)
-    dev = T.require_cuda(qt, kt)
-    assert qt.dtype == kt.dtype, "All tensors must have the same dtype."
-    b, hq, nq, d, qsb, qsh, qsn = T.bhnd(qt, tensor_layout)
-    bk, hkv, nk, dk, ksb, ksh, ksn = T.bhnd(kt, tensor_layout)
-    assert b == bk and d == dk, "q and k must agree in batch and head_dim"
-    if d not in (64, 128):
-        raise ValueError(f"Unsupported head_dim: {d} (the kernels take 64 or 128; core pads smaller ones)")
-    if sm_scale is None:
-        sm_scale = d ** -0.5
-    kd = d * kbits // 8 if (kpack and kbits < 8) else d
-    q_c = torch.empty(qt.shape, dtype=torch.int8, device=dev)
-    k_c = torch.empty(list(kt.shape[:-1]) + [kd], dtype=torch.int8, device=dev)
-    q_s = torch.empty((b, hq, (nq + 127) // 128), dtype=torch.float32, device=dev)
-    k_s = torch.empty((b, hkv, (nk + 63) // 64), dtype=torch.float32, device=dev)
-    km = torch.empty((b, hkv, d), dtype=kt.dtype, device=dev) if smooth_k else None
-    _, _, _, _, qosb, qosh, qosn = T.bhnd(q_c, tensor_layout)
-    _, _, _, _, kosb, kosh, kosn = T.bhnd(k_c, tensor_layout)
-    ws, epoch = _prep_workspace(dev, N.lib().lowbit_prep_qk_workspace_bytes(b, hkv, nk, d))
-    N.call("lowbit_prep_qk", qt.data_ptr(), kt.data_ptr(), km.data_ptr() if smooth_k else None,
-           q_c.data_ptr(), q_s.data_ptr(), k_c.data_ptr(), k_s.data_ptr(), ws.data_ptr(), epoch,
-           b, hq, hkv, nq, nk, d, qsb, qsh, qsn, ksb, ksh, ksn, qosb, qosh, qosn, kosb, kosh, kosn,
-           float(sm_scale * LOG2E), qbits, kbits, int(bool(kpack)), _MODES[backend], int(bool(smooth_k)),
-           T.dtype_code(qt.dtype), T.stream_ptr(dev))
-    if km is not None:
-        km = km.unsqueeze(2) if tensor_layout == "HND" else km.unsqueeze(1)
-    return T.like(q_c, q), T.like(q_s, q), T.like(k_c, k), T.like(k_s, k), T.like(km, k)
-
 
 def per_block_int8(q, k, km=None, BLKQ=128, BLKK=64, sm_scale=None, tensor_layout="HND", backend="triton"):
     """-> (q_int8, q_scale [B,Hq,ceil(Nq/BLKQ)] f32, k_int8, k_scale [B,Hkv,ceil(Nk/BLKK)] f32).
@@ -297,7 +242,7 @@ def per_block_k_mixed(k, km=None, kbits=None, hi=0.2, lo=0.05, tensor_layout="HN
     thr4 = float(torch.tensor(lo / 4, dtype=torch.float32))
     N.call("lowbit_quant_k_mixed", kt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
            kin.data_ptr() if kin is not None else None, codes.data_ptr(), scale.data_ptr(), bits.data_ptr(),
-           b, h, n, d, sb, sh, sn, osb, osh, osn, thr8, thr4, _MODES[backend], T.dtype_code(kt.dtype), T.stream_ptr(dev))
+           b, h, n, d, sb, sh, sn, osb, osh, osn, thr8, thr4, _MODES[backend], T.dtype_code(kt.dtype), T.stream_ptr(dev), device=dev)
     return T.like(codes, k), T.like(scale, k), T.like(bits, k)
 
 
@@ -318,7 +263,7 @@ def _per_thread(q, k, km, BLKQ, BLKK, WARPQ, WARPK, tensor_layout, bits):
         scale = torch.empty((b, h, n_scale), dtype=torch.float32, device=dev)
         N.call("lowbit_quant_per_thread", xt.data_ptr(), kmt.data_ptr() if kmt is not None else None,
                codes.data_ptr(), scale.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osn, warp_blk, n_scale, is_key,
-               bits, T.dtype_code(xt.dtype), T.stream_ptr(dev))
+               bits, T.dtype_code(xt.dtype), T.stream_ptr(dev), device=dev)
         outs += [T.like(codes, x), T.like(scale, x)]
     return tuple(outs)
 
@@ -364,7 +309,7 @@ def triton_quantize_and_pack_along_last_dim(data, group_size: int, bit: int):
     scale = torch.empty((B, D, nh, ng), dtype=torch.float16, device=dev)
     mn = torch.empty((B, D, nh, ng), dtype=torch.float16, device=dev)
     N.call("lowbit_quant_pack_lastdim", dt.data_ptr(), code.data_ptr(), scale.data_ptr(), mn.data_ptr(),
-           B * D * nh, Tn, group_size, bit, N.F16, T.stream_ptr(dev))
+           B * D * nh, Tn, group_size, bit, N.F16, T.stream_ptr(dev), device=dev)
     return T.like(code, data), T.like(scale, data), T.like(mn, data)
 
 
@@ -388,8 +333,36 @@ def per_channel_fp8(v, tensor_layout="HND", scale_max=448.0, smooth_v=True):
     ws = torch.empty(N.lib().lowbit_v_fp8_workspace_bytes(b, h, n, d), dtype=torch.uint8, device=dev)
     N.call("lowbit_v_fp8_per_channel", vt.data_ptr(), v8.data_ptr(), v_scale.data_ptr(),
            vm.data_ptr() if vm is not None else None, ws.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osd,
-           float(scale_max), T.dtype_code(vt.dtype), T.stream_ptr(dev))
+           float(scale_max), T.dtype_code(vt.dtype), T.stream_ptr(dev), device=dev)
     return T.like(v8, v), T.like(v_scale, v), T.like(vm, v)
+
+
+def sub_mean(v, tensor_layout="HND"):
+    """src/quant.py:175-207: (v_smoothed fp16 = v - mean_n(v), vm [B,H,D] in v's dtype).  The mean is this package's
+    exact K-mean kernel (fp16: exact sum, one rounding; see k_mean); the subtraction follows SubMeanKernel
+    (fused.cu:243-248): taken in the input dtype, then converted to fp16."""
+    vt = T.as_torch(v)
+    dev = T.require_cuda(vt)
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    b, h, n, d, sb, sh, sn = T.bhnd(vt, tensor_layout)
+    vm = _km_bhd(k_mean(vt, tensor_layout), b, h, d, tensor_layout)
+    return sub_mean_given(vt, vm, tensor_layout), T.like(vm, v)
+
+
+def sub_mean_given(v, vm, tensor_layout="HND"):
+    """The SubMeanKernel step alone for a mean the caller hands over ([B,H,D], v's dtype): fp16(v - vm)."""
+    vt, vmt = T.as_torch(v), T.as_torch(vm).contiguous()
+    dev = T.require_cuda(vt, vmt)
+    b, h, n, d, sb, sh, sn = T.bhnd(vt, tensor_layout)
+    assert tuple(vmt.shape) == (b, h, d) and vmt.dtype == vt.dtype, "vm must be [B,H,D] in v's dtype"
+    if d % 8 != 0:
+        raise ValueError(f"Unsupported head_dim: {d}")
+    out = torch.empty(vt.shape, dtype=torch.float16, device=dev)
+    _, _, _, _, osb, osh, osn = T.bhnd(out, tensor_layout)
+    N.call("lowbit_sub_mean", vt.data_ptr(), vmt.data_ptr(), out.data_ptr(), b, h, n, d, sb, sh, sn, osb, osh, osn,
+           T.dtype_code(vt.dtype), T.stream_ptr(dev), device=dev)
+    return T.like(out, v)
 
 
 def abs_max(x, tensor_layout="HND"):
@@ -399,5 +372,5 @@ def abs_max(x, tensor_layout="HND"):
     b, h, n, d, sb, sh, sn = T.bhnd(xt, tensor_layout)
     out = torch.empty((), dtype=torch.float32, device=dev)
     N.call("lowbit_abs_max", xt.data_ptr(), out.data_ptr(), b, h, n, d, sb, sh, sn, T.dtype_code(xt.dtype),
-           T.stream_ptr(dev))
+           T.stream_ptr(dev), device=dev)
     return out

@@ -58,7 +58,7 @@ def _quant_packed(x, km, cu32, max_seqlen, blk, bits, pack, sm_arg, mode):
         N.call("lowbit_quant_per_block_varlen", x.data_ptr(), km.data_ptr() if km is not None else None,
                codes.data_ptr(), scale.data_ptr(), cu32.data_ptr(), cs.data_ptr(), nseq, h, int(max_seqlen), d,
                x.stride(1), x.stride(0), codes.stride(1), codes.stride(0), scale.stride(0), blk, bits,
-               int(bool(pack)), float(sm_arg), mode, T.dtype_code(x.dtype), T.stream_ptr(dev))
+               int(bool(pack)), float(sm_arg), mode, T.dtype_code(x.dtype), T.stream_ptr(dev), device=dev)
     return codes, scale, cs, cap
 
 
@@ -74,7 +74,7 @@ def _attend_packed(q_c, k_c, v, q_s, k_s, cu_q, cu_k, cqs, cks, max_seqlen_q, ou
                cks.data_ptr(), o.data_ptr(), cu_q.numel() - 1, hq, hkv, tq, tk, int(max_seqlen_q), d,
                q_c.stride(1), q_c.stride(0), k_c.stride(1), k_c.stride(0), v.stride(1), v.stride(0), o.stride(1),
                o.stride(0), q_s.stride(0), k_s.stride(0), qk_mode, T.dtype_code(out_dtype),
-               N.ATTN_CAUSAL if causal else 0, T.stream_ptr(dev))
+               N.ATTN_CAUSAL if causal else 0, T.stream_ptr(dev), device=dev)
     return o
 
 

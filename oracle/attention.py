@@ -215,15 +215,16 @@ def lowbit_fa_api(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, 
     return o
 
 
-def cpu_quantize_and_attend(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, smooth_k=True):
+def cpu_quantize_and_attend(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None, smooth_k=True, kbits=8):
     """The CPU baseline the bench times ("port"): the reference's pure-Paddle quantize-and-attend math
-    on torch-CPU -- Q1 per-block INT8 quantize via tensor ops, dequantize, then the corrected
-    manual_scaled_dot_product_attention (src/core.py:46-69, K transpose fixed per SURVEY 2.3-I) in fp32."""
+    on torch-CPU -- Q1 per-block INT8 quantize via tensor ops (kbits=4: K codes in [-7,7], the q_int8 / k_int4
+    quantizer quant_per_block.py:391-458), dequantize, then the corrected manual_scaled_dot_product_attention
+    (src/core.py:46-69, K transpose fixed per SURVEY 2.3-I) in fp32."""
     d = q.shape[-1]
     if sm_scale is None:
         sm_scale = 1.0 / d ** 0.5
     km = Q.k_mean(k, tensor_layout) if smooth_k else None
-    qi, qs, ki, ks = Q.per_block_int8_q1(q, k, km, sm_scale=sm_scale, tensor_layout=tensor_layout)
+    qi, qs, ki, ks = Q.per_block_int8_q1(q, k, km, sm_scale=sm_scale, tensor_layout=tensor_layout, kbits=kbits)
     qh = _hnd(qi, tensor_layout).float() * qs.repeat_interleave(128, dim=2)[:, :, :_hnd(qi, tensor_layout).shape[2], None]
     kh = _hnd(ki, tensor_layout).float() * ks.repeat_interleave(64, dim=2)[:, :, :_hnd(ki, tensor_layout).shape[2], None]
     vh = _hnd(v, tensor_layout).float()

@@ -451,5 +451,12 @@ def sub_mean(v, tensor_layout="HND"):
     v_smoothed = fp16(v - vm).  Returns (v_smoothed fp16, vm [B,H,D] in v's dtype)."""
     seq = 1 if tensor_layout == "NHD" else 2
     vm = v.mean(dim=seq)
-    vs = (v.float() - vm.unsqueeze(seq).float()).to(torch.float16)
-    return vs, vm
+    return sub_mean_given(v, vm, tensor_layout)
+
+
+def sub_mean_given(v, vm, tensor_layout="HND"):
+    """SubMeanKernel (fused.cu:201-261) for a mean the caller hands over: the difference is taken IN THE INPUT DTYPE
+    (__hsub2 on half2 / bfloat162, :243: one rounding of the exact difference) and then converted to fp16 (:245-248).
+    Pinned by tests/golden/fused_*.npz (the reference kernel itself)."""
+    seq = 1 if tensor_layout == "NHD" else 2
+    return (v.float() - vm.unsqueeze(seq).float()).to(v.dtype).to(torch.float16), vm

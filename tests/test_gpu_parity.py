@@ -664,9 +664,9 @@ def test_host_streaming_matches_device_call(L, cuda_dev, layout, b, hq, hkv, n, 
     ("NHD", 3, 4, 4, 300, 64, False, None),
 ])
 def test_host_streaming_replays_a_captured_graph(L, cuda_dev, layout, b, hq, hkv, n, d, causal, chunks):
-    """A caller that returns with the same pinned buffers gets the pipeline as one CUDA graph (captured at the second
-    call, replayed afterwards).  The buffers are refilled in place between calls: every replay must read the new
-    contents and stay bit-identical to the plain operator call; graph=False never captures."""
+    """graph=True: a caller that returns with the same pinned buffers gets the pipeline as one CUDA graph (captured at
+    the second call, replayed afterwards).  The buffers are refilled in place between calls: every replay must read the
+    new contents and stay bit-identical to the plain operator call; the default (graph=False) never captures."""
     from lowbit_quant_fa2_paddle_b200 import host as H
     H.drop_graphs()
     q = mk(b, hq, n, d, layout, torch.float16, 31).pin_memory()
@@ -679,7 +679,8 @@ def test_host_streaming_replays_a_captured_graph(L, cuda_dev, layout, b, hq, hkv
             k.copy_(mk(b, hkv, n, d, layout, torch.float16, 50 + it, bias=1.0))
             v.copy_(mk(b, hkv, n, d, layout, torch.float16, 60 + it))
         out.zero_()
-        got = L.lowbit_fa_host(q, k, v, out=out, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev)
+        got = L.lowbit_fa_host(q, k, v, out=out, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev,
+                               graph=True)
         ref = L.lowbit_fa_qk_int8_pv_fp16_triton(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout,
                                                  is_causal=causal)
         torch.cuda.synchronize()
@@ -687,7 +688,7 @@ def test_host_streaming_replays_a_captured_graph(L, cuda_dev, layout, b, hq, hkv
     entries = [e for e in H._graphs.values()]
     assert len(entries) == 1 and entries[0][1] is not None and entries[0][0] == 4  # seen 4 times, graph captured
     out.zero_()
-    L.lowbit_fa_host(q, k, v, out=out, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev, graph=False)
+    L.lowbit_fa_host(q, k, v, out=out, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev)
     torch.cuda.synchronize()
     assert torch.equal(out, ref.cpu()) and entries[0][0] == 4
     H.drop_graphs()
@@ -718,51 +719,6 @@ def test_triton_gpu_division_mode_is_within_one_step_of_ieee(L, cuda_dev, dtype,
 
 
 # ------------------------------------------------------------------------------------------------ fused preparation
-@pytest.mark.parametrize("layout", ["HND", "NHD"])
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("b,hq,hkv,nq,nk,d", [
-    (1, 2, 2, 512, 512, 64),      # config 1
-    (2, 6, 2, 200, 333, 128),     # GQA, ragged tails, odd number of K blocks
-    (1, 1, 1, 1, 1, 64),          # single row
-    (3, 4, 4, 1500, 1500, 64),    # several K-sum chunks per slice, several stages
-])
-def test_prep_qk_matches_separate_kernels(L, cuda_dev, layout, dtype, b, hq, hkv, nq, nk, d):
-    """lowbit_prep_qk (K mean + smoothing + both quantizers in one persistent launch) is bit-identical to
-    k_mean + per_block quantizers (which the golden / oracle tests pin), for every rounding convention, packed
-    INT4 K, with and without smoothing, and across repeated calls on the same workspace (epoch protocol)."""
-    q = mk(b, hq, nq, d, layout, dtype, 31).to(cuda_dev)
-    k = mk(b, hkv, nk, d, layout, dtype, 32, bias=2.0).to(cuda_dev)
-    km = L.k_mean(k, layout)
-    for rep in range(2):
-        for backend in ("triton", "cuda", "triton_gpu"):
-            ref = L.per_block_int8(q, k, km=km, tensor_layout=layout, backend=backend)
-            got = L.prep_qk(q, k, True, None, layout, backend)
-            assert torch.equal(got[4], km)
-            for g, r in zip(got[:4], ref):
-                assert torch.equal(g, r), f"{backend} rep {rep}"
-    ref = L.per_block_q_int8_k_int4(q, k, km=km, tensor_layout=layout)
-    got = L.prep_qk(q, k, True, None, layout, "triton", 8, 4, True)
-    for g, r in zip(got[:4], ref):
-        assert torch.equal(g, r)
-    ref = L.per_block_int8(q, k, km=None, sm_scale=0.3, tensor_layout=layout)
-    got = L.prep_qk(q, k, False, 0.3, layout, "triton")
-    assert got[4] is None
-    for g, r in zip(got[:4], ref):
-        assert torch.equal(g, r)
-
-
-def test_prep_qk_full_size_config2(L, cuda_dev):
-    """BASELINE config 2 at full size (B4 H32 N4096 D64): fused preparation == separate kernels, bit for bit."""
-    torch.manual_seed(0)
-    q, k = (torch.randn(4, 32, 4096, 64, dtype=torch.float16, device=cuda_dev) for _ in range(2))
-    km = L.k_mean(k)
-    ref = L.per_block_int8(q, k, km=km)
-    got = L.prep_qk(q, k)
-    assert torch.equal(got[4], km)
-    for g, r in zip(got[:4], ref):
-        assert torch.equal(g, r)
-
-
 # ------------------------------------------------------------------------------------------------ varlen (packed) path
 VARLEN = golden_names("varlen_")
 
@@ -972,3 +928,43 @@ def test_tiny_sequences_every_k_format(L, cuda_dev, n, d):
         o = L.lowbit_fa_qk_int4_pv_fp8(dq, dk, dv, is_causal=causal)
         ref = OA.lowbit_fa_api(q, k, v, "HND", causal, compat_tail=False, pv_accum="fp32", qk="int4", pv="fp8")
         assert (o.cpu().float() - ref.float()).abs().max().item() <= 0.125 * float(v.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ SDPA plug-in (f-3)
+@pytest.mark.parametrize("op_name", ["lowbit_fa_qk_int8_pv_fp16_triton", "lowbit_fa_q_int8_k_int4_pv_fp16"])
+def test_sdpa_monkey_patch_cogvideox_shape(L, cuda_dev, op_name):
+    """The reference's plug-in path (example/sageattn_cogvideo.py:9-14): F.scaled_dot_product_attention replaced by the
+    operator and called the way diffusers calls it -- positional q, k, v in [B,H,N,D], bf16, N = 17776 (not a multiple
+    of 64 or 128), with attn_mask / dropout_p / is_causal keywords.  Checked against torch's own SDPA in fp32 on a head
+    slice (max-abs, MSE, cos-sim) and at the block level through examples/cogvideox_block.Attention."""
+    import torch.nn.functional as F
+    from lowbit_quant_fa2_paddle_b200.plugin import patch_sdpa
+    torch.manual_seed(0)
+    b, h, n, d = 1, 6, 17776, 64
+    q, k, v = (torch.randn(b, h, n, d, device=cuda_dev, dtype=torch.bfloat16) for _ in range(3))
+    k = k + 0.5 * torch.randn(1, h, 1, d, device=cuda_dev, dtype=torch.bfloat16)  # a channel bias for the smoothing
+    orig = F.scaled_dot_product_attention
+    with patch_sdpa(getattr(L, op_name)):
+        assert F.scaled_dot_product_attention is not orig
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
+    assert F.scaled_dot_product_attention is orig, "the patch must be undone"
+    assert o.shape == q.shape and o.dtype == torch.bfloat16
+    ref = orig(q[:, :2].float(), k[:, :2].float(), v[:, :2].float())
+    got = o[:, :2].float()
+    cos = cos_sim(got.cpu(), ref.cpu())
+    assert cos >= (0.999 if "int8_pv" in op_name else 0.98), cos  # 4-bit K codes: format error, not kernel error
+    assert (got - ref).pow(2).mean().item() <= (2e-5 if "int8_pv" in op_name else 1e-3)
+    # block level: the synthetic CogVideoX attention block, patched vs not
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("cogvideox_block", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "examples", "cogvideox_block.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    blk = mod.Attention().to(cuda_dev, torch.bfloat16).eval()
+    x = torch.randn(1, 4096 + 48, 3072, device=cuda_dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        y0 = blk(x)
+        with patch_sdpa(getattr(L, op_name)):
+            y1 = blk(x)
+    assert cos_sim(y1.float().cpu(), y0.float().cpu()) >= 0.9999

@@ -67,32 +67,38 @@ def main():
         sd_loc = take(sd.contiguous())
         e_ring = (o.float() - sd_loc).abs()
         e_one = (o_loc.float() - sd_loc).abs()
-        dots = torch.stack([(o.float() * sd_loc).sum(), (o.float() ** 2).sum(), (sd_loc ** 2).sum()]).double()
+        of, o1 = o.float(), o_loc.float()
+        dots = torch.stack([(of * sd_loc).sum(), (of ** 2).sum(), (sd_loc ** 2).sum(), (o1 * sd_loc).sum(), (o1 ** 2).sum()]).double()
         dist.all_reduce(dots)
         cos = float(dots[0] / (dots[1].sqrt() * dots[2].sqrt()))
-        # rows that see fewer than 64 keys (the head of a causal sequence) carry un-averaged e4m3 rounding of P
-        # (2^-4 relative per element): report them apart from the bulk
+        cos1 = float(dots[3] / (dots[4].sqrt() * dots[2].sqrt()))
+        # rows that see few keys (the head of a causal sequence) carry un-averaged e4m3 rounding of P (2^-4 relative per
+        # element): the ring / single-pass difference is reported per band of visible keys
         pos = torch.cat([torch.arange(c.offset, c.offset + c.length, device=dev) for c in chunks])
-        few = (pos < 64) if causal else torch.zeros_like(pos, dtype=torch.bool)
-        few_b = few.view(1, 1, -1, 1) if layout == "HND" else few.view(1, -1, 1, 1)
+        vis = pos if causal else torch.full_like(pos, n)
+        diff = (of - o1).abs()
+        dmax = diff.amax(dim=(0, 1, 3)) if layout == "HND" else diff.amax(dim=(0, 2, 3))  # per local row
         zero = torch.zeros((), device=dev)
-        d_bulk = torch.where(few_b, zero, (o.float() - o_loc.float()).abs()).max()
-        stats = torch.stack([err, lerr, e_ring.max(), e_one.max(), d_bulk, e_ring.mean(), e_one.mean()])
+        band = lambda lo, hi: torch.where((vis >= lo) & (vis < hi), dmax, zero).max()
+        stats = torch.stack([err, lerr, e_ring.max(), e_one.max(), band(256, 1 << 30), e_ring.mean(), e_one.mean(),
+                             band(0, 64), band(64, 256)])
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        cos_floor = 0.999 if qk == "int8" else 0.98  # INT4 / mixed K is a coarse code by design (single pass: ~0.99)
         if pv == "fp16":
-            good = bool(stats[0] <= 4e-3) and bool(stats[1] <= 1e-2) and cos >= 0.999
+            good = (bool(stats[0] <= 4e-3) and bool(stats[1] <= 1e-2) and cos >= cos_floor and cos >= cos1 - 1e-5)
         else:
             # FP8 P.V: the ring rounds P~ to e4m3 against per-shard reference maxima, a single pass against one running
-            # maximum -- two different (equally valid) roundings of the same softmax, 2^-4 relative per element.  The bar
-            # is therefore accuracy against exact attention: cos-sim >= 0.999, the ring no worse than the single pass
-            # (max error within 1.25x, mean error within 1.1x), and the two within 0.05 of each other away from the
-            # first 64 causal rows.
-            good = (cos >= 0.999 and bool(stats[2] <= 1.25 * stats[3] + 1e-3) and bool(stats[5] <= 1.1 * stats[6] + 1e-4)
-                    and bool(stats[4] <= 0.05) and bool(stats[1] <= 5e-2))
+            # maximum -- two different, equally valid roundings of the same softmax, 2^-4 relative per element, which
+            # average out over the keys a row sees.  The bar is therefore accuracy against exact attention: the ring no
+            # worse than the single pass (cos-sim within 2e-4, max error within 1.25x, mean error within 1.05x), and
+            # the two within 0.05 of each other on every row that sees at least 256 keys.
+            good = (cos >= cos_floor and cos >= cos1 - 2e-4 and bool(stats[2] <= 1.25 * stats[3] + 1e-3)
+                    and bool(stats[5] <= 1.05 * stats[6] + 1e-4) and bool(stats[4] <= 0.05) and bool(stats[1] <= 5e-2))
         ok = ok and good
         if rank == 0:
             print(f"ring world={world} {layout} causal={causal} qk={qk} pv={pv} d={d} n={n}: max|o-o1|={float(stats[0]):.3e} "
-                  f"(rows>=64: {float(stats[4]):.3e}) max|lse-lse1|={float(stats[1]):.3e} | vs fp32 SDPA: cos={cos:.6f} "
+                  f"(rows seeing <64 / 64-255 / >=256 keys: {float(stats[7]):.3e} / {float(stats[8]):.3e} / {float(stats[4]):.3e}) "
+                  f"max|lse-lse1|={float(stats[1]):.3e} | vs fp32 SDPA: cos ring {cos:.6f} / single {cos1:.6f}, "
                   f"max err ring {float(stats[2]):.3e} / single {float(stats[3]):.3e}, mean err ring {float(stats[5]):.3e} / "
                   f"single {float(stats[6]):.3e} {'OK' if good else 'MISMATCH'}", flush=True)
     # head sharding: each rank computes its head slice; gathered result == single-GPU result, bit for bit

@@ -53,7 +53,6 @@ for name in (sys.argv[1:] or ["c2", "c3"]):
     ]
     # fused preparation: Q and K of the same shape (rotating pairs): 2 x (2 B read + 1 B written) per element of one
     # tensor = 6 B/elem algorithmic (K crosses HBM once; its second read is an L2 hit)
-    cases.append(("prep_qk fused (mean+K+Q)", lambda x: L.prep_qk(x2(x), x, True, None, layout), 6.0))
     if L.k_smooth_quant_supported(xs[0], layout):
         cases.append(("K fused (cluster): mean + K int8", lambda x: L.k_smooth_quant(x, 8, False, layout), 3.0))
         cases.append(("K separate: k_mean + K int8", lambda x: Qz._quant_one(x, L.k_mean(x, layout), 64, 8, False, 1.0, NV.QMODE_TRITON, layout), 3.0))
