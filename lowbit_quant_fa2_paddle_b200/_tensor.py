@@ -41,6 +41,12 @@ def like(result, original):
     return result
 
 
+def aligned16(t):
+    """The kernels load 16 bytes at a time: a view whose storage offset breaks that alignment (e.g. x[..., 4:68] of a
+    fused buffer -- legal for the reference's Triton kernels) is copied to a fresh, aligned tensor."""
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def dtype_code(dt):
     if dt == torch.float16:
         return N.F16

@@ -53,6 +53,7 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
     d_to = 64 if head_dim_og <= 64 else 128
     qt, kt, vt = _pad_head(qt, d_to), _pad_head(kt, d_to), _pad_head(vt, d_to)
     assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    qt, kt, vt = T.aligned16(qt), T.aligned16(kt), T.aligned16(vt)
     with torch.cuda.device(dev):
         v_scale = v_mean = None
         if pv == "fp8":  # V -> e4m3 per channel, transposed (src/quant.py:210-291; core.py:882-884)
@@ -201,9 +202,11 @@ def compute_scale(tensor, bits=8, symmetric=True, tensor_layout="HND"):
         raise NotImplementedError("asymmetric compute_scale is not on the hot path")
     t = T.as_torch(tensor)
     d = t.shape[-1]
+    if d > 128:
+        raise ValueError(f"Unsupported head_dim: {d}")
     if d not in (64, 128):
         t = _pad_head(t, 64 if d <= 64 else 128)
-    return Qz.abs_max(t, tensor_layout) / (2 ** (bits - 1) - 1)
+    return Qz.abs_max(T.aligned16(t), tensor_layout) / (2 ** (bits - 1) - 1)
 
 
 def select_quantization(q, k, v, tensor_layout="HND"):

@@ -877,7 +877,8 @@ int lowbit_quant_per_block_varlen(const void* in, const void* km, void* codes, f
   LOWBIT_CHECK(blk == 64 || blk == 128, "lowbit_quant_per_block_varlen: block size must be 64 or 128 (got %d)", blk);
   LOWBIT_CHECK(bits == 8 || bits == 4 || bits == 2, "lowbit_quant_per_block_varlen: bits must be 8, 4 or 2 (got %d)", bits);
   LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_quant_per_block_varlen: bad mode %d", mode);
-  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0, "lowbit_quant_per_block_varlen: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && ((uintptr_t)in & 15) == 0,
+               "lowbit_quant_per_block_varlen: input base address and strides must keep 16-byte alignment");
   const int div = pack ? 8 / bits : 1;
   LOWBIT_CHECK((osn * div) % 8 == 0, "lowbit_quant_per_block_varlen: code rows must keep 8-byte alignment");
   dim3 grid((max_seqlen + blk - 1) / blk, H, nseq);
@@ -909,7 +910,8 @@ int lowbit_quant_k_mixed(const void* k, const void* km, const int32_t* kbits_in,
   LOWBIT_CHECK(k && codes && scale && kbits_out, "lowbit_quant_k_mixed: null pointer");
   LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_quant_k_mixed: empty tensor");
   LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_quant_k_mixed: bad mode %d", mode);
-  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0, "lowbit_quant_k_mixed: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0 && ((uintptr_t)k & 15) == 0,
+               "lowbit_quant_k_mixed: input base address and strides must keep 16-byte alignment");
   LOWBIT_CHECK(osn % 16 == 0 && osh % 16 == 0 && osb % 16 == 0 && ((uintptr_t)codes & 15) == 0,
                "lowbit_quant_k_mixed: container rows must keep 16-byte alignment");
   const int nblk = (N + 63) / 64;
@@ -937,7 +939,8 @@ int lowbit_k_mean(const void* k, void* km_out, void* workspace, int B, int H, in
   LOWBIT_CHECK(D == 64 || D == 128, "lowbit_k_mean: head_dim must be 64 or 128 (got %d)", D);
   LOWBIT_CHECK(k && km_out && workspace, "lowbit_k_mean: null pointer");
   LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_k_mean: empty tensor");
-  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0, "lowbit_k_mean: strides must keep 16-byte alignment");
+  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0 && ((uintptr_t)k & 15) == 0,
+               "lowbit_k_mean: base address and strides must keep 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
   const int chunk = mean_chunk_rows(N);
   const int nchunk = (N + chunk - 1) / chunk;
@@ -994,7 +997,8 @@ int lowbit_quant_per_block(const void* in, const void* km, void* codes, float* s
   LOWBIT_CHECK(bits == 8 || bits == 4 || bits == 2, "lowbit_quant_per_block: bits must be 8, 4 or 2 (got %d)", bits);
   LOWBIT_CHECK((mode & 0xff) == LOWBIT_QMODE_TRITON || (mode & 0xff) == LOWBIT_QMODE_CUDA, "lowbit_quant_per_block: bad mode %d", mode);
   LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_quant_per_block: empty tensor");
-  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0, "lowbit_quant_per_block: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0 && ((uintptr_t)in & 15) == 0,
+               "lowbit_quant_per_block: input base address and strides must keep 16-byte alignment");
   const int ob = (pack && bits < 8) ? bits : 8;  // bytes of 8 codes
   LOWBIT_CHECK(osn % ob == 0 && osh % ob == 0 && osb % ob == 0, "lowbit_quant_per_block: output strides misaligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1004,7 +1008,7 @@ int lowbit_quant_per_block(const void* in, const void* km, void* codes, float* s
   // LOWBIT_QUANT_TMA=0 / 2 force neither / both (A/B measurements).
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("LOWBIT_QUANT_TMA"); use_tma = e ? atoi(e) : 1; }
-  const bool tma_ok = use_tma && ((uintptr_t)in & 15) == 0;
+  const bool tma_ok = use_tma != 0;
 #define BY_BLK(T, DD)                                                                        \
   switch (blk) {                                                                             \
     case 32: return launch_qpb<T, DD, 32>(ARGS);                                             \
@@ -1025,6 +1029,8 @@ int lowbit_abs_max(const void* x, float* out, int B, int H, int N, int D, int64_
                    int dtype, void* stream) {
   LOWBIT_CHECK(x && out, "lowbit_abs_max: null pointer");
   LOWBIT_CHECK(D == 64 || D == 128, "lowbit_abs_max: head_dim must be 64 or 128 (got %d)", D);
+  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0 && ((uintptr_t)x & 15) == 0,
+               "lowbit_abs_max: base address and strides must keep 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;
   LOWBIT_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   const int rows_per_cta = (256 / (D / 8)) * 8;

@@ -351,7 +351,8 @@ int lowbit_quant_per_thread(const void* in, const void* km, void* codes, float* 
   LOWBIT_CHECK((is_key && warp_blk == 64) || (!is_key && warp_blk == 32),
                "lowbit_quant_per_thread: WARPQ must be 32 and WARPK 64 (got %d)", warp_blk);
   LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_quant_per_thread: empty tensor");
-  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0, "lowbit_quant_per_thread: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(isn % 8 == 0 && ish % 8 == 0 && isb % 8 == 0 && ((uintptr_t)in & 15) == 0,
+               "lowbit_quant_per_thread: input base address and strides must keep 16-byte alignment");
   LOWBIT_CHECK(osn % 8 == 0 && osh % 8 == 0 && osb % 8 == 0, "lowbit_quant_per_thread: output strides misaligned");
   const int ng = is_key ? 4 : 8;
   LOWBIT_CHECK(n_scale % ng == 0 && n_scale / ng >= (N + warp_blk - 1) / warp_blk, "lowbit_quant_per_thread: n_scale too small");
@@ -402,7 +403,8 @@ int lowbit_v_fp8_per_channel(const void* v, void* v8, float* v_scale, float* vm,
   LOWBIT_CHECK(v && v8 && v_scale && workspace, "lowbit_v_fp8_per_channel: null pointer");
   LOWBIT_CHECK(D == 64 || D == 128, "lowbit_v_fp8_per_channel: head_dim must be 64 or 128 (got %d)", D);
   LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_v_fp8_per_channel: empty tensor");
-  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0, "lowbit_v_fp8_per_channel: input strides must keep 16-byte alignment");
+  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0 && ((uintptr_t)v & 15) == 0,
+               "lowbit_v_fp8_per_channel: input base address and strides must keep 16-byte alignment");
   LOWBIT_CHECK(osb % 16 == 0 && osh % 16 == 0 && osd % 16 == 0 && ((uintptr_t)v8 & 15) == 0,
                "lowbit_v_fp8_per_channel: output must keep 16-byte alignment");
   cudaStream_t st = (cudaStream_t)stream;

@@ -172,6 +172,7 @@ def sageattn_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: int, max_
     if head_dim_og != d_to:
         qt, kt, vt = (torch.nn.functional.pad(t, (0, d_to - head_dim_og)) for t in (qt, kt, vt))
     assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    qt, kt, vt = T.aligned16(qt), T.aligned16(kt), T.aligned16(vt)
     backend = kwargs.get("quantization_backend", "triton")
     if backend not in Qz._MODES:
         raise ValueError(f"Unsupported quantization backend: {backend}")

@@ -968,3 +968,21 @@ def test_sdpa_monkey_patch_cogvideox_shape(L, cuda_dev, op_name):
         with patch_sdpa(getattr(L, op_name)):
             y1 = blk(x)
     assert cos_sim(y1.float().cpu(), y0.float().cpu()) >= 0.9999
+
+
+def test_misaligned_views_and_wide_heads(L, cuda_dev):
+    """A view whose storage offset is not a multiple of 16 bytes (a column slice of a fused buffer: legal for the
+    reference's Triton kernels) goes through the operator (it is re-aligned by a copy), the raw quantizer entry point
+    refuses it with a message instead of faulting, and compute_scale rejects head_dim > 128 like the operators do."""
+    from lowbit_quant_fa2_paddle_b200 import _native as NV
+    torch.manual_seed(11)
+    fused = torch.randn(1, 2, 256, 3 * 64 + 4, dtype=torch.float16, device=cuda_dev)
+    q, k, v = fused[..., 4:68], fused[..., 68:132], fused[..., 132:196]
+    assert q.data_ptr() % 16 != 0
+    o = L.lowbit_fa_qk_int8_pv_fp16_triton(q, k, v)
+    ref = L.lowbit_fa_qk_int8_pv_fp16_triton(q.contiguous(), k.contiguous(), v.contiguous())
+    assert torch.equal(o, ref)
+    with pytest.raises(NV.LowbitNativeError, match="16-byte"):
+        L.k_mean(k)
+    with pytest.raises(ValueError):
+        L.compute_scale(torch.randn(1, 1, 8, 160, dtype=torch.float16, device=cuda_dev))
