@@ -54,8 +54,12 @@ enum {
 enum {
   LOWBIT_QK_I8 = 0,     /* Q int8, K int8 (one code per byte)                               */
   LOWBIT_QK_Q8K4 = 1,   /* Q int8, K int4 packed two codes per byte (low nibble = even d)   */
-  LOWBIT_QK_Q8KMIX = 2  /* Q int8, K per-64-block bit width from `kbits` (8/4/2) in the mixed
+  LOWBIT_QK_Q8KMIX = 2, /* Q int8, K per-64-block bit width from `kbits` (8/4/2) in the mixed
                            container written by lowbit_quant_k_mixed                          */
+  LOWBIT_QK_F16 = 3     /* no quantization: q_codes / k_codes are the fp16 / bf16 tensors themselves (in the
+                           output dtype), QK^T on tcgen05 kind::f16 with fp32 scores -- the "FP16" class of
+                           lowbit_fa_multi_precision (src/core.py:1075-1076, `default_attn`).  q_scale points
+                           at ONE float, sm_scale * log2(e); k_scale is not read.  fp16 P.V, padded tensors. */
 };
 enum { LOWBIT_PV_F16 = 0, LOWBIT_PV_E4M3 = 1 };
 

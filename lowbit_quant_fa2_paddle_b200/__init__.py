@@ -19,6 +19,7 @@ from .core import (  # noqa: F401
     lowbit_fa_q_int8_k_dynamic,
     lowbit_fa_qk_int8_pv_fp8_cuda,
     lowbit_fa_qk_int4_pv_fp8,
+    lowbit_fa_fp16,
     compute_scale,
     select_quantization,
 )

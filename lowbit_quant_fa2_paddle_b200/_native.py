@@ -14,7 +14,7 @@ F16, BF16 = 0, 1
 QMODE_TRITON, QMODE_CUDA = 0, 1
 QMODE_FLAG_DIV_FULL = 0x200  # Q1 with PTX div.full.f32: the reference kernels as Triton JIT-compiles them for a GPU
 QMODE_FLAG_IEEE_DIV = 0x100  # validation: Q1 quotient by IEEE division instead of the 3-instruction exact sequence
-QK_I8, QK_Q8K4, QK_Q8KMIX = 0, 1, 2
+QK_I8, QK_Q8K4, QK_Q8KMIX, QK_F16 = 0, 1, 2, 3
 PV_F16, PV_E4M3 = 0, 1
 ATTN_CAUSAL, ATTN_COMPAT_TAIL, ATTN_NARROW = 1, 2, 4
 

@@ -40,13 +40,17 @@ def _common(q, k, v, q_scale, k_scale, tensor_layout, qk_mode, pv_mode, v_scale,
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"tensor_layout {tensor_layout} not supported")
     qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
-    qs, ks = T.as_torch(q_scale), T.as_torch(k_scale)
+    qs = T.as_torch(q_scale)
+    ks = T.as_torch(k_scale) if k_scale is not None else qs  # QK_F16: one scale for every score, k_scale unused
     dev = T.require_cuda(qt, kt, vt, qs, ks)
     b, hq, nq, d, qsb, qsh, qsn = T.bhnd(qt, tensor_layout)
     _, hkv, nk, dk, ksb, ksh, ksn = T.bhnd(kt, tensor_layout)
     assert dk == (d // 2 if qk_mode == N.QK_Q8K4 else d), "K codes have the wrong last dimension for this qk_mode"
     vsb, vsh, vsn = _v_strides(vt, tensor_layout, pv_mode)
-    assert qt.dtype == torch.int8 and kt.dtype == torch.int8
+    if qk_mode == N.QK_F16:
+        assert qt.dtype == kt.dtype and qt.dtype in (torch.float16, torch.bfloat16), "QK_F16 takes fp16 / bf16 q and k"
+    else:
+        assert qt.dtype == torch.int8 and kt.dtype == torch.int8
     assert qs.dtype == torch.float32 and ks.dtype == torch.float32 and qs.is_contiguous() and ks.is_contiguous()
     vs = vm = None
     if pv_mode == N.PV_E4M3:

@@ -222,13 +222,55 @@ def select_quantization(q, k, v, tensor_layout="HND"):
     return "INT4"
 
 
+_scale_cache = {}  # (device index, value) -> 1-element f32 device tensor holding sm_scale * log2(e)
+
+
+def lowbit_fa_fp16(q, k, v, tensor_layout: str = "HND", is_causal: bool = False, sm_scale: Optional[float] = None,
+                   return_lse: bool = False, **kwargs: Any):
+    """Un-quantized attention on the same kernel: the "FP16" class of `lowbit_fa_multi_precision`, which the reference
+    serves with `default_attn` (plain scaled-dot-product attention, src/core.py:46-69,1075-1076).  Q.K^T runs on
+    tcgen05 kind::f16 over the fp16 / bf16 inputs as they are (fp32 scores), the rest of the pipeline (base-2 online
+    softmax, fp16 P.V with fp32 accumulation) is shared with the low-bit modes; no K smoothing (softmax is invariant
+    under it and nothing is quantized).  Returns o, or (o, lse [B,Hq,Nq] natural log) with return_lse."""
+    qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
+    dtype = qt.dtype
+    assert dtype in [torch.float16, torch.bfloat16], \
+        "Input tensors must be in dtype of torch.float16 or torch.bfloat16"
+    assert qt.device == kt.device == vt.device, "All tensors must be on the same device."
+    assert qt.dtype == kt.dtype == vt.dtype, "All tensors must have the same dtype."
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    head_dim_og = qt.shape[-1]
+    if head_dim_og > 128:
+        raise ValueError(f"Unsupported head_dim: {head_dim_og}")
+    dev = T.require_cuda(qt, kt, vt)
+    d_to = 64 if head_dim_og <= 64 else 128
+    qt, kt, vt = (T.aligned16(_pad_head(t, d_to)) for t in (qt, kt, vt))
+    assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    if sm_scale is None:
+        sm_scale = 1.0 / head_dim_og ** 0.5
+    key = (dev.index, float(sm_scale))
+    sc = _scale_cache.get(key)
+    if sc is None:
+        if len(_scale_cache) > 64:
+            _scale_cache.clear()
+        sc = _scale_cache[key] = torch.full((1,), float(sm_scale) * LOG2E, dtype=torch.float32, device=dev)
+    if dtype == torch.bfloat16:
+        vt = vt.to(torch.float16)  # P.V runs in fp16 like every other mode (core.py:307-308)
+    o, lse = A._forward(qt, kt, vt, sc, None, tensor_layout, dtype, return_lse, bool(is_causal), qk_mode=N.QK_F16)
+    o = o[..., :head_dim_og]
+    if return_lse:
+        return T.like(o, q), T.like(lse / LOG2E, q)
+    return T.like(o, q)
+
+
 def sageattn_multi_precision(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
                              sm_scale: Optional[float] = None, return_lse: bool = False, **kwargs: Any):
-    """core.py:1064-1096.  The reference's "FP16" branch calls a pure-Paddle SDPA that is wrong for either
-    layout and is not part of the low-bit path; here the widest low-bit format (INT8) serves
-    that class."""
+    """core.py:1064-1096: the mean of the three global scales picks the format -- "FP16" (> 0.2): un-quantized
+    attention (the reference calls `default_attn`, :1075-1076; here the same kernel with fp16 Q.K^T,
+    `lowbit_fa_fp16`), "INT8" (> 0.05), else "INT4"."""
     kind = select_quantization(q, k, v, tensor_layout)
-    fn = sageattn_qk_int4_pv_fp16_triton if kind == "INT4" else sageattn_qk_int8_pv_fp16_triton
+    fn = {"FP16": lowbit_fa_fp16, "INT8": sageattn_qk_int8_pv_fp16_triton, "INT4": sageattn_qk_int4_pv_fp16_triton}[kind]
     return fn(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal, sm_scale=sm_scale, return_lse=return_lse)
 
 

@@ -65,7 +65,8 @@ static int32_t* g_attn_debug = nullptr;
 constexpr int kBM = 128;      // Q rows per CTA (= TMEM lanes)
 constexpr int kScaleBlk = 64; // k_scale granularity of the reference quantizer (BLKK)
 
-enum { KM_I8 = 0, KM_K4 = 1, KM_MIX = 2 };  // KM_K4 / KM_MIX: K tiles are expanded in shared memory
+enum { KM_I8 = 0, KM_K4 = 1, KM_MIX = 2, KM_F16 = 3 };  // KM_K4 / KM_MIX: K tiles are expanded in shared memory;
+                                                        // KM_F16: Q, K stay fp16 / bf16 (kind::f16 QK^T, fp32 scores)
 enum { PV_F16 = 0, PV_E4M3 = 1 };
 
 // Two kernels share this file:
@@ -78,7 +79,7 @@ enum { PV_F16 = 0, PV_E4M3 = 1 };
 // K tiles that need expansion (packed INT4 / mixed width): a dedicated expander warp does it, so the softmax warps --
 // the critical path -- carry no unpack instructions and the expansion runs ahead of them.
 template <int D, int KM> struct AttnRoles {
-  static constexpr bool kExpander = (KM != KM_I8);
+  static constexpr bool kExpander = (KM == KM_K4 || KM == KM_MIX);
   static constexpr int kThreads = 128 + 32 + (kExpander ? 32 : 0);  // softmax warps + helper warp (+ expander warp)
 };
 
@@ -100,27 +101,32 @@ template <> struct PvCfg<PV_E4M3> { static constexpr float THR = 2.f, OFF = 6.80
 template <int D, int KM, int PV>
 struct AttnSmem {
   using C = AttnCfg<D>;
-  static constexpr int kQ = kBM * D;                                  // int8
-  static constexpr int kK = C::BN * D;                                // int8 operand stage
-  static constexpr int kKStages = (KM == KM_I8) ? C::KS : 2;
+  static constexpr int kEQ = (KM == KM_F16) ? 2 : 1;                  // bytes per Q / K operand element
+  static constexpr int kQ = kBM * D * kEQ;                            // int8 (fp16 / bf16)
+  static constexpr int kK = C::BN * D * kEQ;                          // operand stage
+  static constexpr int kKStages = (KM == KM_I8) ? C::KS : ((KM == KM_F16 && D == 64) ? C::KS : 2);
+  static constexpr int kVStages = (KM == KM_F16 && D == 128) ? 2 : C::VS;  // fp16 operands at D=128: 96 KB per CTA
   static constexpr int kKp = (KM == KM_MIX) ? C::BN * D : C::BN * D / 2;  // packed staging stage (worst case)
   static constexpr int kKpStages = (KM == KM_K4) ? 4 : (KM == KM_MIX ? 3 : 0);
   static constexpr int kV = (PV == PV_F16) ? C::BN * D * 2 : C::BN * D;  // fp16 [key][d] / e4m3 [d][key]
-  static constexpr int kBytes = kQ + kKStages * kK + C::VS * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kBytes = kQ + kKStages * kK + kVStages * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 // One softmax step over a BN-key block for one query row: p = exp2(S*sc + nm), packed to fp16 pairs, row sum in fp32
 // (packed fp32x2 arithmetic, FFMA2 / FADD2: one instruction scales, or accumulates, two scores).
 // MASKED: columns > lim contribute 0 (causal diagonal band / masked tail keys).
-template <int BN, bool MASKED>
+template <bool FS> __device__ __forceinline__ float score_f32(uint32_t v) {
+  return FS ? __uint_as_float(v) : __int2float_rn((int)v);  // FS: the QK^T accumulator is fp32 (kind::f16), else int32
+}
+template <int BN, bool MASKED, bool FS = false>
 __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ s, float sc, float nm, int lim,
                                                    uint32_t* __restrict__ pk) {
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
   float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < BN; c += 4) {
-    const float2 x0 = __ffma2_rn(make_float2(__int2float_rn((int)s[c]), __int2float_rn((int)s[c + 1])), sc2, nm2);
-    const float2 x1 = __ffma2_rn(make_float2(__int2float_rn((int)s[c + 2]), __int2float_rn((int)s[c + 3])), sc2, nm2);
+    const float2 x0 = __ffma2_rn(make_float2(score_f32<FS>(s[c]), score_f32<FS>(s[c + 1])), sc2, nm2);
+    const float2 x1 = __ffma2_rn(make_float2(score_f32<FS>(s[c + 2]), score_f32<FS>(s[c + 3])), sc2, nm2);
     float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
     float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
     if (MASKED) {
@@ -142,7 +148,7 @@ __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ 
 // is taken over the ROUNDED values (accumulate_d_f8, attn_utils.cuh:550-562), here through exact e4m3 -> f16
 // conversion and short f16x2 partial sums.  Key c of an aligned 16-group sits at the K index the reference's V layout
 // expects (fused.cu:290-292): word w of a group = keys {2w, 2w+1, 8+2w, 9+2w}.
-template <int BN, bool MASKED>
+template <int BN, bool MASKED, bool FS = false>
 __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__ s, float sc, float nm, int lim,
                                                     uint32_t* __restrict__ pk) {
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
@@ -153,8 +159,8 @@ __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int c0 = 16 * g + 2 * w, c1 = c0 + 8;
-      const float2 x0 = __ffma2_rn(make_float2(__int2float_rn((int)s[c0]), __int2float_rn((int)s[c0 + 1])), sc2, nm2);
-      const float2 x1 = __ffma2_rn(make_float2(__int2float_rn((int)s[c1]), __int2float_rn((int)s[c1 + 1])), sc2, nm2);
+      const float2 x0 = __ffma2_rn(make_float2(score_f32<FS>(s[c0]), score_f32<FS>(s[c0 + 1])), sc2, nm2);
+      const float2 x1 = __ffma2_rn(make_float2(score_f32<FS>(s[c1]), score_f32<FS>(s[c1 + 1])), sc2, nm2);
       float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
       float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
       if (MASKED) {
@@ -424,10 +430,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   using C = AttnCfg<D>;
   using SM = AttnSmem<D, KM, PV>;
   using PC = PvCfg<PV>;
-  constexpr int BN = C::BN, VS = C::VS;
+  constexpr int BN = C::BN, VS = SM::kVStages;
   constexpr int KS = SM::kKStages;                   // int8 operand stages (expanded K: 2, indexed like the S buffers)
-  constexpr bool KX = (KM != KM_I8);                          // K tiles are expanded by the expander warp
-  constexpr int KPS = KX ? SM::kKpStages : C::KS;             // TMA-filled K stages
+  constexpr bool KX = (KM == KM_K4 || KM == KM_MIX);          // K tiles are expanded by the expander warp
+  constexpr bool FQK = (KM == KM_F16);                        // fp16 / bf16 operands, fp32 scores
+  constexpr int KPS = KX ? SM::kKpStages : KS;                // TMA-filled K stages
   constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;     // TMEM columns of one P tile
   constexpr int HW = 4;                                       // index of the helper warp
   // p_ready counts warps, not threads (measured: D=128 causal +3 %, D=64 INT8 K unchanged, but -1.8 % on the D=64
@@ -523,14 +530,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (ptx::elect_one()) {
       constexpr uint32_t kSwzQK = (D == 64) ? ptx::kSwz64 : ptx::kSwz128;
       constexpr uint32_t kSboQK = 8 * D;  // 8 rows of D bytes
-      constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
+      const uint32_t qk_fmt = (p.out_dtype == LOWBIT_F16) ? ptx::kF16 : ptx::kBF16;  // KM_F16: q, k in the output dtype
+      const uint32_t idesc_qk = FQK ? ptx::make_idesc(ptx::kCF32, qk_fmt, qk_fmt, 0, 0, kBM, BN)
+                                    : ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
       constexpr uint32_t idesc_pv = (PV == PV_F16) ? ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D)
                                                    : ptx::make_idesc(ptx::kCF32, ptx::kE4M3, ptx::kE4M3, 0, 0, kBM, D);
       const uint32_t aq = ptx::smem_u32(sQ);
       auto load_k = [&](int j) {  // int8 tile (swizzled) or packed tile (linear) into TMA stage j % KPS
         const int ks = j % KPS;
         ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
-        if constexpr (KM == KM_I8) {
+        if constexpr (FQK) {  // fp16 rows: 64-element (128-byte) swizzle atoms of BN rows each
+          ptx::mbar_expect_tx(kfull + ks, SM::kK);
+#pragma unroll
+          for (int a = 0; a < D / 64; ++a)
+            ptx::tma_load_4d(sK + ks * SM::kK + a * BN * 128, &tmK, kfull + ks, 64 * a, k_row0 + j * BN, hkv, tb);
+        } else if constexpr (KM == KM_I8) {
           ptx::mbar_expect_tx(kfull + ks, SM::kK);
           ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
         } else if constexpr (KM == KM_K4) {
@@ -565,20 +579,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
         const uint32_t tS = tmem_base + (j & 1) * BN;
+        if constexpr (FQK) {
 #pragma unroll
-        for (int kk = 0; kk < D / 32; ++kk) {
-          const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, kSboQK, kSwzQK);
-          const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, kSboQK, kSwzQK);
-          ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+          for (int kk = 0; kk < D / 16; ++kk) {  // K = 16 elements = 32 bytes per MMA; 4 per 128-byte swizzle atom
+            const uint32_t off = (kk % 4) * 32;
+            const uint64_t da = ptx::make_smem_desc(aq + (kk / 4) * kBM * 128 + off, 16, 1024, ptx::kSwz128);
+            const uint64_t db = ptx::make_smem_desc(ak + (kk / 4) * BN * 128 + off, 16, 1024, ptx::kSwz128);
+            ptx::umma_f16_ss(tS, da, db, idesc_qk, kk > 0);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < D / 32; ++kk) {
+            const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, kSboQK, kSwzQK);
+            const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, kSboQK, kSwzQK);
+            ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+          }
         }
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
         if constexpr (!KX) ptx::umma_commit(kfree + ks);  // K stage may be refilled
         else ptx::umma_commit(kopfree + ks);               // operand stage may be overwritten
       };
       ptx::mbar_expect_tx(bar_q, SM::kQ);
-      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
+      if constexpr (FQK) {
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a) ptx::tma_load_4d(sQ + a * kBM * 128, &tmQ, bar_q, 64 * a, q_row0 + qt * kBM, hq, tb);
+      } else {
+        ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
+      }
       for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
-      for (int j = 0; j < min(2, nblk); ++j) load_v(j);
+      for (int j = 0; j < min(VS - 1, nblk); ++j) load_v(j);
       if constexpr (!KX) ptx::mbar_wait(bar_q, 0, 21);
       else ptx::mbar_wait(bar_k01, 0, 21);  // Q permuted
       issue_qk(0);
@@ -608,12 +637,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::umma_commit(vfree + vs);
         ptx::umma_commit(bar_o);
         if (j == nblk - 1) ptx::umma_commit(bar_final);
+        // two K stages only (fp16 operands at D=128): K_{j+2} goes into the stage QK_j read (complete: S_j was
+        // consumed) BEFORE QK_{j+2} waits for it
+        if constexpr (!KX && KPS == 2) {
+          if (j + 2 < nblk) load_k(j + 2);
+        }
         if (j + 2 < nblk) issue_qk(j + 2);  // overwrites S/P buffer (j&1): ordered after PV_j on the tensor pipe
         // refill: the K stage consumed longest ago and the V stage of PV_{j-1} (complete in steady state)
-        if constexpr (!KX) {
+        if constexpr (!KX && KPS > 2) {
           if (j + KPS < nblk) load_k(j + KPS);
         }
-        if (j + 2 < nblk) load_v(j + 2);
+        if (j + VS - 1 < nblk) load_v(j + VS - 1);
       }
     }
   } else if (KX && warp == HW + 1) {
@@ -637,9 +671,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = tid & (kBM - 1);                // query row inside the tile = TMEM lane
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;  // TMEM lane quadrant of this warp
     const int row = qt * kBM + r;  // query row owned by this thread
-    float qs = p.q_scale[qs_idx];
+    // KM_F16: one factor for every score, sm_scale * log2(e), handed over as q_scale[0]; k_scale is not read
+    float qs = FQK ? p.q_scale[0] : p.q_scale[qs_idx];
     if (KM == KM_K4) qs *= 0.0625f;  // K operand holds code*16
-    const float* ks_ptr = p.k_scale + ks_base;
+    const float* ks_ptr = FQK ? p.q_scale : p.k_scale + ks_base;
     auto kfac = [&](int jj) -> float {  // the expanded operand holds code, code*16 or code*64
       if constexpr (KM == KM_MIX) { const int bb = kb(jj); return bb == 8 ? 1.f : (bb == 4 ? 0.0625f : 0.015625f); }
       else return 1.f;
@@ -666,8 +701,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int c = 0; c < BN; ++c) p.dbg[r * 64 + j * BN + c] = (int)s[c];
         }
       }
-      const int imax = chunk::row_max_i<BN, MASKED>(s, lim);
-      const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+      float mblk;
+      if constexpr (FQK) {
+        float fm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < BN; ++c) fm[c & 3] = fmaxf(fm[c & 3], (!MASKED || c <= lim) ? __uint_as_float(s[c]) : -INFINITY);
+        mblk = fmaxf(fmaxf(fm[0], fm[1]), fmaxf(fm[2], fm[3])) * sc;  // sc > 0; -inf stays -inf
+      } else {
+        const int imax = chunk::row_max_i<BN, MASKED>(s, lim);
+        mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+      }
       // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision,
       // tcgen05.ld/st are warp collectives)
       if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
@@ -693,8 +736,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       uint32_t pk[PCOLS];
       const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED>(s, sc, nm, lim, pk);
-      else l += softmax_block_e4m3<BN, MASKED>(s, sc, nm, lim, pk);
+      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, FQK>(s, sc, nm, lim, pk);
+      else l += softmax_block_e4m3<BN, MASKED, FQK>(s, sc, nm, lim, pk);
       tmem_st_n<PCOLS>(tSb, pk);  // P aliases the first columns of its S buffer
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -713,19 +756,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // unrolled by two so buffer / barrier addresses are loop constants
     int j = 0;
     uint32_t ph = 0;
-    float ks_cur = ks_ptr[0];
+    float ks_cur = FQK ? 1.f : ks_ptr[0];
     for (; j + 1 < n_full; j += 2, ph ^= 1) {
       const float sc0 = qs * ks_cur;
       float sc1 = sc0;
-      if (kPerScale == 1) sc1 = qs * ks_ptr[j + 1];
-      const float ks_nxt = ks_ptr[min((j + 2) / kPerScale, nkb - 1)];  // prefetch for the next pair
+      if (kPerScale == 1 && !FQK) sc1 = qs * ks_ptr[j + 1];
+      const float ks_nxt = FQK ? 1.f : ks_ptr[min((j + 2) / kPerScale, nkb - 1)];  // prefetch for the next pair
       step(std::false_type{}, tS0, bar_s + 0, p_ready + 0, ph, j, sc0, 0);
       step(std::false_type{}, tS1, bar_s + 1, p_ready + 1, ph, j + 1, sc1, 0);
       ks_cur = ks_nxt;
     }
     // remaining blocks (odd leftover, causal diagonal band, masked tail): generic path
     for (; j < nblk; ++j) {
-      const float sc = qs * ks_ptr[min(j / kPerScale, nkb - 1)];
+      const float sc = FQK ? qs : qs * ks_ptr[min(j / kPerScale, nkb - 1)];
       const int c0 = j * BN;
       int lim = BN;  // columns [0, lim] are live
       if (causal) lim = min(lim, p.delta + row - c0);
@@ -746,18 +789,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ================================================================================================================
-// attn_fwd_n64_kernel -- head_dim 64, INT8 K, fp16 P.V: 64-key steps at FOUR CTAs per SM.
+// attn_fwd_n64_kernel -- head_dim 64, INT8 / packed-INT4 K, fp16 P.V: 64-key steps at FOUR CTAs per SM.
 //
-// Keeps what makes attn_fwd_kernel fast at head_dim 64 -- 16 softmax warps per SM, 96 registers, exact lazy maximum --
-// and halves its per-step overhead (barrier round, TMEM round trip, vote, scale lookup, loop control: 2.5 of its 6.5
-// warp instructions per score).  TMEM per CTA stays at 128 columns: S [0,64) single-buffered | O [64,128); P_j (32
-// columns fp16) aliases the UPPER half of S.  A thread streams its row through registers 32 scores at a time:
-//   pass 1  ld S[0,32) -> max;  ld S[32,64) -> max           (the upper chunk stays in registers)
-//   pass 2  exp(upper chunk) -> P[16,32) -> TMEM cols [48,64)  (its own, consumed columns)
-//           ld S[0,32) again; exp -> P[0,16) -> TMEM cols [32,48)
-// so that at most 32 scores + 16 packed P words are live.  With one S buffer, QK_{j+1} follows PV_j on the tensor
-// pipe (same issuing thread: in order) and a CTA waits for its next scores once per step; four resident CTAs cover
-// that.
+// 16 softmax warps per SM at 96 registers, 128 TMEM columns per CTA: S [0,64) | O [64,128).  A key block is scored
+// as two 32-key HALVES with their own MMAs and barriers: S_lo in columns [0,32), S_hi in [32,64); P_j (32 columns of
+// fp16 pairs) goes over S_hi.  A thread streams its row through registers one half at a time and the halves are
+// software-pipelined ACROSS key blocks, so that the softmax warps never wait for the tensor pipe in steady state:
+//
+//   softmax, block j                                   issuer
+//   wait S_lo(j); ld -> regs; arrive lo_free(j) ---->  QK_lo(j+1) -> columns [0,32)          (K_{j+1} rows 0..31)
+//   P_lo = exp2(...)   (kept in 16 registers)
+//   wait S_hi(j); ld -> regs
+//   P_hi = exp2(...)
+//   st P_lo, P_hi -> columns [32,64); arrive p_ready(j) ->  PV(j);  QK_hi(j+1) -> columns [32,64)  (in order behind PV(j))
+//   block j+1: S_lo(j+1) has been ready for half a step; S_hi(j+1) lands while P_lo(j+1) is computed.
+//
+// (With one S buffer and QK_{j+1} issued whole after PV_j, every softmax warp spent ~23 % of its time waiting for the
+// next scores -- ncu source view, profiles/r2_attn_c2_ncu_summary.json.)
+//
+// Running maximum: a 32-score chunk is first exponentiated against the row's current reference maximum ("optimistic");
+// only when its row sum shows a p >= 2^15 (or the chunk is masked, or the row has no reference yet) is the chunk redone
+// from its registers with the exact maximum, O and the pending P_lo being rescaled.  Nothing ever re-reads S.
 // ================================================================================================================
 template <int KM>
 struct N64Smem {
@@ -768,6 +820,13 @@ struct N64Smem {
   static constexpr int kBytes = kQ + KS * kK + VS * kV + (KM == KM_I8 ? 0 : KPS * kKp) + 256 /*barriers*/ + 1024 /*align*/;
 };
 
+// fp16 pair * alpha in fp32 (rare path: the pending P_lo when the maximum moves inside the hi chunk)
+__device__ __forceinline__ uint32_t scale_f16x2(uint32_t v, float alpha) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&v);
+  const float2 f = __half22float2(h);
+  return ptx::pack_f16x2(f.x * alpha, f.y * alpha);
+}
+
 template <int KM, int PF, bool DBG>
 __global__ void __launch_bounds__(160, 4)
 attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -775,7 +834,7 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   static_assert(KM == KM_I8 || KM == KM_K4, "mixed-width K runs on attn_fwd_kernel");
   using SM = N64Smem<KM>;
   using PC = PvCfg<PV_F16>;
-  constexpr int D = 64, BN = 64, KS = SM::KS, KPS = SM::KPS, VS = SM::VS;
+  constexpr int D = 64, BN = 64, HN = 32, KS = SM::KS, KPS = SM::KPS, VS = SM::VS;
   constexpr bool KX = (KM != KM_I8);
   constexpr uint32_t kTmemCols = 128, kColP = 32, kColO = 64;
   extern __shared__ uint8_t smem_raw[];
@@ -790,8 +849,10 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* kfree = kfull + KPS;     // [KPS]
   uint64_t* vfull = kfree + KPS;     // [VS]
   uint64_t* vfree = vfull + VS;      // [VS]
-  uint64_t* bar_s = vfree + VS;      // QK_j done                         (phase j)
-  uint64_t* p_ready = bar_s + 1;     // 4 softmax warps wrote P_j         (phase j)
+  uint64_t* bar_slo = vfree + VS;    // QK_lo(j) done: columns [0,32) hold scores          (phase j)
+  uint64_t* bar_shi = bar_slo + 1;   // QK_hi(j) done (and with it PV(j-1))               (phase j)
+  uint64_t* lo_free = bar_shi + 1;   // 4 softmax warps have S_lo(j) in registers          (phase j)
+  uint64_t* p_ready = lo_free + 1;   // 4 softmax warps wrote P_j                          (phase j)
   uint64_t* bar_final = p_ready + 1; // last PV done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
 
@@ -824,7 +885,9 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     ptx::mbar_init(bar_q, 1);
     for (int i = 0; i < KPS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
     for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
-    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_slo, 1);
+    ptx::mbar_init(bar_shi, 1);
+    ptx::mbar_init(lo_free, 4);
     ptx::mbar_init(p_ready, 4);
     ptx::mbar_init(bar_final, 1);
     ptx::fence_barrier_init();
@@ -840,12 +903,12 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 4) {
     // ================================ helper warp ================================
     // one elected lane: TMA producer + tcgen05 issuer.  Packed INT4 K: all 32 lanes also expand the K tiles into the
-    // int8 operand stages, two blocks ahead of their QK (right after QK_{j+1} is issued, K_{j+2} goes into the stage
-    // QK_j read -- complete, since S_j has been consumed).
+    // int8 operand stages, two blocks ahead of their QK (K_{j+2} goes into the stage QK_j read -- complete, since
+    // S_hi(j) has been consumed).
     const int lane = tid & 31;
     auto run = [&](auto whole_warp_tag) {
       constexpr bool WW = decltype(whole_warp_tag)::value;  // every lane runs this; single-lane work is elected
-    constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, BN);
+    constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, HN);
     constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
     const uint32_t aq = ptx::smem_u32(sQ);
     const uint32_t tS = tmem_base, tP = tmem_base + kColP, tO = tmem_base + kColO;
@@ -877,19 +940,26 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (j + KPS < nblk) load_k(j + KPS);
       }
     };
-    auto issue_qk = [&](int j) {  // lead lane
+    // lead lane: scores of keys [32 half, 32 half + 32) of block j -> columns [32 half, 32 half + 32)
+    auto issue_qk = [&](int j, int half) {
       const int ks = j % KS;
-      if constexpr (!KX) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+      if constexpr (!KX) {
+        if (half == 0) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+      }
       ptx::tc_fence_after();
-      const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK);
+      const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK) + half * (HN * D);  // 32 rows of 64 bytes = 4 swizzle atoms
 #pragma unroll
       for (int kk = 0; kk < D / 32; ++kk) {  // K-major operands, rows of 64 bytes, 64B swizzle, 8 rows = 512 B (SBO)
         const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, 8 * D, ptx::kSwz64);
         const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, 8 * D, ptx::kSwz64);
-        ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+        ptx::umma_i8_ss(tS + half * HN, da, db, idesc_qk, kk > 0);
       }
-      ptx::umma_commit(bar_s);
-      if constexpr (!KX) ptx::umma_commit(kfree + ks);
+      if (half == 0) {
+        ptx::umma_commit(bar_slo);
+      } else {
+        ptx::umma_commit(bar_shi);
+        if constexpr (!KX) ptx::umma_commit(kfree + ks);
+      }
     };
     if (!WW || ptx::elect_one()) {
       ptx::mbar_expect_tx(bar_q, SM::kQ);
@@ -908,13 +978,18 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     if (!WW || ptx::elect_one()) {
       if constexpr (!KX) ptx::mbar_wait(bar_q, 0, 21);
-      issue_qk(0);
+      issue_qk(0, 0);
+      issue_qk(0, 1);
     }
     for (int j = 0; j < nblk; ++j) {
       if (!WW || ptx::elect_one()) {
         const int vs = j % VS;
+        if (j + 1 < nblk) {
+          ptx::mbar_wait(lo_free, j & 1, 25);  // every softmax warp holds S_lo(j) in registers
+          issue_qk(j + 1, 0);
+        }
         ptx::mbar_wait(vfull + vs, (j / VS) & 1, 23);
-        ptx::mbar_wait_spin(p_ready, j & 1, 22);  // latency critical: the next scores wait behind this
+        ptx::mbar_wait(p_ready, j & 1, 22);
         ptx::tc_fence_after();
         const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
 #pragma unroll
@@ -925,11 +1000,11 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         ptx::umma_commit(vfree + vs);
         if (j == nblk - 1) ptx::umma_commit(bar_final);
-        if (j + 1 < nblk) issue_qk(j + 1);  // overwrites S / P_j: ordered after PV_j on the tensor pipe
+        if (j + 1 < nblk) issue_qk(j + 1, 1);  // overwrites P_j: ordered after PV_j on the tensor pipe
         if constexpr (!KX) {
-          if (j + KPS < nblk) load_k(j + KPS);  // the stage of QK_j (complete: S_j was consumed)
+          if (j + KPS < nblk) load_k(j + KPS);  // the stage of QK_j (complete: S_hi(j) was consumed)
         }
-        if (j + VS - 1 < nblk) load_v(j + VS - 1);  // the stage of PV_{j-1} (complete: QK_j's commit followed it)
+        if (j + VS - 1 < nblk) load_v(j + VS - 1);  // the stage of PV_{j-1} (complete: QK_hi(j)'s commit followed it)
       }
       if constexpr (KX) {
         __syncwarp();
@@ -953,79 +1028,78 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tSl = tmem_base + lane_off, tPl = tSl + kColP, tOl = tSl + kColO;
     float m_ref = -INFINITY, l = 0.f;
 
-    auto step = [&](auto masked_tag, const int j, const float sc, const int lim) {
+    // One 32-score chunk, in registers: pk = fp16 pairs of exp2(s * sc - m_ref), l += their sum.  HI: the chunk is the
+    // upper half of block j and plo holds the lower half's P, not yet stored.
+    auto chunk_step = [&](auto masked_tag, auto hi_tag, const uint32_t (&s)[32], uint32_t (&pk)[16], uint32_t (&plo)[16],
+                          const int j, const float sc, const int lim) {
       constexpr bool MASKED = decltype(masked_tag)::value;
-      ptx::mbar_wait(bar_s, j & 1, 30);
-      ptx::tc_fence_after();
-      uint32_t s[32], pk[16];
-      auto dump = [&](int half) {
-        if constexpr (DBG) {
-          if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      constexpr bool HI = decltype(hi_tag)::value;
+      if constexpr (DBG) {
+        if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) p.dbg[tid * 64 + 32 * half + c] = (int)s[c];
-          }
+          for (int c = 0; c < 32; ++c) p.dbg[tid * 64 + (HI ? 32 : 0) + c] = (int)s[c];
         }
-      };
-      // Optimistic step (every unmasked block after a row's first): keep the reference maximum, P at once, two TMEM
-      // loads.  Nothing is stored before the block's row sum has shown that no p reached 2^15 (finite in fp16);
-      // otherwise the exact step below redoes the block from the scores, which are still intact in TMEM.
+      }
       bool exact = MASKED;
       if (!exact) exact = __any_sync(0xffffffffu, m_ref == -INFINITY);
       if (!exact) {
-        uint32_t ph[16];
-        const float nm = PC::OFF - m_ref;
-        ptx::tmem_ld_x32(tSl + 32, s);
-        ptx::tmem_wait_ld();
-        float lsum = chunk::chunk_f16<false, PF>(s, sc, nm, 0, ph);
-        ptx::tmem_ld_x32(tSl, s);
-        ptx::tmem_wait_ld();
-        lsum += chunk::chunk_f16<false, PF>(s, sc, nm, 0, pk);
+        // optimistic: keep the reference maximum; the chunk's row sum proves that no p reached 2^15 (finite in fp16)
+        const float lsum = chunk::chunk_f16<false, PF>(s, sc, PC::OFF - m_ref, 0, pk);
         exact = __any_sync(0xffffffffu, !(lsum < 32768.f));
-        if (!exact) {
-          l += lsum;
-          ptx::tmem_st_x16(tPl + 16, ph);
-          ptx::tmem_st_x16(tPl, pk);
-        }
+        if (!exact) l += lsum;
       }
       if (exact) {
-      // pass 1: block maximum.  lower chunk, then the upper chunk, which stays in registers
-      ptx::tmem_ld_x32(tSl, s);
-      ptx::tmem_wait_ld();
-      dump(0);
-      int imax = chunk::row_max_i<32, MASKED>(s, lim);
-      ptx::tmem_ld_x32(tSl + 32, s);
-      ptx::tmem_wait_ld();
-      dump(1);
-      imax = max(imax, chunk::row_max_i<32, MASKED>(s, lim - 32));
-      const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
-      // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision)
-      if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
-        const float m_new = fmaxf(m_ref, mblk);
-        const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
-        l *= alpha;
-        m_ref = m_new;
-        if (j > 0) {
-          // S_j being ready implies PV_{j-1} completed (QK_j follows it on the tensor pipe): O is up to date
+        const int imax = chunk::row_max_i<32, MASKED>(s, lim);
+        const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+        // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision)
+        if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
+          const float m_new = fmaxf(m_ref, mblk);
+          const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
+          l *= alpha;
+          m_ref = m_new;
+          if constexpr (HI) {
 #pragma unroll
-          for (int c = 0; c < D; c += 16) {
-            uint32_t o[16];
-            ptx::tmem_ld_x16(tOl + c, o);
-            ptx::tmem_wait_ld();
+            for (int i = 0; i < 16; ++i) plo[i] = scale_f16x2(plo[i], alpha);
+          }
+          if (j > 0) {
+            // O must hold PV_{j-1}: S_hi(j) ready implies it (QK_hi(j) follows PV_{j-1} on the tensor pipe); the lo
+            // chunk waits for that barrier here (it always completes: it needs nothing from this step)
+            if constexpr (!HI) {
+              ptx::mbar_wait(bar_shi, j & 1, 35);
+              ptx::tc_fence_after();
+            }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st_x16(tOl + c, o);
+            for (int c = 0; c < D; c += 16) {
+              uint32_t o[16];
+              ptx::tmem_ld_x16(tOl + c, o);
+              ptx::tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              ptx::tmem_st_x16(tOl + c, o);
+            }
           }
         }
+        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
+        l += softmax_block_f16<32, MASKED>(s, sc, nm, lim, pk);
       }
-      const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-      // pass 2: upper chunk (in registers) -> P[16,32) over its own columns; lower chunk re-read -> P[0,16)
-      l += softmax_block_f16<32, MASKED>(s, sc, nm, lim - 32, pk);
+    };
+
+    auto step = [&](auto masked_tag, const int j, const float sc, const int lim) {
+      uint32_t s[32], plo[16], phi[16];
+      ptx::mbar_wait(bar_slo, j & 1, 30);
+      ptx::tc_fence_after();
       ptx::tmem_ld_x32(tSl, s);
-      ptx::tmem_st_x16(tPl + 16, pk);
       ptx::tmem_wait_ld();
-      l += softmax_block_f16<32, MASKED>(s, sc, nm, lim, pk);
-      ptx::tmem_st_x16(tPl, pk);
-      }
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(lo_free);  // columns [0,32) may take the next block's scores
+      chunk_step(masked_tag, std::false_type{}, s, plo, plo, j, sc, lim);
+      ptx::mbar_wait(bar_shi, j & 1, 31);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_x32(tSl + HN, s);
+      ptx::tmem_wait_ld();
+      chunk_step(masked_tag, std::true_type{}, s, phi, plo, j, sc, lim - HN);
+      ptx::tmem_st_x16(tPl, plo);
+      ptx::tmem_st_x16(tPl + 16, phi);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       if (lane == 0) ptx::mbar_arrive(p_ready);
@@ -1202,7 +1276,7 @@ static int dispatch_n64(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
 }
 static bool use_n64(int D, int km, int pv, int flags) {
   static const int on = env_int("LOWBIT_ATTN_N64", 1);
-  return on != 0 && !(flags & LOWBIT_ATTN_NARROW) && D == 64 && km != KM_MIX && pv == PV_F16;
+  return on != 0 && !(flags & LOWBIT_ATTN_NARROW) && D == 64 && (km == KM_I8 || km == KM_K4) && pv == PV_F16;
 }
 
 template <int D>
@@ -1212,6 +1286,7 @@ static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     if (pv == PV_F16) return launch_attn<D, KM_MIX, PV_F16>(tq, tk, tv, p, B, st, tk8, tk2);
     return launch_attn<D, KM_MIX, PV_E4M3>(tq, tk, tv, p, B, st, tk8, tk2);
   }
+  if (km == KM_F16) return launch_attn<D, KM_F16, PV_F16>(tq, tk, tv, p, B, st);
   if (km == KM_I8 && pv == PV_F16) {
     if (p.dbg != nullptr) return launch_attn<D, KM_I8, PV_F16, true>(tq, tk, tv, p, B, st);
     return launch_attn<D, KM_I8, PV_F16>(tq, tk, tv, p, B, st);
@@ -1234,28 +1309,36 @@ struct AttnArgs {
 };
 
 static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStream_t st) {
-  LOWBIT_CHECK(a.q_codes && a.k_codes && a.v && a.q_scale && a.k_scale, "%s: null pointer", who);
+  LOWBIT_CHECK(a.q_codes && a.k_codes && a.v && a.q_scale && (a.k_scale || a.qk_mode == LOWBIT_QK_F16), "%s: null pointer", who);
   LOWBIT_CHECK(a.D == 64 || a.D == 128, "%s: head_dim must be 64 or 128 (got %d)", who, a.D);
   LOWBIT_CHECK(a.B > 0 && a.Hq > 0 && a.Hkv > 0 && a.Nq > 0 && a.Nk > 0, "%s: empty tensor", who);
   LOWBIT_CHECK(a.Hq % a.Hkv == 0, "%s: num_qo_heads (%d) must be divisible by num_kv_heads (%d)", who, a.Hq, a.Hkv);
-  LOWBIT_CHECK(a.qk_mode == LOWBIT_QK_I8 || a.qk_mode == LOWBIT_QK_Q8K4 || a.qk_mode == LOWBIT_QK_Q8KMIX,
-               "%s: bad qk_mode %d", who, a.qk_mode);
+  LOWBIT_CHECK(a.qk_mode == LOWBIT_QK_I8 || a.qk_mode == LOWBIT_QK_Q8K4 || a.qk_mode == LOWBIT_QK_Q8KMIX ||
+                   a.qk_mode == LOWBIT_QK_F16, "%s: bad qk_mode %d", who, a.qk_mode);
+  LOWBIT_CHECK(a.qk_mode != LOWBIT_QK_F16 || (a.pv_mode == LOWBIT_PV_F16 && a.cu_q == nullptr),
+               "%s: the fp16-QK mode runs with fp16 P.V on padded tensors only", who);
   LOWBIT_CHECK(a.qk_mode != LOWBIT_QK_Q8KMIX || a.kbits != nullptr, "%s: mixed-width K needs kbits", who);
   LOWBIT_CHECK(a.pv_mode == LOWBIT_PV_F16 || a.pv_mode == LOWBIT_PV_E4M3, "%s: bad pv_mode %d", who, a.pv_mode);
   LOWBIT_CHECK(a.pv_mode != LOWBIT_PV_E4M3 || a.v_scale != nullptr, "%s: the FP8 P.V path needs v_scale", who);
   const int D = a.D;
-  const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : (a.qk_mode == LOWBIT_QK_Q8KMIX ? KM_MIX : KM_I8);
+  const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : (a.qk_mode == LOWBIT_QK_Q8KMIX ? KM_MIX : (a.qk_mode == LOWBIT_QK_F16 ? KM_F16 : KM_I8));
   const int pv = (a.pv_mode == LOWBIT_PV_E4M3) ? PV_E4M3 : PV_F16;
   const bool n64 = use_n64(D, km, pv, a.flags);
   const int BN = n64 ? 64 : ((D == 64) ? AttnCfg<64>::BN : AttnCfg<128>::BN);  // keys per step = rows of a K / V box
 
   CUtensorMap tq, tk, tv, tk8, tk2;
   const CUtensorMapSwizzle swz_qk = (D == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  {
+  if (km == KM_F16) {  // fp16 / bf16 q, k: 64-element (128-byte) swizzle atoms, like V
+    const int64_t dq_[4] = {D, a.Nq, a.Hq, a.B}, sq_[3] = {a.qsn, a.qsh, a.qsb};
+    const int64_t dk_[4] = {D, a.Nk, a.Hkv, a.B}, sk_[3] = {a.ksn, a.ksh, a.ksb};
+    if (cached_map(&tq, a.q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dq_, sq_, 64, kBM, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (cached_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk_, sk_, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else {
     const int64_t dim[4] = {D, a.Nq, a.Hq, a.B}, str[3] = {a.qsn, a.qsh, a.qsb};
     if (cached_map(&tq, a.q_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, kBM, swz_qk)) return 1;
   }
-  if (km == KM_I8) {
+  if (km == KM_F16) {
+  } else if (km == KM_I8) {
     const int64_t dim[4] = {D, a.Nk, a.Hkv, a.B}, str[3] = {a.ksn, a.ksh, a.ksb};
     if (cached_map(&tk, a.k_codes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, dim, str, D, BN, swz_qk)) return 1;
   } else if (km == KM_K4) {  // packed INT4: rows of D/2 bytes, landed linearly (no swizzle) for the in-kernel expansion

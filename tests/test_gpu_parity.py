@@ -986,3 +986,42 @@ def test_misaligned_views_and_wide_heads(L, cuda_dev):
         L.k_mean(k)
     with pytest.raises(ValueError):
         L.compute_scale(torch.randn(1, 1, 8, 160, dtype=torch.float16, device=cuda_dev))
+
+
+# ------------------------------------------------------------------------------------------------ E4: the FP16 class
+@pytest.mark.parametrize("case", [
+    # b, hq, hkv, n, d, layout, causal, dtype
+    (1, 2, 2, 512, 64, "HND", False, torch.float16),
+    (2, 4, 2, 333, 128, "NHD", True, torch.float16),
+    (1, 2, 2, 200, 64, "NHD", True, torch.bfloat16),
+    (1, 3, 3, 1030, 128, "HND", False, torch.bfloat16),
+    (1, 2, 1, 65, 80, "HND", False, torch.float16),   # head_dim padded to 128
+    (1, 1, 1, 1, 64, "HND", True, torch.float16),
+])
+def test_fp16_class_attention_vs_sdpa(L, cuda_dev, case):
+    """lowbit_fa_fp16 (QK_F16: tcgen05 kind::f16 Q.K^T over the fp16 / bf16 inputs, fp32 scores) -- what
+    lowbit_fa_multi_precision runs for the "FP16" class, where the reference calls plain SDPA (core.py:1075-1076).
+    Against fp32 SDPA: max-abs <= 2e-3 (fp16) / 1.6e-2 (bf16 output rounding), cos >= 0.9999; lse <= 2e-3."""
+    from oracle import attention as OA
+    b, hq, hkv, n, d, layout, causal, dtype = case
+    q, k, v = mk(b, hq, n, d, layout, dtype, 91), mk(b, hkv, n, d, layout, dtype, 92, bias=1.0), mk(b, hkv, n, d, layout, dtype, 93)
+    o, lse = L.lowbit_fa_fp16(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev), tensor_layout=layout, is_causal=causal,
+                              return_lse=True)
+    ref, lref = OA.sdpa_fp32(q, k, v, layout, causal, return_lse=True)
+    assert o.shape == q.shape and o.dtype == dtype
+    assert (o.cpu().float() - ref.float()).abs().max().item() <= (2e-3 if dtype == torch.float16 else 1.6e-2)
+    assert (lse.cpu() - lref).abs().max().item() <= 2e-3
+    if n >= 64:
+        assert cos_sim(o.cpu(), ref) >= 0.9999
+
+
+def test_multi_precision_routes_every_class(L, cuda_dev):
+    """select_quantization's three classes (core.py:1050-1061) each reach their own operator: inputs scaled so that the
+    mean of max|x|/127 lands above 0.2 (FP16: un-quantized kernel, bit-identical to lowbit_fa_fp16), between (INT8),
+    and below 0.05 (INT4)."""
+    base = [mk(1, 2, 256, 64, "HND", torch.float16, s).to(cuda_dev) for s in (31, 32, 33)]
+    for scale, kind, fn in ((12.0, "FP16", L.lowbit_fa_fp16), (2.5, "INT8", L.lowbit_fa_qk_int8_pv_fp16_triton),
+                            (0.5, "INT4", L.lowbit_fa_qk_int4_pv_fp16_triton)):
+        q, k, v = ((t.float() * scale).half() for t in base)
+        assert L.select_quantization(q, k, v) == kind
+        assert torch.equal(L.lowbit_fa_multi_precision(q, k, v, sm_scale=0.05), fn(q, k, v, sm_scale=0.05))

@@ -1,4 +1,3 @@
-OUT=gpurun_out/r2_call18; mkdir -p $OUT
-python bench.py --workload c2 --steps 3 --warmup 3 > $OUT/plain.json 2> $OUT/plain.err && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c2.csv python bench.py --workload c2 --steps 3 --warmup 3 > $OUT/ncu.log 2>&1
-tail -2 $OUT/ncu.log
-python tools/time_attn.py d128 > $OUT/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:attn_fwd_kernel -s 10 -c 1 -o $OUT/d128 python tools/time_attn.py d128 > $OUT/ncu2.log 2>&1; tail -2 $OUT/ncu2.log
+OUT=gpurun_out/r2_call21; mkdir -p $OUT
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fp16_class or multi_precision or api_vs_oracle or golden or int4 or causal or lse" 2>&1 | tail -15
+for pf in 2 3 1; do LOWBIT_ATTN_PF=$pf timeout 300 python tools/time_attn.py c2 c2c c2:k4f16 c4:k4f16 2>&1 | tee -a $OUT/time.log; done
