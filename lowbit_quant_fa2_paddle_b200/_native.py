@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblowbit_fa_b200.so")
+LIB_PATH = os.environ.get("LOWBIT_LIB") or os.path.join(_HERE, "liblowbit_fa_b200.so")  # LOWBIT_LIB: A/B builds (tools/)
 
 F16, BF16 = 0, 1
 QMODE_TRITON, QMODE_CUDA = 0, 1

@@ -115,18 +115,24 @@ struct AttnSmem {
 // One softmax step over a BN-key block for one query row: p = exp2(S*sc + nm), packed to fp16 pairs, row sum in fp32
 // (packed fp32x2 arithmetic, FFMA2 / FADD2: one instruction scales, or accumulates, two scores).
 // MASKED: columns > lim contribute 0 (causal diagonal band / masked tail keys).
-template <bool FS> __device__ __forceinline__ float score_f32(uint32_t v) {
-  return FS ? __uint_as_float(v) : __int2float_rn((int)v);  // FS: the QK^T accumulator is fp32 (kind::f16), else int32
+// FS: 0 = the QK^T accumulator is int32, 1 = fp32 (kind::f16), 2 = int32 on top of the bias 0x4B400000 (attn_fwd_n64_kernel)
+template <int FS> __device__ __forceinline__ float score_f32(uint32_t v) {
+  return FS == 0 ? __int2float_rn((int)v) : __uint_as_float(v);
 }
-template <int BN, bool MASKED, bool FS = false>
+// FS == 2: (12582912 + s) - 12582912 is exact in fp32 and costs one packed add per two scores
+template <int FS> __device__ __forceinline__ float2 score_pair(uint32_t a, uint32_t b) {
+  const float2 v = make_float2(score_f32<FS>(a), score_f32<FS>(b));
+  return FS == 2 ? __fadd2_rn(v, make_float2(-chunk::kScoreBiasF, -chunk::kScoreBiasF)) : v;
+}
+template <int BN, bool MASKED, int FS = 0>
 __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ s, float sc, float nm, int lim,
                                                    uint32_t* __restrict__ pk) {
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
   float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < BN; c += 4) {
-    const float2 x0 = __ffma2_rn(make_float2(score_f32<FS>(s[c]), score_f32<FS>(s[c + 1])), sc2, nm2);
-    const float2 x1 = __ffma2_rn(make_float2(score_f32<FS>(s[c + 2]), score_f32<FS>(s[c + 3])), sc2, nm2);
+    const float2 x0 = __ffma2_rn(score_pair<FS>(s[c], s[c + 1]), sc2, nm2);
+    const float2 x1 = __ffma2_rn(score_pair<FS>(s[c + 2], s[c + 3]), sc2, nm2);
     float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
     float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
     if (MASKED) {
@@ -148,7 +154,7 @@ __device__ __forceinline__ float softmax_block_f16(const uint32_t* __restrict__ 
 // is taken over the ROUNDED values (accumulate_d_f8, attn_utils.cuh:550-562), here through exact e4m3 -> f16
 // conversion and short f16x2 partial sums.  Key c of an aligned 16-group sits at the K index the reference's V layout
 // expects (fused.cu:290-292): word w of a group = keys {2w, 2w+1, 8+2w, 9+2w}.
-template <int BN, bool MASKED, bool FS = false>
+template <int BN, bool MASKED, int FS = 0>
 __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__ s, float sc, float nm, int lim,
                                                     uint32_t* __restrict__ pk) {
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
@@ -736,8 +742,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       uint32_t pk[PCOLS];
       const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, FQK>(s, sc, nm, lim, pk);
-      else l += softmax_block_e4m3<BN, MASKED, FQK>(s, sc, nm, lim, pk);
+      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, FQK ? 1 : 0>(s, sc, nm, lim, pk);
+      else l += softmax_block_e4m3<BN, MASKED, FQK ? 1 : 0>(s, sc, nm, lim, pk);
       tmem_st_n<PCOLS>(tSb, pk);  // P aliases the first columns of its S buffer
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -796,13 +802,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // fp16 pairs) goes over S_hi.  A thread streams its row through registers one half at a time and the halves are
 // software-pipelined ACROSS key blocks, so that the softmax warps never wait for the tensor pipe in steady state:
 //
-//   softmax, block j                                   issuer
-//   wait S_lo(j); ld -> regs; arrive lo_free(j) ---->  QK_lo(j+1) -> columns [0,32)          (K_{j+1} rows 0..31)
+//   softmax, block j  (S_lo(j) is already in registers)          issuer
 //   P_lo = exp2(...)   (kept in 16 registers)
-//   wait S_hi(j); ld -> regs
-//   P_hi = exp2(...)
-//   st P_lo, P_hi -> columns [32,64); arrive p_ready(j) ->  PV(j);  QK_hi(j+1) -> columns [32,64)  (in order behind PV(j))
-//   block j+1: S_lo(j+1) has been ready for half a step; S_hi(j+1) lands while P_lo(j+1) is computed.
+//   wait S_hi(j); ld -> regs;  P_hi = exp2(...)
+//   st P_lo, P_hi -> columns [32,64)
+//   wait S_lo(j+1); ld -> regs                                     (issued one whole step ago: no wait)
+//   arrive p_ready(j)  ------------------------------------------>  PV(j);  QK_hi(j+1) -> columns [32,64) (behind PV(j));
+//                                                                   QK_lo(j+2) -> columns [0,32)
+//   block j+1: P_lo(j+1) is computed while PV(j) and QK_hi(j+1) run.
 //
 // (With one S buffer and QK_{j+1} issued whole after PV_j, every softmax warp spent ~23 % of its time waiting for the
 // next scores -- ncu source view, profiles/r2_attn_c2_ncu_summary.json.)
@@ -814,10 +821,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 template <int KM>
 struct N64Smem {
   static constexpr int D = 64, BN = 64, VS = 3;
-  static constexpr int KS = (KM == KM_I8) ? 3 : 2;              // int8 operand stages
-  static constexpr int KPS = (KM == KM_I8) ? KS : 4;            // TMA-filled stages (packed INT4: staging ring)
+  static constexpr int KS = 3;                                  // int8 operand stages: K_{j+1}, K_{j+2} in use, one refilling
+  static constexpr int KPS = 3;                                 // TMA-filled stages (packed INT4: staging ring)
   static constexpr int kQ = kBM * D, kK = BN * D, kKp = BN * D / 2, kV = BN * D * 2;
-  static constexpr int kBytes = kQ + KS * kK + VS * kV + (KM == KM_I8 ? 0 : KPS * kKp) + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kC = 2304;     // constant operand of the bias MMA (see the kernel)
+  static constexpr int kKsc = 512;    // k_scale window: 128 blocks
+  static constexpr int kBytes = kQ + KS * kK + VS * kV + (KM == KM_I8 ? 0 : KPS * kKp) + kC + kKsc + 256 /*barriers*/ +
+                                1024 /*align*/;
 };
 
 // fp16 pair * alpha in fp32 (rare path: the pending P_lo when the maximum moves inside the hi chunk)
@@ -835,26 +845,33 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   using SM = N64Smem<KM>;
   using PC = PvCfg<PV_F16>;
   constexpr int D = 64, BN = 64, HN = 32, KS = SM::KS, KPS = SM::KPS, VS = SM::VS;
+  static_assert(KS == 3 && VS == 3, "the issuer's stage arithmetic is written for three stages");
   constexpr bool KX = (KM != KM_I8);
   constexpr uint32_t kTmemCols = 128, kColP = 32, kColO = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + SM::kQ;
-  uint8_t* sV = sK + KS * SM::kK;
-  uint8_t* sKp = sV + VS * SM::kV;   // packed INT4 staging ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + (KX ? KPS * SM::kKp : 0));
-  uint64_t* bar_q = bars + 0;
-  uint64_t* kfull = bars + 1;        // [KPS]
-  uint64_t* kfree = kfull + KPS;     // [KPS]
-  uint64_t* vfull = kfree + KPS;     // [VS]
-  uint64_t* vfree = vfull + VS;      // [VS]
-  uint64_t* bar_slo = vfree + VS;    // QK_lo(j) done: columns [0,32) hold scores          (phase j)
-  uint64_t* bar_shi = bar_slo + 1;   // QK_hi(j) done (and with it PV(j-1))               (phase j)
-  uint64_t* lo_free = bar_shi + 1;   // 4 softmax warps have S_lo(j) in registers          (phase j)
-  uint64_t* p_ready = lo_free + 1;   // 4 softmax warps wrote P_j                          (phase j)
-  uint64_t* bar_final = p_ready + 1; // last PV done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
+  // Everything in the hot loops is addressed as (sb + compile-time offset) in the 32-bit shared window: one base
+  // register instead of a generic -> shared conversion per barrier operation.
+  constexpr uint32_t oQ = 0, oK = SM::kQ, oV = oK + KS * SM::kK, oKp = oV + VS * SM::kV;
+  constexpr uint32_t oC = oKp + (KX ? KPS * SM::kKp : 0);   // bias-MMA operand
+  constexpr uint32_t oKsc = oC + SM::kC;                    // k_scale window
+  constexpr uint32_t oBar = oKsc + SM::kKsc;
+  constexpr uint32_t oBarQ = oBar;
+  constexpr uint32_t oKfull = oBarQ + 8;           // [KPS]
+  constexpr uint32_t oKfree = oKfull + 8 * KPS;    // [KPS]
+  constexpr uint32_t oVfull = oKfree + 8 * KPS;    // [VS]
+  constexpr uint32_t oVfree = oVfull + 8 * VS;     // [VS]
+  constexpr uint32_t oSlo = oVfree + 8 * VS;       // QK_lo(j) done: columns [0,32) hold scores          (phase j)
+  constexpr uint32_t oShi = oSlo + 8;              // QK_hi(j) done (and with it PV(j-1))               (phase j)
+  constexpr uint32_t oLoFree = oShi + 8;           // 4 softmax warps have S_lo(0) in registers          (once)
+  constexpr uint32_t oPready = oLoFree + 8;        // 4 softmax warps wrote P_j and hold S_lo(j+1)       (phase j)
+  constexpr uint32_t oFinal = oPready + 8;         // last PV done
+  constexpr uint32_t oSlot = oFinal + 8;           // TMEM base address
+  static_assert(oSlot + 4 <= oBar + 256, "barrier block overflow");
+  const uint32_t sb = ptx::pin_u32(ptx::smem_u32(smem));
+  uint8_t* sQ = smem + oQ;
+  uint8_t* sK = smem + oK;
+  uint8_t* sKp = smem + oKp;   // packed INT4 staging ring
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
@@ -878,137 +895,171 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 
   if (warp == 4) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_alloc(reinterpret_cast<uint32_t*>(smem + oSlot), kTmemCols);
     ptx::tmem_relinquish();
   }
   if (tid == 0) {
-    ptx::mbar_init(bar_q, 1);
-    for (int i = 0; i < KPS; ++i) { ptx::mbar_init(kfull + i, 1); ptx::mbar_init(kfree + i, 1); }
-    for (int i = 0; i < VS; ++i) { ptx::mbar_init(vfull + i, 1); ptx::mbar_init(vfree + i, 1); }
-    ptx::mbar_init(bar_slo, 1);
-    ptx::mbar_init(bar_shi, 1);
-    ptx::mbar_init(lo_free, 4);
-    ptx::mbar_init(p_ready, 4);
-    ptx::mbar_init(bar_final, 1);
+    auto init = [&](uint32_t off, uint32_t count) { ptx::mbar_init(reinterpret_cast<uint64_t*>(smem + off), count); };
+    init(oBarQ, 1);
+    for (int i = 0; i < KPS; ++i) { init(oKfull + 8 * i, 1); init(oKfree + 8 * i, 1); }
+    for (int i = 0; i < VS; ++i) { init(oVfull + 8 * i, 1); init(oVfree + 8 * i, 1); }
+    init(oSlo, 1);
+    init(oShi, 1);
+    init(oLoFree, 4);
+    init(oPready, 4);
+    init(oFinal, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
   }
+  // Bias operand: every 16-byte row chunk holds fp16 {1024 x 6, 0 x 2}.  The bias MMA (kind::f16, M 128, N 32, K 16,
+  // A = B = this tile, no swizzle, every core matrix 128 bytes after the previous one in both directions) puts
+  // 12 * 1024 * 1024 = 12582912.0f = 0x4B400000 into each score column; the int8 MMAs then ACCUMULATE on those bits as
+  // int32, so a score leaves TMEM as the fp32 number 12582912 + s and the softmax needs no int -> float conversion
+  // (softmax_chunk.cuh, BIASED).  |s| <= 64 * 128 * 128 = 2^20 < 2^22: exact.
+  if (tid < SM::kC / 16) ptx::sts_v4_a(sb + oC + tid * 16, 0x64006400u, 0x64006400u, 0x64006400u, 0u);
+  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + oSlot);
 
   if (warp == 4) {
     // ================================ helper warp ================================
     // one elected lane: TMA producer + tcgen05 issuer.  Packed INT4 K: all 32 lanes also expand the K tiles into the
-    // int8 operand stages, two blocks ahead of their QK (K_{j+2} goes into the stage QK_j read -- complete, since
+    // int8 operand stages, three blocks ahead of their QK (K_{j+3} goes into the stage QK_j read -- complete, since
     // S_hi(j) has been consumed).
     const int lane = tid & 31;
     auto run = [&](auto whole_warp_tag) {
       constexpr bool WW = decltype(whole_warp_tag)::value;  // every lane runs this; single-lane work is elected
     constexpr uint32_t idesc_qk = ptx::make_idesc(ptx::kCS32, ptx::kS8, ptx::kS8, 0, 0, kBM, HN);
     constexpr uint32_t idesc_pv = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 1, kBM, D);
-    const uint32_t aq = ptx::smem_u32(sQ);
+    constexpr uint32_t idesc_bias = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 0, kBM, HN);
     const uint32_t tS = tmem_base, tP = tmem_base + kColP, tO = tmem_base + kColO;
-    auto load_k = [&](int j) {  // lead lane: int8 tile (swizzled) or packed INT4 tile (linear) into TMA stage j % KPS
-      const int ks = j % KPS;
-      ptx::mbar_wait(kfree + ks, ((j / KPS) & 1) ^ 1, 10);
-      if constexpr (!KX) {
-        ptx::mbar_expect_tx(kfull + ks, SM::kK);
-        ptx::tma_load_4d(sK + ks * SM::kK, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
-      } else {
-        ptx::mbar_expect_tx(kfull + ks, SM::kKp);
-        ptx::tma_load_4d(sKp + ks * SM::kKp, &tmK, kfull + ks, 0, k_row0 + j * BN, hkv, tb);
-      }
+    const uint64_t dc0 = ptx::make_smem_desc(sb + oC, 128, 128, ptx::kSwzNone);
+    // operand descriptors: K-major int8 rows of 64 bytes, 64B swizzle, 8 rows = 512 B (SBO); V: MN-major (d
+    // contiguous), 128B swizzle, 8 key rows = 1024 B (SBO), one 64-wide d atom.  Stage / half / k-slice are byte
+    // offsets added to the start-address field.
+    const uint64_t dq0 = ptx::make_smem_desc(sb + oQ, 16, 8 * D, ptx::kSwz64);
+    const uint64_t dk0 = ptx::make_smem_desc(sb + oK, 16, 8 * D, ptx::kSwz64);
+    const uint64_t dv0 = ptx::make_smem_desc(sb + oV, BN * 128, 1024, ptx::kSwz128);
+    // three-stage rings: tile t lives in stage t % 3 and completes phase (t / 3) & 1 of its barriers; (j3, jd) =
+    // (j % 3, j / 3) are carried, not divided
+    int j3 = 0, jd = 0;
+    auto ring = [&](int off, int& st, uint32_t& par) {  // stage and parity of tile j + off, off in [0, 3]
+      int s3 = j3 + off;
+      const int w = (s3 >= 3) ? 1 : 0;
+      st = s3 - 3 * w;
+      par = (uint32_t)(jd + w) & 1u;
     };
-    auto load_v = [&](int j) {
-      const int vs = j % VS;
-      ptx::mbar_wait(vfree + vs, ((j / VS) & 1) ^ 1, 11);
-      ptx::mbar_expect_tx(vfull + vs, SM::kV);
-      ptx::tma_load_4d(sV + vs * SM::kV, &tmV, vfull + vs, 0, k_row0 + j * BN, hkv, tb);
+    auto load_k_at = [&](int j, int ks, uint32_t par) {  // lead lane: int8 tile (swizzled) into K stage ks (INT8 K only)
+      ptx::mbar_wait_a(sb + oKfree + 8 * ks, par ^ 1, 10);
+      ptx::mbar_expect_tx_a(sb + oKfull + 8 * ks, SM::kK);
+      ptx::tma_load_4d_a(sb + oK + ks * SM::kK, &tmK, sb + oKfull + 8 * ks, 0, k_row0 + j * BN, hkv, tb);
+    };
+    auto load_kp = [&](int j) {  // lead lane: packed INT4 tile (linear) into staging stage j % 4
+      const int ks = j % KPS;
+      ptx::mbar_wait_a(sb + oKfree + 8 * ks, ((j / KPS) & 1) ^ 1, 10);
+      ptx::mbar_expect_tx_a(sb + oKfull + 8 * ks, SM::kKp);
+      ptx::tma_load_4d_a(sb + oKp + ks * SM::kKp, &tmK, sb + oKfull + 8 * ks, 0, k_row0 + j * BN, hkv, tb);
+    };
+    auto load_v_at = [&](int j, int vs, uint32_t par) {
+      ptx::mbar_wait_a(sb + oVfree + 8 * vs, par ^ 1, 11);
+      ptx::mbar_expect_tx_a(sb + oVfull + 8 * vs, SM::kV);
+      ptx::tma_load_4d_a(sb + oV + vs * SM::kV, &tmV, sb + oVfull + 8 * vs, 0, k_row0 + j * BN, hkv, tb);
     };
     auto expand = [&](int j) {  // whole warp: packed K_j -> operand stage j % KS; frees and refills its staging stage
       const int kps = j % KPS;
-      ptx::mbar_wait(kfull + kps, (j / KPS) & 1, 34);
+      ptx::mbar_wait_a(sb + oKfull + 8 * kps, (j / KPS) & 1, 34);
       unpack_k4_tile<D, BN, 32>(sKp + kps * SM::kKp, sK + (j % KS) * SM::kK, lane);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (!WW || ptx::elect_one()) {
-        ptx::mbar_arrive(kfree + kps);
-        if (j + KPS < nblk) load_k(j + KPS);
+        ptx::mbar_arrive_a(sb + oKfree + 8 * kps);
+        if (j + KPS < nblk) load_kp(j + KPS);
       }
     };
-    // lead lane: scores of keys [32 half, 32 half + 32) of block j -> columns [32 half, 32 half + 32)
-    auto issue_qk = [&](int j, int half) {
-      const int ks = j % KS;
+    // lead lane: scores of keys [32 half, 32 half + 32) of the tile in K stage ks -> columns [32 half, 32 half + 32)
+    auto issue_qk = [&](int ks, uint32_t par, int half) {
       if constexpr (!KX) {
-        if (half == 0) ptx::mbar_wait(kfull + ks, (j / KS) & 1, 20);
+        if (half == 0) ptx::mbar_wait_a(sb + oKfull + 8 * ks, par, 20);
       }
       ptx::tc_fence_after();
-      const uint32_t ak = ptx::smem_u32(sK + ks * SM::kK) + half * (HN * D);  // 32 rows of 64 bytes = 4 swizzle atoms
-#pragma unroll
-      for (int kk = 0; kk < D / 32; ++kk) {  // K-major operands, rows of 64 bytes, 64B swizzle, 8 rows = 512 B (SBO)
-        const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, 8 * D, ptx::kSwz64);
-        const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, 8 * D, ptx::kSwz64);
-        ptx::umma_i8_ss(tS + half * HN, da, db, idesc_qk, kk > 0);
-      }
+      const uint64_t dk = ptx::desc_add(dk0, ks * SM::kK + half * (HN * D));  // 32 rows of 64 bytes = 4 swizzle atoms
+      ptx::umma_f16_ss(tS + half * HN, dc0, dc0, idesc_bias, 0);  // every column = 0x4B400000
+      ptx::umma_i8_ss(tS + half * HN, dq0, dk, idesc_qk, 1);
+      ptx::umma_i8_ss(tS + half * HN, ptx::desc_add(dq0, 32), ptx::desc_add(dk, 32), idesc_qk, 1);
       if (half == 0) {
-        ptx::umma_commit(bar_slo);
+        ptx::umma_commit_a(sb + oSlo);
       } else {
-        ptx::umma_commit(bar_shi);
-        if constexpr (!KX) ptx::umma_commit(kfree + ks);
+        ptx::umma_commit_a(sb + oShi);
+        if constexpr (!KX) ptx::umma_commit_a(sb + oKfree + 8 * ks);
       }
     };
     if (!WW || ptx::elect_one()) {
-      ptx::mbar_expect_tx(bar_q, SM::kQ);
-      ptx::tma_load_4d(sQ, &tmQ, bar_q, 0, q_row0 + qt * kBM, hq, tb);
-      for (int j = 0; j < min(KPS, nblk); ++j) load_k(j);
-      for (int j = 0; j < min(VS - 1, nblk); ++j) load_v(j);
+      ptx::mbar_expect_tx_a(sb + oBarQ, SM::kQ);
+      ptx::tma_load_4d_a(sb + oQ, &tmQ, sb + oBarQ, 0, q_row0 + qt * kBM, hq, tb);
+      if constexpr (!KX) {
+        for (int j = 0; j < min(KS, nblk); ++j) load_k_at(j, j, 0);
+      } else {
+        for (int j = 0; j < min(KPS, nblk); ++j) load_kp(j);
+      }
+      for (int j = 0; j < min(VS - 1, nblk); ++j) load_v_at(j, j, 0);
     }
     if constexpr (KX) {
       __syncwarp();
-      ptx::mbar_wait(bar_q, 0, 33);
+      ptx::mbar_wait_a(sb + oBarQ, 0, 33);
       permute_q_tile<D, 32>(sQ, lane);
       ptx::fence_proxy_async_smem();
       expand(0);
       if (nblk > 1) expand(1);
+      if (nblk > 2) expand(2);
       __syncwarp();
     }
     if (!WW || ptx::elect_one()) {
-      if constexpr (!KX) ptx::mbar_wait(bar_q, 0, 21);
-      issue_qk(0, 0);
-      issue_qk(0, 1);
+      if constexpr (!KX) ptx::mbar_wait_a(sb + oBarQ, 0, 21);
+      issue_qk(0, 0, 0);
+      issue_qk(0, 0, 1);
+      if (nblk > 1) {
+        ptx::mbar_wait_a(sb + oLoFree, 0, 25);  // every softmax warp holds S_lo(0) in registers
+        issue_qk(1, 0, 0);
+      }
     }
     for (int j = 0; j < nblk; ++j) {
       if (!WW || ptx::elect_one()) {
-        const int vs = j % VS;
-        if (j + 1 < nblk) {
-          ptx::mbar_wait(lo_free, j & 1, 25);  // every softmax warp holds S_lo(j) in registers
-          issue_qk(j + 1, 0);
-        }
-        ptx::mbar_wait(vfull + vs, (j / VS) & 1, 23);
-        ptx::mbar_wait(p_ready, j & 1, 22);
+        int st;
+        uint32_t par;
+        ring(0, st, par);
+        ptx::mbar_wait_a(sb + oVfull + 8 * st, par, 23);
+        ptx::mbar_wait_a(sb + oPready, j & 1, 22);
         ptx::tc_fence_after();
-        const uint32_t av = ptx::smem_u32(sV + vs * SM::kV);
+        const uint64_t dv = ptx::desc_add(dv0, st * SM::kV);
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          // V tile: MN-major (d contiguous), 128B swizzle: 8 key rows = 1024 B (SBO); one 64-wide d atom
-          const uint64_t db = ptx::make_smem_desc(av + kk * 16 * 128, BN * 128, 1024, ptx::kSwz128);
-          ptx::umma_f16_ts(tO, tP + kk * 8, db, idesc_pv, (j > 0) || (kk > 0));
+        for (int kk = 0; kk < BN / 16; ++kk)
+          ptx::umma_f16_ts(tO, tP + kk * 8, ptx::desc_add(dv, kk * 16 * 128), idesc_pv, (j > 0) || (kk > 0));
+        ptx::umma_commit_a(sb + oVfree + 8 * st);
+        if (j == nblk - 1) ptx::umma_commit_a(sb + oFinal);
+        if (j + 1 < nblk) {  // overwrites P_j: ordered after PV_j on the tensor pipe
+          ring(1, st, par);
+          issue_qk(st, par, 1);
         }
-        ptx::umma_commit(vfree + vs);
-        if (j == nblk - 1) ptx::umma_commit(bar_final);
-        if (j + 1 < nblk) issue_qk(j + 1, 1);  // overwrites P_j: ordered after PV_j on the tensor pipe
+        if (j + 2 < nblk) {  // columns [0,32): S_lo(j+1) is in registers (p_ready(j))
+          ring(2, st, par);
+          issue_qk(st, par, 0);
+          load_v_at(j + 2, st, par);  // the stage of PV_{j-1} (complete: QK_hi(j)'s commit followed it)
+        }
         if constexpr (!KX) {
-          if (j + KPS < nblk) load_k(j + KPS);  // the stage of QK_j (complete: S_hi(j) was consumed)
+          if (j + 3 < nblk) {  // the stage of QK_j (complete: S_hi(j) was consumed)
+            ring(3, st, par);
+            load_k_at(j + 3, st, par);
+          }
         }
-        if (j + VS - 1 < nblk) load_v(j + VS - 1);  // the stage of PV_{j-1} (complete: QK_hi(j)'s commit followed it)
+        if (++j3 == 3) { j3 = 0; ++jd; }
       }
       if constexpr (KX) {
         __syncwarp();
-        if (j + 2 < nblk) expand(j + 2);
+        if (j + 3 < nblk) expand(j + 3);
         __syncwarp();
       }
     }
@@ -1026,32 +1077,37 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool mask_tail = (nk_lim % BN) != 0;
     const int last_kblk = (nk_lim + BN - 1) / BN - 1;
     const uint32_t tSl = tmem_base + lane_off, tPl = tSl + kColP, tOl = tSl + kColO;
+    constexpr float kScMax = 1.0e-3f;
     float m_ref = -INFINITY, l = 0.f;
+    bool have_ref = false;  // warp-uniform: every row of this warp has a finite reference maximum (it never goes back)
 
     // One 32-score chunk, in registers: pk = fp16 pairs of exp2(s * sc - m_ref), l += their sum.  HI: the chunk is the
     // upper half of block j and plo holds the lower half's P, not yet stored.
     auto chunk_step = [&](auto masked_tag, auto hi_tag, const uint32_t (&s)[32], uint32_t (&pk)[16], uint32_t (&plo)[16],
-                          const int j, const float sc, const int lim) {
+                          const int j, const float sc, const int lim, const bool fast_ok) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       constexpr bool HI = decltype(hi_tag)::value;
       if constexpr (DBG) {
         if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) p.dbg[tid * 64 + (HI ? 32 : 0) + c] = (int)s[c];
+          for (int c = 0; c < 32; ++c) p.dbg[tid * 64 + (HI ? 32 : 0) + c] = (int)(s[c] - chunk::kScoreBias);
         }
       }
-      bool exact = MASKED;
-      if (!exact) exact = __any_sync(0xffffffffu, m_ref == -INFINITY);
+      // The optimistic path reads the biased scores as fp32 (no conversion); the bias leaves through the FMA addend
+      // nm - 12582912 * sc, whose rounding puts a common factor of up to 2^(2^-25 * 12582912 * sc) on the chunk's
+      // P: <= 1.0004 while sc <= kScMax (typical INT8 / packed-INT4 scales: 1e-4 .. 3e-4, i.e. < 1.0001 -- below the
+      // fp16 rounding of P).  Coarser scales (INT4 codes handed over one per int8, tiny head scales) take the exact
+      // path, which converts the integer score itself.
+      bool exact = MASKED || !fast_ok;
       if (!exact) {
         // optimistic: keep the reference maximum; the chunk's row sum proves that no p reached 2^15 (finite in fp16)
-        const float lsum = chunk::chunk_f16<false, PF>(s, sc, PC::OFF - m_ref, 0, pk);
+        const float lsum = chunk::chunk_f16<false, PF, true>(s, sc, PC::OFF - m_ref, 0, pk);
         exact = __any_sync(0xffffffffu, !(lsum < 32768.f));
         if (!exact) l += lsum;
       }
       if (exact) {
-        const int imax = chunk::row_max_i<32, MASKED>(s, lim);
-        const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
-        // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision)
+        const int imax = chunk::row_max_i<32, MASKED>(s, lim);  // biased scores keep their order as int32
+        const float mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)(imax - (int)chunk::kScoreBias) * sc;
         if (__any_sync(0xffffffffu, mblk > m_ref + PC::THR)) {
           const float m_new = fmaxf(m_ref, mblk);
           const float alpha = (m_new == -INFINITY) ? 1.f : ptx::ex2(m_ref - m_new);  // m_ref == -inf -> 0
@@ -1062,10 +1118,8 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int i = 0; i < 16; ++i) plo[i] = scale_f16x2(plo[i], alpha);
           }
           if (j > 0) {
-            // O must hold PV_{j-1}: S_hi(j) ready implies it (QK_hi(j) follows PV_{j-1} on the tensor pipe); the lo
-            // chunk waits for that barrier here (it always completes: it needs nothing from this step)
             if constexpr (!HI) {
-              ptx::mbar_wait(bar_shi, j & 1, 35);
+              ptx::mbar_wait_a(sb + oShi, j & 1, 35);
               ptx::tc_fence_after();
             }
 #pragma unroll
@@ -1079,39 +1133,58 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
         }
-        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-        l += softmax_block_f16<32, MASKED>(s, sc, nm, lim, pk);
+        if (!have_ref) have_ref = __all_sync(0xffffffffu, m_ref != -INFINITY);
+        const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;
+        l += softmax_block_f16<32, MASKED, 2>(s, sc, nm, lim, pk);  // converts the exact int32 score
       }
     };
 
+    uint32_t s[32];  // on entry to a step: S_lo(j)
     auto step = [&](auto masked_tag, const int j, const float sc, const int lim) {
-      uint32_t s[32], plo[16], phi[16];
-      ptx::mbar_wait(bar_slo, j & 1, 30);
+      uint32_t plo[16], phi[16];
+      const bool coarse = sc > kScMax;  // warp-uniform (one scale per Q tile and key block)
+      chunk_step(masked_tag, std::false_type{}, s, plo, plo, j, sc, lim, have_ref && !coarse);
+      ptx::mbar_wait_a(sb + oShi, j & 1, 31);
       ptx::tc_fence_after();
-      ptx::tmem_ld_x32(tSl, s);
+      ptx::tmem_ld_x16(tSl + HN, s);
+      ptx::tmem_ld_x16(tSl + HN + 16, s + 16);
       ptx::tmem_wait_ld();
-      ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(lo_free);  // columns [0,32) may take the next block's scores
-      chunk_step(masked_tag, std::false_type{}, s, plo, plo, j, sc, lim);
-      ptx::mbar_wait(bar_shi, j & 1, 31);
-      ptx::tc_fence_after();
-      ptx::tmem_ld_x32(tSl + HN, s);
-      ptx::tmem_wait_ld();
-      chunk_step(masked_tag, std::true_type{}, s, phi, plo, j, sc, lim - HN);
-      ptx::tmem_st_x16(tPl, plo);
-      ptx::tmem_st_x16(tPl + 16, phi);
+      chunk_step(masked_tag, std::true_type{}, s, phi, plo, j, sc, lim - HN, have_ref && !coarse);
+      ptx::tmem_st_x8(tPl, plo);
+      ptx::tmem_st_x8(tPl + 8, plo + 8);
+      ptx::tmem_st_x8(tPl + 16, phi);
+      ptx::tmem_st_x8(tPl + 24, phi + 8);
+      if (j + 1 < nblk) {  // the next block's lower scores: issued a whole step ago
+        ptx::mbar_wait_a(sb + oSlo, (j + 1) & 1, 30);
+        ptx::tc_fence_after();
+        ptx::tmem_ld_x16(tSl, s);
+        ptx::tmem_ld_x16(tSl + 16, s + 16);
+        ptx::tmem_wait_ld();
+      }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(p_ready);
+      ptx::mbar_arrive_elect_a(sb + oPready);  // P_j is in place and columns [0,32) may take S_lo(j+2)
     };
+    ptx::mbar_wait_a(sb + oSlo, 0, 30);
+    ptx::tc_fence_after();
+    ptx::tmem_ld_x16(tSl, s);
+    ptx::tmem_ld_x16(tSl + 16, s + 16);
+    ptx::tmem_wait_ld();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive_elect_a(sb + oLoFree);
 
     int n_full = nblk;  // blocks [0, n_full) need no mask
     if (causal) n_full = max(0, min(n_full, (dq + 1) / BN));
     if (mask_tail) n_full = min(n_full, last_kblk);
-    float kcur = ks_ptr[0];
+    // k_scale: a window of 128 blocks in shared memory, refilled by the 128 softmax threads (a per-step global load
+    // sat behind its own spill store); one uniform shared load per step
     for (int j = 0; j < nblk; ++j) {
-      const float sc = qs * kcur;
-      kcur = ks_ptr[min(j + 1, nkb - 1)];  // prefetch for the next block
+      if ((j & 127) == 0) {
+        if (j > 0) ptx::bar_sync(1, 128);  // every warp is done with the previous window
+        ptx::sts_f32_a(sb + oKsc + tid * 4, ks_ptr[min(j + tid, nkb - 1)]);
+        ptx::bar_sync(1, 128);
+      }
+      const float sc = qs * ptx::lds_f32_a(sb + oKsc + (j & 127) * 4);
       if (j < n_full) {
         step(std::false_type{}, j, sc, 0);
       } else {
@@ -1124,7 +1197,7 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------
-    ptx::mbar_wait(bar_final, 0, 32);
+    ptx::mbar_wait_a(sb + oFinal, 0, 32);
     ptx::tc_fence_after();
     attn_epilogue<D, PV_F16>(p, tOl, l, m_ref, row, Nq, b, hq, orow_base, nullptr, nullptr);
   }

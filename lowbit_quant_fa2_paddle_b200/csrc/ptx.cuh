@@ -86,6 +86,81 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, i
   mbar_wait(bar, parity, tag);
 }
 
+// ---- the same operations on 32-bit shared-window addresses.  A kernel that keeps ONE base address (smem_u32 of its
+// aligned buffer) and adds compile-time offsets saves the generic -> shared conversion (S2UR / ULEA / ULOP3, ~10
+// uniform instructions) that every call on a generic pointer costs inside a hot loop.
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f32_a(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32_a(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4_a(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// one arrival per warp, by an elected lane, without a branch (warp-convergent callers only)
+__device__ __forceinline__ void mbar_arrive_elect_a(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+// a value the compiler must keep in a register instead of recomputing it at every use (the generic -> shared
+// conversion of a dynamic shared-memory pointer is "cheap" to rematerialise: five uniform instructions per use)
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow_a(uint32_t bar, uint32_t parity, int tag) {
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
+    if (ok) return;
+    if (spins > (1u << 20)) {
+#ifdef LOWBIT_DEBUG_WAIT
+      printf("lowbit_fa: mbarrier wait timed out (tag %d, block %d,%d,%d thread %d parity %u)\n", tag, blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, parity);
+#endif
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  mbar_wait_slow_a(bar, parity, tag);
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -146,6 +221,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout << 61;
   return d;
+}
+// descriptor of (base + byte_off): the start-address field is the only one that moves, and a shared-memory address
+// (< 256 KB) never carries out of its 14 bits, so the offset is added to the low word
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) {
+  return d + (uint64_t)(byte_off >> 4);
 }
 // instruction descriptor (32-bit): c_format[4,6) a_format[7,10) b_format[10,13) a_major[15] b_major[16]
 // n>>3 at [17,23), m>>4 at [24,29)

