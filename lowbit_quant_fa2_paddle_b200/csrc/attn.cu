@@ -109,7 +109,8 @@ struct AttnSmem {
   static constexpr int kKp = (KM == KM_MIX) ? C::BN * D : C::BN * D / 2;  // packed staging stage (worst case)
   static constexpr int kKpStages = (KM == KM_K4) ? 4 : (KM == KM_MIX ? 3 : 0);
   static constexpr int kV = (PV == PV_F16) ? C::BN * D * 2 : C::BN * D;  // fp16 [key][d] / e4m3 [d][key]
-  static constexpr int kBytes = kQ + kKStages * kK + kVStages * kV + kKpStages * kKp + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kC = (KM == KM_F16) ? 0 : 2304;                // constant operand of the bias MMA
+  static constexpr int kBytes = kQ + kKStages * kK + kVStages * kV + kKpStages * kKp + kC + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 // One softmax step over a BN-key block for one query row: p = exp2(S*sc + nm), packed to fp16 pairs, row sum in fp32
@@ -165,8 +166,8 @@ __device__ __forceinline__ float softmax_block_e4m3(const uint32_t* __restrict__
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int c0 = 16 * g + 2 * w, c1 = c0 + 8;
-      const float2 x0 = __ffma2_rn(make_float2(score_f32<FS>(s[c0]), score_f32<FS>(s[c0 + 1])), sc2, nm2);
-      const float2 x1 = __ffma2_rn(make_float2(score_f32<FS>(s[c1]), score_f32<FS>(s[c1 + 1])), sc2, nm2);
+      const float2 x0 = __ffma2_rn(score_pair<FS>(s[c0], s[c0 + 1]), sc2, nm2);
+      const float2 x1 = __ffma2_rn(score_pair<FS>(s[c1], s[c1 + 1]), sc2, nm2);
       float2 p0 = make_float2(ptx::ex2(x0.x), ptx::ex2(x0.y));
       float2 p1 = make_float2(ptx::ex2(x1.x), ptx::ex2(x1.y));
       if (MASKED) {
@@ -440,6 +441,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int KS = SM::kKStages;                   // int8 operand stages (expanded K: 2, indexed like the S buffers)
   constexpr bool KX = (KM == KM_K4 || KM == KM_MIX);          // K tiles are expanded by the expander warp
   constexpr bool FQK = (KM == KM_F16);                        // fp16 / bf16 operands, fp32 scores
+  // int8 scores are accumulated on top of 0x4B400000 written by a small fp16 MMA: they leave TMEM as the fp32 number
+  // 12582912 + s and the softmax needs no int -> float conversion (attn_fwd_n64_kernel, softmax_chunk.cuh); exact
+  // while |s| < 2^22 (head_dim 128: |s| <= 2^21)
+  constexpr bool BIASED = !FQK;
   constexpr int KPS = KX ? SM::kKpStages : KS;                // TMA-filled K stages
   constexpr int PCOLS = (PV == PV_F16) ? BN / 2 : BN / 4;     // TMEM columns of one P tile
   constexpr int HW = 4;                                       // index of the helper warp
@@ -453,7 +458,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sK = sQ + SM::kQ;
   uint8_t* sV = sK + KS * SM::kK;
   uint8_t* sKp = sV + VS * SM::kV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKp + SM::kKpStages * SM::kKp);
+  uint8_t* sC = sKp + SM::kKpStages * SM::kKp;  // bias-MMA operand (see attn_fwd_n64_kernel)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + SM::kC);
   uint64_t* bar_q = bars + 0;
   uint64_t* kfull = bars + 1;        // [KPS] TMA -> consumer (MMA issuer, or the expander warp)
   uint64_t* kfree = kfull + KPS;     // [KPS] consumer -> TMA
@@ -519,6 +525,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       s_vs[tid] = p.v_scale[((int64_t)b * p.Hkv + hkv) * D + tid];
       s_vm[tid] = p.v_mean ? p.v_mean[((int64_t)b * p.Hkv + hkv) * D + tid] : 0.f;
     }
+  }
+  if constexpr (BIASED) {  // every 16-byte row chunk = fp16 {1024 x 6, 0 x 2}: 12 * 2^20 = 12582912.0f = 0x4B400000 per score
+    if (tid < SM::kC / 16) ptx::sts_v4_a(ptx::smem_u32(sC) + tid * 16, 0x64006400u, 0x64006400u, 0x64006400u, 0u);
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -594,11 +604,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ptx::umma_f16_ss(tS, da, db, idesc_qk, kk > 0);
           }
         } else {
+          constexpr uint32_t idesc_bias = ptx::make_idesc(ptx::kCF32, ptx::kF16, ptx::kF16, 0, 0, kBM, BN);
+          const uint64_t dc = ptx::make_smem_desc(ptx::smem_u32(sC), 128, 128, ptx::kSwzNone);
+          ptx::umma_f16_ss(tS, dc, dc, idesc_bias, 0);  // every score column = 0x4B400000
 #pragma unroll
           for (int kk = 0; kk < D / 32; ++kk) {
             const uint64_t da = ptx::make_smem_desc(aq + kk * 32, 16, kSboQK, kSwzQK);
             const uint64_t db = ptx::make_smem_desc(ak + kk * 32, 16, kSboQK, kSwzQK);
-            ptx::umma_i8_ss(tS, da, db, idesc_qk, kk > 0);
+            ptx::umma_i8_ss(tS, da, db, idesc_qk, 1);
           }
         }
         ptx::umma_commit(bar_s + (j & 1));  // scores ready for the softmax warps
@@ -690,6 +703,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tS0 = tmem_base + lane_off, tS1 = tS0 + BN;  // my score columns in S buffer 0 / 1 (P aliases S)
     const uint32_t tOl = tO + lane_off;
     float m_ref = -INFINITY, l = 0.f;
+    constexpr float kScMax = 1.0e-3f;
 
     // one key block: wait for S, row max, (rare) rescale of O, P = exp2(S*sc - m) -> TMEM, signal the issuer
     auto step = [&](auto masked_tag, const uint32_t tSb, uint64_t* bs, uint64_t* pr, const uint32_t ph, const int j,
@@ -704,7 +718,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (DBG) {
         if (p.dbg != nullptr && j * BN < 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
-          for (int c = 0; c < BN; ++c) p.dbg[r * 64 + j * BN + c] = (int)s[c];
+          for (int c = 0; c < BN; ++c) p.dbg[r * 64 + j * BN + c] = (int)(s[c] - (BIASED ? chunk::kScoreBias : 0u));
         }
       }
       float mblk;
@@ -714,8 +728,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int c = 0; c < BN; ++c) fm[c & 3] = fmaxf(fm[c & 3], (!MASKED || c <= lim) ? __uint_as_float(s[c]) : -INFINITY);
         mblk = fmaxf(fmaxf(fm[0], fm[1]), fmaxf(fm[2], fm[3])) * sc;  // sc > 0; -inf stays -inf
       } else {
-        const int imax = chunk::row_max_i<BN, MASKED>(s, lim);
-        mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)imax * sc;
+        const int imax = chunk::row_max_i<BN, MASKED>(s, lim);  // biased scores keep their order as int32
+        mblk = (MASKED && imax == INT_MIN) ? -INFINITY : (float)(imax - (int)(BIASED ? chunk::kScoreBias : 0u)) * sc;
       }
       // lazy rescale: move the reference max only when it grows by more than 2^THR (warp-uniform decision,
       // tcgen05.ld/st are warp collectives)
@@ -742,8 +756,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       uint32_t pk[PCOLS];
       const float nm = (m_ref == -INFINITY) ? 0.f : PC::OFF - m_ref;  // fully masked row so far: p is zeroed by the mask
-      if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, FQK ? 1 : 0>(s, sc, nm, lim, pk);
-      else l += softmax_block_e4m3<BN, MASKED, FQK ? 1 : 0>(s, sc, nm, lim, pk);
+      if constexpr (FQK) {
+        if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, 1>(s, sc, nm, lim, pk);
+        else l += softmax_block_e4m3<BN, MASKED, 1>(s, sc, nm, lim, pk);
+      } else if (sc > kScMax) {  // coarse scale (warp-uniform): subtract the bias exactly (one packed add per pair)
+        if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, 2>(s, sc, nm, lim, pk);
+        else l += softmax_block_e4m3<BN, MASKED, 2>(s, sc, nm, lim, pk);
+      } else {  // the bias leaves through the FMA addend: common factor <= 2^(2^-25 * 12582912 * sc) on the block's P
+        const float nmb = fmaf(-chunk::kScoreBiasF, sc, nm);
+        if constexpr (PV == PV_F16) l += softmax_block_f16<BN, MASKED, 1>(s, sc, nmb, lim, pk);
+        else l += softmax_block_e4m3<BN, MASKED, 1>(s, sc, nmb, lim, pk);
+      }
       tmem_st_n<PCOLS>(tSb, pk);  // P aliases the first columns of its S buffer
       ptx::tmem_wait_st();
       ptx::tc_fence_before();

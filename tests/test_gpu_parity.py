@@ -329,13 +329,13 @@ K4_CASES = [
 
 
 @pytest.mark.parametrize("case", K4_CASES)
-def test_packed_int4_k_is_bit_identical_to_unpacked(L, cuda_dev, case):
+def test_packed_int4_k_matches_unpacked(L, cuda_dev, case):
     """qk_mode Q8K4 (K packed two codes per byte in HBM, expanded to code*16 in shared memory, Q tile permuted,
-    1/16 folded into the scale) against the same codes fed one per int8: the integer scores are identical.  head_dim
-    128 (one kernel, same arithmetic): bit-identical O and lse.  head_dim 64: the scores leave TMEM as fp32
-    1.5 * 2^23 + s and the constant goes out through the addend of the scaling FMA, nm - 12582912 * scale, whose
-    rounding depends on the scale (scale / 16 for the packed operand): the exponents differ by <= 2^-11, i.e. P by
-    less than its own fp16 rounding -- O within 2 fp16 ulps of its magnitude, lse within 1e-3."""
+    1/16 folded into the scale) against the same codes fed one per int8: the integer scores are identical.  The
+    scores leave TMEM as fp32 1.5 * 2^23 + s; for fine scales the constant goes out through the addend of the scaling
+    FMA, nm - 12582912 * scale, whose rounding depends on the scale (scale / 16 for the packed operand), so the two
+    forms' exponents differ by <= 2^-11, i.e. P by less than its own fp16 rounding (the unpacked INT4 codes have a
+    coarse scale and take the exact-subtraction path): O within 2 fp16 ulps of its magnitude, lse within 1e-3."""
     from lowbit_quant_fa2_paddle_b200 import _native as NV
     b, hq, hkv, n, d, layout, causal = case
     q = mk(b, hq, n, d, layout, torch.float16, 41).to(cuda_dev)
@@ -348,12 +348,9 @@ def test_packed_int4_k_is_bit_identical_to_unpacked(L, cuda_dev, case):
     fn = L.forward_causal if causal else L.forward
     o_u, lse_u = fn(qc, k4, v, qs, ks, tensor_layout=layout, return_lse=True)
     o_p, lse_p = fn(qc, k4p, v, qs, ks, tensor_layout=layout, return_lse=True, qk_mode=NV.QK_Q8K4)
-    if d == 128:
-        assert torch.equal(o_u, o_p) and torch.equal(lse_u, lse_p)
-    else:
-        tol = 2.0 * 2.0 ** -10 * max(o_u.float().abs().max().item(), 2.0 ** -10)
-        assert (o_u.float() - o_p.float()).abs().max().item() <= tol
-        assert (lse_u - lse_p).abs().max().item() <= 1e-3
+    tol = 2.0 * 2.0 ** -10 * max(o_u.float().abs().max().item(), 2.0 ** -10)
+    assert (o_u.float() - o_p.float()).abs().max().item() <= tol
+    assert (lse_u - lse_p).abs().max().item() <= 1e-3
 
 
 @pytest.mark.parametrize("entry", ["int4", "q8k4"])
@@ -854,8 +851,10 @@ def test_mixed_k_quantizer_bit_exact(L, cuda_dev, layout, dtype, n, d):
 ])
 def test_mixed_k_attention_identical_to_int8_path(L, cuda_dev, layout, hq, hkv, n, d, causal, pv):
     """The mixed-width kernel path (TMA box per bit width, 8/4/2-bit expansion in shared memory, power-of-two factor
-    folded into the scale) yields exactly the same integer scores as the INT8 path fed the unpacked codes, so the
-    outputs are bit-identical."""
+    folded into the scale) yields exactly the same integer scores as the INT8 path fed the unpacked codes; the
+    effective scale differs by that power of two, and with it the rounding of the exponent offset that carries the
+    score bias (see test_packed_int4_k_matches_unpacked): O within 2 fp16 ulps of its magnitude (fp16 P; one e4m3
+    step of P for FP8 P.V), lse within 1e-3."""
     from lowbit_quant_fa2_paddle_b200 import _native as NV
     from oracle import quant as OQ
     q = mk(1, hq, n, d, layout, torch.float16, 71).to(cuda_dev)
@@ -873,7 +872,9 @@ def test_mixed_k_attention_identical_to_int8_path(L, cuda_dev, layout, hq, hkv, 
     o_mix, lse_mix = fn(qc, kc, v, qs, ks, tensor_layout=layout, return_lse=True, qk_mode=NV.QK_Q8KMIX, kbits=kb, **kw)
     # the mixed-width path runs 32-key steps: compare with the same kernel family (narrow=True)
     o_i8, lse_i8 = fn(qc, k_unp, v, qs, ks, tensor_layout=layout, return_lse=True, narrow=True, **kw)
-    assert torch.equal(o_mix, o_i8) and torch.equal(lse_mix, lse_i8)
+    omax = max(o_i8.float().abs().max().item(), 2.0 ** -10)
+    assert (o_mix.float() - o_i8.float()).abs().max().item() <= (2.0 * 2.0 ** -10 if pv == "fp16" else 2.0 ** -4) * omax
+    assert (lse_mix - lse_i8).abs().max().item() <= (1e-3 if pv == "fp16" else 3e-2)
     if d == 64:  # the default 64-key-step kernel: same softmax, different reference maxima / exp2 pipe
         o_w, lse_w = fn(qc, k_unp, v, qs, ks, tensor_layout=layout, return_lse=True, **kw)
         assert (o_w.float() - o_i8.float()).abs().max().item() <= (2e-3 if pv == "fp16" else 5e-2)
