@@ -1,2 +1,2 @@
-OUT=gpurun_out/r2_call32; mkdir -p $OUT
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -12
+OUT=gpurun_out/r2_call39; mkdir -p $OUT
+timeout 600 python -m pytest tests/test_qattn_golden.py -q -s -m gpu > $OUT/test.log 2>&1; grep -E "npz f8|npz f16|passed|failed" $OUT/test.log
