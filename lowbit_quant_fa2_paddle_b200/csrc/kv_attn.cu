@@ -5,25 +5,48 @@
 //     (the prototype's driver, :637-690, feeds it new_pack.py:247-300 codes: K packed along the sequence per channel,
 //      V packed along the channels per token, asymmetric, group 32, scale + minimum)
 // Arithmetic that defines the result (attn_4bit_per_block.py:260-262, 330-372; new_pack.py:69-144):
-//   K^[d,n] = fma(code, scale[d, n/G], mn[d, n/G])      V^[n,d] = fma(code, scale[n, d/G], mn[n, d/G])     (fp32)
-//   S = q . K^ (fp32),  p = exp(S * softmax_scale - m),  o = (sum_n p V^) / l,  lse = m + log(l)
+//   K^[d,n] = fma(code, scale[d, n/G], mn[d, n/G])      V^[n,d] = fma(code, scale[n, d/G], mn[n, d/G])
+//   S = q . K^,  p = exp(S * softmax_scale - m),  o = (sum_n p V^) / l,  lse = m + log(l)
 // The reference kernel is a prototype that does not run as written, so parity for this entry is
 // unpinned: the tests' CPU restatement follows the formulas above over the reference's own (pinned) pack format.
 //
-// This is a decode-shaped, HBM-bound path (a few query rows against a long packed cache), not a tensor-core one:
-// the cache is read exactly once.  Grid (key splits x query-row tiles, heads, batch); a CTA of 128 threads walks
-// its key range in 128-key tiles staged in shared memory:
-//   scores : thread t <-> key t of the tile (a warp = one 32-key scale group of K), loop over channels
-//   softmax: online, base 2, row maximum / sum by warp shuffles + one shared-memory hop
-//   P.V    : thread c <-> channel c (a warp = one 32-channel scale group of V), loop over the tile's keys
-// and leaves (m, l, o) of its split in a workspace; kv_attn_merge_kernel folds the splits (flash-decoding).
+// A decode-shaped, HBM-bound path: up to 8 query rows against a long packed cache that is read exactly once.  The
+// first version dequantized every code with shift / mask / I2F / FMA (14.8 thread instructions per code, 27 % of
+// the HBM roofline, issue bound).  This one never converts a code:
+//
+//  * both contractions run on mma.sync.m16n8k16 (fp16 in, fp32 accumulate) with the CODES as the A operand
+//    (m = 16 keys resp. 16 channels, k = 16 channels resp. 16 keys) and the query side as B (n = 8 query rows);
+//  * a packed 32-bit word (8 4-bit or 16 2-bit codes of ONE channel resp. token) and its neighbour along k are merged
+//    by one PRMT into "lo half = 16 code bits of k, hi half = 16 code bits of k + 1", and every A register is then one
+//    LOP3 of that word with a mask: the bits land in the mantissa of an fp16 pair.  Read as fp16 DENORMALS they are
+//    code * f * 2^-24 with f = 2^(bit position) -- exact -- and the power of two leaves through one fp32 multiply per
+//    score / output element.  (MAGIC variant: OR in 0x6400 and subtract 1024 in fp16, for hardware that would flush);
+//  * the affine parts are factored out as before:  S[n] = sum_d (q[d] sc[d,g]) code[d,n] + sum_d q[d] mn[d,g]; the
+//    second sum is one more MMA against a tile of ones (all rows equal), likewise for P.V;
+//  * the B operands are fp16 products q * sc, q * mn, p * vs, p * vm (one HMUL2 per register; scales staged
+//    TRANSPOSED in shared memory so that a register's two k-neighbours are one 32-bit load).
+//
+// Grid (key splits x query-row tiles, heads, batch); CTA = 4 warps; a 128-key tile is staged by 16-byte cp.async
+// into a 3-deep ring (codes exactly as they lie in HBM, rows padded against bank conflicts); warp w owns keys
+// [32 w, 32 w + 32) of every tile for BOTH contractions with its own online-softmax state, so the main loop has one
+// __syncthreads per tile (ring hand-over) and no cross-warp exchange; the four states are merged once per CTA and the
+// split's (m, l, o) goes to the workspace that kv_attn_merge_kernel folds (flash-decoding).
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lowbit {
 
-constexpr int kKvThreads = 128;
-constexpr int kKvTile = 128;   // keys per tile
+constexpr int kKvWarps = 8;
+constexpr int kKvThreads = 32 * kKvWarps;
+constexpr int kKvTile = 32 * kKvWarps;   // keys per tile: one 32-key scale group per warp; a K row of a tile is a whole 128-byte line (4-bit)
 constexpr int kKvGroup = 32;   // quantization group (new_pack.py driver: group_size=32)
+constexpr int kKvRows = 8;     // query rows per CTA: n of the m16n8k16 MMA
+constexpr int kKvStages = 2;
+constexpr int kKvCtasPerSm = 2;
+constexpr int kKvPStride = 40; // halves per row of the per-warp P tile (32 keys + pad: conflict-free both ways)
 
 __device__ __forceinline__ float kv_ex2(float x) {
   float y;
@@ -31,292 +54,545 @@ __device__ __forceinline__ float kv_ex2(float x) {
   return y;
 }
 
-// R query rows per CTA.  Workspace layout per (b, h, row, split): [m, l, o[D]] fp32.
-//
-// Both contractions walk the packed words as they are: one 32-bit word holds 8 (4-bit) or 16 (2-bit) codes that share
-// their scale group, so a thread takes 8 codes per shared-memory load and the affine part is factored out,
-//   S[n]  = sum_d (q[d] sc[d,g]) code[d,n]  +  sum_d q[d] mn[d,g]          (g = group of key n)
-//   o[c]  = sum_n (p[n] vs[n,g]) code[n,c]  +  sum_n p[n] vm[n,g]          (g = group of channel c)
-// which leaves one conversion and one FMA per code in the inner loops (the first version dequantized every element
-// with its own loads: 9 instructions per code, 1.0 TB/s).
-//   scores : thread (ko, ds) <-> key octet ko of the tile x channel slice {d = 8 j + ds}; the 8 slices of an octet are
-//            adjacent lanes and meet by three xor-shuffles
-//   P.V    : thread (co, ks) <-> channel octet co x key slice ks; the slices meet once per CTA, at the end
-template <int D, int BITS, int R>
-__global__ void __launch_bounds__(kKvThreads)
+template <int BYTES>
+__device__ __forceinline__ void kv_cp_async(uint32_t dst, const void* src, int valid) {
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid) : "memory");
+  else if constexpr (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void kv_cp_async_full(uint32_t dst, const void* src) {
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void kv_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void kv_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// D(16x8, fp32) += A(16x16, fp16, row) . B(16x8, fp16, col)
+__device__ __forceinline__ void kv_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t kv_hmul2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t kv_pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// shared-memory loads at (32-bit shared address + compile-time offset): the offset lands in the instruction's immediate
+template <int OFF> __device__ __forceinline__ uint32_t kv_lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF> __device__ __forceinline__ uint4 kv_lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+
+// Four A registers (fp16 pairs: lo half <- the first word's code, hi half <- the second word's) out of x, the PRMT
+// merge of two packed words.  A lane owns 4 consecutive codes of each word: 4-bit -- the 16 bits ARE its codes, at
+// bit 0, 4, 8, 12 (the upper two are brought down by 8 so that they stay inside the 10 mantissa bits); 2-bit -- the 16
+// bits hold 8 codes, the lane's four start at bit 8 * quad.  Code i comes out multiplied by kFactor[i] (* 2^-24).
+template <int BITS, bool MAGIC>
+struct KvDec {
+  static __device__ __forceinline__ uint32_t fin(uint32_t v) {
+    if constexpr (MAGIC) {
+      uint32_t d;
+      asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(v | 0x64006400u), "r"(0x64006400u));
+      return d;
+    } else {
+      return v;
+    }
+  }
+  static __device__ __forceinline__ void run(uint32_t x, int quad8, uint32_t (&o)[4]) {
+    if constexpr (BITS == 4) {
+      const uint32_t y = x >> 8;
+      o[0] = fin(x & 0x000F000Fu);
+      o[1] = fin(x & 0x00F000F0u);
+      o[2] = fin(y & 0x000F000Fu);
+      o[3] = fin(y & 0x00F000F0u);
+    } else {
+      const uint32_t y = x >> quad8;
+      o[0] = fin(y & 0x00030003u);
+      o[1] = fin(y & 0x000C000Cu);
+      o[2] = fin(y & 0x00300030u);
+      o[3] = fin(y & 0x00C000C0u);
+    }
+  }
+  // 1 / (power of two the code came out with), times 2^24 when the registers were read as denormals
+  static __device__ __forceinline__ float inv_factor(int i) {
+    const float base = MAGIC ? 1.f : 16777216.f;
+    if constexpr (BITS == 4) return (i & 1) ? base * 0.0625f : base;
+    else return base * (i == 0 ? 1.f : i == 1 ? 0.25f : i == 2 ? 0.0625f : 0.015625f);
+  }
+};
+
+constexpr int kv_row_stride_words(int words) { return words == 4 ? 4 : words + 4; }  // see the bank maps in the kernel
+
+template <int D, int BITS>
+struct KvSmem {
+  static constexpr int KRB = kKvTile * BITS / 8;           // bytes of one channel row of a K tile (64 / 32)
+  static constexpr int KST = kv_row_stride_words(KRB / 4); // its stride in words
+  static constexpr int VB = D * BITS / 8;                  // bytes of one token row of V (64 / 32 / 16)
+  static constexpr int VST = kv_row_stride_words(VB / 4);
+  static constexpr int KG = kKvTile / kKvGroup;            // K scale groups per tile (4)
+  static constexpr int VG = D / kKvGroup;                  // V scale groups per token (4 / 2)
+  static constexpr int kStageK = D * KST * 4, kStageV = kKvTile * VST * 4, kStage = kStageK + kStageV;
+  static constexpr int kScales = (2 * KG * D + 2 * VG * kKvTile) * 2;   // one buffer: K sc, K mn, V sc, V mn (fp16, transposed)
+  static constexpr int kP = kKvWarps * kKvRows * kKvPStride * 2;
+  static constexpr int kEpi = kKvWarps * kKvRows * (D + 4 + 2) * 4;               // per-warp (m, l, o) at the end (reuses the ring)
+  static constexpr int kRing = kKvStages * kStage > kEpi ? kKvStages * kStage : kEpi;
+  static constexpr int kBytes = kRing + 2 * kScales + kP;
+};
+
+// Workspace layout per (b, h, row, split): [m (base 2), l, o[D]] fp32.
+template <int D, int BITS, bool MAGIC>
+__global__ void __launch_bounds__(kKvThreads, kKvCtasPerSm)
 kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__ kcode,
                        const __half* __restrict__ kscale, const __half* __restrict__ kmn,
                        const uint8_t* __restrict__ vcode, const __half* __restrict__ vscale,
                        const __half* __restrict__ vmn, float* __restrict__ ws, int H, int Nq, int N, int nsplit,
-                       int keys_per_split, float scale_log2e, int64_t qsb, int64_t qsn, int64_t qsh) {
-  constexpr int VB = D * BITS / 8;              // bytes of one token row of V
-  constexpr uint32_t CM = (1u << BITS) - 1u;
-  constexpr int KG = kKvTile / kKvGroup;        // K scale groups per tile (4)
-  constexpr int VG = D / kKvGroup;              // V scale groups per token
-  constexpr int KW = kKvTile * BITS / 32;       // words per channel row of a K tile
-  constexpr int VW = D * BITS / 32;             // words per token row of V
-  constexpr int KWP = KW + 4, VWP = VW + 1;     // padded row strides: the access patterns below are conflict-free
-  constexpr int DS = D / 8;                     // channels per score thread
-  constexpr int NCO = D / 8;                    // channel octets
-  constexpr int KPS = kKvTile / (kKvThreads / NCO);  // keys per P.V thread and tile
-  static_assert(kKvThreads == 128 && kKvTile == 128, "thread <-> (octet, slice) maps assume 128 x 128");
-  __shared__ __align__(16) float sQ[R][D];
-  __shared__ uint32_t sK[D][KWP];
-  __shared__ float2 sKs[D][KG];                 // (scale, mn)
-  __shared__ uint32_t sV[kKvTile][VWP];
-  __shared__ float2 sVs[kKvTile][VG];           // (scale, mn)
-  __shared__ float2 sPV[R][kKvTile][VG];        // (p * scale, p * mn); reused for the final cross-warp fold
-  __shared__ float sRedM[R][4], sRedL[R][4];
+                       int keys_per_split, float scale_log2e, int64_t qsb, int64_t qsn, int64_t qsh, int kchunk) {
+  using SM = KvSmem<D, BITS>;
+  using Dec = KvDec<BITS, MAGIC>;
+  constexpr int KST = SM::KST, VST = SM::VST, KG = SM::KG, VG = SM::VG, VB = SM::VB, KRB = SM::KRB;
+  constexpr int KSTEPS = D / 16;
+  constexpr uint32_t kOnes = 0x3C003C00u;
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* ring = smem;
+  __half* scl = reinterpret_cast<__half*>(smem + SM::kRing);          // [2][K sc | K mn | V sc | V mn]
+  __half* sP = reinterpret_cast<__half*>(smem + SM::kRing + 2 * SM::kScales);
+  const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(ring);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int split = blockIdx.x % nsplit, qtile = blockIdx.x / nsplit;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int row0 = qtile * R;
+  const int gq = lane >> 2, t = lane & 3;
+  // heads vary fastest across CTAs: the 32-byte sectors of V scales (4 heads) and the 2 KB of V codes of one token (all
+  // heads) are then touched by co-resident CTAs within a short window (L2 sector reuse, DRAM page hits)
+  const int split = blockIdx.y % nsplit, qtile = blockIdx.y / nsplit;
+  const int h = blockIdx.x, b = blockIdx.z;
+  const int row0 = qtile * kKvRows;
   const int n_begin = split * keys_per_split, n_end = min(N, n_begin + keys_per_split);
+  const int ntiles = (n_end - n_begin + kKvTile - 1) / kKvTile;
 
-  // queries of this tile, pre-multiplied by softmax_scale * log2(e) (the softmax below runs in base 2)
-  for (int i = tid; i < R * D; i += kKvThreads) {
-    const int r = i / D, d = i % D;
-    float v = 0.f;
-    if (row0 + r < Nq) v = __half2float(q[b * qsb + (int64_t)(row0 + r) * qsn + h * qsh + d]) * scale_log2e;
-    sQ[r][d] = v;
-  }
+  // lane <-> codes: which packed word of a 32-code group, which 16-bit half of it, (2-bit) which quad of that half
+  const int wsel = (BITS == 4) ? (gq & 3) : (gq & 1);
+  const int hsel = (BITS == 4) ? (gq >> 2) : ((gq >> 1) & 1);
+  const int quad8 = (BITS == 4) ? 0 : 8 * (gq >> 2);
+  const int cb = (BITS == 4) ? 8 * wsel + 4 * hsel : 16 * wsel + 8 * hsel + 4 * (gq >> 2);  // first of my 4 codes in the group
+  const uint32_t prmt_sel = hsel ? 0x7632u : 0x5410u;
+  constexpr int WPG = 32 * BITS / 32;  // words per 32-code group (4 / 2)
 
-  // cache addressing: kcode [B][D][H][N*BITS/8], kscale/kmn [B][D][H][N/G]; vcode [B][N][H][VB], vscale/vmn [B][N][H][VG]
+  // ---- cache addressing: kcode [B][D][H][N*BITS/8], kscale/kmn [B][D][H][N/G]; vcode [B][N][H][VB], vscale/vmn [B][N][H][VG]
   const int64_t krow_bytes = (int64_t)N * BITS / 8, kgroups = N / kKvGroup;
-  const uint8_t* kc_base = kcode + ((int64_t)b * D * H + h) * krow_bytes;     // + d * H * krow_bytes
+  const uint8_t* kc_base = kcode + ((int64_t)b * D * H + h) * krow_bytes;
+  const int64_t kc_stride = (int64_t)H * krow_bytes;
   const __half* ks_base = kscale + ((int64_t)b * D * H + h) * kgroups;
   const __half* km_base = kmn + ((int64_t)b * D * H + h) * kgroups;
-  const uint8_t* vc_base = vcode + ((int64_t)b * N * H + h) * VB;            // + n * H * VB
+  const int64_t ks_stride = (int64_t)H * kgroups;
+  const uint8_t* vc_base = vcode + ((int64_t)b * N * H + h) * VB;
+  const int64_t vc_stride = (int64_t)H * VB;
   const __half* vs_base = vscale + ((int64_t)b * N * H + h) * VG;
   const __half* vm_base = vmn + ((int64_t)b * N * H + h) * VG;
+  const int64_t vs_stride = (int64_t)H * VG;
+  static_assert(KG == 8, "the K scale registers are written for 8 groups per tile");
+  const bool ks_fast = ((N & 255) == 0) && ((reinterpret_cast<uintptr_t>(kscale) | reinterpret_cast<uintptr_t>(kmn)) & 15) == 0;
 
-  // thread maps
-  const int ko = tid >> 3, ds = tid & 7;        // scores: key octet (a warp = 4 octets = one scale group), channel slice
-  const int kwidx = (ko * 8 * BITS) / 32, kwsh = (ko * 8 * BITS) % 32;
-  const int co = tid % NCO, ks = tid / NCO;     // P.V: channel octet, key slice
-  const int vwidx = (co * 8 * BITS) / 32, vwsh = (co * 8 * BITS) % 32;
-  const int gch = co / 4;                       // scale group of my channels (32 channels = 4 octets)
-
-  float m_run[R], l_run[R], o_acc[R][8];
+  // ---- staging ----
+  // cp.async thread map.  A 16-byte-per-lane shared store is processed a quarter-warp at a time, so the 8 lanes of a
+  // quarter take 8 CONSECUTIVE ROWS of ONE chunk column: with the padded row strides above those 8 x 16 bytes fall
+  // into 32 different banks (the first version gave a quarter 2 rows x 4 columns: 27 wavefronts per instruction
+  // instead of 4, and the copies alone kept the shared-memory pipe busier than all the LDS of the contractions).
+  // From tile to tile a thread's source pointers advance by a constant (tiles are issued in order).
+  // K: a warp-instruction covers 8 rows x 4 chunk columns; rows hold kcpr = 8 or 4 chunks, i.e. kcb = 2 or 1 column blocks
+  const int kcpr = KRB / kchunk, kcb = kcpr / 4;
+  const int k_col = 4 * (warp % kcb) + (lane >> 3), k_row0 = 8 * (warp / kcb) + (lane & 7);
+  const uint8_t* k_src = kc_base + k_row0 * kc_stride + (int64_t)n_begin * BITS / 8 + k_col * kchunk;
+  const int64_t k_step = (int64_t)(8 * kKvWarps / kcb) * kc_stride;
+  int64_t k_left = krow_bytes - ((int64_t)n_begin * BITS / 8 + k_col * kchunk);   // bytes of my column before the row ends
+  const uint32_t k_dst0 = (uint32_t)(k_row0 * (KST * 4) + k_col * kchunk);
+  constexpr int CPV = VB / 16, VRPP = kKvThreads / CPV;  // V chunks per row, rows per pass
+  const int v_col = (lane >> 3) % CPV, v_row0 = (32 / CPV) * warp + (lane & 7) + 8 * ((lane >> 3) / CPV);
+  const uint8_t* v_src = vc_base + (int64_t)(n_begin + v_row0) * vc_stride + v_col * 16;
+  const int64_t v_step = (int64_t)VRPP * vc_stride;
+  int v_n = n_begin + v_row0;                            // token of my first row of the next tile to issue
+  const uint32_t v_dst0 = (uint32_t)(v_row0 * (VST * 4) + v_col * 16);
+  auto issue_codes = [&](int tile) {  // cp.async of the NEXT tile (call order = tile order) into ring stage tile % kKvStages
+    const uint32_t sk = ring_a + (tile % kKvStages) * SM::kStage, sv = sk + SM::kStageK;
+    auto k_rows = [&](auto chunk_tag) {
+      constexpr int CH = decltype(chunk_tag)::value;
+      constexpr int RPP = 8 * kKvWarps / (KRB / CH / 4), PASSES = D / RPP;
+      static_assert(KRB / CH == 4 || KRB / CH == 8, "K rows are 4 or 8 chunks");
+      uint32_t dst = sk + k_dst0;
+      if (k_left >= CH) {                                // the common case: no zero fill
+        const uint8_t* src = k_src;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    m_run[r] = -INFINITY;
-    l_run[r] = 0.f;
+        for (int j = 0; j < PASSES; ++j, src += k_step, dst += RPP * KST * 4) kv_cp_async_full<CH>(dst, src);
+      } else {
+        const int valid = k_left > 0 ? (int)k_left : 0;
+        const uint8_t* src = valid > 0 ? k_src : kc_base;
+        const int64_t step = valid > 0 ? k_step : 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o_acc[r][i] = 0.f;
-  }
-
-  // ---- tile staging, split in two halves: `fetch` issues the global loads of a tile into registers (4-byte words,
-  //      consecutive threads on consecutive words of a row, every thread keeps its column and walks the rows with a
-  //      constant pointer stride), `commit` parks them in shared memory.  The loads of tile i+1 are issued before
-  //      the arithmetic of tile i, so their latency hides behind it. ----
-  constexpr int KRS = kKvThreads / KW, NKW = D / KRS;        // K rows per pass, K words per thread
-  constexpr int SRS = kKvThreads / KG, NKS = D / SRS;        // K scale rows per pass, entries per thread
-  constexpr int VRS = kKvThreads / VW, NVW = kKvTile / VRS;  // V rows per pass, V words per thread
-  constexpr int TRS = kKvThreads / VG, NVS = kKvTile / TRS;  // V scale rows per pass, entries per thread
-  const int kw = tid % KW, kd0 = tid / KW;
-  const int sg = tid % KG, sd0 = tid / KG;
-  const int vw = tid % VW, vn0 = tid / VW;
-  const int tg = tid % VG, tn0 = tid / VG;
-  uint32_t rk[NKW], rv[NVW];
-  __half rks[NKS], rkm[NKS], rvs[NVS], rvm[NVS];
-  auto fetch = [&](int n0) {
-    const bool k_ok = (n0 + kw * (32 / BITS)) < N;  // N is a multiple of 32: a word never straddles the end
-    const uint8_t* kp = kc_base + (int64_t)kd0 * H * krow_bytes + (int64_t)n0 * BITS / 8 + kw * 4;
-    const int64_t kstep = (int64_t)KRS * H * krow_bytes;
-#pragma unroll
-    for (int i = 0; i < NKW; ++i, kp += kstep) rk[i] = k_ok ? *reinterpret_cast<const uint32_t*>(kp) : 0u;
-    const int gi = n0 / kKvGroup + sg;
-    const bool s_ok = gi < kgroups;
-    const __half* sp = ks_base + (int64_t)sd0 * H * kgroups + gi;
-    const __half* mp = km_base + (int64_t)sd0 * H * kgroups + gi;
-    const int64_t sstep = (int64_t)SRS * H * kgroups;
-#pragma unroll
-    for (int i = 0; i < NKS; ++i, sp += sstep, mp += sstep) {
-      rks[i] = s_ok ? *sp : __float2half_rn(0.f);
-      rkm[i] = s_ok ? *mp : __float2half_rn(0.f);
+        for (int j = 0; j < PASSES; ++j, src += step, dst += RPP * KST * 4) kv_cp_async<CH>(dst, src, valid);
+      }
+    };
+    if constexpr (KRB / 8 > 8) {   // 4-bit rows are always multiples of 16 bytes
+      k_rows(std::integral_constant<int, 16>{});
+    } else {
+      if (kchunk == 16) k_rows(std::integral_constant<int, 16>{});
+      else k_rows(std::integral_constant<int, 8>{});
     }
-    const uint8_t* vp = vc_base + (int64_t)(n0 + vn0) * H * VB + vw * 4;
-    const int64_t vstep = (int64_t)VRS * H * VB;
+    k_src += KRB;
+    k_left -= KRB;
+    {
+      const uint8_t* src = v_src;
+      uint32_t dst = sv + v_dst0;
+      if (v_n + (CPV - 1) * VRPP < N) {
 #pragma unroll
-    for (int i = 0; i < NVW; ++i, vp += vstep) rv[i] = (n0 + vn0 + i * VRS < N) ? *reinterpret_cast<const uint32_t*>(vp) : 0u;
-    const __half* tsp = vs_base + (int64_t)(n0 + tn0) * H * VG + tg;
-    const __half* tmp_ = vm_base + (int64_t)(n0 + tn0) * H * VG + tg;
-    const int64_t tstep = (int64_t)TRS * H * VG;
+        for (int j = 0; j < CPV; ++j, src += v_step, dst += VRPP * VST * 4) kv_cp_async_full<16>(dst, src);
+      } else {
 #pragma unroll
-    for (int i = 0; i < NVS; ++i, tsp += tstep, tmp_ += tstep) {
-      const bool ok = (n0 + tn0 + i * TRS) < N;
-      rvs[i] = ok ? *tsp : __float2half_rn(0.f);
-      rvm[i] = ok ? *tmp_ : __float2half_rn(0.f);
+        for (int j = 0; j < CPV; ++j, src += v_step, dst += VRPP * VST * 4) {
+          const bool ok = v_n + j * VRPP < N;
+          kv_cp_async<16>(dst, ok ? src : vc_base, ok ? 16 : 0);
+        }
+      }
     }
+    v_src += (int64_t)kKvTile * vc_stride;
+    v_n += kKvTile;
   };
-  auto commit = [&]() {
+  // scales travel through registers (global [d][group] / [token][group] -> shared [group][d] / [group][token])
+  uint32_t rks[KG / 2], rkm[KG / 2];   // KG fp16 values each
+  uint2 rvs = make_uint2(0, 0), rvm = make_uint2(0, 0);
 #pragma unroll
-    for (int i = 0; i < NKW; ++i) sK[kd0 + i * KRS][kw] = rk[i];
+  for (int g = 0; g < KG / 2; ++g) rks[g] = rkm[g] = 0u;
+  auto fetch_scales = [&](int tile) {
+    const int n0 = n_begin + tile * kKvTile;
+    if (tid < D) {
+      const int64_t g0 = n0 / kKvGroup;
+      const __half* sp = ks_base + tid * ks_stride + g0;
+      const __half* mp = km_base + tid * ks_stride + g0;
+      if (ks_fast) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sp), m4 = *reinterpret_cast<const uint4*>(mp);
+        rks[0] = a.x, rks[1] = a.y, rks[2] = a.z, rks[3] = a.w;
+        rkm[0] = m4.x, rkm[1] = m4.y, rkm[2] = m4.z, rkm[3] = m4.w;
+      } else {
 #pragma unroll
-    for (int i = 0; i < NKS; ++i) sKs[sd0 + i * SRS][sg] = make_float2(__half2float(rks[i]), __half2float(rkm[i]));
-#pragma unroll
-    for (int i = 0; i < NVW; ++i) sV[vn0 + i * VRS][vw] = rv[i];
-#pragma unroll
-    for (int i = 0; i < NVS; ++i) sVs[tn0 + i * TRS][tg] = make_float2(__half2float(rvs[i]), __half2float(rvm[i]));
-  };
-
-  fetch(n_begin);
-  for (int n0 = n_begin; n0 < n_end; n0 += kKvTile) {
-    __syncthreads();  // previous tile fully consumed (also orders the sQ fill before its first use)
-    commit();
-    __syncthreads();
-    if (n0 + kKvTile < n_end) fetch(n0 + kKvTile);  // in flight during this tile's arithmetic
-
-    // ---- scores of my key octet over my channel slice, then the 8 slices meet ----
-    float s[R][8], cst[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cst[r] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[r][i] = 0.f;
-    }
-#pragma unroll 2
-    for (int j = 0; j < DS; ++j) {
-      const int d = j * 8 + ds;
-      const uint32_t codes = sK[d][kwidx] >> kwsh;
-      const float2 sm = sKs[d][warp];  // the warp's keys share one scale group
-      float qs[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float qv = sQ[r][d];
-        qs[r] = qv * sm.x;
-        cst[r] = fmaf(qv, sm.y, cst[r]);
+        for (int g = 0; g < KG / 2; ++g) {
+          const bool ok0 = g0 + 2 * g < kgroups, ok1 = g0 + 2 * g + 1 < kgroups;
+          const uint32_t a0 = ok0 ? *reinterpret_cast<const uint16_t*>(sp + 2 * g) : 0u;
+          const uint32_t a1 = ok1 ? *reinterpret_cast<const uint16_t*>(sp + 2 * g + 1) : 0u;
+          const uint32_t m0 = ok0 ? *reinterpret_cast<const uint16_t*>(mp + 2 * g) : 0u;
+          const uint32_t m1 = ok1 ? *reinterpret_cast<const uint16_t*>(mp + 2 * g + 1) : 0u;
+          rks[g] = a0 | (a1 << 16);
+          rkm[g] = m0 | (m1 << 16);
+        }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float cf = (float)((codes >> (i * BITS)) & CM);
-#pragma unroll
-        for (int r = 0; r < R; ++r) s[r][i] = fmaf(qs[r], cf, s[r][i]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int off = 1; off < 8; off <<= 1) {
-        cst[r] += __shfl_xor_sync(0xffffffffu, cst[r], off);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s[r][i] += __shfl_xor_sync(0xffffffffu, s[r][i], off);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[r][i] += cst[r];
-    }
-    // ---- online softmax (base 2); every lane of an octet holds the same 8 scores ----
-    const int nk = n0 + ko * 8;  // first key of my octet
-    float mloc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float v = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v = fmaxf(v, (nk + i < n_end) ? s[r][i] : -INFINITY);
-      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
-      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
-      mloc[r] = v;
-      if (lane == 0) sRedM[r][warp] = v;
-    }
-    __syncthreads();
-    float alpha[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float mt = fmaxf(fmaxf(sRedM[r][0], sRedM[r][1]), fmaxf(sRedM[r][2], sRedM[r][3]));
-      const float m_new = fmaxf(m_run[r], mt);   // finite: every tile holds at least one live key
-      alpha[r] = kv_ex2(m_run[r] - m_new);       // first tile: exp2(-inf) = 0
-      m_run[r] = m_new;
-      float lsum = 0.f, pmine = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float pi = (nk + i < n_end) ? kv_ex2(s[r][i] - m_new) : 0.f;
-        lsum += pi;
-        pmine = (i == ds) ? pi : pmine;  // lane ds of the octet publishes key ds
-      }
-      lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
-      lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
-      if (lane == 0) sRedL[r][warp] = lsum;
-      const int nl = ko * 8 + ds;
-#pragma unroll
-      for (int g = 0; g < VG; ++g) {
-        const float2 vsm = sVs[nl][g];
-        sPV[r][nl][g] = make_float2(pmine * vsm.x, pmine * vsm.y);
-      }
-    }
-    (void)mloc;
-    __syncthreads();
-    // ---- P.V over my channel octet and key slice ----
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      l_run[r] = l_run[r] * alpha[r] + ((sRedL[r][0] + sRedL[r][1]) + (sRedL[r][2] + sRedL[r][3]));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o_acc[r][i] *= alpha[r];
     }
     {
-      float cv[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) cv[r] = 0.f;
-#pragma unroll 2
-      for (int nn = 0; nn < KPS; ++nn) {
-        const int nl = ks * KPS + nn;
-        const uint32_t codes = sV[nl][vwidx] >> vwsh;
-        float pv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float2 t = sPV[r][nl][gch];
-          pv[r] = t.x;
-          cv[r] += t.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float cf = (float)((codes >> (i * BITS)) & CM);
-#pragma unroll
-          for (int r = 0; r < R; ++r) o_acc[r][i] = fmaf(pv[r], cf, o_acc[r][i]);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o_acc[r][i] += cv[r];
+      const int n = n0 + tid;
+      const bool ok = n < N;
+      const __half* sp = vs_base + (ok ? n : 0) * vs_stride;
+      const __half* mp = vm_base + (ok ? n : 0) * vs_stride;
+      if constexpr (VG == 4) {
+        rvs = ok ? *reinterpret_cast<const uint2*>(sp) : make_uint2(0, 0);
+        rvm = ok ? *reinterpret_cast<const uint2*>(mp) : make_uint2(0, 0);
+      } else {
+        rvs.x = ok ? *reinterpret_cast<const uint32_t*>(sp) : 0u;
+        rvm.x = ok ? *reinterpret_cast<const uint32_t*>(mp) : 0u;
       }
     }
-  }
+  };
+  // Shared layout of one scale buffer: 16-byte units {sc(k), sc(k+1), sc(k+8), sc(k+9), mn(k), mn(k+1), mn(k+8), mn(k+9)} --
+  // exactly the fp16 pairs that multiply one lane's two B registers of one MMA k-step -- so a k-step costs ONE LDS.128.
+  // K: unit (group g, k-step ks, t) at g * D/4 + 4 ks + t, k = channel 16 ks + 2 t;  V: unit (group g, 16-token block nb, t)
+  // at KG * D/4 + g * (tile / 4) + 4 nb + t, k = token 16 nb + 2 t of the tile.
+  auto unit_slot = [](int e) { return 2 * ((e >> 3) & 1) + (e & 1); };   // position of element e (mod 16) inside its unit
+  auto park_scales = [&](int buf) {
+    uint16_t* base = reinterpret_cast<uint16_t*>(scl) + buf * (SM::kScales / 2);
+    if (tid < D) {
+      uint16_t* u = base + ((tid >> 4) * 4 + ((tid & 7) >> 1)) * 8 + unit_slot(tid);
+#pragma unroll
+      for (int g = 0; g < KG; ++g) {
+        u[g * (D / 4) * 8] = (uint16_t)((g & 1) ? rks[g / 2] >> 16 : rks[g / 2] & 0xffff);
+        u[g * (D / 4) * 8 + 4] = (uint16_t)((g & 1) ? rkm[g / 2] >> 16 : rkm[g / 2] & 0xffff);
+      }
+    }
+    {
+      uint16_t* u = base + KG * (D / 4) * 8 + ((tid >> 4) * 4 + ((tid & 7) >> 1)) * 8 + unit_slot(tid);
+      const uint32_t sc[4] = {rvs.x & 0xffff, rvs.x >> 16, rvs.y & 0xffff, rvs.y >> 16};
+      const uint32_t mn[4] = {rvm.x & 0xffff, rvm.x >> 16, rvm.y & 0xffff, rvm.y >> 16};
+#pragma unroll
+      for (int g = 0; g < VG; ++g) {
+        u[g * (kKvTile / 4) * 8] = (uint16_t)sc[g];
+        u[g * (kKvTile / 4) * 8 + 4] = (uint16_t)mn[g];
+      }
+    }
+  };
 
-  // ---- partial result of this split: fold the key slices (lanes, then warps) ----
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
+  for (int s = 0; s < kKvStages - 1; ++s) {
+    if (s < ntiles) issue_codes(s);
+    kv_cp_commit();
+  }
+  fetch_scales(0);
+
+  // ---- query fragment: B operand rows (k = channel pair) of query row gq, pre-multiplied by softmax_scale * log2(e)
+  uint32_t q2[KSTEPS][2];
+  {
+    const bool row_ok = row0 + gq < Nq;
+    const __half* qp = q + b * qsb + (int64_t)(row_ok ? row0 + gq : 0) * qsn + h * qsh;
 #pragma unroll
-    for (int off = NCO; off < 32; off <<= 1) {
+    for (int ks = 0; ks < KSTEPS; ++ks) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o_acc[r][i] += __shfl_xor_sync(0xffffffffu, o_acc[r][i], off);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int d0 = 16 * ks + 8 * hh + 2 * t;
+        const float a = row_ok ? __half2float(qp[d0]) * scale_log2e : 0.f;
+        const float c = row_ok ? __half2float(qp[d0 + 1]) * scale_log2e : 0.f;
+        q2[ks][hh] = kv_pack_f16x2(a, c);
+      }
     }
   }
-  __syncthreads();  // sPV is free
-  float* sO = reinterpret_cast<float*>(&sPV[0][0][0]);  // [4 warps][R][D]
-  if (lane < NCO) {
+  park_scales(0);
+  if (ntiles > 1) fetch_scales(1);
+
+  // running state of this warp's key slice: rows 2t, 2t+1 (the accumulator columns this lane owns)
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float accO[VG][2][4], accV[VG][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+  for (int g = 0; g < VG; ++g) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sO[(warp * R + r) * D + co * 8 + i] = o_acc[r][i];
+    for (int c = 0; c < 4; ++c) accO[g][0][c] = accO[g][1][c] = accV[g][c] = 0.f;
+  }
+  __half* sPw = sP + warp * (kKvRows * kKvPStride);
+  // per-lane byte offsets inside a stage / a scale buffer / the P tile; everything else is an immediate
+  const uint32_t scl_a0 = (uint32_t)__cvta_generic_to_shared(scl);
+  const uint32_t k_lane_off = (uint32_t)((2 * t) * KST + warp * WPG + wsel) * 4u;
+  const uint32_t v_lane_off = (uint32_t)((warp * 32 + 2 * t) * VST + wsel) * 4u;
+  const uint32_t ks_lane_off = (uint32_t)(warp * (D / 4) + t) * 16u;
+  const uint32_t vs_lane_off = (uint32_t)(KG * (D / 4) + 8 * warp + t) * 16u;
+  const uint32_t p_rd = (uint32_t)__cvta_generic_to_shared(sPw) + (uint32_t)(gq * kKvPStride + 2 * t) * 2u;
+
+  for (int i = 0; i < ntiles; ++i) {
+    kv_cp_wait<kKvStages - 2>();
+    __syncthreads();  // tile i landed for everyone; tile i-1 fully consumed; scale buffer i&1 visible
+    if (i + kKvStages - 1 < ntiles) issue_codes(i + kKvStages - 1);
+    kv_cp_commit();
+    if (i + 1 < ntiles) park_scales((i + 1) & 1);
+    if (i + 2 < ntiles) fetch_scales(i + 2);
+
+    const int n0 = n_begin + i * kKvTile;
+    const uint32_t stage_a = ring_a + (i % kKvStages) * SM::kStage;
+    const uint32_t scl_a = scl_a0 + (i & 1) * SM::kScales;
+
+    // ---- scores of my 32 keys: S^T (keys x rows) = codes^T . (q * sc), + ones . (q * mn) ----
+    float accS[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accC[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const uint32_t ka = stage_a + k_lane_off;            // word (channel 2 t, my column) of the K tile
+      const uint32_t sa = scl_a + ks_lane_off;             // unit (group = warp, k-step 0, t)
+      struct KLoad { uint4 sm; uint32_t w00, w01, w10, w11; };
+      auto kload = [&](auto ks_tag) {
+        constexpr int ks = decltype(ks_tag)::value;
+        constexpr int RO = 16 * ks * KST * 4;
+        KLoad L;
+        L.sm = kv_lds128<ks * 64>(sa);
+        L.w00 = kv_lds32<RO>(ka), L.w01 = kv_lds32<RO + KST * 4>(ka);
+        L.w10 = kv_lds32<RO + 8 * KST * 4>(ka), L.w11 = kv_lds32<RO + 9 * KST * 4>(ka);
+        return L;
+      };
+      auto kmath = [&](auto ks_tag, const KLoad& L) {
+        constexpr int ks = decltype(ks_tag)::value;
+        uint32_t lo[4], hi[4];
+        Dec::run(__byte_perm(L.w00, L.w01, prmt_sel), quad8, lo);
+        Dec::run(__byte_perm(L.w10, L.w11, prmt_sel), quad8, hi);
+        const uint32_t b0 = kv_hmul2(q2[ks][0], L.sm.x), b1 = kv_hmul2(q2[ks][1], L.sm.y);
+        kv_mma(accS[0], lo[0], lo[1], hi[0], hi[1], b0, b1);
+        kv_mma(accS[1], lo[2], lo[3], hi[2], hi[3], b0, b1);
+        kv_mma(accC, kOnes, kOnes, kOnes, kOnes, kv_hmul2(q2[ks][0], L.sm.z), kv_hmul2(q2[ks][1], L.sm.w));
+      };
+      // loads run one k-step ahead of the arithmetic
+#define KV_KSTEP(A, B, LA, LB) KLoad LB = kload(std::integral_constant<int, B>{}); kmath(std::integral_constant<int, A>{}, LA);
+      KLoad L0 = kload(std::integral_constant<int, 0>{});
+      KV_KSTEP(0, 1, L0, L1)
+      KV_KSTEP(1, 2, L1, L2)
+      KV_KSTEP(2, 3, L2, L3)
+      if constexpr (KSTEPS == 8) {
+        KV_KSTEP(3, 4, L3, L4)
+        KV_KSTEP(4, 5, L4, L5)
+        KV_KSTEP(5, 6, L5, L6)
+        KV_KSTEP(6, 7, L6, L7)
+        kmath(std::integral_constant<int, 7>{}, L7);
+      } else {
+        kmath(std::integral_constant<int, 3>{}, L3);
+      }
+#undef KV_KSTEP
+    }
+    // ---- online softmax (base 2), rows 2t + j; the 32 keys of a row sit in the 8 lanes that share t ----
+    float p[4][2], alpha[2];
+    const int key0 = n0 + warp * 32 + cb;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float s[4];
+      s[0] = fmaf(accS[0][j], Dec::inv_factor(0), accC[j]);
+      s[1] = fmaf(accS[0][2 + j], Dec::inv_factor(1), accC[j]);
+      s[2] = fmaf(accS[1][j], Dec::inv_factor(2), accC[j]);
+      s[3] = fmaf(accS[1][2 + j], Dec::inv_factor(3), accC[j]);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        s[k4] = (key0 + k4 < N) ? s[k4] : -INFINITY;
+        mx = fmaxf(mx, s[k4]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      const float m_new = fmaxf(m_run[j], mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // a slice with no live key yet
+      alpha[j] = kv_ex2(m_run[j] - m_use);
+      m_run[j] = m_new;
+      float lsum = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        p[k4][j] = kv_ex2(s[k4] - m_use);
+        lsum += p[k4][j];
+      }
+      l_run[j] = fmaf(l_run[j], alpha[j], lsum);
+      // P^T tile of this warp: [row][key] fp16; my 4 keys of row 2t+j are 8 contiguous bytes
+      *reinterpret_cast<uint2*>(sPw + (2 * t + j) * kKvPStride + cb) =
+          make_uint2(kv_pack_f16x2(p[0][j], p[1][j]), kv_pack_f16x2(p[2][j], p[3][j]));
+    }
+    if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {
+#pragma unroll
+      for (int g = 0; g < VG; ++g) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          accO[g][0][c] *= alpha[c & 1];
+          accO[g][1][c] *= alpha[c & 1];
+          accV[g][c] *= alpha[c & 1];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- P.V over my 32 keys: O^T (channels x rows) += codes^T . (p * vs), + ones . (p * vm) ----
+    {
+      const uint32_t va = stage_a + SM::kStageK + v_lane_off;   // word (token 32 w + 2 t, my column of group 0)
+      const uint32_t sa = scl_a + vs_lane_off;                  // unit (group 0, token block 2 w, t)
+      struct VLoad { uint4 sm; uint32_t w00, w01, w10, w11; };
+      auto vload = [&](auto k2_tag, auto g_tag) {
+        constexpr int k2 = decltype(k2_tag)::value, g = decltype(g_tag)::value;
+        constexpr int RO = 16 * k2 * VST * 4 + g * WPG * 4;
+        VLoad L;
+        L.sm = kv_lds128<(g * (kKvTile / 4) + 4 * k2) * 16>(sa);
+        L.w00 = kv_lds32<RO>(va), L.w01 = kv_lds32<RO + VST * 4>(va);
+        L.w10 = kv_lds32<RO + 8 * VST * 4>(va), L.w11 = kv_lds32<RO + 9 * VST * 4>(va);
+        return L;
+      };
+      auto vmath = [&](auto g_tag, const VLoad& L, uint32_t p_a, uint32_t p_b) {
+        constexpr int g = decltype(g_tag)::value;
+        uint32_t lo[4], hi[4];
+        Dec::run(__byte_perm(L.w00, L.w01, prmt_sel), quad8, lo);
+        Dec::run(__byte_perm(L.w10, L.w11, prmt_sel), quad8, hi);
+        const uint32_t b0 = kv_hmul2(p_a, L.sm.x), b1 = kv_hmul2(p_b, L.sm.y);
+        kv_mma(accO[g][0], lo[0], lo[1], hi[0], hi[1], b0, b1);
+        kv_mma(accO[g][1], lo[2], lo[3], hi[2], hi[3], b0, b1);
+        kv_mma(accV[g], kOnes, kOnes, kOnes, kOnes, kv_hmul2(p_a, L.sm.z), kv_hmul2(p_b, L.sm.w));
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      using I3 = std::integral_constant<int, 3>;
+      const uint32_t pa0 = kv_lds32<0>(p_rd), pb0 = kv_lds32<16>(p_rd), pa1 = kv_lds32<32>(p_rd), pb1 = kv_lds32<48>(p_rd);
+      VLoad A = vload(I0{}, I0{});
+      VLoad B = vload(I0{}, I1{});
+      vmath(I0{}, A, pa0, pb0);
+      if constexpr (VG == 4) {
+        A = vload(I0{}, I2{});
+        vmath(I1{}, B, pa0, pb0);
+        B = vload(I0{}, I3{});
+        vmath(I2{}, A, pa0, pb0);
+        A = vload(I1{}, I0{});
+        vmath(I3{}, B, pa0, pb0);
+        B = vload(I1{}, I1{});
+        vmath(I0{}, A, pa1, pb1);
+        A = vload(I1{}, I2{});
+        vmath(I1{}, B, pa1, pb1);
+        B = vload(I1{}, I3{});
+        vmath(I2{}, A, pa1, pb1);
+        vmath(I3{}, B, pa1, pb1);
+      } else {
+        A = vload(I1{}, I0{});
+        vmath(I1{}, B, pa0, pb0);
+        B = vload(I1{}, I1{});
+        vmath(I0{}, A, pa1, pb1);
+        vmath(I1{}, B, pa1, pb1);
+      }
+    }
+  }
+  kv_cp_wait<0>();
+
+  // ---- the four warps' states meet once: (m, l, o) of the split ----
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    l_run[j] += __shfl_xor_sync(0xffffffffu, l_run[j], 4);
+    l_run[j] += __shfl_xor_sync(0xffffffffu, l_run[j], 8);
+    l_run[j] += __shfl_xor_sync(0xffffffffu, l_run[j], 16);
+  }
+  __syncthreads();  // the ring is free
+  float* eM = reinterpret_cast<float*>(ring);          // [warps][8]
+  float* eL = eM + kKvWarps * kKvRows;                 // [warps][8]
+  float* eO = eL + kKvWarps * kKvRows;                 // [warps][8][D + 4]
+  if (gq == 0) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      eM[warp * kKvRows + 2 * t + j] = m_run[j];
+      eL[warp * kKvRows + 2 * t + j] = l_run[j];
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < VG; ++g) {
+#pragma unroll
+    for (int mm = 0; mm < 2; ++mm) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int code = 2 * mm + (c >> 1);            // which of my 4 channels
+        const int ch = g * 32 + cb + code, r = 2 * t + (c & 1);
+        eO[(warp * kKvRows + r) * (D + 4) + ch] = fmaf(accO[g][mm][c], Dec::inv_factor(code), accV[g][c & 1]);
+      }
     }
   }
   __syncthreads();
-  for (int i = tid; i < R * D; i += kKvThreads) {
-    const int r = i / D, c = i % D;
-    if (row0 + r >= Nq) continue;
-    const float v = (sO[(0 * R + r) * D + c] + sO[(1 * R + r) * D + c]) + (sO[(2 * R + r) * D + c] + sO[(3 * R + r) * D + c]);
-    float* dst = ws + ((((int64_t)b * H + h) * Nq + (row0 + r)) * nsplit + split) * (D + 2);
-    dst[2 + c] = v;
-  }
-  if (tid == 0) {
+  const int rows = min(kKvRows, Nq - row0);
+  for (int idx = tid; idx < rows * D; idx += kKvThreads) {
+    const int r = idx / D, c = idx % D;
+    float M = -INFINITY;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (row0 + r >= Nq) continue;
-      float* dst = ws + ((((int64_t)b * H + h) * Nq + (row0 + r)) * nsplit + split) * (D + 2);
-      dst[0] = m_run[r];
-      dst[1] = l_run[r];
+    for (int w = 0; w < kKvWarps; ++w) M = fmaxf(M, eM[w * kKvRows + r]);
+    const float Mu = (M == -INFINITY) ? 0.f : M;
+    float acc = 0.f, lsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kKvWarps; ++w) {
+      const float wt = kv_ex2(eM[w * kKvRows + r] - Mu);
+      acc = fmaf(eO[(w * kKvRows + r) * (D + 4) + c], wt, acc);
+      lsum = fmaf(eL[w * kKvRows + r], wt, lsum);
+    }
+    float* dst = ws + ((((int64_t)b * H + h) * Nq + (row0 + r)) * nsplit + split) * (D + 2);
+    dst[2 + c] = acc;
+    if (c == 0) {
+      dst[0] = M;
+      dst[1] = lsum;
     }
   }
 }
@@ -339,17 +615,36 @@ __global__ void kv_attn_merge_kernel(const float* __restrict__ ws, __half* __res
   if (c == 0 && lse != nullptr) lse[((int64_t)b * H + h) * lse_stride + row] = 0.6931471805599453f * (M + log2f(L));
 }
 
-static int kv_splits(int B, int H, int Nq, int N, int R, int* keys_per_split) {
-  // splits of whole tiles, none of them empty; about four waves of the resident capacity (148 SMs x 6-7 CTAs) so
-  // that the partial last wave costs little (the first version's 10 splits made 1.24 waves: 38 % of the run at a
-  // quarter of the occupancy)
+static int kv_splits(int B, int H, int Nq, int N, int* keys_per_split) {
+  // splits of whole tiles, none of them empty; about four waves of the resident capacity (148 SMs x 2 CTAs of 8 warps) so that
+  // the partial last wave costs little
   const int tiles = (N + kKvTile - 1) / kKvTile;
-  const int64_t base = (int64_t)B * H * ((Nq + R - 1) / R);
-  int want = (int)((148 * 6 * 4) / base);
+  const int64_t base = (int64_t)B * H * ((Nq + kKvRows - 1) / kKvRows);
+  int want = (int)((148 * kKvCtasPerSm * 4) / base);
   want = want < 1 ? 1 : (want > tiles ? tiles : want);
   const int tps = (tiles + want - 1) / want;  // tiles per split
   *keys_per_split = tps * kKvTile;
   return (tiles + tps - 1) / tps;
+}
+
+static int kv_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int D, int BITS, bool MAGIC>
+static int kv_launch(dim3 grid, cudaStream_t st, const void* q, const void* kcode, const void* kscale, const void* kmn,
+                     const void* vcode, const void* vscale, const void* vmn, void* workspace, int H, int Nq, int N, int ns,
+                     int kps, float sl2, int64_t qsb, int64_t qsn, int64_t qsh, int kchunk) {
+  auto kern = kv_attn_partial_kernel<D, BITS, MAGIC>;
+  constexpr int bytes = KvSmem<D, BITS>::kBytes;
+  // the opt-in is per device: set before every launch (cheap), not behind a process-wide flag
+  LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  kern<<<grid, kKvThreads, bytes, st>>>((const __half*)q, (const uint8_t*)kcode, (const __half*)kscale, (const __half*)kmn,
+                                        (const uint8_t*)vcode, (const __half*)vscale, (const __half*)vmn, (float*)workspace,
+                                        H, Nq, N, ns, kps, sl2, qsb, qsn, qsh, kchunk);
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace lowbit
@@ -358,8 +653,7 @@ using namespace lowbit;
 
 extern "C" int64_t lowbit_kv_attn_workspace_bytes(int B, int H, int Nq, int N, int D) {
   int kps = 0;
-  const int R = Nq > 1 ? 4 : 1;
-  const int ns = kv_splits(B, H, Nq, N, R, &kps);
+  const int ns = kv_splits(B, H, Nq, N, &kps);
   return (int64_t)B * H * Nq * ns * (D + 2) * 4;
 }
 
@@ -374,25 +668,30 @@ extern "C" int lowbit_kv_attn_fwd(const void* q, const void* kcode, const void* 
   LOWBIT_CHECK(group_size == kKvGroup, "lowbit_kv_attn_fwd: group_size must be 32 (got %d)", group_size);
   LOWBIT_CHECK(B > 0 && H > 0 && Nq > 0 && N > 0, "lowbit_kv_attn_fwd: empty tensor");
   LOWBIT_CHECK(N % kKvGroup == 0, "lowbit_kv_attn_fwd: the cache length must be a multiple of the group size (got %d)", N);
-  LOWBIT_CHECK(((uintptr_t)kcode & 3) == 0 && ((uintptr_t)vcode & 3) == 0, "lowbit_kv_attn_fwd: codes must be 4-byte aligned");
+  LOWBIT_CHECK(((uintptr_t)kcode & 15) == 0, "lowbit_kv_attn_fwd: K codes must be 16-byte aligned");
+  LOWBIT_CHECK(((uintptr_t)vcode & 15) == 0, "lowbit_kv_attn_fwd: V codes must be 16-byte aligned");
+  LOWBIT_CHECK((((uintptr_t)vscale | (uintptr_t)vmn) & 7) == 0, "lowbit_kv_attn_fwd: V scales / minima must be 8-byte aligned");
   LOWBIT_CHECK(lse == nullptr || lse_stride >= Nq, "lowbit_kv_attn_fwd: lse_stride < Nq");
   cudaStream_t st = (cudaStream_t)stream;
-  const int R = Nq > 1 ? 4 : 1;
   int kps = 0;
-  const int ns = kv_splits(B, H, Nq, N, R, &kps);
-  const int qtiles = (Nq + R - 1) / R;
-  dim3 grid((unsigned)(ns * qtiles), H, B);
+  const int ns = kv_splits(B, H, Nq, N, &kps);
+  const int qtiles = (Nq + kKvRows - 1) / kKvRows;
+  dim3 grid(H, (unsigned)(ns * qtiles), B);
   const float sl2 = softmax_scale * 1.4426950408889634f;
-#define KV_LAUNCH(DD, BB, RR)                                                                                          \
-  kv_attn_partial_kernel<DD, BB, RR><<<grid, kKvThreads, 0, st>>>(                                                     \
-      (const __half*)q, (const uint8_t*)kcode, (const __half*)kscale, (const __half*)kmn, (const uint8_t*)vcode,       \
-      (const __half*)vscale, (const __half*)vmn, (float*)workspace, H, Nq, N, ns, kps, sl2, qsb, qsn, qsh)
-#define KV_BY_R(DD, BB) do { if (R == 1) KV_LAUNCH(DD, BB, 1); else KV_LAUNCH(DD, BB, 4); } while (0)
-  if (D == 64) { if (bits == 4) KV_BY_R(64, 4); else KV_BY_R(64, 2); }
-  else { if (bits == 4) KV_BY_R(128, 4); else KV_BY_R(128, 2); }
-#undef KV_BY_R
+  // widest cp.async that every K row start allows: rows are N * bits / 8 bytes apart
+  const int64_t krow = (int64_t)N * bits / 8;
+  const int kchunk = (krow & 15) == 0 ? 16 : 8;   // N % 32 == 0: 4-bit rows are multiples of 16 bytes, 2-bit rows of 8
+  const bool magic = kv_env_int("LOWBIT_KV_MAGIC", 0) != 0;  // 1: never hand fp16 denormals to the tensor core
+  int rc;
+#define KV_LAUNCH(DD, BB)                                                                                              \
+  rc = magic ? kv_launch<DD, BB, true>(grid, st, q, kcode, kscale, kmn, vcode, vscale, vmn, workspace, H, Nq, N, ns,   \
+                                       kps, sl2, qsb, qsn, qsh, kchunk)                                                \
+             : kv_launch<DD, BB, false>(grid, st, q, kcode, kscale, kmn, vcode, vscale, vmn, workspace, H, Nq, N, ns,  \
+                                        kps, sl2, qsb, qsn, qsh, kchunk)
+  if (D == 64) { if (bits == 4) KV_LAUNCH(64, 4); else KV_LAUNCH(64, 2); }
+  else { if (bits == 4) KV_LAUNCH(128, 4); else KV_LAUNCH(128, 2); }
 #undef KV_LAUNCH
-  LOWBIT_CUDA(cudaGetLastError());
+  if (rc != 0) return rc;
   dim3 mgrid(Nq, H, B);
   if (D == 64)
     kv_attn_merge_kernel<64><<<mgrid, 64, 0, st>>>((const float*)workspace, (__half*)o, lse, H, Nq, ns, osb, osn, osh, lse_stride);
