@@ -497,6 +497,39 @@ def quick_tops(L, wl, dev, reps=None):
     return {"workload": desc, "value": ops / ms / 1e9, "unit": "TOPS", "ms_per_step": ms, "steps": reps}
 
 
+def kv_decode_line(L, dev, reps=12):
+    """one query row per (batch, head) against a KIVI-packed 4-bit K/V cache through
+    quantized_flash_attn_forward; an HBM-bound path, so the figure is GB/s over the algorithmic bytes (codes + scales +
+    minima, read once) against the measured copy bandwidth.  Three caches are rotated so that no launch finds its
+    input in the 126 MB L2."""
+    B, H, N, D, bits = 4, 32, 16384, 128, 4
+    torch.manual_seed(0)
+    caches = []
+    for _ in range(3):
+        k, v = (torch.randn(B, N, H, D, dtype=torch.float16, device=dev) for _ in range(2))
+        caches.append(L.quant_and_pack_kv(k, v, 32, bits))
+        del k, v
+    q = torch.randn(B, 1, H, D, dtype=torch.float16, device=dev)
+    nbytes = sum(t.numel() * t.element_size() for t in caches[0])
+    f = lambda i: L.quantized_flash_attn_forward(q, *caches[i % 3], group_size=32, bits=bits)
+    for i in range(3):
+        f(i)
+    stream = torch.cuda.current_stream(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for i in range(reps):
+        f(i)
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / reps
+    del caches, q
+    torch.cuda.empty_cache()
+    hbm = peaks()["hbm_gbs"]
+    return {"workload": f"KV-cache decode: B{B} H{H} N{N} D{D}, {bits}-bit KIVI cache, 1 query row", "value": nbytes / ms / 1e6,
+            "unit": "GB/s", "ms_per_step": ms, "steps": reps, "algorithmic_bytes": nbytes,
+            "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": nbytes / ms / 1e6 / hbm}}
+
+
 def run_single(args, rank, world, local, dev):
     """N = 1 (or --workload with partition "replicate" at N > 1: every rank the same work, weak scaling)."""
     affinity = bind_near_gpu(local)
@@ -549,6 +582,10 @@ def run_single(args, rank, world, local, dev):
         if world == 1 and not args.workload:
             # the other single-GPU configs of BASELINE.json, one short timing each (same process, after the headline)
             line["other_configs"] = {n: quick_tops(L, n, dev) for n in ("c2c", "c3q_8k", "c4s")}
+            try:
+                line["other_configs"]["kv_decode"] = kv_decode_line(L, dev)
+            except Exception as e:  # noqa: BLE001
+                line["other_configs"]["kv_decode"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.manual_seed(0)
             q0, k0, v0 = (torch.randn(B, Hq, N, D, dtype=torch.float16, device=dev) for _ in range(3))
             line["reference_gpu"] = reference_gpu(q0, k0, v0, causal, ops)

@@ -54,4 +54,30 @@ from .plugin import as_sdpa, patch_sdpa  # noqa: F401
 from .kv_cache import quantized_flash_attn_forward, quant_and_pack_kv  # noqa: F401
 from .attention import forward, forward_causal, forward_partial, finalize, PartialState  # noqa: F401
 
+# Every public callable runs on the caller's stream: torch's current stream, or -- for Paddle tensors -- Paddle's
+# (see _tensor.on_callers_stream).  One wrapper per function object, installed under every name that refers to it (here
+# and in the defining module), so aliases stay identical objects.
+import sys as _sys  # noqa: E402
+import types as _types  # noqa: E402
+
+from . import _tensor as _T  # noqa: E402
+
+
+def _install_stream_wrappers():
+    skip = {"plan_chunks", "as_sdpa", "patch_sdpa"}
+    pkg = _sys.modules[__name__]
+    wrapped = {}
+    for name, obj in list(vars(pkg).items()):
+        if isinstance(obj, _types.FunctionType) and not name.startswith("_") and name not in skip:
+            if id(obj) not in wrapped:
+                wrapped[id(obj)] = _T.on_callers_stream(obj)
+    mods = [pkg] + [m for n, m in list(_sys.modules.items()) if n.startswith(__name__ + ".") and m is not None]
+    for m in mods:
+        for name, obj in list(vars(m).items()):
+            if isinstance(obj, _types.FunctionType) and id(obj) in wrapped:
+                setattr(m, name, wrapped[id(obj)])
+
+
+_install_stream_wrappers()
+
 __version__ = "0.1.0"

@@ -41,6 +41,40 @@ def like(result, original):
     return result
 
 
+def _paddle_stream_ptr():
+    """Raw cudaStream_t of Paddle's current stream (0 = the legacy default stream), or None when it cannot be read."""
+    try:
+        return int(paddle.device.cuda.current_stream().cuda_stream)
+    except Exception:
+        try:
+            return int(paddle.device.current_stream().stream_base.cuda_stream)
+        except Exception:
+            return None
+
+
+def on_callers_stream(fn):
+    """Decorator of the public entry points.  torch callers: untouched (kernels go to torch's current stream).  Paddle
+    callers: the call runs with Paddle's CURRENT stream installed as torch's current stream (an ExternalStream), so the
+    kernels, torch's caching allocator and the DLPack hand-back are all ordered on the stream the caller's own work
+    is on -- no reliance on both frameworks happening to use the legacy default stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        if paddle is None:
+            return fn(*args, **kwargs)
+        first = next((a for a in list(args) + list(kwargs.values()) if is_paddle(a)), None)
+        if first is None:
+            return fn(*args, **kwargs)
+        dev = as_torch(first).device
+        ptr = _paddle_stream_ptr() if dev.type == "cuda" else None
+        if not ptr:  # CPU tensor (the entry point raises), unreadable stream, or the legacy default stream (= torch's default)
+            return fn(*args, **kwargs)
+        with torch.cuda.stream(torch.cuda.ExternalStream(ptr, device=dev)):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def aligned16(t):
     """The kernels load 16 bytes at a time: a view whose storage offset breaks that alignment (e.g. x[..., 4:68] of a
     fused buffer -- legal for the reference's Triton kernels) is copied to a fresh, aligned tensor."""
