@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LOWBIT_ABI_VERSION 6
+#define LOWBIT_ABI_VERSION 7
 
 /* element types of the floating-point inputs / outputs */
 enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
@@ -250,6 +250,25 @@ int lowbit_attn_finalize(const float* m, const float* l, const float* o_acc, voi
 int lowbit_lse_fixup(float* lse, const void* q, const void* km, int B, int Hq, int Hkv, int Nq, int D,
                      int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_n,
                      float sm_scale, int dtype, void* stream);
+
+/* The whole hot path in ONE call -- the host orchestration of src/core.py:194-352 (lowbit_fa_qk_int8_pv_fp16_triton,
+ * :945-1036 for INT4 K): km = mean_n(k) (:293), Q codes with q_multiplier = sm_scale * log2(e) folded in and K codes of
+ * k - km (:300-319, K blocks of 64, Q blocks of 128), attention forward (:321-341), and -- when lse != NULL -- the
+ * natural-log lse with the K-smoothing correction (:343-350).  Launches exactly the kernels of lowbit_k_mean,
+ * lowbit_quant_per_block (x2), lowbit_attn_fwd and lowbit_lse_fixup with the same arguments: bit-identical results, one
+ * FFI call instead of five.  q, k: fp16 / bf16 (`dtype`), v: fp16, all [B,H,N,D] by strides; layout_nhd only fixes the
+ * layout of the internal code tensors (that of their sources).  k_bits 8, or 4 with k_pack = 1 (two codes per byte).
+ * workspace: lowbit_fa_fwd_workspace_bytes(...) bytes, 256-byte aligned; its contents are scratch.
+ * flags: LOWBIT_ATTN_* as for lowbit_attn_fwd. */
+int64_t lowbit_fa_fwd_workspace_bytes(int B, int Hq, int Hkv, int Nq, int Nk, int D, int k_bits, int k_pack);
+int lowbit_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, void* workspace,
+                  int B, int Hq, int Hkv, int Nq, int Nk, int D, int layout_nhd,
+                  int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_n,
+                  int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_n,
+                  int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_n,
+                  int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_n,
+                  float sm_scale, float q_multiplier, int k_bits, int k_pack, int smooth_k, int quant_mode, int dtype,
+                  int out_dtype, int flags, void* stream);
 
 /* diagnostics (not part of the reference surface): when set to a device buffer of 128*64 int32, the next
  * lowbit_attn_fwd launches make CTA (0,0,0) dump its raw int32 Q.K^T scores of key block 0. NULL disables. */

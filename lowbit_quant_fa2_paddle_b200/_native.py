@@ -46,6 +46,8 @@ SIGNATURES = {
     "lowbit_attn_finalize": (_I, [_P] * 5 + [_I] * 4 + [_L] * 3 + [_I, _P]),
     "lowbit_attn_set_debug_buffer": (None, [_P]),
     "lowbit_lse_fixup": (_I, [_P, _P, _P] + [_I] * 5 + [_L] * 3 + [_F, _I, _P]),
+    "lowbit_fa_fwd_workspace_bytes": (_L, [_I] * 8),
+    "lowbit_fa_fwd": (_I, [_P] * 6 + [_I] * 7 + [_L] * 12 + [_F, _F] + [_I] * 7 + [_P]),
 }
 
 _lib = None
@@ -67,10 +69,15 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.lowbit_version() != 6:
+        if handle.lowbit_version() != 7:
             raise LowbitNativeError("liblowbit_fa_b200.so ABI version mismatch")
         _lib = handle
     return _lib
+
+
+def _current_device():
+    import torch
+    return torch.cuda.current_device()
 
 
 def call(name, *args, device=None):
@@ -78,7 +85,7 @@ def call(name, *args, device=None):
     the tensors (and the stream argument) belong to -- made current for the call, so that a process that drives
     several GPUs launches on the right one whatever torch's current device is."""
     L = lib()
-    if device is not None:
+    if device is not None and device.index is not None and device.index != _current_device():
         import torch
         with torch.cuda.device(device):
             rc = getattr(L, name)(*args)

@@ -17,6 +17,7 @@ reference's two *rounding conventions* ("triton": Q1, "cuda": Q2), both executed
 reference kernels for a GPU -- bit-identical to those kernels on a B200, whereas "triton" is the IEEE arithmetic of
 the same kernels under the Triton interpreter (what the golden vectors pin).
 """
+import os
 from typing import Any, Optional
 
 import torch
@@ -32,6 +33,40 @@ LOG2E = 1.44269504
 def _pad_head(x, to):
     d = x.shape[-1]
     return x if d == to else torch.nn.functional.pad(x, (0, to - d))
+
+
+# The INT8 / packed-INT4 K, FP16 P.V operator goes through ONE C-ABI call (csrc/op.cu: same kernels, same arguments,
+# bit-identical results; LOWBIT_ONE_CALL=0 keeps the five-call path below, which serves every other format).
+_ONE_CALL = os.environ.get("LOWBIT_ONE_CALL", "1") != "0"
+
+
+def _lowbit_fa_one_call(q, qt, kt, vt, dev, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
+                        qk, compat_tail):
+    dtype = qt.dtype
+    if dtype == torch.bfloat16:
+        vt = vt.to(torch.float16)
+    b, hq, nq, d, qsb, qsh, qsn = T.bhnd(qt, tensor_layout)
+    _, hkv, nk, _, ksb, ksh, ksn = T.bhnd(kt, tensor_layout)
+    _, _, _, _, vsb, vsh, vsn = T.bhnd(vt, tensor_layout)
+    if is_causal:
+        assert nq == nk, "qo_len and kv_len must be equal for causal attention"
+    if sm_scale is None:
+        sm_scale = 1.0 / d ** 0.5
+    kbits, packed = (8, 0) if qk == "int8" else (4, 1)
+    lib = N.lib()
+    o = torch.empty(qt.shape, dtype=dtype, device=dev)
+    _, _, _, _, osb, osh, osn = T.bhnd(o, tensor_layout)
+    lse = torch.empty((b, hq, nq), dtype=torch.float32, device=dev) if return_lse else None
+    ws = torch.empty(lib.lowbit_fa_fwd_workspace_bytes(b, hq, hkv, nq, nk, d, kbits, packed), dtype=torch.uint8, device=dev)
+    flags = (N.ATTN_CAUSAL if is_causal else 0) | (N.ATTN_COMPAT_TAIL if compat_tail else 0)
+    N.call("lowbit_fa_fwd", qt.data_ptr(), kt.data_ptr(), vt.data_ptr(), o.data_ptr(),
+           lse.data_ptr() if lse is not None else None, ws.data_ptr(), b, hq, hkv, nq, nk, d,
+           1 if tensor_layout == "NHD" else 0, qsb, qsh, qsn, ksb, ksh, ksn, vsb, vsh, vsn, osb, osh, osn,
+           float(sm_scale), float(sm_scale * LOG2E), kbits, packed, int(bool(smooth_k)), Qz._MODES[quantization_backend],
+           T.dtype_code(dtype), T.dtype_code(dtype), flags, T.stream_ptr(dev), device=dev)
+    if return_lse:
+        return T.like(o, q), T.like(lse, q)
+    return T.like(o, q)
 
 
 def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k, return_lse,
@@ -54,6 +89,10 @@ def _lowbit_fa(q, k, v, tensor_layout, quantization_backend, is_causal, sm_scale
     qt, kt, vt = _pad_head(qt, d_to), _pad_head(kt, d_to), _pad_head(vt, d_to)
     assert qt.stride(-1) == 1 and kt.stride(-1) == 1 and vt.stride(-1) == 1, "Last dim of qkv must be contiguous."
     qt, kt, vt = T.aligned16(qt), T.aligned16(kt), T.aligned16(vt)
+    if (pv == "fp16" and qk in ("int8", "int4", "q8k4") and head_dim_og in (64, 128) and _ONE_CALL
+            and (qk == "int8" or A.PACKED_K4_KERNEL) and os.environ.get("LOWBIT_K_FUSED", "0") != "1"):
+        return _lowbit_fa_one_call(q, qt, kt, vt, dev, tensor_layout, quantization_backend, is_causal, sm_scale, smooth_k,
+                                   return_lse, qk, compat_tail)
     with torch.cuda.device(dev):
         v_scale = v_mean = None
         if pv == "fp8":  # V -> e4m3 per channel, transposed (src/quant.py:210-291; core.py:882-884)

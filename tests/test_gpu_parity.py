@@ -1035,3 +1035,39 @@ def test_multi_precision_routes_every_class(L, cuda_dev):
         q, k, v = ((t.float() * scale).half() for t in base)
         assert L.select_quantization(q, k, v) == kind
         assert torch.equal(L.lowbit_fa_multi_precision(q, k, v, sm_scale=0.05), fn(q, k, v, sm_scale=0.05))
+
+
+# ------------------------------------------------------------------------------------------------ one-call operator
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    # B, Hq, Hkv, Nq, Nk, D, layout, dtype, causal, entry, lse
+    (1, 2, 2, 512, 512, 64, "HND", torch.float16, False, "int8", False),
+    (2, 4, 2, 200, 333, 64, "NHD", torch.float16, False, "int8", True),
+    (1, 4, 4, 1030, 1030, 64, "HND", torch.bfloat16, True, "int8", True),
+    (1, 2, 1, 384, 384, 128, "NHD", torch.float16, True, "int4", False),
+    (2, 6, 3, 2200, 2200, 64, "NHD", torch.float16, False, "q8k4", True),
+    (1, 32, 32, 4096, 4096, 64, "HND", torch.float16, False, "int8", False),   # large enough for the side-stream fork
+    (1, 8, 8, 1024, 1024, 128, "HND", torch.bfloat16, False, "q8k4", True),
+], ids=lambda c: f"{c[9]}-{c[6]}-d{c[5]}-n{c[3]}x{c[4]}-{'c' if c[8] else 'nc'}-{str(c[7]).split('.')[-1]}")
+def test_one_call_operator_is_bit_identical_to_the_five_call_path(case, monkeypatch):
+    """lowbit_fa_fwd (csrc/op.cu) launches the kernels of the separate entry points with the same arguments: o and lse
+    must be bit for bit what the five-call host path gives (LOWBIT_ONE_CALL=0)."""
+    import lowbit_quant_fa2_paddle_b200 as L
+    from lowbit_quant_fa2_paddle_b200 import core
+    B, Hq, Hkv, Nq, Nk, D, layout, dt, causal, entry, want_lse = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    shp = lambda h, n: (B, h, n, D) if layout == "HND" else (B, n, h, D)
+    q, k, v = (torch.randn(shp(h, n), generator=g).to(dt).to(dev) for h, n in ((Hq, Nq), (Hkv, Nk), (Hkv, Nk)))
+    fn = {"int8": L.lowbit_fa_qk_int8_pv_fp16_triton, "int4": L.lowbit_fa_qk_int4_pv_fp16_triton,
+          "q8k4": L.lowbit_fa_q_int8_k_int4_pv_fp16}[entry]
+    kw = dict(tensor_layout=layout, is_causal=causal, return_lse=want_lse)
+    monkeypatch.setattr(core, "_ONE_CALL", True)
+    a = fn(q, k, v, **kw)
+    monkeypatch.setattr(core, "_ONE_CALL", False)
+    b = fn(q, k, v, **kw)
+    torch.cuda.synchronize()
+    if want_lse:
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    else:
+        assert torch.equal(a, b)

@@ -1,4 +1,6 @@
-OUT=gpurun_out/r2_call51; mkdir -p $OUT
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee $OUT/tests.log
-timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; tail -c 1500 $OUT/bench_c2.json | head -c 1200; echo
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+OUT=gpurun_out/r2_call53; mkdir -p $OUT
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "one_call" 2>&1 | tail -5 | tee $OUT/test.log
+timeout 300 python tools/time_small.py 2>&1 | tail -5 | tee $OUT/small.log
+LOWBIT_ONE_CALL=0 timeout 300 python tools/time_small.py 2>&1 | tail -5 | sed 's/$/ (five-call path)/' | tee -a $OUT/small.log
+timeout 300 python tools/time_prep.py 2>&1 | head -2 | tee -a $OUT/small.log
+timeout 300 python -m pytest tests/test_tensor_handoff.py -m gpu -q 2>&1 | tail -2
