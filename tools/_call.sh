@@ -1,6 +1,7 @@
-OUT=gpurun_out/r2_call53; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "one_call" 2>&1 | tail -5 | tee $OUT/test.log
-timeout 300 python tools/time_small.py 2>&1 | tail -5 | tee $OUT/small.log
-LOWBIT_ONE_CALL=0 timeout 300 python tools/time_small.py 2>&1 | tail -5 | sed 's/$/ (five-call path)/' | tee -a $OUT/small.log
-timeout 300 python tools/time_prep.py 2>&1 | head -2 | tee -a $OUT/small.log
-timeout 300 python -m pytest tests/test_tensor_handoff.py -m gpu -q 2>&1 | tail -2
+OUT=gpurun_out/r2_call54; mkdir -p $OUT
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee $OUT/tests.log
+timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; python - <<'P'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_call54/bench_c2.json') if l.startswith('{')][0])
+print('value',d['value'],'ms',d['ms_per_step'],'attn',d['attn_only'],'e2e',d['e2e']['ms'],d['e2e']['value'])
+P
