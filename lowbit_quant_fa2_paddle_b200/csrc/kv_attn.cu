@@ -36,6 +36,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace lowbit {
 
@@ -143,39 +144,46 @@ struct KvDec {
 
 constexpr int kv_row_stride_words(int words) { return words == 4 ? 4 : words + 4; }  // see the bank maps in the kernel
 
-template <int D, int BITS>
+// TMA = true: tiles are fetched by cp.async.bulk.tensor with the hardware swizzle of their row width (rows unpadded, every
+// LDS pattern of the contractions stays conflict-free under the XOR); false: 16 / 8-byte cp.async into padded rows (the
+// fallback for 2-bit caches whose K rows are not multiples of 16 bytes, which TMA cannot address).
+template <int D, int BITS, bool TMA = false>
 struct KvSmem {
-  static constexpr int KRB = kKvTile * BITS / 8;           // bytes of one channel row of a K tile (64 / 32)
-  static constexpr int KST = kv_row_stride_words(KRB / 4); // its stride in words
+  static constexpr int KRB = kKvTile * BITS / 8;           // bytes of one channel row of a K tile (128 / 64)
+  static constexpr int KST = TMA ? KRB / 4 : kv_row_stride_words(KRB / 4); // its stride in words
   static constexpr int VB = D * BITS / 8;                  // bytes of one token row of V (64 / 32 / 16)
-  static constexpr int VST = kv_row_stride_words(VB / 4);
+  static constexpr int VST = TMA ? VB / 4 : kv_row_stride_words(VB / 4);
   static constexpr int KG = kKvTile / kKvGroup;            // K scale groups per tile (4)
   static constexpr int VG = D / kKvGroup;                  // V scale groups per token (4 / 2)
-  static constexpr int kStageK = D * KST * 4, kStageV = kKvTile * VST * 4, kStage = kStageK + kStageV;
+  static constexpr int kStageK = (D * KST * 4 + 1023) / 1024 * 1024, kStageV = (kKvTile * VST * 4 + 1023) / 1024 * 1024;
+  static constexpr int kStage = kStageK + kStageV;
   static constexpr int kScales = (2 * KG * D + 2 * VG * kKvTile) * 2;   // one buffer: K sc, K mn, V sc, V mn (fp16, transposed)
   static constexpr int kP = kKvWarps * kKvRows * kKvPStride * 2;
   static constexpr int kEpi = kKvWarps * kKvRows * (D + 4 + 2) * 4;               // per-warp (m, l, o) at the end (reuses the ring)
   static constexpr int kRing = kKvStages * kStage > kEpi ? kKvStages * kStage : kEpi;
-  static constexpr int kBytes = kRing + 2 * kScales + kP;
+  static constexpr int kBytes = kRing + 2 * kScales + kP + 64 /*mbarriers*/ + 1024 /*alignment of the ring*/;
 };
 
 // Workspace layout per (b, h, row, split): [m (base 2), l, o[D]] fp32.
-template <int D, int BITS, bool MAGIC>
+template <int D, int BITS, bool MAGIC, bool TMA>
 __global__ void __launch_bounds__(kKvThreads, kKvCtasPerSm)
-kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__ kcode,
+kv_attn_partial_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                       const __half* __restrict__ q, const uint8_t* __restrict__ kcode,
                        const __half* __restrict__ kscale, const __half* __restrict__ kmn,
                        const uint8_t* __restrict__ vcode, const __half* __restrict__ vscale,
                        const __half* __restrict__ vmn, float* __restrict__ ws, int H, int Nq, int N, int nsplit,
-                       int keys_per_split, float scale_log2e, int64_t qsb, int64_t qsn, int64_t qsh, int kchunk) {
-  using SM = KvSmem<D, BITS>;
+                       int keys_per_split, float scale_log2e, int64_t qsb, int64_t qsn, int64_t qsh, int kchunk, int dbg) {
+  using SM = KvSmem<D, BITS, TMA>;
   using Dec = KvDec<BITS, MAGIC>;
   constexpr int KST = SM::KST, VST = SM::VST, KG = SM::KG, VG = SM::VG, VB = SM::VB, KRB = SM::KRB;
   constexpr int KSTEPS = D / 16;
   constexpr uint32_t kOnes = 0x3C003C00u;
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   __half* scl = reinterpret_cast<__half*>(smem + SM::kRing);          // [2][K sc | K mn | V sc | V mn]
   __half* sP = reinterpret_cast<__half*>(smem + SM::kRing + 2 * SM::kScales);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kRing + 2 * SM::kScales + SM::kP);   // [kKvStages], TMA only
   const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(ring);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -230,8 +238,18 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
   const int64_t v_step = (int64_t)VRPP * vc_stride;
   int v_n = n_begin + v_row0;                            // token of my first row of the next tile to issue
   const uint32_t v_dst0 = (uint32_t)(v_row0 * (VST * 4) + v_col * 16);
-  auto issue_codes = [&](int tile) {  // cp.async of the NEXT tile (call order = tile order) into ring stage tile % kKvStages
+  auto issue_codes = [&](int tile) {  // copies of the NEXT tile (call order = tile order) into ring stage tile % kKvStages
     const uint32_t sk = ring_a + (tile % kKvStages) * SM::kStage, sv = sk + SM::kStageK;
+    if constexpr (TMA) {  // one thread, two boxes: K [D rows x KRB bytes] of (b, h), V [tile tokens x VB bytes]; out-of-range bytes arrive as zeros
+      if (tid == 0) {
+        const uint32_t bar = ptx::smem_u32(&full[tile % kKvStages]);
+        const int n0 = n_begin + tile * kKvTile;
+        ptx::mbar_expect_tx_a(bar, D * KRB + kKvTile * VB);
+        ptx::tma_load_4d_a(sk, &tmK, bar, n0 * BITS / 8, 0, h, b);
+        ptx::tma_load_4d_a(sv, &tmV, bar, 0, n0, h, b);
+      }
+      return;
+    }
     auto k_rows = [&](auto chunk_tag) {
       constexpr int CH = decltype(chunk_tag)::value;
       constexpr int RPP = 8 * kKvWarps / (KRB / CH / 4), PASSES = D / RPP;
@@ -249,7 +267,8 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
         for (int j = 0; j < PASSES; ++j, src += step, dst += RPP * KST * 4) kv_cp_async<CH>(dst, src, valid);
       }
     };
-    if constexpr (KRB / 8 > 8) {   // 4-bit rows are always multiples of 16 bytes
+    if (dbg & 2) {
+    } else if constexpr (KRB / 8 > 8) {   // 4-bit rows are always multiples of 16 bytes
       k_rows(std::integral_constant<int, 16>{});
     } else {
       if (kchunk == 16) k_rows(std::integral_constant<int, 16>{});
@@ -257,7 +276,7 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
     }
     k_src += KRB;
     k_left -= KRB;
-    {
+    if (!(dbg & 4)) {
       const uint8_t* src = v_src;
       uint32_t dst = sv + v_dst0;
       if (v_n + (CPV - 1) * VRPP < N) {
@@ -280,6 +299,7 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
 #pragma unroll
   for (int g = 0; g < KG / 2; ++g) rks[g] = rkm[g] = 0u;
   auto fetch_scales = [&](int tile) {
+    if (dbg & 8) return;
     const int n0 = n_begin + tile * kKvTile;
     if (tid < D) {
       const int64_t g0 = n0 / kKvGroup;
@@ -343,6 +363,16 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
     }
   };
 
+  if constexpr (TMA) {
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < kKvStages; ++s) ptx::mbar_init(&full[s], 1);
+      ptx::fence_barrier_init();
+      ptx::prefetch_tmap(&tmK);
+      ptx::prefetch_tmap(&tmV);
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int s = 0; s < kKvStages - 1; ++s) {
     if (s < ntiles) issue_codes(s);
@@ -380,19 +410,33 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
   __half* sPw = sP + warp * (kKvRows * kKvPStride);
   // per-lane byte offsets inside a stage / a scale buffer / the P tile; everything else is an immediate
   const uint32_t scl_a0 = (uint32_t)__cvta_generic_to_shared(scl);
-  const uint32_t k_lane_off = (uint32_t)((2 * t) * KST + warp * WPG + wsel) * 4u;
-  const uint32_t v_lane_off = (uint32_t)((warp * 32 + 2 * t) * VST + wsel) * 4u;
+  // byte offset of my word in row `row` of a tile whose rows are RB bytes: plain (padded rows), or under the TMA
+  // swizzle of that row width -- address bits [4, 4 + log2(RB/16)) ^= bits [7, ...)
+  auto word_off = [](int row, int cw, int rb, int stride_words) -> uint32_t {
+    if constexpr (!TMA) return (uint32_t)(row * stride_words + cw) * 4u;
+    const int f = ((row * rb) >> 7) & (rb / 16 - 1);
+    return (uint32_t)(row * rb + ((((cw >> 2) ^ f)) << 4) + (cw & 3) * 4);
+  };
+  const int kcw = warp * WPG + wsel;
+  // rows 2t, 2t+8 (+16 ks) share one swizzle phase, rows 2t+1, 2t+9 another (they differ only for 128-byte rows)
+  const uint32_t k_lane_off_e = word_off(2 * t, kcw, KRB, KST);
+  const uint32_t k_lane_off_o = word_off(2 * t + 1, kcw, KRB, KST) - (uint32_t)(KST * 4);
+  uint32_t v_lane_off[VG];   // per channel group; the four token rows of a k-step share one swizzle phase (VB <= 64)
+#pragma unroll
+  for (int g = 0; g < VG; ++g) v_lane_off[g] = word_off(warp * 32 + 2 * t, g * WPG + wsel, VB, VST);
   const uint32_t ks_lane_off = (uint32_t)(warp * (D / 4) + t) * 16u;
   const uint32_t vs_lane_off = (uint32_t)(KG * (D / 4) + 8 * warp + t) * 16u;
   const uint32_t p_rd = (uint32_t)__cvta_generic_to_shared(sPw) + (uint32_t)(gq * kKvPStride + 2 * t) * 2u;
 
   for (int i = 0; i < ntiles; ++i) {
-    kv_cp_wait<kKvStages - 2>();
+    if constexpr (TMA) ptx::mbar_wait(&full[i % kKvStages], (uint32_t)(i / kKvStages) & 1u, 40);
+    else kv_cp_wait<kKvStages - 2>();
     __syncthreads();  // tile i landed for everyone; tile i-1 fully consumed; scale buffer i&1 visible
     if (i + kKvStages - 1 < ntiles) issue_codes(i + kKvStages - 1);
     kv_cp_commit();
     if (i + 1 < ntiles) park_scales((i + 1) & 1);
     if (i + 2 < ntiles) fetch_scales(i + 2);
+    if (dbg & 1) continue;   // LOWBIT_KV_DEBUG timing experiments (results are garbage)
 
     const int n0 = n_begin + i * kKvTile;
     const uint32_t stage_a = ring_a + (i % kKvStages) * SM::kStage;
@@ -401,7 +445,7 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
     // ---- scores of my 32 keys: S^T (keys x rows) = codes^T . (q * sc), + ones . (q * mn) ----
     float accS[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accC[4] = {0.f, 0.f, 0.f, 0.f};
     {
-      const uint32_t ka = stage_a + k_lane_off;            // word (channel 2 t, my column) of the K tile
+      const uint32_t ka = stage_a + k_lane_off_e, kb = stage_a + k_lane_off_o;   // my word of rows 2t (+8) / 2t+1 (+9)
       const uint32_t sa = scl_a + ks_lane_off;             // unit (group = warp, k-step 0, t)
       struct KLoad { uint4 sm; uint32_t w00, w01, w10, w11; };
       auto kload = [&](auto ks_tag) {
@@ -409,8 +453,8 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
         constexpr int RO = 16 * ks * KST * 4;
         KLoad L;
         L.sm = kv_lds128<ks * 64>(sa);
-        L.w00 = kv_lds32<RO>(ka), L.w01 = kv_lds32<RO + KST * 4>(ka);
-        L.w10 = kv_lds32<RO + 8 * KST * 4>(ka), L.w11 = kv_lds32<RO + 9 * KST * 4>(ka);
+        L.w00 = kv_lds32<RO>(ka), L.w01 = kv_lds32<RO + KST * 4>(kb);
+        L.w10 = kv_lds32<RO + 8 * KST * 4>(ka), L.w11 = kv_lds32<RO + 9 * KST * 4>(kb);
         return L;
       };
       auto kmath = [&](auto ks_tag, const KLoad& L) {
@@ -488,12 +532,13 @@ kv_attn_partial_kernel(const __half* __restrict__ q, const uint8_t* __restrict__
     __syncwarp();
     // ---- P.V over my 32 keys: O^T (channels x rows) += codes^T . (p * vs), + ones . (p * vm) ----
     {
-      const uint32_t va = stage_a + SM::kStageK + v_lane_off;   // word (token 32 w + 2 t, my column of group 0)
+      const uint32_t vbase = stage_a + SM::kStageK;             // + v_lane_off[g]: word (token 32 w + 2 t, my column of group g)
       const uint32_t sa = scl_a + vs_lane_off;                  // unit (group 0, token block 2 w, t)
       struct VLoad { uint4 sm; uint32_t w00, w01, w10, w11; };
       auto vload = [&](auto k2_tag, auto g_tag) {
         constexpr int k2 = decltype(k2_tag)::value, g = decltype(g_tag)::value;
-        constexpr int RO = 16 * k2 * VST * 4 + g * WPG * 4;
+        constexpr int RO = 16 * k2 * VST * 4;
+        const uint32_t va = vbase + v_lane_off[g];
         VLoad L;
         L.sm = kv_lds128<(g * (kKvTile / 4) + 4 * k2) * 16>(sa);
         L.w00 = kv_lds32<RO>(va), L.w01 = kv_lds32<RO + VST * 4>(va);
@@ -615,34 +660,52 @@ __global__ void kv_attn_merge_kernel(const float* __restrict__ ws, __half* __res
   if (c == 0 && lse != nullptr) lse[((int64_t)b * H + h) * lse_stride + row] = 0.6931471805599453f * (M + log2f(L));
 }
 
+static int kv_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 static int kv_splits(int B, int H, int Nq, int N, int* keys_per_split) {
-  // splits of whole tiles, none of them empty; about four waves of the resident capacity (148 SMs x 2 CTAs of 8 warps) so that
-  // the partial last wave costs little
+  // splits of whole tiles, none of them empty.  LOWBIT_KV_SPLITS forces a count (tuning aid).
   const int tiles = (N + kKvTile - 1) / kKvTile;
   const int64_t base = (int64_t)B * H * ((Nq + kKvRows - 1) / kKvRows);
-  int want = (int)((148 * kKvCtasPerSm * 4) / base);
+  static const int forced = kv_env_int("LOWBIT_KV_SPLITS", 0);
+  int want = forced > 0 ? forced : (int)((148 * kKvCtasPerSm * 4) / base);
   want = want < 1 ? 1 : (want > tiles ? tiles : want);
   const int tps = (tiles + want - 1) / want;  // tiles per split
   *keys_per_split = tps * kKvTile;
   return (tiles + tps - 1) / tps;
 }
 
-static int kv_env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
-template <int D, int BITS, bool MAGIC>
+template <int D, int BITS, bool MAGIC, bool TMA>
 static int kv_launch(dim3 grid, cudaStream_t st, const void* q, const void* kcode, const void* kscale, const void* kmn,
-                     const void* vcode, const void* vscale, const void* vmn, void* workspace, int H, int Nq, int N, int ns,
-                     int kps, float sl2, int64_t qsb, int64_t qsn, int64_t qsh, int kchunk) {
-  auto kern = kv_attn_partial_kernel<D, BITS, MAGIC>;
-  constexpr int bytes = KvSmem<D, BITS>::kBytes;
+                     const void* vcode, const void* vscale, const void* vmn, void* workspace, int B, int H, int Nq, int N,
+                     int ns, int kps, float sl2, int64_t qsb, int64_t qsn, int64_t qsh, int kchunk) {
+  const int dbg = kv_env_int("LOWBIT_KV_DEBUG", 0);  // timing experiments only: 1 no arithmetic, 2 no K codes, 4 no V codes, 8 no scales
+  auto kern = kv_attn_partial_kernel<D, BITS, MAGIC, TMA>;
+  using SM = KvSmem<D, BITS, TMA>;
+  constexpr int bytes = SM::kBytes;
+  CUtensorMap tmK, tmV;
+  memset(&tmK, 0, sizeof(tmK));
+  memset(&tmV, 0, sizeof(tmV));
+  if (TMA) {
+    auto swz = [](int row_bytes) {
+      return row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    };
+    const int64_t krow = (int64_t)N * BITS / 8;
+    // K codes [B][D][H][krow bytes] as (byte, d, h, b); V codes [B][N][H][VB bytes] as (byte, n, h, b)
+    const int64_t kdim[4] = {krow, D, H, B}, kstr[3] = {(int64_t)H * krow, krow, (int64_t)D * H * krow};
+    if (make_map(&tmK, kcode, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kdim, kstr, SM::KRB, D, swz(SM::KRB)) != 0) return 1;
+    const int64_t vdim[4] = {SM::VB, N, H, B}, vstr[3] = {(int64_t)H * SM::VB, SM::VB, (int64_t)N * H * SM::VB};
+    if (make_map(&tmV, vcode, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, vdim, vstr, SM::VB, kKvTile, swz(SM::VB)) != 0) return 1;
+  }
   // the opt-in is per device: set before every launch (cheap), not behind a process-wide flag
   LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  kern<<<grid, kKvThreads, bytes, st>>>((const __half*)q, (const uint8_t*)kcode, (const __half*)kscale, (const __half*)kmn,
-                                        (const uint8_t*)vcode, (const __half*)vscale, (const __half*)vmn, (float*)workspace,
-                                        H, Nq, N, ns, kps, sl2, qsb, qsn, qsh, kchunk);
+  kern<<<grid, kKvThreads, bytes, st>>>(tmK, tmV, (const __half*)q, (const uint8_t*)kcode, (const __half*)kscale,
+                                        (const __half*)kmn, (const uint8_t*)vcode, (const __half*)vscale, (const __half*)vmn,
+                                        (float*)workspace, H, Nq, N, ns, kps, sl2, qsb, qsn, qsh, kchunk, dbg);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -682,14 +745,17 @@ extern "C" int lowbit_kv_attn_fwd(const void* q, const void* kcode, const void* 
   const int64_t krow = (int64_t)N * bits / 8;
   const int kchunk = (krow & 15) == 0 ? 16 : 8;   // N % 32 == 0: 4-bit rows are multiples of 16 bytes, 2-bit rows of 8
   const bool magic = kv_env_int("LOWBIT_KV_MAGIC", 0) != 0;  // 1: never hand fp16 denormals to the tensor core
+  // TMA needs every stride to be a multiple of 16 bytes: true for 4-bit caches (N % 32 == 0), and for 2-bit ones when
+  // N % 64 == 0; the rest (and the MAGIC form, a validation aid) take the cp.async path
+  const bool tma = !magic && (krow & 15) == 0 && kv_env_int("LOWBIT_KV_TMA", 1) != 0;
   int rc;
+#define KV_ARGS grid, st, q, kcode, kscale, kmn, vcode, vscale, vmn, workspace, B, H, Nq, N, ns, kps, sl2, qsb, qsn, qsh, kchunk
 #define KV_LAUNCH(DD, BB)                                                                                              \
-  rc = magic ? kv_launch<DD, BB, true>(grid, st, q, kcode, kscale, kmn, vcode, vscale, vmn, workspace, H, Nq, N, ns,   \
-                                       kps, sl2, qsb, qsn, qsh, kchunk)                                                \
-             : kv_launch<DD, BB, false>(grid, st, q, kcode, kscale, kmn, vcode, vscale, vmn, workspace, H, Nq, N, ns,  \
-                                        kps, sl2, qsb, qsn, qsh, kchunk)
+  rc = tma ? kv_launch<DD, BB, false, true>(KV_ARGS)                                                                  \
+           : (magic ? kv_launch<DD, BB, true, false>(KV_ARGS) : kv_launch<DD, BB, false, false>(KV_ARGS))
   if (D == 64) { if (bits == 4) KV_LAUNCH(64, 4); else KV_LAUNCH(64, 2); }
   else { if (bits == 4) KV_LAUNCH(128, 4); else KV_LAUNCH(128, 2); }
+#undef KV_ARGS
 #undef KV_LAUNCH
   if (rc != 0) return rc;
   dim3 mgrid(Nq, H, B);

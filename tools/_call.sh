@@ -1,7 +1,7 @@
-OUT=gpurun_out/r2_call54; mkdir -p $OUT
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee $OUT/tests.log
-timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; python - <<'P'
-import json
-d=json.loads([l for l in open('gpurun_out/r2_call54/bench_c2.json') if l.startswith('{')][0])
-print('value',d['value'],'ms',d['ms_per_step'],'attn',d['attn_only'],'e2e',d['e2e']['ms'],d['e2e']['value'])
-P
+OUT=gpurun_out/r2_call59; mkdir -p $OUT
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kv_attn_partial -s 4 -c 1 -o $OUT/kv_v7 -f python tools/time_kv.py 4 32 16384 128 4 > $OUT/ncu.log 2>&1; tail -2 $OUT/ncu.log
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:kv_attn -s 6 -c 4 --csv --log-file $OUT/r2_kv_attn_ncu.csv python tools/time_kv.py 4 32 16384 128 4 > /dev/null 2>&1
+for m in 2 4 8; do
+LOWBIT_KV_DEBUG=$((m+1)) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kv_attn_partial -s 6 -c 2 --csv --log-file $OUT/l_$m.csv python tools/time_kv.py 4 32 16384 128 4 > /dev/null 2>&1
+echo "tma no-arith, without stream $m: $(grep -E 'partial' $OUT/l_$m.csv | awk -F'","' '{print $(NF)}' | tr -d '"' | tr '\n' ' ')" | tee -a $OUT/dbg.log
+done

@@ -23,7 +23,7 @@ ref = L.lowbit_fa_qk_int8_pv_fp16_triton(q.to(dev), k.to(dev), v.to(dev)).cpu()
 ops = 4 * b * h * n * n * d
 stream = torch.cuda.current_stream(dev)
 for chunks in [int(a) for a in sys.argv[1:]] or [8, 16, 32, 64]:
-    for graph in (False, None):
+    for graph in (False, True):
         out.zero_()
         for _ in range(3):
             L.lowbit_fa_host(q, k, v, out=out, chunks=chunks, graph=graph)
