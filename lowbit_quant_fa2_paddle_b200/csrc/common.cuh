@@ -48,6 +48,26 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
   return r;
 }
 
+// four 128-bit streaming loads issued back to back in ONE asm statement (a predicate that is off leaves zeros): ptxas
+// cannot recycle one destination quad for all of them, which serialises load -> use -> load in a register-tight kernel
+__device__ __forceinline__ void ld_stream_v4_x4(const void* p0, const void* p1, const void* p2, const void* p3,
+                                                bool k0, bool k1, bool k2, bool k3, uint4 (&r)[4]) {
+  asm volatile(
+      "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
+      "setp.ne.u32 q0, %20, 0;\n\tsetp.ne.u32 q1, %21, 0;\n\tsetp.ne.u32 q2, %22, 0;\n\tsetp.ne.u32 q3, %23, 0;\n\t"
+      "mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0; mov.u32 %3, 0;\n\t"
+      "mov.u32 %4, 0; mov.u32 %5, 0; mov.u32 %6, 0; mov.u32 %7, 0;\n\t"
+      "mov.u32 %8, 0; mov.u32 %9, 0; mov.u32 %10, 0; mov.u32 %11, 0;\n\t"
+      "mov.u32 %12, 0; mov.u32 %13, 0; mov.u32 %14, 0; mov.u32 %15, 0;\n\t"
+      "@q0 ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%16];\n\t"
+      "@q1 ld.global.nc.L1::no_allocate.v4.u32 {%4,%5,%6,%7}, [%17];\n\t"
+      "@q2 ld.global.nc.L1::no_allocate.v4.u32 {%8,%9,%10,%11}, [%18];\n\t"
+      "@q3 ld.global.nc.L1::no_allocate.v4.u32 {%12,%13,%14,%15}, [%19];\n\t}"
+      : "=&r"(r[0].x), "=&r"(r[0].y), "=&r"(r[0].z), "=&r"(r[0].w), "=&r"(r[1].x), "=&r"(r[1].y), "=&r"(r[1].z), "=&r"(r[1].w),
+        "=&r"(r[2].x), "=&r"(r[2].y), "=&r"(r[2].z), "=&r"(r[2].w), "=&r"(r[3].x), "=&r"(r[3].y), "=&r"(r[3].z), "=&r"(r[3].w)
+      : "l"(p0), "l"(p1), "l"(p2), "l"(p3), "r"((uint32_t)k0), "r"((uint32_t)k1), "r"((uint32_t)k2), "r"((uint32_t)k3));
+}
+
 template <typename T>
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
   const T* h = reinterpret_cast<const T*>(&raw);
@@ -88,38 +108,54 @@ __device__ __forceinline__ void prep_row8(const uint4& raw, const float (&kmf)[8
   }
 }
 
-// Exact per-thread accumulation.  fp16: every value is an integer X = x * 2^24 with |X| < 2^40; it is split
-// without any conversion instruction into hi = RN(16 x) and lo = X - hi * 2^20 (|lo| <= 2^19) by two magic-constant
-// FMAs (1.5 * 2^23: the integer lands in the low mantissa bits), and the RAW float bits are summed in two int32
-// lanes (the constant's bits are subtracted once at the end; wrap-around is harmless while the true sums fit 31
-// bits, hence the flush every 256 rows).  bf16: fp64 accumulation in a fixed order.
+// Exact per-thread accumulation.  fp16: every value is an integer X = x * 2^24 with |X| < 2^40; it is split without any
+// conversion instruction into hi = RN(16 x) (an integer-valued float, |hi| < 2^20) and lo = x - hi / 16 (a multiple of
+// 2^-24, |lo| <= 2^-5) by magic-constant arithmetic (1.5 * 2^23) on packed fp32 pairs, and both parts are summed IN
+// FP32 -- exactly, for up to 16 rows (|sum hi| < 2^24, |sum lo * 2^24| < 2^24) -- then folded into two int32 lanes
+// (two F2I per column and 16 rows: the caller calls fold() at least every 16 add()s), which flush() moves to int64
+// at least every 256 rows.  3.5 instructions per
+// element instead of the 7 of the first version (raw float bits summed in integer lanes: two IADD per element).
+// bf16: fp64 accumulation in a fixed order.
 template <typename T> struct RowAcc;
 template <> struct RowAcc<__half> {
-  int hi[8], lo[8], n;
+  float2 hf[4], lf[4];
+  int hi[8], lo[8];
   __device__ __forceinline__ void clear() {
 #pragma unroll
+    for (int i = 0; i < 4; ++i) hf[i] = lf[i] = make_float2(0.f, 0.f);
+#pragma unroll
     for (int i = 0; i < 8; ++i) hi[i] = lo[i] = 0;
-    n = 0;
+  }
+  __device__ __forceinline__ void fold() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hi[2 * i] += __float2int_rn(hf[i].x);
+      hi[2 * i + 1] += __float2int_rn(hf[i].y);
+      lo[2 * i] += __float2int_rn(lf[i].x * 16777216.0f);
+      lo[2 * i + 1] += __float2int_rn(lf[i].y * 16777216.0f);
+      hf[i] = lf[i] = make_float2(0.f, 0.f);
+    }
   }
   __device__ __forceinline__ void add(const uint4& raw) {
-    const __half* hv = reinterpret_cast<const __half*>(&raw);
+    const __half2* hv = reinterpret_cast<const __half2*>(&raw);
     const float kM = 12582912.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x = __half2float(hv[i]);
-      const float a = __fmaf_rn(x, 16.0f, kM);
-      const float rem = __fmaf_rn(__fadd_rn(a, -kM), -0.0625f, x);  // exact: |rem| <= 2^-5, multiple of 2^-24
-      const float bq = __fmaf_rn(rem, 16777216.0f, kM);
-      hi[i] += __float_as_int(a);
-      lo[i] += __float_as_int(bq);
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(hv[i]);
+      const float2 a = __ffma2_rn(x, make_float2(16.0f, 16.0f), make_float2(kM, kM));
+      const float2 t = __fadd2_rn(a, make_float2(-kM, -kM));                   // RN(16 x), exact
+      const float2 rem = __ffma2_rn(t, make_float2(-0.0625f, -0.0625f), x);   // exact: |rem| <= 2^-5, multiple of 2^-24
+      hf[i] = __fadd2_rn(hf[i], t);
+      lf[i] = __fadd2_rn(lf[i], rem);
     }
-    ++n;
   }
   __device__ __forceinline__ void flush(long long (&acc)[8]) {
-    const int off = n * 0x4B400000;  // n * bits(1.5 * 2^23), modulo 2^32 like the lanes themselves
+    fold();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += (long long)(hi[i] - off) * 1048576ll + (long long)(lo[i] - off);
-    clear();
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += (long long)hi[i] * 1048576ll + (long long)lo[i];
+      hi[i] = lo[i] = 0;
+    }
   }
 };
 template <> struct RowAcc<__nv_bfloat16> {
@@ -133,6 +169,7 @@ template <> struct RowAcc<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] += (double)__bfloat162float(hv[i]);
   }
+  __device__ __forceinline__ void fold() {}
   __device__ __forceinline__ void flush(double (&acc)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += s[i];

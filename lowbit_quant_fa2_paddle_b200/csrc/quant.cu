@@ -266,11 +266,40 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
                               blockIdx.x, blockIdx.y, blockIdx.z, s_w);
 }
 
+// The hot configuration of the K chain -- Q1 rounding, int8 codes, smoothing fused, scale factor 1 -- with those
+// arguments as literals: the same body, bit for bit, minus its run-time dispatch (the general kernel spends ~40 % of
+// its instructions on mode / width / packing branches, constant-bank loads and row bookkeeping), NSUB blocks per CTA.
+template <typename T, int D, int BLK, int NSUB>
+__global__ void __launch_bounds__(kQuantThreads)
+quant_k8_q1_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_t* __restrict__ out,
+                   float* __restrict__ scale, int N, int nblk,
+                   int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn, int H) {
+  __shared__ float s_w[NSUB * (kQuantThreads / 32)];
+  quant_block_body<T, D, BLK, NSUB>(in, km, out, scale, N, nblk, isb, ish, isn, osb, osh, osn, 1.0f, 8, 0,
+                                    LOWBIT_QMODE_TRITON, H, blockIdx.x * NSUB, blockIdx.y, blockIdx.z, s_w);
+}
+
 template <typename T, int D, int BLK>
 static int launch_qpb(const void* in, const void* km, void* codes, float* scale, int B, int H, int N,
                       int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn,
                       float sm, int bits, int pack, int mode, cudaStream_t st) {
   const int nblk = (N + BLK - 1) / BLK;
+  if constexpr (BLK == 64) {
+    static const int fast = [] { const char* e = getenv("LOWBIT_QUANT_FAST"); return e ? atoi(e) : 1; }();
+    if (fast && km != nullptr && bits == 8 && sm == 1.0f && mode == LOWBIT_QMODE_TRITON) {
+      if (fast == 4) {
+        dim3 grid((nblk + 3) / 4, H, B);
+        quant_k8_q1_kernel<T, D, BLK, 4><<<grid, kQuantThreads, 0, st>>>(
+            (const T*)in, (const T*)km, (int8_t*)codes, scale, N, nblk, isb, ish, isn, osb, osh, osn, H);
+      } else {
+        dim3 grid((nblk + 1) / 2, H, B);
+        quant_k8_q1_kernel<T, D, BLK, 2><<<grid, kQuantThreads, 0, st>>>(
+            (const T*)in, (const T*)km, (int8_t*)codes, scale, N, nblk, isb, ish, isn, osb, osh, osn, H);
+      }
+      LOWBIT_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   dim3 grid(nblk, H, B);
   quant_per_block_kernel<T, D, BLK><<<grid, kQuantThreads, 0, st>>>(
       (const T*)in, (const T*)km, (int8_t*)codes, scale, N, nblk, isb, ish, isn, osb, osh, osn, sm, bits, pack, mode, H);
@@ -419,11 +448,19 @@ template <int D, int BLK> struct QuantTmaCfg {
   static constexpr int kSmem = kStages * kTileBytes + 1024 + 256;
 };
 
-template <typename T, int D, int BLK>
+// HOT: the Q side of the hot path (Q1 rounding, int8 codes, no mean) with those arguments as literals -- the same code
+// minus its run-time dispatch, bit-identical by construction.
+template <typename T, int D, int BLK, bool HOT = false>
 __global__ void __launch_bounds__(kQuantThreads)
 quant_per_block_tma_kernel(const __grid_constant__ CUtensorMap tmIn, const T* __restrict__ km,
                            int8_t* __restrict__ out, float* __restrict__ scale, int N, int nblk, int H, int total,
                            int64_t osb, int64_t osh, int64_t osn, float sm, int bits, int pack, int mode) {
+  if constexpr (HOT) {
+    km = nullptr;
+    bits = 8;
+    pack = 0;
+    mode = LOWBIT_QMODE_TRITON;
+  }
   using C = QuantTmaCfg<D, BLK>;
   constexpr int S = C::kStages;
   constexpr int TPR = D / 8;                 // threads per row
@@ -550,7 +587,9 @@ static int launch_qpb_tma(const void* in, const void* km, void* codes, float* sc
   CUtensorMap tm;
   const int64_t dim[4] = {D, N, H, B}, str[3] = {isn, ish, isb};
   if (make_map(&tm, in, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dim, str, D, BLK, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-  auto kern = quant_per_block_tma_kernel<T, D, BLK>;
+  static const int fast = [] { const char* e = getenv("LOWBIT_QUANT_FAST"); return e ? atoi(e) : 1; }();
+  const bool hot = fast && BLK == 128 && km == nullptr && bits == 8 && mode == LOWBIT_QMODE_TRITON;
+  auto kern = hot ? quant_per_block_tma_kernel<T, D, BLK, true> : quant_per_block_tma_kernel<T, D, BLK, false>;
   // the > 48 KB opt-in is a per-device function attribute: set on every launch (cheap), not once per process
   LOWBIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
   int ctas_per_sm = (227 * 1024) / (C::kSmem + 1024);
@@ -605,15 +644,21 @@ __device__ __forceinline__ void ksum_chunk_body(const T* __restrict__ k, typenam
   int since_flush = 0;
   // rows in a fixed order inside a thread (matters only for bf16/fp64); 8 loads in flight per thread
   for (int row = ch * chunk + r0; row < row_end; row += 8 * RPP) {
-    uint4 raw[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      raw[u] = make_uint4(0, 0, 0, 0);
-      if (row + u * RPP < row_end) raw[u] = ld_stream_v4(src + (int64_t)(row + u * RPP) * sn);
+    uint4 ra0[4], ra1[4];
+    {
+      const T* p = src + (int64_t)row * sn;
+      const int64_t st = (int64_t)RPP * sn;
+      ld_stream_v4_x4(p, p + st, p + 2 * st, p + 3 * st, row < row_end, row + RPP < row_end, row + 2 * RPP < row_end,
+                      row + 3 * RPP < row_end, ra0);
+      ld_stream_v4_x4(p + 4 * st, p + 5 * st, p + 6 * st, p + 7 * st, row + 4 * RPP < row_end, row + 5 * RPP < row_end,
+                      row + 6 * RPP < row_end, row + 7 * RPP < row_end, ra1);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) ra.add(raw[u]);
+    for (int u = 0; u < 4; ++u) ra.add(ra0[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ra.add(ra1[u]);
     since_flush += 8;
+    if ((since_flush & 15) == 0) ra.fold();
     if (since_flush >= 256) { ra.flush(acc); since_flush = 0; }
   }
   ra.flush(acc);
@@ -628,7 +673,7 @@ __device__ __forceinline__ void ksum_chunk_body(const T* __restrict__ k, typenam
 }
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_mean_partial_kernel(const T* __restrict__ k, typename MeanAcc<T>::type* __restrict__ part, int N, int chunk,
                       int nchunk, int64_t sb, int64_t sh, int64_t sn, int H) {
   using A = typename MeanAcc<T>::type;
@@ -761,7 +806,9 @@ k_smooth_quant_cluster_kernel(const T* __restrict__ k, T* __restrict__ km_out, i
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (int r = r0; r < rows_cta; r += RPP) {
       ra.add(tile[r * TPR + cq]);  // absent rows add exact zeros
-      if (++since_flush >= 240) { ra.flush(acc); since_flush = 0; }
+      ++since_flush;
+      if ((since_flush & 15) == 0) ra.fold();
+      if (since_flush >= 240) { ra.flush(acc); since_flush = 0; }
     }
     ra.flush(acc);
     // lanes that share lane % TPR hold the same columns: fold them, then one row of sums per warp

@@ -180,6 +180,7 @@ v_stats_partial_kernel(const T* __restrict__ v, VPartial* __restrict__ part, int
     }
     if (SUM) {
       since_flush += 8;
+      if ((since_flush & 15) == 0) ra.fold();
       if (since_flush >= 256) { ra.flush(acc); since_flush = 0; }
     }
   }
