@@ -56,6 +56,7 @@ struct AttnParams {
   int64_t osb, osh, osn;
   int delta;             // q_offset - k_offset: global position of query row 0 minus that of key 0 (causal)
   int flags, out_dtype, first;
+  int csec;              // causal tile order: (batch, head) pairs per longest-first section (tile_coords)
   int32_t* dbg;          // diagnostics: when non-null, CTA (0,0,0) dumps the int32 scores of key block 0 ([128][64])
 };
 
@@ -369,6 +370,27 @@ struct TileView {
   bool done;                // nothing left to do for this CTA
 };
 
+// Which (Q tile, head, batch) a CTA works on.  Non-causal: the grid coordinates.  Causal: a tile's work grows with its
+// index (2 .. 2 nqt key blocks), and CTAs are dispatched in linear block order, so the order is longest-first over
+// sections of p.csec (batch, head) pairs (32; LOWBIT_CAUSAL_SECTION) -- all their heaviest tiles, then the next lighter ones ... -- instead of
+// longest-first inside each (batch, head): the grid then ends on the lightest tiles of the last section (a few key
+// blocks each) rather than on heavy tiles of the last heads that started late, and a section's K / V (kSec x
+// (N x D x 3 bytes)) stays L2-resident while its tiles run.
+__device__ __forceinline__ void tile_coords(const bool causal, const int kCausalSection, int& qt, int& hq, int& b) {
+  if (!causal) {
+    qt = blockIdx.x; hq = blockIdx.y; b = blockIdx.z;
+    return;
+  }
+  const int nqt = gridDim.x, nbh = gridDim.y * gridDim.z;
+  const int id = blockIdx.x + nqt * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int sec = id / (kCausalSection * nqt), base = sec * kCausalSection;
+  const int cnt = min(kCausalSection, nbh - base), r = id - base * nqt;
+  qt = nqt - 1 - r / cnt;
+  const int bh = base + r % cnt;
+  hq = bh % (int)gridDim.y;
+  b = bh / (int)gridDim.y;
+}
+
 // Resolves the CTA's view and handles the degenerate tiles (past the end of a varlen sequence; a sequence without keys).
 template <int D>
 __device__ __forceinline__ TileView tile_view(const AttnParams& p, const int qt, const int hq, const int hkv, const int b,
@@ -476,8 +498,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
-  const int qt = causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
-  const int hq = blockIdx.y, b = blockIdx.z;
+  int qt, hq, b;
+  tile_coords(causal, p.csec, qt, hq, b);
   const int hkv = hq / (p.Hq / p.Hkv);
 
   const TileView tv = tile_view<D>(p, qt, hq, hkv, b, tid);
@@ -898,8 +920,8 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool causal = (p.flags & LOWBIT_ATTN_CAUSAL) != 0;
-  const int qt = causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
-  const int hq = blockIdx.y, b = blockIdx.z;
+  int qt, hq, b;
+  tile_coords(causal, p.csec, qt, hq, b);
   const int hkv = hq / (p.Hq / p.Hkv);
 
   const TileView tv = tile_view<D>(p, qt, hq, hkv, b, tid);
@@ -1121,10 +1143,12 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // P: <= 1.0004 while sc <= kScMax (typical INT8 / packed-INT4 scales: 1e-4 .. 3e-4, i.e. < 1.0001 -- below the
       // fp16 rounding of P).  Coarser scales (INT4 codes handed over one per int8, tiny head scales) take the exact
       // path, which converts the integer score itself.
-      bool exact = MASKED || !fast_ok;
+      bool exact = !fast_ok;
       if (!exact) {
-        // optimistic: keep the reference maximum; the chunk's row sum proves that no p reached 2^15 (finite in fp16)
-        const float lsum = chunk::chunk_f16<false, PF, true>(s, sc, PC::OFF - m_ref, 0, pk);
+        // optimistic: keep the reference maximum; the chunk's row sum proves that no p reached 2^15 (finite in fp16).
+        // Masked chunks (causal diagonal, tail keys) take it too: a masked column's p is replaced by 0 after the exp2,
+        // whatever it was, and stays out of the row sum
+        const float lsum = chunk::chunk_f16<MASKED, PF, true>(s, sc, PC::OFF - m_ref, lim, pk);
         exact = __any_sync(0xffffffffu, !(lsum < 32768.f));
         if (!exact) l += lsum;
       }
@@ -1417,6 +1441,19 @@ static int run_attn(const char* who, const AttnArgs& a, AttnParams& p, cudaStrea
   LOWBIT_CHECK(a.pv_mode == LOWBIT_PV_F16 || a.pv_mode == LOWBIT_PV_E4M3, "%s: bad pv_mode %d", who, a.pv_mode);
   LOWBIT_CHECK(a.pv_mode != LOWBIT_PV_E4M3 || a.v_scale != nullptr, "%s: the FP8 P.V path needs v_scale", who);
   const int D = a.D;
+  {
+    // causal tile order (tile_coords): as many (batch, head) pairs per longest-first section as keep the section's K / V
+    // within ~64 MB of the 126 MB L2 (measured at C2-causal, C3 @ 8K / 16K and D=128 INT8 @ 8K: sections beyond
+    // the L2 cost up to 15 %, sections of one head up to 10 %; profiles/r2_causal_order.txt).  LOWBIT_CAUSAL_SECTION overrides.
+    static const int forced = [] { const char* e = getenv("LOWBIT_CAUSAL_SECTION"); return e ? atoi(e) : 0; }();
+    const double kb = (a.qk_mode == LOWBIT_QK_Q8K4) ? 0.5 : (a.qk_mode == LOWBIT_QK_F16 ? 2.0 : 1.0);
+    const double vb = (a.pv_mode == LOWBIT_PV_E4M3) ? 1.0 : 2.0;
+    const double per_head = (double)a.Nk * a.D * (kb + vb) / (double)(a.Hq / a.Hkv);
+    const double fit = 64.0 * 1024 * 1024 / (per_head > 1.0 ? per_head : 1.0);
+    const int nbh = a.B * a.Hq, cap = fit < 1.0 ? 1 : (fit > (double)nbh ? nbh : (int)fit);
+    const int nsec = (nbh + cap - 1) / cap;            // equal sections: a short last one would start its heavy tiles
+    p.csec = forced > 0 ? forced : (nbh + nsec - 1) / nsec;  // when little else is left to run next to them
+  }
   const int km = (a.qk_mode == LOWBIT_QK_Q8K4) ? KM_K4 : (a.qk_mode == LOWBIT_QK_Q8KMIX ? KM_MIX : (a.qk_mode == LOWBIT_QK_F16 ? KM_F16 : KM_I8));
   const int pv = (a.pv_mode == LOWBIT_PV_E4M3) ? PV_E4M3 : PV_F16;
   const bool n64 = use_n64(D, km, pv, a.flags);
