@@ -266,16 +266,16 @@ quant_per_block_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_
                               blockIdx.x, blockIdx.y, blockIdx.z, s_w);
 }
 
-// The hot configuration of the K chain -- Q1 rounding, int8 codes, smoothing fused, scale factor 1 -- with those
+// The hot configurations of the K chain -- Q1 rounding, int8 or packed INT4 codes, smoothing fused, scale factor 1 -- with those
 // arguments as literals: the same body, bit for bit, minus its run-time dispatch (the general kernel spends ~40 % of
 // its instructions on mode / width / packing branches, constant-bank loads and row bookkeeping), NSUB blocks per CTA.
-template <typename T, int D, int BLK, int NSUB>
+template <typename T, int D, int BLK, int NSUB, int BITS, int PACK>
 __global__ void __launch_bounds__(kQuantThreads)
-quant_k8_q1_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_t* __restrict__ out,
-                   float* __restrict__ scale, int N, int nblk,
-                   int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn, int H) {
+quant_k_q1_kernel(const T* __restrict__ in, const T* __restrict__ km, int8_t* __restrict__ out,
+                  float* __restrict__ scale, int N, int nblk,
+                  int64_t isb, int64_t ish, int64_t isn, int64_t osb, int64_t osh, int64_t osn, int H) {
   __shared__ float s_w[NSUB * (kQuantThreads / 32)];
-  quant_block_body<T, D, BLK, NSUB>(in, km, out, scale, N, nblk, isb, ish, isn, osb, osh, osn, 1.0f, 8, 0,
+  quant_block_body<T, D, BLK, NSUB>(in, km, out, scale, N, nblk, isb, ish, isn, osb, osh, osn, 1.0f, BITS, PACK,
                                     LOWBIT_QMODE_TRITON, H, blockIdx.x * NSUB, blockIdx.y, blockIdx.z, s_w);
 }
 
@@ -286,16 +286,15 @@ static int launch_qpb(const void* in, const void* km, void* codes, float* scale,
   const int nblk = (N + BLK - 1) / BLK;
   if constexpr (BLK == 64) {
     static const int fast = [] { const char* e = getenv("LOWBIT_QUANT_FAST"); return e ? atoi(e) : 1; }();
-    if (fast && km != nullptr && bits == 8 && sm == 1.0f && mode == LOWBIT_QMODE_TRITON) {
-      if (fast == 4) {
-        dim3 grid((nblk + 3) / 4, H, B);
-        quant_k8_q1_kernel<T, D, BLK, 4><<<grid, kQuantThreads, 0, st>>>(
+    const bool i8 = bits == 8, i4p = bits == 4 && pack;   // int8 codes (C2) / packed INT4 codes (C3, C4)
+    if (fast && km != nullptr && (i8 || i4p) && sm == 1.0f && mode == LOWBIT_QMODE_TRITON) {
+      dim3 grid((nblk + 1) / 2, H, B);
+      if (i8)
+        quant_k_q1_kernel<T, D, BLK, 2, 8, 0><<<grid, kQuantThreads, 0, st>>>(
             (const T*)in, (const T*)km, (int8_t*)codes, scale, N, nblk, isb, ish, isn, osb, osh, osn, H);
-      } else {
-        dim3 grid((nblk + 1) / 2, H, B);
-        quant_k8_q1_kernel<T, D, BLK, 2><<<grid, kQuantThreads, 0, st>>>(
+      else
+        quant_k_q1_kernel<T, D, BLK, 2, 4, 1><<<grid, kQuantThreads, 0, st>>>(
             (const T*)in, (const T*)km, (int8_t*)codes, scale, N, nblk, isb, ish, isn, osb, osh, osn, H);
-      }
       LOWBIT_CUDA(cudaGetLastError());
       return 0;
     }
