@@ -119,6 +119,7 @@ def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, kee
 
     staged = stage(0)
     for i, (b, h0, h1) in enumerate(plan):
+        torch.cuda.nvtx.range_push(f"lowbit.host chunk {i} (b {b}, kv heads {h0}:{h1})")  # host-side enqueue of the chunk
         dq, dk, dv, ev = staged
         if i + 1 < len(plan):
             staged = stage(i + 1)  # enqueue the next H2D before this chunk's kernels
@@ -134,6 +135,7 @@ def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, kee
             keep.append(o)
         else:
             o.record_stream(s_out)
+        torch.cuda.nvtx.range_pop()
     cur.wait_stream(s_in)
     cur.wait_stream(s_out)
 

@@ -196,10 +196,20 @@ def _exchange(dist, group, send_buf, recv_buf, world, rank):
     return dist.batch_isend_irecv(ops)
 
 
+def ring_group(timeout_s: float = 60.0, ranks=None, backend: Optional[str] = None):
+    """A process group for `ring_attention` whose collectives and P2P transfers time out after `timeout_s` seconds
+    (the default NCCL timeout is 10 minutes): with torch's asynchronous NCCL error handling a peer that died mid-ring
+    then aborts the communicator instead of hanging the job.  `ranks` = None: all ranks of the world."""
+    import datetime
+
+    import torch.distributed as dist
+    return dist.new_group(ranks=ranks, timeout=datetime.timedelta(seconds=float(timeout_s)), backend=backend)
+
+
 def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False, sm_scale: Optional[float] = None,
                    smooth_k: bool = True, qk: str = "int4", pv: str = "fp16", zigzag: Optional[bool] = None,
                    return_lse: bool = False, group=None, backend=None, n_total: Optional[int] = None,
-                   timings: Optional[dict] = None):
+                   timings: Optional[dict] = None, check: bool = False):
     """Sequence-parallel low-bit attention over the ranks of `group` (default: the world).
 
     q, k, v: this rank's shard, [B,H,n_local,D] (HND) or [B,n_local,H,D] (NHD), n_local = N / world, holding the
@@ -209,7 +219,12 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
     `timings`: a dict that receives this rank's phase times in ms (CUDA events on the compute stream; the call
     synchronises the device to read them): "k_mean", "quantize", per ring step "compute" (attention kernels of the
     resident shard) and "p2p_exposed" (what the step waited for the exchange beyond its own compute), "finalize",
-    and "p2p_bytes_per_step" (the flat K/V message one rank sends per step)."""
+    and "p2p_bytes_per_step" (the flat K/V message one rank sends per step).
+    Failure detection: NCCL reports a dead peer or a stuck transfer asynchronously -- after the group's timeout
+    (`ring_group(timeout_s)` makes a group with a short one) the watchdog aborts the communicator and the error
+    surfaces at the next synchronisation.  `check=True` synchronises the comm stream at the end of every ring step
+    and turns such an error into a RuntimeError that names the step and the rank (it serialises host and device once
+    per step: a debugging / canary mode, not the default).  Every phase is also an NVTX range (`lowbit.ring.*`)."""
     import torch.distributed as dist
     if tensor_layout not in ("HND", "NHD"):
         raise ValueError(f"Unknown tensor layout: {tensor_layout}")
@@ -234,7 +249,15 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
     import os
     marks = [] if (on_cuda and (timings is not None or os.environ.get("LOWBIT_RING_TIMING"))) else None  # (label, event)
 
+    nvtx_open = [False]
+
     def mark(label):
+        if on_cuda:  # NVTX: one range per phase, closed by the next mark (no-ops without a profiler attached)
+            if nvtx_open[0]:
+                torch.cuda.nvtx.range_pop()
+            nvtx_open[0] = label != "finalize"
+            if nvtx_open[0]:
+                torch.cuda.nvtx.range_push("lowbit.ring after " + label)
         if marks is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record(torch.cuda.current_stream(q.device))
@@ -293,6 +316,12 @@ def ring_attention(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
                 with torch.cuda.stream(comm_stream):
                     for w in works:
                         w.wait()
+                if check:
+                    try:
+                        comm_stream.synchronize()
+                    except RuntimeError as e:  # NCCL watchdog abort / CUDA error of the exchange
+                        raise RuntimeError(f"ring_attention: exchange of step {step} failed on rank {rank} "
+                                           f"(peers {(rank - 1) % world} -> {rank} -> {(rank + 1) % world}): {e}") from e
                 compute_stream.wait_stream(comm_stream)
             else:
                 for w in works:

@@ -105,8 +105,10 @@ def _worker(rank, world, port, cfg, ret):
         chunks = P.seq_chunks(n, world, rank, zigzag)
         take = lambda x: torch.cat([x.narrow(seq, c.offset, c.length) for c in chunks], dim=seq).contiguous()
         be = OracleBackend(layout, qk, pv, d ** -0.5)
+        # the NHD configurations run over a ring_group (own process group with a short timeout) in check mode
+        grp = P.ring_group(timeout_s=120.0, backend="gloo") if layout == "NHD" else None
         o, lse = P.ring_attention(take(q), take(k), take(v), tensor_layout=layout, is_causal=causal, qk=qk, pv=pv,
-                                  zigzag=zigzag, return_lse=True, backend=be)
+                                  zigzag=zigzag, return_lse=True, backend=be, group=grp, check=grp is not None)
         ret[rank] = (o, lse, [(c.offset, c.length) for c in chunks])
     finally:
         dist.destroy_process_group()
