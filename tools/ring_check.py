@@ -43,8 +43,10 @@ def main():
         zig = causal
         chunks = P.seq_chunks(n, world, rank, zig)
         take = lambda x: torch.cat([x.narrow(seq, c.offset, c.length) for c in chunks], dim=seq).contiguous()
+        # the NHD configurations run over a ring_group (short timeout) in check mode (per-step error surfacing)
+        grp = P.ring_group(timeout_s=120.0) if layout == "NHD" else None
         o, lse = P.ring_attention(take(q), take(k), take(v), tensor_layout=layout, is_causal=causal, qk=qk, pv=pv,
-                                  return_lse=True)
+                                  return_lse=True, group=grp, check=grp is not None)
         # reference: the single-GPU entry point on the full tensors
         if qk == "mixed":
             fn = L.lowbit_fa_q_int8_k_dynamic
