@@ -1132,12 +1132,14 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                           const int j, const float sc, const int lim, const bool fast_ok) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       constexpr bool HI = decltype(hi_tag)::value;
+#ifndef LOWBIT_TRACE
       if constexpr (DBG) {
         if (p.dbg != nullptr && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) p.dbg[tid * 64 + (HI ? 32 : 0) + c] = (int)(s[c] - chunk::kScoreBias);
         }
       }
+#endif
       // The optimistic path reads the biased scores as fp32 (no conversion); the bias leaves through the FMA addend
       // nm - 12582912 * sc, whose rounding puts a common factor of up to 2^(2^-25 * 12582912 * sc) on the chunk's
       // P: <= 1.0004 while sc <= kScMax (typical INT8 / packed-INT4 scales: 1e-4 .. 3e-4, i.e. < 1.0001 -- below the
@@ -1187,30 +1189,46 @@ attn_fwd_n64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
 
     uint32_t s[32];  // on entry to a step: S_lo(j)
+#ifdef LOWBIT_TRACE
+    const bool tracer = DBG && p.dbg != nullptr && blockIdx.x == 16 && blockIdx.y == 5 && blockIdx.z == 1 && (tid & 31) == 0;
+    auto stamp = [&](int j, int k) {
+      if (tracer) { int c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); p.dbg[(warp * 64 + j) * 8 + k] = c; }
+    };
+#else
+    auto stamp = [&](int, int) {};
+#endif
     auto step = [&](auto masked_tag, const int j, const float sc, const int lim) {
       uint32_t plo[16], phi[16];
       const bool coarse = sc > kScMax;  // warp-uniform (one scale per Q tile and key block)
+      stamp(j, 0);
       chunk_step(masked_tag, std::false_type{}, s, plo, plo, j, sc, lim, have_ref && !coarse);
+      stamp(j, 1);
       ptx::mbar_wait_a(sb + oShi, j & 1, 31);
+      stamp(j, 2);
       ptx::tc_fence_after();
       ptx::tmem_ld_x16(tSl + HN, s);
       ptx::tmem_ld_x16(tSl + HN + 16, s + 16);
       ptx::tmem_wait_ld();
+      stamp(j, 3);
       chunk_step(masked_tag, std::true_type{}, s, phi, plo, j, sc, lim - HN, have_ref && !coarse);
+      stamp(j, 4);
       ptx::tmem_st_x8(tPl, plo);
       ptx::tmem_st_x8(tPl + 8, plo + 8);
       ptx::tmem_st_x8(tPl + 16, phi);
       ptx::tmem_st_x8(tPl + 24, phi + 8);
       if (j + 1 < nblk) {  // the next block's lower scores: issued a whole step ago
         ptx::mbar_wait_a(sb + oSlo, (j + 1) & 1, 30);
+        stamp(j, 5);
         ptx::tc_fence_after();
         ptx::tmem_ld_x16(tSl, s);
         ptx::tmem_ld_x16(tSl + 16, s + 16);
         ptx::tmem_wait_ld();
       }
+      stamp(j, 6);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::mbar_arrive_elect_a(sb + oPready);  // P_j is in place and columns [0,32) may take S_lo(j+2)
+      stamp(j, 7);
     };
     ptx::mbar_wait_a(sb + oSlo, 0, 30);
     ptx::tc_fence_after();
