@@ -137,12 +137,19 @@ def roofline(kernel, B, Hq, Hkv, N, D, causal, qk, pv, attn_ms, sm_mhz, traffic=
                       "note": "a kernel that takes exp2 off the MUFU pipe (2 of 8 score pairs here) can beat mufu_ms"}}
 
 
-def instrumented(instr_ms, attn_ms, ms_per_step):
+def cool_down(dev, seconds=1.5):
+    """Idle between timed regions: back-to-back regions of ~100 steps were seen to run the second one at a lower
+    clock (attention 0.61 -> 0.66 ms); every region gets its own clock samples as well."""
+    torch.cuda.synchronize(dev)
+    time.sleep(seconds)
+
+
+def instrumented(instr_ms, attn_ms, ms_per_step, clocks=None):
     """Where `roofline.ms_per_launch` was measured: a second timed region of the same K steps with a CUDA-event pair
     around the attention launch; the headline steps carry no events."""
     return {"measured_in": "instrumented pass: the same K steps, operator cut at the attention launch, CUDA-event pair around it "
                            "on the launching stream; `ms_per_step` of the line is the un-instrumented public call",
-            "instrumented_ms_per_step": instr_ms, "share_of_instrumented_step": (attn_ms / instr_ms) if instr_ms else None,
+            "instrumented_ms_per_step": instr_ms, "instrumented_clocks": clocks, "share_of_instrumented_step": (attn_ms / instr_ms) if instr_ms else None,
             "share_of_step": attn_ms / ms_per_step}
 
 
@@ -568,9 +575,12 @@ def run_single(args, rank, world, local, dev):
     # instrumented pass: the same K steps cut at the attention launch with a CUDA-event pair around it (the events and
     # the Python-side fork / join of the quantizer streams cost time, so this pass is not the headline)
     instr_ms_local, attn_ms = None, None
+    instr_clocks = None
     if attn_ev:
-        instr_ms_local, _ = timed_steps(step, K, W, world, dev, local, with_clocks=False)
+        cool_down(dev)
+        instr_ms_local, instr_clocks = timed_steps(step, K, W, world, dev, local)
         attn_ms = sum(a.elapsed_time(b) for a, b in attn_ev) / K
+        cool_down(dev)
     attn_alone_ms = attn_only(max(10, min(K, 50))) if attn_only else None
     e2e = None
     if decomposable and wl in ("c2", "c2c", "c4s", "c4"):
@@ -591,7 +601,7 @@ def run_single(args, rank, world, local, dev):
             line["attn_only"] = {"value": world * ops / (attn_alone_m * 1e-3) / 1e12, "unit": "TOPS", "ms": attn_alone_m}
             line["roofline"] = roofline("attn_fwd_n64_kernel" if D == 64 else "attn_fwd_kernel", B, Hq, Hkv, N, D, causal, qk, pv,
                                         attn_ms_m, (clocks or {}).get("sm_mhz"), ncu_traffic_bytes() if wl == "c2" else None)
-            line["roofline"].update(instrumented(instr_ms, attn_ms_m, ms_per_step))
+            line["roofline"].update(instrumented(instr_ms, attn_ms_m, ms_per_step, instr_clocks))
         if e2e:
             line["e2e"] = {"value": world * ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOPS", "ms": e2e_ms,
                            "api": "lowbit_fa_host(graph=True): pinned host q,k,v -> pinned host o; (batch, head-group) chunks on 3 streams, replayed as one CUDA graph",
@@ -687,8 +697,10 @@ def run_multi(args, rank, world, local, dev):
     del o_api
     api_step = lambda i=None: P.lowbit_fa_head_sharded(q, k, v, fn, world, rank, tensor_layout=layout, is_causal=causal)
     ms_local, clocks = timed_steps(api_step, K, W, world, dev, local)            # headline: the public call
-    instr_ms_local, _ = timed_steps(step, K, W, world, dev, local, with_clocks=False)   # instrumented pass (see run_single)
+    cool_down(dev)
+    instr_ms_local, instr_clocks = timed_steps(step, K, W, world, dev, local)   # instrumented pass (see run_single)
     attn_ms = sum(a.elapsed_time(b) for a, b in attn_ev) / K
+    cool_down(dev)
     attn_alone_ms = attn_only(max(10, min(K, 30)))
     # the same workload on ONE GPU, in this run (rank 0; the other ranks wait at the barrier)
     single_ms = 0.0
@@ -739,7 +751,7 @@ def run_multi(args, rank, world, local, dev):
                 "roofline": roofline("attn_fwd_n64_kernel", B, hq_loc, hkv1 - hkv0, N, D, causal, qk, pv, attn_ms_m,
                                      (clocks or {}).get("sm_mhz")),
                 "ring": ring}
-        line["roofline"].update(instrumented(instr_ms, attn_ms_m, ms_per_step))
+        line["roofline"].update(instrumented(instr_ms, attn_ms_m, ms_per_step, instr_clocks))
         print(json.dumps(line), flush=True)
 
 
