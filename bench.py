@@ -704,6 +704,7 @@ def run_multi(args, rank, world, local, dev):
     attn_alone_ms = attn_only(max(10, min(K, 30)))
     # the same workload on ONE GPU, in this run (rank 0; the other ranks wait at the barrier)
     single_ms = 0.0
+    cool_down(dev)
     if rank == 0:
         fs = lambda i=None: fn(q, k, v, tensor_layout=layout, is_causal=causal)
         for _ in range(3):
