@@ -76,7 +76,7 @@ def plan_chunks(B: int, Hq: int, Hkv: int, tensor_layout: str, chunks: Optional[
     return plan
 
 
-def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=None):
+def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=None, lse_out=None):
     """Enqueue the three-stream pipeline on the caller's current stream of `dev` (eagerly, or into a CUDA graph that
     is being captured on that stream: every event waited on is recorded inside this call and both side streams
     fork from and re-join the current stream, which is what stream capture requires).  `keep`: a list that receives
@@ -125,16 +125,24 @@ def _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, kee
             staged = stage(i + 1)  # enqueue the next H2D before this chunk's kernels
         cur.wait_event(ev)
         o = op(dq, dk, dv, tensor_layout=tensor_layout, **op_kwargs)
+        lse = None
+        if lse_out is not None:  # return_lse=True: (o, lse [1, q heads of the chunk, N] fp32)
+            o, lse = o
         done = torch.cuda.Event()
         done.record(cur)  # the slot may be overwritten once these kernels are done
         free[i % _NSLOT] = done
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
             view(out, b, h0 * grp, h1 * grp).copy_(o, non_blocking=True)
+            if lse is not None:
+                lse_out[b:b + 1, h0 * grp:h1 * grp].copy_(lse, non_blocking=True)
         if keep is not None:
             keep.append(o)
+            keep.append(lse)
         else:
             o.record_stream(s_out)
+            if lse is not None:
+                lse.record_stream(s_out)
         torch.cuda.nvtx.range_pop()
     cur.wait_stream(s_in)
     cur.wait_stream(s_out)
@@ -145,12 +153,13 @@ _GRAPH_CACHE = 4
 
 
 def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, tensor_layout: str = "HND",
-                   chunks: Optional[int] = None, device=None, graph: bool = False, **op_kwargs: Any):
+                   chunks: Optional[int] = None, device=None, graph: bool = False, lse_out=None, **op_kwargs: Any):
     """Run `op` (default `lowbit_fa_qk_int8_pv_fp16_triton`) on HOST tensors q, k, v (pinned memory for asynchronous
     DMA) and return the HOST tensor `out` (allocated pinned when not given), overlapping the copies with the kernels.
     Work is ordered on the caller's current stream of `device`: when this returns, everything is enqueued and the
     current stream has been made to wait for the last copy-out -- synchronize it (or an event on it) before reading
-    `out` on the host.  `return_lse` is not supported on this entry point.
+    `out` on the host.  With `return_lse=True` the call returns `(out, lse)`, lse `[B, Hq, N]` fp32 on the host
+    (`lse_out`, allocated pinned when not given), copied out chunk by chunk like `out`.
 
     `graph=True` (opt-in): a caller that comes back with the SAME pinned buffers (a serving loop that refills them in
     place) gets the whole pipeline -- every copy, kernel and cross-stream dependency of every chunk -- as one CUDA
@@ -162,8 +171,7 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
     frozen as captured.  The default enqueues eagerly."""
     from . import core
     op = op or core.lowbit_fa_qk_int8_pv_fp16_triton
-    if op_kwargs.get("return_lse"):
-        raise ValueError("lowbit_fa_host does not return lse")
+    want_lse = bool(op_kwargs.get("return_lse"))
     qt, kt, vt = T.as_torch(q), T.as_torch(k), T.as_torch(v)
     assert qt.device.type == "cpu" and kt.device.type == "cpu" and vt.device.type == "cpu", \
         "lowbit_fa_host takes host tensors; device tensors go to the operator directly"
@@ -183,11 +191,20 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
     assert out.shape == qt.shape and out.dtype == qt.dtype and out.device.type == "cpu" and out.is_contiguous()
     grp = Hq // Hkv
     plan = plan_chunks(B, Hq, Hkv, tensor_layout, chunks)
+    if want_lse:
+        n_q = qt.shape[2] if tensor_layout == "HND" else qt.shape[1]
+        if lse_out is None:
+            lse_out = torch.empty((B, Hq, n_q), dtype=torch.float32, pin_memory=True)
+        assert tuple(lse_out.shape) == (B, Hq, n_q) and lse_out.dtype == torch.float32 and lse_out.device.type == "cpu"
+    else:
+        lse_out = None
+    ret = (out, lse_out) if want_lse else out
 
     key = None
-    if graph and all(t.is_pinned() for t in (qt, kt, vt, out)):
+    if graph and all(t.is_pinned() for t in (qt, kt, vt, out)) and (lse_out is None or lse_out.is_pinned()):
         try:
-            key = (dev.index, qt.data_ptr(), kt.data_ptr(), vt.data_ptr(), out.data_ptr(), tuple(qt.shape),
+            key = (dev.index, qt.data_ptr(), kt.data_ptr(), vt.data_ptr(), out.data_ptr(),
+                   lse_out.data_ptr() if lse_out is not None else 0, tuple(qt.shape),
                    tuple(kt.shape), tuple(vt.shape), qt.dtype, tensor_layout, len(plan), op,
                    tuple(sorted(op_kwargs.items())))
             hash(key)
@@ -195,15 +212,15 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
             key = None  # an unhashable operator argument: enqueue eagerly
     with _lock, torch.cuda.device(dev):
         if key is None:
-            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)
-            return out
+            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, lse_out=lse_out)
+            return ret
         entry = _graphs.get(key)
         if entry is None:
             if len(_graphs) >= _GRAPH_CACHE:
                 _graphs.pop(next(iter(_graphs)))
             _graphs[key] = [1, None, None]
-            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)  # first sighting: eager (warms the kernels)
-            return out
+            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, lse_out=lse_out)  # first sighting: eager (warms the kernels)
+            return ret
         entry[0] += 1
         if entry[1] is None:
             cur = torch.cuda.current_stream(dev)
@@ -213,15 +230,15 @@ def lowbit_fa_host(q, k, v, out=None, op: Optional[Callable[..., Any]] = None, t
             try:
                 # thread_local: CUDA calls of other threads (e.g. a NCCL watchdog polling events) do not break the capture
                 with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
-                    _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=keep)
+                    _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, keep=keep, lse_out=lse_out)
                 entry[1], entry[2] = g, keep
             except RuntimeError:
                 entry[1] = False  # this operator cannot be captured (it synchronises): same kernels, enqueued eagerly
         if entry[1] is False:
-            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs)
+            _pipeline(qt, kt, vt, out, op, tensor_layout, plan, grp, dev, op_kwargs, lse_out=lse_out)
         else:
             entry[1].replay()
-    return out
+    return ret
 
 
 def drop_graphs() -> None:

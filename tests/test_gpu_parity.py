@@ -662,6 +662,17 @@ def test_host_streaming_matches_device_call(L, cuda_dev, layout, b, hq, hkv, n, 
                                              is_causal=causal)
     torch.cuda.synchronize()
     assert torch.equal(out4, ref4.cpu())
+    # return_lse: (out, lse [B, Hq, N] fp32 on the host), eagerly and as a replayed graph -- bit-identical to the device call
+    ref_o, ref_lse = L.lowbit_fa_qk_int8_pv_fp16_triton(q.to(cuda_dev), k.to(cuda_dev), v.to(cuda_dev),
+                                                         tensor_layout=layout, is_causal=causal, return_lse=True)
+    lse_keep = None
+    for graph in (False, True, True, True):
+        o2, lse2 = L.lowbit_fa_host(q, k, v, tensor_layout=layout, chunks=chunks, is_causal=causal, device=cuda_dev,
+                                    return_lse=True, graph=graph, out=out4, lse_out=lse_keep)
+        torch.cuda.synchronize()
+        lse_keep = lse2
+        assert lse2.device.type == "cpu" and tuple(lse2.shape) == (b, hq, n)
+        assert torch.equal(o2, ref_o.cpu()) and torch.equal(lse2, ref_lse.cpu())
 
 
 @pytest.mark.parametrize("layout,b,hq,hkv,n,d,causal,chunks", [
