@@ -48,8 +48,9 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
   return r;
 }
 
-// four 128-bit streaming loads issued back to back in ONE asm statement (a predicate that is off leaves zeros): ptxas
-// cannot recycle one destination quad for all of them, which serialises load -> use -> load in a register-tight kernel
+// four predicated 128-bit streaming loads in one asm statement (a predicate that is off leaves zeros).  NB: this alone
+// does not keep them in flight together -- ptxas still sinks each load to its first use and recycles one destination quad
+// (load -> use -> load) when it is short of registers; the callers' __launch_bounds__(256, 2) is what gives it the room
 __device__ __forceinline__ void ld_stream_v4_x4(const void* p0, const void* p1, const void* p2, const void* p3,
                                                 bool k0, bool k1, bool k2, bool k3, uint4 (&r)[4]) {
   asm volatile(
@@ -113,9 +114,8 @@ __device__ __forceinline__ void prep_row8(const uint4& raw, const float (&kmf)[8
 // 2^-24, |lo| <= 2^-5) by magic-constant arithmetic (1.5 * 2^23) on packed fp32 pairs, and both parts are summed IN
 // FP32 -- exactly, for up to 16 rows (|sum hi| < 2^24, |sum lo * 2^24| < 2^24) -- then folded into two int32 lanes
 // (two F2I per column and 16 rows: the caller calls fold() at least every 16 add()s), which flush() moves to int64
-// at least every 256 rows.  3.5 instructions per
-// element instead of the 7 of the first version (raw float bits summed in integer lanes: two IADD per element).
-// bf16: fp64 accumulation in a fixed order.
+// at least every 256 rows.  3.5 instructions per element instead of the 7 of the first version (raw float bits
+// summed in integer lanes: two IADD per element).  bf16: fp64 accumulation in a fixed order.
 template <typename T> struct RowAcc;
 template <> struct RowAcc<__half> {
   float2 hf[4], lf[4];
