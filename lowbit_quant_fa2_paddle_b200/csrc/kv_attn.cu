@@ -7,8 +7,9 @@
 // Arithmetic that defines the result (attn_4bit_per_block.py:260-262, 330-372; new_pack.py:69-144):
 //   K^[d,n] = fma(code, scale[d, n/G], mn[d, n/G])      V^[n,d] = fma(code, scale[n, d/G], mn[n, d/G])
 //   S = q . K^,  p = exp(S * softmax_scale - m),  o = (sum_n p V^) / l,  lse = m + log(l)
-// The reference kernel is a prototype that does not run as written, so parity for this entry is
-// unpinned: the tests' CPU restatement follows the formulas above over the reference's own (pinned) pack format.
+// The reference kernel is a prototype that does not run as written; parity is pinned to what its
+// own driver checks it against (:637-788): attention over the caches dequantized by the reference's unpack_and_dequant_*
+// functions, run unmodified (tests/golden/kvcache_*.npz, tools/make_golden_kvcache.py), on the pinned pack format.
 //
 // A decode-shaped, HBM-bound path: up to 8 query rows against a long packed cache that is read exactly once.  The
 // first version dequantized every code with shift / mask / I2F / FMA (14.8 thread instructions per code, 27 % of

@@ -1,15 +1,23 @@
 """TEST INFRASTRUCTURE -- CPU oracle of the KV-cache path.  Only tests/ and measurement tools may
 import this; the product path never does.
 
-PARITY UNPINNED: the reference's `_fwd_kernel` (src/triton/quantization/attn_4bit_per_block.py:28-421) is a prototype
-that does not run as written (`tl.arange` over a runtime length, `static_print`s, an int32-vs-int8 packing mismatch
-with its own driver -- SURVEY 2.1 row 12), so no golden vector can be produced from it.  What IS pinned is the cache
-format: `quantize_and_pack_along_last_dim` in oracle/quant.py is bit-exact against the reference's pack kernels
-(tests/golden/kivi_*.npz).  On top of that format this file restates the arithmetic the prototype states:
+PARITY: the reference's `_fwd_kernel` (src/triton/quantization/attn_4bit_per_block.py:28-421) is a prototype that does
+not run as written (`tl.arange` over a runtime length, `static_print`s, an int32-vs-int8 packing mismatch with its own
+driver -- SURVEY 2.1 row 12), so no golden vector can come from the kernel itself.  It is pinned to what the
+prototype's own driver checks the kernel against (`main`, :637-788: FlashAttention over `dequant_k`, `dequant_v`):
+  * the cache format: `quantize_and_pack_along_last_dim` in oracle/quant.py is bit-exact against the reference's pack
+    kernels (tests/golden/kivi_*.npz);
+  * the dequantization: `kivi_unpack_and_dequant` in oracle/quant.py is bit-identical to the reference's
+    `unpack_and_dequant_kcache` / `unpack_and_dequant_vcache` (new_pack.py:68-144), which tools/make_golden_kvcache.py
+    executes UNMODIFIED through a Paddle shim (tests/golden/kvcache_*.npz: dequant_k, dequant_v);
+  * the attention: exact softmax attention (fp64) over those dequantized fp16 caches is stored as o / lse in the same
+    fixtures; this oracle is within 3.4e-4 / 1.1e-4 of it, the CUDA kernel within 5.4e-4 / 4.8e-4
+    (tests/test_kv_cache.py).
+On top of that format this file restates the arithmetic the prototype kernel states:
   K^ = fma(code, scale, mn), V^ = fma(code, scale, mn) in fp32            attn_4bit_per_block.py:260-262, 355-357
   S = q . K^ (fp32), p = exp(S * softmax_scale - m), o = sum p V^ / l     :330-372
   lse = m + log(l) (natural)                                              :372
-and, for the dequantization alone, `unpack_and_dequant_{k,v}cache` (new_pack.py:69-144).
+(the fp32 fma differs from the reference's fp16 `code * scale + mn` by the two fp16 roundings, <= 3e-3 absolute).
 """
 import math
 
