@@ -15,9 +15,13 @@ Pinned / unpinned status:
   Q4  per_block_int4_unpack (Triton)   pinned   -- golden vectors from the reference kernel
   Q3  per_thread_int8/int4 (Triton)    pinned   -- golden vectors from the reference kernel
   Q5  KIVI min/max + pack (Triton)     pinned for the two kernels; the Paddle element-wise glue between
-                                       them is restated from source ("parity unpinned" for that glue)
-  Q2  per_block_int8 (CUDA, fused.cu)  parity unpinned: csrc/ is not buildable here (needs Paddle+torch headers)
-  Q6  per_channel_fp8 (CUDA, fused.cu) parity unpinned (same reason)
+                                       them is restated from source ("parity unpinned" for that glue);
+                                       kivi_unpack_and_dequant is bit-identical to the reference's
+                                       unpack_and_dequant_{k,v}cache run unmodified (tests/golden/kvcache_*.npz)
+  Q2  per_block_int8 (CUDA, fused.cu)  pinned (round 2) -- golden vectors from the reference's own fused.cu, compiled
+  Q6  per_channel_fp8 (CUDA, fused.cu) unmodified and run on a B200 (oracle/build_ref_fused.py, tools/make_golden_fused.py,
+      + sub_mean                       tests/golden/fused_*.npz, tests/test_fused_golden.py); only the fp32 block-reduction
+                                       order of the smooth_v mean is left to a tolerance (2e-6 relative)
   INT2 / packed INT4 / kbits map       parity unpinned: no coherent reference kernel exists
 """
 import numpy as np
@@ -429,7 +433,8 @@ def per_channel_fp8(v, tensor_layout="HND", scale_max=448.0, smooth_v=True):
     mnv = x.amin(dim=-1)
     if smooth_v:
         # fixed-order contract for the sum: fp32 accumulation is order dependent in the reference
-        # (blockReduceSum); we define it as the fp64 sum rounded to fp32 (parity unpinned).
+        # (blockReduceSum); we define it as the fp64 sum rounded to fp32 (held to the reference's fused.cu within
+        # 2e-6 relative, tests/test_fused_golden.py).
         vm = (x.double().sum(dim=-1)).float() / _f32(n16)
         amax = torch.maximum((mx - vm).abs(), (mnv - vm).abs())
         xs = vt.float() - vm[..., None]

@@ -297,8 +297,8 @@ def test_kivi_pack_matches_reference_golden(L, cuda_dev, bit):
 @pytest.mark.parametrize("shape,dtype", [((1, 2, 200, 64), torch.float16), ((2, 3, 77, 128), torch.bfloat16),
                                          ((1, 2, 1024, 128), torch.float16)])
 def test_v_fp8_per_channel_vs_oracle(L, cuda_dev, layout, smooth_v, shape, dtype):
-    """Q6: e4m3 bytes, scales and means bit-exact against the IEEE restatement of fused.cu (parity unpinned:
-    the reference CUDA cannot be built here)."""
+    """Q6: e4m3 bytes, scales and means bit-exact against the IEEE restatement of fused.cu (the restatement itself is
+    pinned to the reference's own fused.cu kernels by tests/test_fused_golden.py)."""
     from oracle import quant as OQ
     b, h, n, d = shape
     v = mk(b, h, n, d, layout, dtype, 51, bias=1.0)
