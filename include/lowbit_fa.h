@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LOWBIT_ABI_VERSION 7
+#define LOWBIT_ABI_VERSION 8
 
 /* element types of the floating-point inputs / outputs */
 enum { LOWBIT_F16 = 0, LOWBIT_BF16 = 1 };
@@ -201,6 +201,11 @@ int lowbit_sub_mean(const void* v, const void* vm, void* out, int B, int H, int 
 
 /* E4 -- global max|x| of a tensor (compute_scale, src/core.py:1039-1047).  out: one f32 (device). */
 int lowbit_abs_max(const void* x, float* out, int B, int H, int N, int D,
+                   int64_t stride_b, int64_t stride_h, int64_t stride_n, int dtype, void* stream);
+
+/* E4 -- global maximum and minimum of a tensor (the asymmetric branch of compute_scale, src/core.py:1043-1045:
+ * `(max - min) / (2^bits - 1)`).  out: two f32 (device): out[0] = max, out[1] = min. */
+int lowbit_min_max(const void* x, float* out, int B, int H, int N, int D,
                    int64_t stride_b, int64_t stride_h, int64_t stride_n, int dtype, void* stream);
 
 /* A1/A2/A3 -- fused low-bit attention forward.

@@ -41,6 +41,7 @@ SIGNATURES = {
     "lowbit_v_fp8_workspace_bytes": (_L, [_I] * 4),
     "lowbit_v_fp8_per_channel": (_I, [_P, _P, _P, _P, _P] + [_I] * 4 + [_L] * 6 + [_F, _I, _P]),
     "lowbit_abs_max": (_I, [_P, _P] + [_I] * 4 + [_L] * 3 + [_I, _P]),
+    "lowbit_min_max": (_I, [_P, _P] + [_I] * 4 + [_L] * 3 + [_I, _P]),
     "lowbit_attn_fwd": (_I, [_P] * 10 + [_I] * 6 + [_L] * 12 + [_I] * 4 + [_P]),
     "lowbit_attn_fwd_partial": (_I, [_P] * 11 + [_I] * 6 + [_L] * 9 + [_L, _L] + [_I] * 4 + [_P]),
     "lowbit_attn_finalize": (_I, [_P] * 5 + [_I] * 4 + [_L] * 3 + [_I, _P]),
@@ -69,7 +70,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.lowbit_version() != 7:
+        if handle.lowbit_version() != 8:
             raise LowbitNativeError("liblowbit_fa_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -236,13 +236,18 @@ def lowbit_fa_q_int8_k_dynamic(q, k, v, tensor_layout: str = "HND", is_causal: b
 
 
 def compute_scale(tensor, bits=8, symmetric=True, tensor_layout="HND"):
-    """core.py:1039-1047 -- symmetric: max|x| / (2^(bits-1) - 1), as a 0-d device tensor."""
-    if not symmetric:
-        raise NotImplementedError("asymmetric compute_scale is not on the hot path")
+    """core.py:1039-1047 -- symmetric: max|x| / (2^(bits-1) - 1); asymmetric: (max - min) / (2^bits - 1); a 0-d device
+    tensor either way."""
     t = T.as_torch(tensor)
     d = t.shape[-1]
     if d > 128:
         raise ValueError(f"Unsupported head_dim: {d}")
+    if not symmetric:
+        if d not in (64, 128):  # pad by repeating the last channel: zeros would change the extremes
+            seg = t[..., -1:].expand(*t.shape[:-1], (64 if d <= 64 else 128) - d)
+            t = torch.cat([t, seg], dim=-1)
+        mm = Qz.min_max(T.aligned16(t.contiguous() if t.stride(-1) != 1 else t), tensor_layout)
+        return (mm[0] - mm[1]) / (2 ** bits - 1)
     if d not in (64, 128):
         t = _pad_head(t, 64 if d <= 64 else 128)
     return Qz.abs_max(T.aligned16(t), tensor_layout) / (2 ** (bits - 1) - 1)

@@ -714,6 +714,37 @@ abs_max_kernel(const T* __restrict__ x, unsigned int* __restrict__ out, int N, i
   if ((tid & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
+// global max and min (asymmetric compute_scale, core.py:1043-1045): floats ordered as unsigned integers
+// (negative -> ~bits, non-negative -> bits | sign bit), one atomicMax / atomicMin per warp
+__device__ __forceinline__ unsigned int float_ordered(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+min_max_kernel(const T* __restrict__ x, unsigned int* __restrict__ out, int N, int64_t sb, int64_t sh, int64_t sn) {
+  constexpr int TPR = D / 8, RPP = 256 / TPR;
+  const int tid = threadIdx.x, c8 = (tid % TPR) * 8, r0 = tid / TPR;
+  const T* src = x + blockIdx.z * sb + blockIdx.y * sh + c8;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int row = blockIdx.x * RPP * 8 + r0; row < min(N, (int)(blockIdx.x + 1) * RPP * 8); row += RPP) {
+    float f[8];
+    unpack8<T>(ld_stream_v4(src + (int64_t)row * sn), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mx = fmaxf(mx, f[i]); mn = fminf(mn, f[i]); }
+  }
+  const unsigned int omx = __reduce_max_sync(0xffffffffu, float_ordered(mx));
+  const unsigned int omn = __reduce_min_sync(0xffffffffu, float_ordered(mn));
+  if ((tid & 31) == 0) {
+    atomicMax(out, omx);
+    atomicMin(out + 1, omn);
+  }
+}
+__global__ void min_max_finish_kernel(unsigned int* __restrict__ out) {  // ordered integers -> float bits, in place
+  const unsigned int u = out[threadIdx.x];
+  out[threadIdx.x] = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+}
+
 template <typename T>
 __global__ void lse_fixup_kernel(float* __restrict__ lse, const T* __restrict__ q, const T* __restrict__ km,
                                  int Hq, int Hkv, int Nq, int D, int64_t sb, int64_t sh, int64_t sn, float sm_scale) {
@@ -1090,6 +1121,32 @@ int lowbit_abs_max(const void* x, float* out, int B, int H, int N, int D, int64_
   } else {
     return fail("lowbit_abs_max: unsupported dtype %d", dtype);
   }
+  LOWBIT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int lowbit_min_max(const void* x, float* out, int B, int H, int N, int D, int64_t sb, int64_t sh, int64_t sn,
+                   int dtype, void* stream) {
+  LOWBIT_CHECK(x && out, "lowbit_min_max: null pointer");
+  LOWBIT_CHECK(D == 64 || D == 128, "lowbit_min_max: head_dim must be 64 or 128 (got %d)", D);
+  LOWBIT_CHECK(B > 0 && H > 0 && N > 0, "lowbit_min_max: empty tensor");
+  LOWBIT_CHECK(sn % 8 == 0 && sh % 8 == 0 && sb % 8 == 0 && ((uintptr_t)x & 15) == 0,
+               "lowbit_min_max: base address and strides must keep 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  LOWBIT_CUDA(cudaMemsetAsync(out, 0x00, sizeof(float), st));        // ordered minimum: below every float
+  LOWBIT_CUDA(cudaMemsetAsync(out + 1, 0xff, sizeof(float), st));    // ordered maximum: above every float
+  const int rows_per_cta = (256 / (D / 8)) * 8;
+  dim3 grid((N + rows_per_cta - 1) / rows_per_cta, H, B);
+  if (dtype == LOWBIT_F16) {
+    if (D == 64) min_max_kernel<__half, 64><<<grid, 256, 0, st>>>((const __half*)x, (unsigned*)out, N, sb, sh, sn);
+    else min_max_kernel<__half, 128><<<grid, 256, 0, st>>>((const __half*)x, (unsigned*)out, N, sb, sh, sn);
+  } else if (dtype == LOWBIT_BF16) {
+    if (D == 64) min_max_kernel<__nv_bfloat16, 64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (unsigned*)out, N, sb, sh, sn);
+    else min_max_kernel<__nv_bfloat16, 128><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (unsigned*)out, N, sb, sh, sn);
+  } else {
+    return fail("lowbit_min_max: unsupported dtype %d", dtype);
+  }
+  min_max_finish_kernel<<<1, 2, 0, st>>>((unsigned*)out);
   LOWBIT_CUDA(cudaGetLastError());
   return 0;
 }

@@ -374,3 +374,14 @@ def abs_max(x, tensor_layout="HND"):
     N.call("lowbit_abs_max", xt.data_ptr(), out.data_ptr(), b, h, n, d, sb, sh, sn, T.dtype_code(xt.dtype),
            T.stream_ptr(dev), device=dev)
     return out
+
+
+def min_max(x, tensor_layout="HND"):
+    """Global (max, min) of x as a 2-element fp32 device tensor (asymmetric compute_scale, core.py:1043-1045)."""
+    xt = T.as_torch(x)
+    dev = T.require_cuda(xt)
+    b, h, n, d, sb, sh, sn = T.bhnd(xt, tensor_layout)
+    out = torch.empty((2,), dtype=torch.float32, device=dev)
+    N.call("lowbit_min_max", xt.data_ptr(), out.data_ptr(), b, h, n, d, sb, sh, sn, T.dtype_code(xt.dtype),
+           T.stream_ptr(dev), device=dev)
+    return out

@@ -36,7 +36,7 @@ def test_header_symbols_exported(native):
 
 def test_version_and_error_string(native):
     L = native.lib()
-    assert L.lowbit_version() == 7
+    assert L.lowbit_version() == 8
     assert isinstance(L.lowbit_last_error(), bytes)
 
 

@@ -250,6 +250,25 @@ def test_multi_precision_and_select(L, cuda_dev):
     assert o.shape == q.shape and not torch.isnan(o).any()
 
 
+@pytest.mark.parametrize("shape,dtype,layout", [((2, 3, 300, 64), torch.float16, "HND"), ((1, 2, 77, 128), torch.bfloat16, "HND"),
+                                                ((2, 129, 2, 128), torch.float16, "NHD"), ((1, 2, 50, 40), torch.float16, "HND"),
+                                                ((1, 1, 9, 96), torch.bfloat16, "HND")])
+@pytest.mark.parametrize("shift", [0.0, 3.0, -5.0])
+def test_compute_scale_asymmetric(L, cuda_dev, shape, dtype, layout, shift):
+    """compute_scale(symmetric=False) = (max - min) / (2^bits - 1) (core.py:1043-1045): exact extremes from the
+    lowbit_min_max kernel (all-positive, all-negative and mixed tensors; head dims that need padding)."""
+    g = torch.Generator().manual_seed(hash((shape, shift)) % 1000)
+    x = (torch.randn(shape, generator=g) + shift).to(dtype).to(cuda_dev)
+    from lowbit_quant_fa2_paddle_b200 import quant as Qz
+    if shape[-1] in (64, 128):
+        mm = Qz.min_max(x, layout).cpu()
+        assert mm[0].item() == x.float().max().item() and mm[1].item() == x.float().min().item()
+    for bits in (8, 4):
+        sc = float(L.compute_scale(x, bits=bits, symmetric=False, tensor_layout=layout))
+        ref = (x.float().max().item() - x.float().min().item()) / (2 ** bits - 1)
+        assert abs(sc - ref) <= 1e-6 * max(1.0, abs(ref))
+
+
 # ------------------------------------------------------------------------------------------------ Q3 / Q5 / Q6
 @pytest.mark.parametrize("name", [n for n in ATTN if "causal" not in n])
 @pytest.mark.parametrize("bits", [8, 4])
