@@ -90,11 +90,41 @@ template <> __device__ __forceinline__ float2 round_trip2<__nv_bfloat16>(float2 
 // A row that is out of range must contribute exact zeros: without km that is what the zero-filled load gives
 // (0 * sm); with km the caller substitutes km's own bits for the row (km - km = 0), which is cheaper than a select
 // per element.  Same IEEE operations per lane as the scalar form, so the same bits.
+// packed pair types of the input dtypes, and `a - b` in that dtype (one correctly rounded HSUB2 per pair)
+template <typename T> struct Pair;
+template <> struct Pair<__half> {
+  using type = __half2;
+  static __device__ __forceinline__ type from_f32(float2 v) { return __float22half2_rn(v); }
+  static __device__ __forceinline__ float2 to_f32(type v) { return __half22float2(v); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  using type = __nv_bfloat162;
+  static __device__ __forceinline__ type from_f32(float2 v) { return __float22bfloat162_rn(v); }
+  static __device__ __forceinline__ float2 to_f32(type v) { return __bfloat1622float2(v); }
+};
+
 template <typename T, bool HAS_KM, bool ROUND_KM>
 __device__ __forceinline__ void prep_row8(const uint4& raw, const float (&kmf)[8], float sm, float (&x)[8], float& amax) {
+  const float2 sm2 = make_float2(sm, sm);
+  if constexpr (HAS_KM && ROUND_KM) {
+    // `k - km` in the tensor's dtype is ONE subtraction there: RN_dtype(a - b).  The fp32 route below (convert,
+    // subtract, round back) gives the same bits -- fp32's 24 bits are >= 2 * 11 + 2, so the double rounding is
+    // innocuous -- at twice the instructions; km comes back to its packed form exactly (hoisted out of the row loop).
+    using P = Pair<T>;
+    const typename P::type* h2 = reinterpret_cast<const typename P::type*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const typename P::type km2 = P::from_f32(make_float2(kmf[2 * i], kmf[2 * i + 1]));
+      float2 v = P::to_f32(__hsub2(h2[i], km2));
+      v = __fmul2_rn(v, sm2);
+      x[2 * i] = v.x;
+      x[2 * i + 1] = v.y;
+      amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));
+    }
+    return;
+  }
   float f[8];
   unpack8<T>(raw, f);
-  const float2 sm2 = make_float2(sm, sm);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float2 v = make_float2(f[2 * i], f[2 * i + 1]);
