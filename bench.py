@@ -625,7 +625,7 @@ def run_single(args, rank, world, local, dev):
 
 
 # ------------------------------------------------------------------------------------------------ our arm, N > 1
-def run_ring(L, P, wl, world, rank, dev, steps=3, warm=2):
+def run_ring(L, P, wl, world, rank, dev, steps=5, warm=2):
     B, Hq, Hkv, N, D, layout, causal, qk, pv, part, desc = WL[wl]
     n_loc = N // world
     torch.manual_seed(1000 + rank)
